@@ -1,0 +1,256 @@
+/*
+ * parasuite_b200.h -- C ABI of libparasuite_b200.so
+ *
+ * B200-native replacement of the two counting loops of PARA-suite (reference: akloetgen/PARA-suite):
+ *
+ *   error profile : src/src/utils/errorprofile/ErrorProfiling.java:146-409   (tool `error`, `map --refine`)
+ *   T>C pileup    : src/src/utils/pileupclusters/PileupClusters.java:137-500 (tool `clust`)
+ *
+ * The reference has no FFI of its own (pure Java).  This header is the boundary a thin JNI shim
+ * binds (jni/parasuite_jni.c): plain C types, caller-owned output arrays, negative
+ * PS_ERR_* status codes, no exception or CUDA error ever crosses it.  There is NO CPU fallback:
+ * without a usable sm_100 GPU every compute entry point returns PS_ERR_NO_DEVICE.
+ *
+ * Each entry point cites the reference lines it stands in for.
+ */
+#ifndef PARASUITE_B200_H
+#define PARASUITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define PS_OK 0
+#define PS_ERR_INVALID_ARG (-1)
+#define PS_ERR_NO_DEVICE (-2)          /* no CUDA device / not sm_100: there is no CPU fallback */
+#define PS_ERR_CUDA (-3)
+#define PS_ERR_OOM (-4)
+#define PS_ERR_IO (-5)
+#define PS_ERR_FORMAT (-6)             /* malformed BAM / FASTA / .fai */
+#define PS_ERR_UNSORTED (-7)           /* header SO != coordinate (ErrorProfiling.java:124-132) */
+#define PS_ERR_REFERENCE_WOULD_THROW (-8) /* input on which the JVM dies with an uncaught exception */
+#define PS_ERR_STATE (-9)              /* call order violated (e.g. batch before begin) */
+#define PS_ERR_UNSUPPORTED (-10)
+
+/* reason codes reported with PS_ERR_REFERENCE_WOULD_THROW (ps_fault.code) */
+#define PS_THROW_NONE 0
+#define PS_THROW_REF_RANGE 1       /* FASTA fetch past contig end / unknown contig (htsjdk SAMException) */
+#define PS_THROW_EMPTY_REF 2       /* refSequenceForRead[0] on an empty array (ErrorProfiling.java:180) */
+#define PS_THROW_INDEL_FILL 3      /* I/D fill beyond mappingLength (ErrorProfiling.java:257,277) */
+#define PS_THROW_INDEL_POS 4       /* insertions/deletionsPerPos index >= maxReadLength (:266,:287) */
+#define PS_THROW_POS_MAXLEN 5      /* positionConversions[i], i >= maxReadLength (:377) */
+#define PS_THROW_QUAL_RANGE 6      /* readQualities[i] out of range (:388, :405) */
+#define PS_THROW_MASK51 7          /* mutationMapInRead[i], i >= 51 (PileupClusters.java:654) */
+#define PS_THROW_BLOCK_RANGE 8     /* alignment block beyond the read bases (PileupClusters.java:594) */
+
+/* ---- packed reference ---------------------------------------------------------------------
+ * All contigs concatenated into one coordinate space ("global offset", 0-based, < 2^32).
+ *   seq2 : 2 bits/base, 16 bases per uint32, base p at bits [2*(p%16), 2*(p%16)+1] of word p/16;
+ *          A=0 C=1 G=2 T=3 (case folded: ErrorProfiling.java:633-664 counts acgt like ACGT)
+ *   inv  : 1 bit/base, bit p%32 of word p/32; set for every byte that is not one of ACGTacgt
+ *          (such positions are never counted; seq2 holds 0 there)
+ * Both arrays must be padded with >= 16 readable bytes past the last used word.
+ */
+typedef struct ps_reference {
+  uint64_t n_bases;            /* total concatenated length */
+  const uint32_t* seq2;        /* ceil(n_bases/16) words (+ padding) */
+  const uint32_t* inv;         /* ceil(n_bases/32) words (+ padding) */
+  uint32_t n_contigs;
+  const uint64_t* contig_off;  /* [n_contigs+1] global offset of each contig's first base */
+} ps_reference;
+
+/* ---- SoA read batch -----------------------------------------------------------------------
+ * What the host batcher makes of the records htsjdk would hand the Java loops, in file order.
+ * Reads are grouped in tiles of PS_TILE_READS; variable-length streams are addressed by one
+ * offset per tile plus an in-tile prefix sum over `meta`, so the per-read algorithmic bytes are
+ *   ceil(L/4) + L + 4*n_cigar + 4 (ref_start) + 4 (meta)        (SURVEY.md 8(d)).
+ */
+#define PS_TILE_READS 256u
+
+/* meta word: bits 0..15 L (read length), bits 16..23 n_cigar, bits 24..31 flags below */
+#define PS_META_LEN(m) ((m) & 0xFFFFu)
+#define PS_META_NCIGAR(m) (((m) >> 16) & 0xFFu)
+#define PS_META_FLAGS(m) ((m) >> 24)
+#define PS_MAKE_META(len, ncig, fl) (((uint32_t)(len) & 0xFFFFu) | (((uint32_t)(ncig) & 0xFFu) << 16) | ((uint32_t)(fl) << 24))
+#define PS_RF_UNMAPPED 0x01u     /* BAM flag 0x4   */
+#define PS_RF_REVERSE 0x02u      /* BAM flag 0x10  */
+#define PS_RF_DUPLICATE 0x04u    /* BAM flag 0x400 */
+#define PS_RF_POS_ZERO 0x08u     /* getAlignmentStart()==0 */
+#define PS_RF_QUAL_MISSING 0x10u /* first quality byte 0xFF -> getBaseQualities() is empty */
+#define PS_RF_HAS_INVALID 0x20u  /* read holds non-ACGT bases, listed in `exc` */
+#define PS_RF_REF_RANGE 0x40u    /* FASTA fetch [start,end] would raise SAMException */
+#define PS_RF_CIGAR_OVERFLOW 0x80u /* record had > 255 cigar ops; cigar stream holds none (unsupported) */
+
+typedef struct ps_read_batch {
+  uint64_t n_reads;
+  const uint32_t* meta;           /* [n_reads] */
+  const uint32_t* ref_start;      /* [n_reads] global 0-based offset of POS; undefined if unmapped/POS==0 */
+  const uint8_t* bases2;          /* 2-bit codes, read r: ceil(L/4) bytes, base p at bits 2*(p%4) of byte p/4 */
+  const uint8_t* qual;            /* raw phred bytes, L per read (kept even when missing) */
+  const uint32_t* cigar;          /* BAM encoding len<<4|op, op 0..8 = MIDNSHP=X */
+  const uint64_t* tile_base_off;  /* [n_tiles+1] byte offset of each tile in bases2 */
+  const uint64_t* tile_qual_off;  /* [n_tiles+1] byte offset of each tile in qual */
+  const uint64_t* tile_cigar_off; /* [n_tiles+1] element offset of each tile in cigar */
+  const uint32_t* tile_exc_off;   /* [n_tiles+1] element offset of each tile in exc */
+  const uint32_t* exc;            /* invalid read bases: (read_in_tile << 16) | position, sorted */
+  uint32_t uniform_len;           /* != 0: every read has this L (offsets are closed-form) */
+  uint32_t uniform_ncigar;        /* != 0: every read has this many cigar ops */
+  uint64_t bases_bytes;           /* total sizes of the streams (for copies) */
+  uint64_t qual_bytes;
+  uint64_t cigar_count;
+  uint64_t exc_count;
+} ps_read_batch;
+
+/* ---- error profile ------------------------------------------------------------------------ */
+typedef struct ps_profile_opts {
+  uint32_t max_read_length;  /* ErrorProfiling ctor arg (ErrorProfiling.java:58-64) */
+  uint32_t infer_qualities;  /* `-q` (ErrorProfiling.java:402-407): also fill the quality histogram */
+} ps_profile_opts;
+
+/* counters[] order (ErrorProfiling.java:134-141, :54) */
+enum {
+  PS_PC_NUM_READS_PROCESSED = 0,
+  PS_PC_UNMAPPED,
+  PS_PC_DUPLICATES,
+  PS_PC_START_ZERO,
+  PS_PC_INDEL_READ,
+  PS_PC_SKIPPED_READS,
+  PS_PC_LONGER_INDELS,
+  PS_PC_TOTAL_BASES_CHECKED,
+  PS_PC_COUNT
+};
+
+typedef struct ps_fault {
+  int32_t code;          /* PS_THROW_* */
+  uint64_t read_ordinal; /* 0-based ordinal (over all batches since begin) of the first such record */
+} ps_fault;
+
+/* Caller-allocated outputs, bit-identical to the Java fields after the loop :146-409.
+ * int32 arrays carry Java's two's-complement wrap-around; the *_wide arrays (optional, may be NULL)
+ * receive the un-wrapped 64-bit sums. */
+typedef struct ps_profile_result {
+  int32_t* position_conversions;      /* [max_read_length*16]  ([i][ref][read]) */
+  int32_t* quality_per_mismatch;      /* [16] */
+  int32_t* quality_per_mismatch_counts; /* [16] */
+  double* insertions_per_pos;         /* [max_read_length] */
+  double* deletions_per_pos;          /* [max_read_length] */
+  int32_t* counters;                  /* [PS_PC_COUNT] */
+  int64_t* quality_hist;              /* [max_read_length*256] or NULL (only with infer_qualities) */
+  int64_t* wide;                      /* [ps_profile_acc_len()] raw accumulator vector or NULL */
+  ps_fault fault;
+} ps_profile_result;
+
+/* accumulator vector layout (int64), the unit of the multi-GPU all-reduce:
+ *   [0, 16*maxLen) positionConversions | +16 qualityPerMismatch | +16 qualityPerMismatchCounts
+ *   | +maxLen insertionsPerPos | +maxLen deletionsPerPos | +PS_PC_COUNT counters
+ *   | (+256*maxLen quality histogram with infer_qualities) */
+size_t ps_profile_acc_len(uint32_t max_read_length, uint32_t infer_qualities);
+
+/* ---- T>C pileup ---------------------------------------------------------------------------- */
+typedef struct ps_cluster {      /* one closed cluster, state at PileupClusters.java:178 (before the SNP filter) */
+  uint64_t first_read;           /* ordinal of the read that opened it */
+  uint32_t running_id;           /* "cl_<running_id>_<chr>"; first cluster is 2 (PileupClusters.java:355) */
+  uint32_t contig;               /* index into the reference contig table */
+  int32_t start;                 /* tempClusterStart, 1-based */
+  int32_t end;                   /* tempClusterEnd */
+  uint32_t num_reads;            /* numReadsPerCluster */
+  uint32_t num_t2c;              /* numT2CMutationPerCluster */
+  uint32_t minus_after_first;    /* minus-strand members after the first read (P6) */
+  uint8_t first_reverse;         /* tempIsReverse */
+  uint8_t combined_strand;       /* 0 "+", 1 "-", 2 "+/-"  (StrandOrientation.java:48-56) */
+  uint16_t reserved;
+  uint64_t mask51;               /* alleleFrequencyPositionsTemp as bits */
+  uint64_t site_begin;           /* [site_begin, site_end) in the site array */
+  uint64_t site_end;
+} ps_cluster;
+
+typedef struct ps_site {         /* one key of mutationMap with its baseCoveredMap value */
+  int32_t pos;                   /* checkPosition, 1-based */
+  uint32_t t2c;                  /* mutationMap value */
+  uint32_t cov;                  /* baseCoveredMap value */
+  uint32_t reserved;
+  uint64_t order_key;            /* (ordinal of the read that first put this key << 6) | i  -- sorting a
+                                    cluster's sites by it gives the HashMap.put order */
+} ps_site;
+
+typedef struct ps_pileup_counters {
+  uint64_t num_reads_processed;  /* PileupClusters.java:138 */
+  uint64_t skipped_due_indel;    /* :156 */
+  uint64_t double_stranded;      /* :496 (incl. the never-flushed last cluster) */
+  uint64_t n_clusters;           /* closed clusters returned */
+  uint64_t n_sites;
+  uint8_t has_open_cluster;      /* the reference never flushes the last cluster (:528-529) */
+} ps_pileup_counters;
+
+typedef struct ps_ctx ps_ctx;
+typedef struct ps_pileup ps_pileup;   /* opaque result handle */
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+int ps_abi_version(void);
+/* One context per GPU (one process per GPU under torch.distributed; a JVM may hold several). */
+int ps_create(ps_ctx** out, int device);
+void ps_destroy(ps_ctx* ctx);
+const char* ps_last_error(const ps_ctx* ctx);
+const char* ps_strerror(int status);
+
+/* ---- reference ------------------------------------------------------------------------------
+ * Replaces `new IndexedFastaSequenceFile(fasta)` + one getSubsequenceAt per read
+ * (ErrorProfiling.java:109-110,169-172; PileupClusters.java:66,598-601): the whole reference is
+ * packed once and stays resident in HBM. */
+int ps_reference_upload(ps_ctx* ctx, const ps_reference* host_ref);
+int ps_reference_load_fasta(ps_ctx* ctx, const char* fasta_path); /* needs <fasta>.fai */
+/* adopt device-resident arrays (no copy; caller keeps them alive) */
+int ps_reference_adopt_device(ps_ctx* ctx, const ps_reference* dev_ref, const uint64_t* host_contig_off);
+
+/* ---- error profile: replaces the loop ErrorProfiling.java:146-409 ---------------------------- */
+int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts);
+/* host-resident batch: staged through pinned memory, H2D, kernels; asynchronous, returns when queued */
+int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* host_batch);
+/* device-resident batch (all pointers are device pointers) on `stream` (a cudaStream_t, may be NULL) */
+int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream);
+/* device address of the int64 accumulator vector (for an NCCL all-reduce by the caller) */
+int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64);
+/* synchronise, wrap to Java int semantics, fill the caller's arrays */
+int ps_profile_end(ps_ctx* ctx, ps_profile_result* out);
+/* whole tool loop from files (BAM must be coordinate sorted) */
+int ps_profile_bam(ps_ctx* ctx, const char* bam_path, const ps_profile_opts* opts, ps_profile_result* out);
+
+/* ---- T>C pileup: replaces the loop PileupClusters.java:137-500 (+ :585-673) ------------------- */
+typedef struct ps_pileup_opts {
+  uint32_t first_running_id;  /* runningID before the first cluster; reference: 1 (PileupClusters.java:133) */
+  /* carry-in from a preceding shard (halo merge); all zero for a whole file */
+  uint32_t carry_valid;
+  uint32_t carry_contig;
+  int32_t carry_cluster_end;
+} ps_pileup_opts;
+
+int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* host_batch, const ps_pileup_opts* opts, ps_pileup** out);
+int ps_pileup_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, const ps_pileup_opts* opts, void* stream,
+                           ps_pileup** out);
+int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out);
+/* copy up to `max_clusters` closed clusters starting at `first` (and their sites) into caller arrays;
+ * returns the number copied (>= 0) or a negative status */
+int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint64_t max_clusters, ps_site* sites,
+                       uint64_t max_sites);
+/* the still-open last cluster (never flushed by the reference); needed for the halo merge */
+int ps_pileup_open_cluster(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites);
+int ps_pileup_fault(const ps_pileup* h, ps_fault* out);
+void ps_pileup_close(ps_pileup* h);
+int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of kernels this context has launched since creation (bench.py "gpu_launches") */
+uint64_t ps_kernel_launches(const ps_ctx* ctx);
+/* device time (ms, CUDA events on the launching stream) of the last ps_*_batch_device call's dominant kernel */
+float ps_last_kernel_ms(const ps_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARASUITE_B200_H */
