@@ -168,8 +168,8 @@ def test_profile_cpp_vs_python_random(oracle, seed, kinds):
 @pytest.mark.parametrize("seed,kinds", [(11, ("M",)), (12, ("M", "clip", "indel")), (13, ("wild", "splice", "M"))])
 def test_pileup_cpp_vs_python_random(oracle, seed, kinds):
     rng = random.Random(seed)
-    contigs = random_genome(rng, n_contigs=2, length=300)
-    recs = random_records(rng, contigs, 250, kinds=kinds, Lrange=(15, 30), flags_special=0.05)
+    contigs = random_genome(rng, n_contigs=2, length=6000, n_frac=0.003, lower_frac=0.05)
+    recs = random_records(rng, contigs, 400, kinds=kinds, Lrange=(15, 30), flags_special=0.05)
     recs = [r for r in recs if r.pos > 0]
     g = po.Genome(dict(contigs))
     ref = PackedReference.from_contigs(contigs)
