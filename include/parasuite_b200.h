@@ -249,6 +249,10 @@ int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts,
 uint64_t ps_kernel_launches(const ps_ctx* ctx);
 /* device time (ms, CUDA events on the launching stream) of the last ps_*_batch_device call's dominant kernel */
 float ps_last_kernel_ms(const ps_ctx* ctx);
+/* device times (ms) of the dominant kernel of every ps_*_batch[_device] call since the last reset, in call
+ * order (at most 512 are kept); returns how many were written.  reset(enabled=0) switches the event pairs off. */
+int ps_kernel_times(ps_ctx* ctx, float* ms, int max);
+void ps_kernel_times_reset(ps_ctx* ctx, int enabled);
 
 #ifdef __cplusplus
 }

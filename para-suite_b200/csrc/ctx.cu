@@ -1,0 +1,330 @@
+// C ABI of libparasuite_b200.so: context, reference residency, error-profile entry points.
+// (include/parasuite_b200.h documents which reference lines each call replaces.)
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+
+int set_error(ps_ctx* ctx, int status, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+int cuda_fail(ps_ctx* ctx, cudaError_t e, const char* what) {
+  std::string m = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();
+  return set_error(ctx, e == cudaErrorMemoryAllocation ? PS_ERR_OOM : PS_ERR_CUDA, m);
+}
+
+static DeviceBatch view_of(const ps_read_batch* b) {
+  DeviceBatch v;
+  v.n_reads = b->n_reads;
+  v.meta = b->meta;
+  v.ref_start = b->ref_start;
+  v.bases2 = b->bases2;
+  v.qual = b->qual;
+  v.cigar = b->cigar;
+  v.tile_base_off = b->tile_base_off;
+  v.tile_qual_off = b->tile_qual_off;
+  v.tile_cigar_off = b->tile_cigar_off;
+  v.tile_exc_off = b->tile_exc_off;
+  v.exc = b->exc;
+  v.uniform_len = b->uniform_len;
+  v.uniform_ncigar = b->uniform_ncigar;
+  return v;
+}
+
+static int check_batch(ps_ctx* ctx, const ps_read_batch* b) {
+  if (!b) return set_error(ctx, PS_ERR_INVALID_ARG, "batch is NULL");
+  if (b->n_reads == 0) return PS_OK;
+  if (!b->meta || !b->ref_start || !b->bases2 || !b->qual || !b->cigar || !b->tile_exc_off || !b->exc)
+    return set_error(ctx, PS_ERR_INVALID_ARG, "batch has NULL streams");
+  if ((!b->uniform_len && (!b->tile_base_off || !b->tile_qual_off)) || (!b->uniform_ncigar && !b->tile_cigar_off))
+    return set_error(ctx, PS_ERR_INVALID_ARG, "variable-length batch without tile offsets");
+  if (b->n_reads / PS_TILE_READS >= 0xFFFFFFFFull)
+    return set_error(ctx, PS_ERR_INVALID_ARG, "batch too large (tile index is 32-bit)");
+  return PS_OK;
+}
+
+// H2D copy of a host batch into one of the two staging slots (async on ctx->stream)
+int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, StagedBatch** out) {
+  const int slot = ctx->staged_next;
+  ctx->staged_next ^= 1;
+  StagedBatch& s = ctx->staged[slot];
+  // the slot may still be read by a kernel queued two batches ago: same stream, so ordering is implicit
+  const uint64_t n = hb->n_reads;
+  const uint64_t nt = (n + PS_TILE_READS - 1) / PS_TILE_READS;
+  struct Item { DevBuf* d; const void* h; size_t bytes; };
+  Item items[] = {
+      {&s.meta, hb->meta, n * 4},
+      {&s.ref_start, hb->ref_start, n * 4},
+      {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
+      {&s.qual, hb->qual, (size_t)hb->qual_bytes},
+      {&s.cigar, hb->cigar, (size_t)hb->cigar_count * 4},
+      {&s.tbo, hb->tile_base_off, hb->tile_base_off ? (nt + 1) * 8 : 0},
+      {&s.tqo, hb->tile_qual_off, hb->tile_qual_off ? (nt + 1) * 8 : 0},
+      {&s.tco, hb->tile_cigar_off, hb->tile_cigar_off ? (nt + 1) * 8 : 0},
+      {&s.teo, hb->tile_exc_off, (nt + 1) * 4},
+      {&s.exc, hb->exc, (size_t)hb->exc_count * 4},
+  };
+  for (auto& it : items) {
+    PS_CUDA(ctx, it.d->reserve(it.bytes + 64));   // +64: kernels may read a few bytes past the last read
+    if (it.bytes) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  DeviceBatch& v = s.view;
+  v.n_reads = n;
+  v.meta = (const uint32_t*)s.meta.p;
+  v.ref_start = (const uint32_t*)s.ref_start.p;
+  v.bases2 = (const uint8_t*)s.bases2.p;
+  v.qual = (const uint8_t*)s.qual.p;
+  v.cigar = (const uint32_t*)s.cigar.p;
+  v.tile_base_off = hb->tile_base_off ? (const uint64_t*)s.tbo.p : nullptr;
+  v.tile_qual_off = hb->tile_qual_off ? (const uint64_t*)s.tqo.p : nullptr;
+  v.tile_cigar_off = hb->tile_cigar_off ? (const uint64_t*)s.tco.p : nullptr;
+  v.tile_exc_off = (const uint32_t*)s.teo.p;
+  v.exc = (const uint32_t*)s.exc.p;
+  v.uniform_len = hb->uniform_len;
+  v.uniform_ncigar = hb->uniform_ncigar;
+  *out = &s;
+  return PS_OK;
+}
+
+void timer_begin(ps_ctx* ctx, cudaStream_t st) {
+  if (!ctx->timers_on || ctx->ev_count >= PS_TIMER_RING) return;
+  cudaEventRecord(ctx->ev_start[ctx->ev_count], st);
+}
+void timer_end(ps_ctx* ctx, cudaStream_t st) {
+  if (!ctx->timers_on || ctx->ev_count >= PS_TIMER_RING) return;
+  cudaEventRecord(ctx->ev_stop[ctx->ev_count], st);
+  ctx->ev_count++;
+}
+
+extern "C" {
+
+int ps_abi_version(void) { return PS_ABI_VERSION; }
+
+const char* ps_strerror(int status) {
+  switch (status) {
+    case PS_OK: return "ok";
+    case PS_ERR_INVALID_ARG: return "invalid argument";
+    case PS_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+    case PS_ERR_CUDA: return "CUDA error";
+    case PS_ERR_OOM: return "out of device memory";
+    case PS_ERR_IO: return "I/O error";
+    case PS_ERR_FORMAT: return "malformed input file";
+    case PS_ERR_UNSORTED: return "BAM file is not sorted. Please provide a sorted BAM-file as input alignment file.";
+    case PS_ERR_REFERENCE_WOULD_THROW: return "the reference implementation would die with an uncaught exception on this input";
+    case PS_ERR_STATE: return "call order violated";
+    case PS_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown status";
+}
+
+int ps_create(ps_ctx** out, int device) {
+  if (!out) return PS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return PS_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PS_ERR_NO_DEVICE;
+  if (prop.major != 10) return PS_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return PS_ERR_NO_DEVICE;
+  ps_ctx* ctx = new ps_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PS_ERR_CUDA; }
+  for (int i = 0; i < PS_TIMER_RING; ++i) {
+    cudaEventCreate(&ctx->ev_start[i]);
+    cudaEventCreate(&ctx->ev_stop[i]);
+  }
+  *out = ctx;
+  return PS_OK;
+}
+
+void ps_destroy(ps_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < PS_TIMER_RING; ++i) {
+    cudaEventDestroy(ctx->ev_start[i]);
+    cudaEventDestroy(ctx->ev_stop[i]);
+  }
+  ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
+  ctx->acc.release(); ctx->fault.release();
+  for (auto& s : ctx->staged) {
+    s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
+    s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();
+  }
+  for (auto& b : ctx->pl_scratch) b.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* ps_last_error(const ps_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+// ---- reference ---------------------------------------------------------------------------------------
+static int set_contigs(ps_ctx* ctx, const uint64_t* host_contig_off, uint32_t n_contigs, uint64_t n_bases) {
+  if (!host_contig_off || n_contigs == 0) return set_error(ctx, PS_ERR_INVALID_ARG, "reference without contigs");
+  if (n_bases >= (1ull << 32)) return set_error(ctx, PS_ERR_UNSUPPORTED, "reference >= 2^32 bases");
+  ctx->contig_off.assign(host_contig_off, host_contig_off + n_contigs + 1);
+  if (ctx->contig_off.back() != n_bases) return set_error(ctx, PS_ERR_INVALID_ARG, "contig table does not sum to n_bases");
+  PS_CUDA(ctx, ctx->ref_contig.reserve((n_contigs + 1) * 8));
+  PS_CUDA(ctx, cudaMemcpy(ctx->ref_contig.p, host_contig_off, (n_contigs + 1) * 8, cudaMemcpyHostToDevice));
+  ctx->ref.contig_off = (const uint64_t*)ctx->ref_contig.p;
+  ctx->ref.n_contigs = n_contigs;
+  ctx->ref.n_bases = n_bases;
+  return PS_OK;
+}
+
+int ps_reference_upload(ps_ctx* ctx, const ps_reference* r) {
+  if (!ctx || !r || !r->seq2 || !r->inv) return set_error(ctx, PS_ERR_INVALID_ARG, "bad reference");
+  cudaSetDevice(ctx->device);
+  int st = set_contigs(ctx, r->contig_off, r->n_contigs, r->n_bases);
+  if (st) return st;
+  size_t b2 = ((r->n_bases + 15) / 16 + 4) * 4, b1 = ((r->n_bases + 31) / 32 + 4) * 4;
+  PS_CUDA(ctx, ctx->ref_seq2.reserve(b2));
+  PS_CUDA(ctx, ctx->ref_inv.reserve(b1));
+  PS_CUDA(ctx, cudaMemcpy(ctx->ref_seq2.p, r->seq2, b2, cudaMemcpyHostToDevice));
+  PS_CUDA(ctx, cudaMemcpy(ctx->ref_inv.p, r->inv, b1, cudaMemcpyHostToDevice));
+  ctx->ref.seq2 = (const uint32_t*)ctx->ref_seq2.p;
+  ctx->ref.inv = (const uint32_t*)ctx->ref_inv.p;
+  ctx->ref_loaded = true;
+  return PS_OK;
+}
+
+int ps_reference_adopt_device(ps_ctx* ctx, const ps_reference* r, const uint64_t* host_contig_off) {
+  if (!ctx || !r || !r->seq2 || !r->inv) return set_error(ctx, PS_ERR_INVALID_ARG, "bad reference");
+  cudaSetDevice(ctx->device);
+  int st = set_contigs(ctx, host_contig_off, r->n_contigs, r->n_bases);
+  if (st) return st;
+  ctx->ref.seq2 = r->seq2;
+  ctx->ref.inv = r->inv;
+  ctx->ref_loaded = true;
+  return PS_OK;
+}
+
+// ---- error profile -----------------------------------------------------------------------------------
+size_t ps_profile_acc_len(uint32_t max_read_length, uint32_t infer_qualities) {
+  return make_layout(max_read_length, infer_qualities).total;
+}
+
+int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
+  if (!ctx || !opts) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
+  if (opts->max_read_length == 0 || opts->max_read_length > 3000)
+    return set_error(ctx, PS_ERR_INVALID_ARG, "max_read_length must be in [1, 3000]");
+  if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
+  cudaSetDevice(ctx->device);
+  ctx->layout = make_layout(opts->max_read_length, opts->infer_qualities ? 1 : 0);
+  PS_CUDA(ctx, ctx->acc.reserve((size_t)ctx->layout.total * 8));
+  PS_CUDA(ctx, ctx->fault.reserve(8));
+  PS_CUDA(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)ctx->layout.total * 8, ctx->stream));
+  PS_CUDA(ctx, cudaMemsetAsync(ctx->fault.p, 0xFF, 8, ctx->stream));
+  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->reads_seen = 0;
+  ctx->profile_open = true;
+  return PS_OK;
+}
+
+int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
+  if (!ctx) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  int st = check_batch(ctx, b);
+  if (st) return st;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  timer_begin(ctx, s);
+  PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s));
+  timer_end(ctx, s);
+  ctx->reads_seen += b->n_reads;
+  return PS_OK;
+}
+
+int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
+  if (!ctx) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  int st = check_batch(ctx, hb);
+  if (st) return st;
+  if (hb->n_reads == 0) return PS_OK;
+  cudaSetDevice(ctx->device);
+  StagedBatch* sb = nullptr;
+  st = stage_batch(ctx, hb, &sb);
+  if (st) return st;
+  timer_begin(ctx, ctx->stream);
+  PS_CUDA(ctx, launch_profile(ctx, sb->view, ctx->reads_seen, ctx->stream));
+  timer_end(ctx, ctx->stream);
+  ctx->reads_seen += hb->n_reads;
+  return PS_OK;
+}
+
+int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64) {
+  if (!ctx || !dev_ptr || !n_int64) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  *dev_ptr = ctx->acc.p;
+  *n_int64 = ctx->layout.total;
+  return PS_OK;
+}
+
+int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
+  if (!ctx || !out) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  cudaSetDevice(ctx->device);
+  PS_CUDA(ctx, cudaDeviceSynchronize());   // kernels may have run on caller streams
+  const ProfileLayout& l = ctx->layout;
+  std::vector<int64_t> acc(l.total);
+  unsigned long long fw = 0;
+  PS_CUDA(ctx, cudaMemcpy(acc.data(), ctx->acc.p, (size_t)l.total * 8, cudaMemcpyDeviceToHost));
+  PS_CUDA(ctx, cudaMemcpy(&fw, ctx->fault.p, 8, cudaMemcpyDeviceToHost));
+  ctx->profile_open = false;
+  out->fault.code = 0;
+  out->fault.read_ordinal = 0;
+  if (fw != PS_FAULT_NONE) {
+    out->fault.code = (int32_t)(fw & 0xFF);
+    out->fault.read_ordinal = fw >> 8;
+    char msg[160];
+    snprintf(msg, sizeof msg, "record %llu: the JVM would die here (PS_THROW code %d)", (unsigned long long)(fw >> 8),
+             (int)(fw & 0xFF));
+    return set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, msg);
+  }
+  auto wrap = [](int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; };   // Java int two's-complement wrap (Q8)
+  const uint32_t m = l.max_len;
+  if (out->position_conversions) for (uint32_t k = 0; k < 16 * m; ++k) out->position_conversions[k] = wrap(acc[l.conv + k]);
+  if (out->quality_per_mismatch) for (int k = 0; k < 16; ++k) out->quality_per_mismatch[k] = wrap(acc[l.qsum + k]);
+  if (out->quality_per_mismatch_counts) for (int k = 0; k < 16; ++k) out->quality_per_mismatch_counts[k] = wrap(acc[l.qcnt + k]);
+  if (out->insertions_per_pos) for (uint32_t k = 0; k < m; ++k) out->insertions_per_pos[k] = (double)acc[l.ins + k];
+  if (out->deletions_per_pos) for (uint32_t k = 0; k < m; ++k) out->deletions_per_pos[k] = (double)acc[l.del + k];
+  if (out->counters) for (int k = 0; k < PS_PC_COUNT; ++k) out->counters[k] = wrap(acc[l.ctr + k]);
+  if (out->quality_hist && l.infer_q) memcpy(out->quality_hist, &acc[l.qhist], (size_t)256 * m * 8);
+  if (out->wide) memcpy(out->wide, acc.data(), (size_t)l.total * 8);
+  return PS_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------------
+uint64_t ps_kernel_launches(const ps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float ps_last_kernel_ms(const ps_ctx* ctx) {
+  if (!ctx || ctx->ev_count == 0) return -1.f;
+  float ms = -1.f;
+  cudaEventSynchronize(ctx->ev_stop[ctx->ev_count - 1]);
+  cudaEventElapsedTime(&ms, ctx->ev_start[ctx->ev_count - 1], ctx->ev_stop[ctx->ev_count - 1]);
+  return ms;
+}
+
+int ps_kernel_times(ps_ctx* ctx, float* ms, int max) {
+  if (!ctx || !ms) return PS_ERR_INVALID_ARG;
+  int n = (int)ctx->ev_count < max ? (int)ctx->ev_count : max;
+  for (int i = 0; i < n; ++i) {
+    cudaEventSynchronize(ctx->ev_stop[i]);
+    cudaEventElapsedTime(&ms[i], ctx->ev_start[i], ctx->ev_stop[i]);
+  }
+  return n;
+}
+
+void ps_kernel_times_reset(ps_ctx* ctx, int enabled) {
+  if (!ctx) return;
+  ctx->ev_count = 0;
+  ctx->timers_on = enabled != 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Device helpers shared by the profile and pileup kernels (sm_100a).
+#pragma once
+#include <cstdint>
+
+#include "internal.h"
+
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { return __ldg(p); }
+
+// 2-bit reference code at global offset g (undefined where the invalid bit is set)
+__device__ __forceinline__ uint32_t ref_code_at(const DeviceRef& ref, uint64_t g) {
+  return (__ldg(ref.seq2 + (g >> 4)) >> (2 * (g & 15))) & 3u;
+}
+__device__ __forceinline__ bool ref_invalid_at(const DeviceRef& ref, uint64_t g) {
+  return (__ldg(ref.inv + (g >> 5)) >> (g & 31)) & 1u;
+}
+// 2-bit read code at position p of a read whose packed bases start at `b`
+__device__ __forceinline__ uint32_t read_code_at(const uint8_t* b, uint32_t p) {
+  return (__ldg(b + (p >> 2)) >> (2 * (p & 3))) & 3u;
+}
+
+// htsjdk Cigar.getReferenceLength: M, D, N, =, X consume the reference
+__device__ __forceinline__ bool op_consumes_ref(uint32_t op) { return (0x18Du >> op) & 1u; }   // bits 0,2,3,7,8
+// M, I, S, =, X consume the read
+__device__ __forceinline__ bool op_consumes_read(uint32_t op) { return (0x193u >> op) & 1u; }  // bits 0,1,4,7,8
+__device__ __forceinline__ bool op_is_match(uint32_t op) { return (0x181u >> op) & 1u; }       // M, =, X
+
+__device__ __forceinline__ void raise_fault(unsigned long long* fault, uint64_t ordinal, uint32_t code) {
+  atomicMin(fault, (unsigned long long)((ordinal << 8) | code));
+}
+
+// contig index of global offset g (contig_off has n_contigs+1 entries, ascending)
+__device__ __forceinline__ uint32_t contig_of(const DeviceRef& ref, uint64_t g) {
+  uint32_t lo = 0, hi = ref.n_contigs;  // invariant: contig_off[lo] <= g < contig_off[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(ref.contig_off + mid) <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// per-read stream offsets inside a tile.  Uniform batches: closed form.  Otherwise a block-wide exclusive
+// scan over (L, ceil(L/4), n_cigar) packed into one 64-bit word (25 | 23 | 16 bits: a tile holds 256 reads
+// of L <= 65535 and <= 255 cigar ops).
+struct ReadOffsets {
+  uint64_t base, qual, cigar;
+};
+
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* warp_sums /* [8] smem */) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    if (lane >= (uint32_t)d) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  uint64_t prefix = 0;
+  for (uint32_t w = 0; w < warp; ++w) prefix += warp_sums[w];
+  __syncthreads();
+  return prefix + x - v;
+}
+
+__device__ __forceinline__ ReadOffsets read_offsets(const DeviceBatch& b, uint64_t tile, uint64_t r, uint32_t meta,
+                                                    bool in_range, uint64_t* scan_smem) {
+  ReadOffsets o;
+  const uint32_t L = PS_META_LEN(meta), nc = PS_META_NCIGAR(meta);
+  if (b.uniform_len && b.uniform_ncigar) {
+    o.base = r * (uint64_t)((b.uniform_len + 3) >> 2);
+    o.qual = r * (uint64_t)b.uniform_len;
+    o.cigar = r * (uint64_t)b.uniform_ncigar;
+    return o;
+  }
+  uint64_t packed = in_range ? ((uint64_t)L | ((uint64_t)((L + 3) >> 2) << 25) | ((uint64_t)nc << 48)) : 0;
+  uint64_t ex = block_exclusive_scan_u64(packed, scan_smem);
+  if (b.uniform_len) {
+    o.base = r * (uint64_t)((b.uniform_len + 3) >> 2);
+    o.qual = r * (uint64_t)b.uniform_len;
+  } else {
+    o.base = __ldg(b.tile_base_off + tile) + ((ex >> 25) & 0x7FFFFFu);
+    o.qual = __ldg(b.tile_qual_off + tile) + (ex & 0x1FFFFFFu);
+  }
+  o.cigar = b.uniform_ncigar ? r * (uint64_t)b.uniform_ncigar : __ldg(b.tile_cigar_off + tile) + (ex >> 48);
+  return o;
+}
+
+// is position p of read `rit` (index inside its tile) listed as an invalid (non-ACGT) base?
+__device__ __forceinline__ bool read_pos_invalid(const DeviceBatch& b, uint64_t tile, uint32_t rit, uint32_t p) {
+  const uint32_t lo = __ldg(b.tile_exc_off + tile), hi = __ldg(b.tile_exc_off + tile + 1);
+  const uint32_t key = (rit << 16) | p;
+  for (uint32_t e = lo; e < hi; ++e)
+    if (__ldg(b.exc + e) == key) return true;
+  return false;
+}

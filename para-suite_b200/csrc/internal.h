@@ -1,0 +1,128 @@
+// Internal declarations shared by the translation units of libparasuite_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "parasuite_b200.h"
+
+#define PS_BLOCK_THREADS 256   // == PS_TILE_READS: one read per thread, one tile per block iteration
+
+// fault word kept on the device: min over (ordinal << 8 | code); ~0 = none
+#define PS_FAULT_NONE 0xFFFFFFFFFFFFFFFFull
+
+struct DeviceRef {
+  const uint32_t* seq2 = nullptr;
+  const uint32_t* inv = nullptr;
+  const uint64_t* contig_off = nullptr;  // device copy
+  uint64_t n_bases = 0;
+  uint32_t n_contigs = 0;
+};
+
+// device-side view of a batch (plain pointers, passed by value to kernels)
+struct DeviceBatch {
+  uint64_t n_reads;
+  const uint32_t* meta;
+  const uint32_t* ref_start;
+  const uint8_t* bases2;
+  const uint8_t* qual;
+  const uint32_t* cigar;
+  const uint64_t* tile_base_off;
+  const uint64_t* tile_qual_off;
+  const uint64_t* tile_cigar_off;
+  const uint32_t* tile_exc_off;
+  const uint32_t* exc;
+  uint32_t uniform_len;
+  uint32_t uniform_ncigar;
+};
+
+struct ProfileLayout {   // offsets (in int64 elements) inside the accumulator vector
+  uint32_t max_len;
+  uint32_t infer_q;
+  uint32_t conv, qsum, qcnt, ins, del, ctr, qhist, total;
+};
+inline ProfileLayout make_layout(uint32_t max_len, uint32_t infer_q) {
+  ProfileLayout l;
+  l.max_len = max_len;
+  l.infer_q = infer_q;
+  l.conv = 0;
+  l.qsum = 16 * max_len;
+  l.qcnt = l.qsum + 16;
+  l.ins = l.qcnt + 16;
+  l.del = l.ins + max_len;
+  l.ctr = l.del + max_len;
+  l.qhist = l.ctr + PS_PC_COUNT;
+  l.total = l.qhist + (infer_q ? 256 * max_len : 0);
+  return l;
+}
+
+// buffer that grows on demand
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct StagedBatch {   // device copy of a host batch
+  DevBuf meta, ref_start, bases2, qual, cigar, tbo, tqo, tco, teo, exc;
+  DeviceBatch view{};
+};
+
+#define PS_TIMER_RING 512
+
+struct ps_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  // reference
+  DeviceRef ref;
+  DevBuf ref_seq2, ref_inv, ref_contig;
+  std::vector<uint64_t> contig_off;  // host copy
+  bool ref_loaded = false;
+  // profile state
+  bool profile_open = false;
+  ProfileLayout layout{};
+  DevBuf acc;        // int64[layout.total]
+  DevBuf fault;      // uint64
+  uint64_t reads_seen = 0;
+  // streams / staging
+  cudaStream_t stream = nullptr;
+  StagedBatch staged[2];
+  cudaEvent_t staged_done[2] = {nullptr, nullptr};
+  int staged_next = 0;
+  // instrumentation
+  uint64_t launches = 0;
+  cudaEvent_t ev_start[PS_TIMER_RING];
+  cudaEvent_t ev_stop[PS_TIMER_RING];
+  uint32_t ev_count = 0;   // pairs recorded since reset
+  bool timers_on = true;
+  // pileup scratch
+  DevBuf pl_scratch[12];
+};
+
+// ---- kernel launchers (defined in the .cu files) ----------------------------------------------------
+cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream);
+
+int set_error(ps_ctx* ctx, int status, const std::string& msg);
+int cuda_fail(ps_ctx* ctx, cudaError_t e, const char* what);
+#define PS_CUDA(ctx, expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #expr); \
+  } while (0)

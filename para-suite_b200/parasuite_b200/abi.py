@@ -149,6 +149,8 @@ EXPORTS = {
     "ps_pileup_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_pileup_opts), C.POINTER(VP)]),
     "ps_kernel_launches": (C.c_uint64, [VP]),
     "ps_last_kernel_ms": (C.c_float, [VP]),
+    "ps_kernel_times": (C.c_int, [VP, VP, C.c_int]),
+    "ps_kernel_times_reset": (None, [VP, C.c_int]),
 }
 
 LIB_NAME = "libparasuite_b200.so"

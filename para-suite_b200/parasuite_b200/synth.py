@@ -1,0 +1,107 @@
+"""Seeded synthetic workloads -- binding of lib/libps_synth.so (csrc/synth.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .batch import PackedReference, ReadBatch
+
+_lib = None
+
+
+class ps_synth_params(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_reads", C.c_uint64), ("read_len", C.c_uint32), ("mode", C.c_uint32),
+                ("threads", C.c_uint32), ("special_ppm", C.c_uint32), ("region_lo", C.c_uint64),
+                ("region_hi", C.c_uint64), ("n_ppm", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        p = os.path.join(abi.LIB_DIR, "libps_synth.so")
+        if not os.path.exists(p):
+            raise abi.NativeLibraryMissing(f"{p} not built: run `python __graft_entry__.py build`")
+        lib = C.CDLL(p)
+        lib.ps_synth_reference.restype = C.c_int
+        lib.ps_synth_reference.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                           C.c_int]
+        lib.ps_synth_reads.restype = C.c_void_p
+        lib.ps_synth_reads.argtypes = [C.POINTER(ps_synth_params), C.POINTER(abi.ps_reference)]
+        lib.ps_synth_batch.restype = C.POINTER(abi.ps_read_batch)
+        lib.ps_synth_batch.argtypes = [C.c_void_p]
+        lib.ps_synth_n_clusters.restype = C.c_uint64
+        lib.ps_synth_n_clusters.argtypes = [C.c_void_p]
+        lib.ps_synth_free.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def default_threads() -> int:
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+# GRCh38 primary assembly lengths (chr1..22, X, Y, M): 3.1 Gb, config 3/4
+GRCH38_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+                  133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285,
+                  58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+GRCH38_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY", "chrM"]
+
+
+def synth_reference(seed: int, contig_lengths, names=None, n_run: int = 10000, threads: int = 0) -> PackedReference:
+    lib = _load()
+    lens = np.asarray(contig_lengths, dtype=np.uint64)
+    n = int(lens.sum())
+    w2, w1 = PackedReference.words_for(n)
+    seq2 = np.zeros(w2, dtype=np.uint32)
+    inv = np.zeros(w1, dtype=np.uint32)
+    lib.ps_synth_reference(seed, len(lens), lens.ctypes.data, n_run, seq2.ctypes.data, inv.ctypes.data,
+                           threads or default_threads())
+    if names is None:
+        names = [f"chr{i + 1}" for i in range(len(lens))]
+    return PackedReference(list(names), [int(x) for x in lens], seq2, inv)
+
+
+class _SynthHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if self.h and _lib is not None:
+            _lib.ps_synth_free(self.h)
+            self.h = None
+
+
+def _view(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    ct = {np.uint8: C.c_uint8, np.uint32: C.c_uint32, np.uint64: C.c_uint64}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+
+
+def synth_reads(ref: PackedReference, n_reads: int, read_len: int, seed: int = 0x5EED0002, mode: int = 0,
+                special_ppm: int = 0, n_ppm: int = 1000, region=None, threads: int = 0) -> ReadBatch:
+    """Generate a coordinate-sorted SoA batch.  Arrays are views into generator-owned memory (kept alive)."""
+    lib = _load()
+    P = ps_synth_params(seed, n_reads, read_len, mode, threads or default_threads(), special_ppm,
+                        region[0] if region else 0, region[1] if region else 0, n_ppm, 0)
+    rs = ref.as_struct()
+    h = lib.ps_synth_reads(C.byref(P), C.byref(rs))
+    if not h:
+        raise ValueError("synthetic workload parameters out of range (region too small for the read count?)")
+    b = lib.ps_synth_batch(h).contents
+    n = int(b.n_reads)
+    nt = (n + abi.PS_TILE_READS - 1) // abi.PS_TILE_READS
+    batch = ReadBatch(
+        n, _view(b.meta, n, np.uint32), _view(b.ref_start, n, np.uint32),
+        _view(b.bases2, int(b.bases_bytes) + 64, np.uint8), _view(b.qual, int(b.qual_bytes) + 64, np.uint8),
+        _view(b.cigar, int(b.cigar_count) + 16, np.uint32), _view(b.tile_base_off, nt + 1, np.uint64),
+        _view(b.tile_qual_off, nt + 1, np.uint64), _view(b.tile_cigar_off, nt + 1, np.uint64),
+        _view(b.tile_exc_off, nt + 1, np.uint32), _view(b.exc, int(b.exc_count) + 16, np.uint32),
+        uniform_len=int(b.uniform_len), uniform_ncigar=int(b.uniform_ncigar), bases_bytes=int(b.bases_bytes),
+        qual_bytes=int(b.qual_bytes), cigar_count=int(b.cigar_count), exc_count=int(b.exc_count))
+    batch._owner = _SynthHandle(h)
+    batch.n_clusters_generated = int(lib.ps_synth_n_clusters(h))
+    return batch

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads, exports every symbol include/parasuite_b200.h declares, and refuses to
+compute without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from parasuite_b200 import abi
+
+HEADER = os.path.join(abi.INCLUDE_DIR, "parasuite_b200.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ps_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(abi.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(abi.lib_path()):
+        pytest.skip("library not built (run __graft_entry__.build())")
+    lib = abi.load_library()          # raises AttributeError on a missing export
+    assert lib.ps_abi_version() == abi.PS_ABI_VERSION
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.ps_profile_acc_len(51, 0) == 16 * 51 + 32 + 2 * 51 + abi.PS_PC_COUNT
+    assert b"sorted" in lib.ps_strerror(abi.PS_ERR_UNSORTED)
+
+
+def test_no_cpu_fallback():
+    if not os.path.exists(abi.lib_path()):
+        pytest.skip("library not built")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = abi.load_library()
+    h = C.c_void_p()
+    assert lib.ps_create(C.byref(h), 0) == abi.PS_ERR_NO_DEVICE
+    assert not h.value
+    from parasuite_b200.runtime import Context
+    with pytest.raises(abi.PsError):
+        Context(0)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(abi, "_lib", None)
+    monkeypatch.setattr(abi, "LIB_DIR", str(tmp_path))
+    with pytest.raises(abi.NativeLibraryMissing):
+        abi.load_library()

@@ -1,0 +1,157 @@
+"""GPU parity (through the C ABI): error-profile kernel vs the CPU oracle.  Bit-exact (integer counting)."""
+import random
+
+import numpy as np
+import pytest
+
+import py_oracle as po
+from helpers import assert_profile_equal, kat_records, random_genome, random_records, to_py
+from kat_vectors import KAT_MAXLEN, KAT_REF, PROFILE_KATS
+from parasuite_b200 import PackedReference, ReadBatch, abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from parasuite_b200.runtime import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def run_gpu(ctx, ref, batch, max_len, infer_q=False):
+    ctx.upload_reference(ref)
+    return ctx.profile(batch, max_len, infer_q)
+
+
+@pytest.mark.parametrize("kid", sorted(PROFILE_KATS))
+def test_kat(ctx, oracle, kid):
+    ref = PackedReference.from_contigs([("chr1", KAT_REF.encode())])
+    batch = ReadBatch.from_records(kat_records(PROFILE_KATS[kid]["reads"]), ref)
+    got = run_gpu(ctx, ref, batch, KAT_MAXLEN)
+    assert_profile_equal(got, oracle.profile(ref, batch, KAT_MAXLEN), kid)
+
+
+def test_kat_all(ctx, oracle):
+    ref = PackedReference.from_contigs([("chr1", KAT_REF.encode())])
+    recs = []
+    for kid in sorted(PROFILE_KATS):
+        recs += kat_records(PROFILE_KATS[kid]["reads"])
+    batch = ReadBatch.from_records(recs * 40, ref)          # > 1 tile, ragged last tile
+    got = run_gpu(ctx, ref, batch, KAT_MAXLEN)
+    assert_profile_equal(got, oracle.profile(ref, batch, KAT_MAXLEN), "all KATs x40")
+
+
+def test_empty_batch(ctx):
+    ref = PackedReference.from_contigs([("chr1", KAT_REF.encode())])
+    batch = ReadBatch.from_records([], ref)
+    got = run_gpu(ctx, ref, batch, KAT_MAXLEN)
+    assert got["position_conversions"].sum() == 0 and got["counters"].sum() == 0
+
+
+@pytest.mark.parametrize("seed,kinds", [(1, ("M",)), (2, ("M", "clip")), (3, ("indel",)), (4, ("splice",)),
+                                        (5, ("wild", "indel", "clip", "M", "splice")), (6, ("wild",))])
+def test_random_records(ctx, oracle, seed, kinds):
+    rng = random.Random(seed)
+    contigs = random_genome(rng, n_contigs=3, length=500)
+    recs = random_records(rng, contigs, 1500, kinds=kinds, flags_special=0.1)
+    ref = PackedReference.from_contigs(contigs)
+    g = po.Genome(dict(contigs))
+    ok, bad = [], []
+    for r in recs:
+        try:
+            po.profile(to_py([r]), g, 48)
+            ok.append(r)
+        except po.ReferenceWouldThrow:
+            bad.append(r)
+    batch = ReadBatch.from_records(ok, ref)
+    for infer_q in (False, True):
+        if infer_q:   # -q also touches every i < mappingLength: keep reads on which that does not throw
+            ok_q = []
+            for r in ok:
+                try:
+                    po.profile(to_py([r]), g, 48, infer_qual=True)
+                    ok_q.append(r)
+                except po.ReferenceWouldThrow:
+                    pass
+            batch = ReadBatch.from_records(ok_q, ref)
+        got = run_gpu(ctx, ref, batch, 48, infer_q)
+        exp = oracle.profile(ref, batch, 48, infer_q)
+        assert_profile_equal(got, exp, f"seed {seed} q={infer_q}")
+        if infer_q:
+            assert np.array_equal(got["quality_hist"], exp["quality_hist"])
+    # faults: same first ordinal and same reason as the oracle
+    if bad:
+        mixed = ok[:300] + [bad[0]] + ok[300:600] + bad[1:3] + ok[600:]
+        mb = ReadBatch.from_records(mixed, ref)
+        with pytest.raises(oracle.OracleFault) as eo:
+            oracle.profile(ref, mb, 48)
+        ctx.upload_reference(ref)
+        with pytest.raises(abi.ReferenceWouldThrow) as eg:
+            ctx.profile(mb, 48)
+        assert eg.value.fault == (eo.value.code, eo.value.ordinal)
+
+
+@pytest.mark.parametrize("mode,L,max_len,n", [(0, 36, 51, 300_000), (0, 50, 51, 200_000), (1, 150, 176, 100_000),
+                                              (0, 17, 20, 50_001)])
+def test_synthetic(ctx, oracle, mode, L, max_len, n):
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(11 + L, [3_000_000, 2_000_000], n_run=2000)
+    batch = synth.synth_reads(ref, n, L, seed=100 + L, mode=mode, special_ppm=500)
+    got = run_gpu(ctx, ref, batch, max_len)
+    assert_profile_equal(got, oracle.profile(ref, batch, max_len, threads=8), f"synthetic mode {mode} L {L}")
+    assert got["position_conversions"].sum() == got["counters"][7]
+
+
+def test_device_resident_and_multibatch(ctx, oracle):
+    """Device-resident entry point, several batches per run (ordinals continue), host path equality."""
+    import torch
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import DeviceBatch
+    ref = synth.synth_reference(5, [2_000_000], n_run=1000)
+    b1 = synth.synth_reads(ref, 120_000, 36, seed=1)
+    b2 = synth.synth_reads(ref, 70_000, 36, seed=2, mode=1)
+    ctx.upload_reference(ref)
+    ctx.profile_begin(51)
+    d1 = DeviceBatch(b1, "cuda:0")
+    d2 = DeviceBatch(b2, "cuda:0")
+    ctx.profile_batch_device(d1, torch.cuda.current_stream().cuda_stream)
+    ctx.profile_batch_device(d2, torch.cuda.current_stream().cuda_stream)
+    ctx.profile_batch(b1)
+    acc_t = ctx.profile_acc_tensor()
+    torch.cuda.synchronize()
+    got = ctx.profile_end()
+    acc = oracle.profile_acc(ref, b1, 51, threads=4)
+    acc = oracle.profile_acc(ref, b2, 51, threads=4, acc=acc)
+    acc = oracle.profile_acc(ref, b1, 51, threads=4, acc=acc)
+    assert_profile_equal(got, oracle.split_acc(acc, 51), "multi-batch")
+    assert np.array_equal(got["wide"], acc)
+    assert acc_t.numel() == acc.size
+
+
+def test_int32_wrap(ctx, oracle):
+    """Java int wrap-around: quality sums exceed 2^31 within a few million reads."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(3, [5_000_000], n_run=0)
+    batch = synth.synth_reads(ref, 3_000_000, 36, seed=3)
+    got = run_gpu(ctx, ref, batch, 51)
+    exp = oracle.profile(ref, batch, 51, threads=8)
+    assert_profile_equal(got, exp, "wrap")
+    assert (got["wide"][16 * 51:16 * 51 + 16] > 2 ** 31).any()
+    assert (got["quality_per_mismatch"] < 0).any()
+
+
+def test_full_size_config2(ctx, oracle):
+    """BASELINE config 2 at full size (10M x 36 nt, 100 Mb reference) against the multi-threaded oracle,
+    plus the size-independent invariants: sum(cells) == totalBasesChecked, counts <= reads per position."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(0x5EED0001, [100_000_000])
+    batch = synth.synth_reads(ref, 10_000_000, 36, seed=0x5EED0002)
+    got = run_gpu(ctx, ref, batch, 51)
+    c = got["counters"]
+    assert got["position_conversions"].astype(np.int64).sum() == int(c[7])
+    assert (got["position_conversions"].reshape(51, 16).sum(axis=1) <= batch.n_reads).all()
+    assert got["position_conversions"][36:].sum() == 0
+    exp = oracle.profile(ref, batch, 51, threads=16)
+    assert_profile_equal(got, exp, "config 2 full size")
