@@ -282,7 +282,8 @@ def main():
             oracle_lib.build()
             cores = os.cpu_count() or 1
             sample = batch.n_reads if cores >= 8 else min(batch.n_reads, 2_000_000)
-            sample -= sample % 256
+            if sample != batch.n_reads:
+                sample -= sample % 256
             t0 = time.perf_counter()
             acc = oracle_lib.profile_acc(ref, batch, max_len, threads=cores, first=0, count=sample)
             dt = time.perf_counter() - t0

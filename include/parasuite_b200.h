@@ -240,6 +240,9 @@ int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint6
                        uint64_t max_sites);
 /* the still-open last cluster (never flushed by the reference); needed for the halo merge */
 int ps_pileup_open_cluster(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites);
+/* with opts->carry_valid: the leading reads that continue the preceding shard's open cluster (returns 1 and the
+ * partial sums to merge into it, or 0).  first_read/start/first_reverse describe the first such read only. */
+int ps_pileup_head_partial(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites);
 int ps_pileup_fault(const ps_pileup* h, ps_fault* out);
 void ps_pileup_close(ps_pileup* h);
 int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);

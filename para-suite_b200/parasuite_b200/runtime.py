@@ -157,6 +157,55 @@ class Context:
         self.profile_batch(batch)
         return self.profile_end()
 
+    # ---- T>C pileup (PileupClusters.java:137-500, 585-673) ----------------------------------------
+    def pileup(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> dict:
+        """batch: ReadBatch / PinnedBatch (host buffers, H2D inside) or DeviceBatch (resident).
+        carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None."""
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+        if carry is not None:
+            opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
+        h = C.c_void_p()
+        if isinstance(batch, DeviceBatch):
+            st = self.lib.ps_pileup_batch_device(self.h, C.byref(batch.struct), C.byref(opts), stream or None,
+                                                 C.byref(h))
+        else:
+            s = batch.struct if hasattr(batch, "struct") else batch.as_struct()
+            st = self.lib.ps_pileup_batch(self.h, C.byref(s), C.byref(opts), C.byref(h))
+        try:
+            if st == abi.PS_ERR_REFERENCE_WOULD_THROW and h:
+                f = abi.ps_fault()
+                self.lib.ps_pileup_fault(h, C.byref(f))
+                _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
+            _check(self.lib, self.h, st)
+            ctr = abi.ps_pileup_counters()
+            self.lib.ps_pileup_counters_get(h, C.byref(ctr))
+            clusters = np.zeros(ctr.n_clusters, dtype=abi.CLUSTER_DTYPE)
+            sites = np.zeros(ctr.n_sites, dtype=abi.SITE_DTYPE)
+            got = self.lib.ps_pileup_next(h, 0, clusters.ctypes.data, ctr.n_clusters, sites.ctypes.data, ctr.n_sites)
+            if got != ctr.n_clusters:
+                raise abi.PsError(int(got), "ps_pileup_next returned fewer clusters than announced")
+            open_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
+            open_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
+            k = self.lib.ps_pileup_open_cluster(h, open_c.ctypes.data, open_s.ctypes.data, open_s.size)
+            if k < 0:
+                raise abi.PsError(k, "open cluster has too many sites")
+            head_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
+            head_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
+            kh = self.lib.ps_pileup_head_partial(h, head_c.ctypes.data, head_s.ctypes.data, head_s.size)
+            if kh < 0:
+                raise abi.PsError(kh, "head partial has too many sites")
+            return {
+                "clusters": clusters, "sites": sites,
+                "open_cluster": open_c[0] if k > 0 else None,
+                "open_sites": open_s[:int(open_c[0]["site_end"])].copy() if k > 0 else open_s[:0],
+                "head_partial": head_c[0] if kh > 0 else None,
+                "head_sites": head_s[:int(head_c[0]["site_end"])].copy() if kh > 0 else head_s[:0],
+                "counters": {f: getattr(ctr, f) for f, _ in abi.ps_pileup_counters._fields_},
+            }
+        finally:
+            if h:
+                self.lib.ps_pileup_close(h)
+
     # ---- instrumentation -------------------------------------------------------------------------
     def kernel_launches(self) -> int:
         return int(self.lib.ps_kernel_launches(self.h))

@@ -59,10 +59,10 @@ def random_genome(rng: random.Random, n_contigs=2, length=400, n_frac=0.03, lowe
     for c in range(n_contigs):
         s = bytearray(rng.choice(b"ACGT") for _ in range(length))
         # N run + lower-case run + a stray IUPAC code
-        a = rng.randrange(0, length - 20)
+        a = rng.randrange(0, length - int(length * n_frac) - 1)
         for k in range(a, a + int(length * n_frac)):
             s[k] = ord("N")
-        b = rng.randrange(0, length - 50)
+        b = rng.randrange(0, length - int(length * lower_frac) - 1)
         for k in range(b, b + int(length * lower_frac)):
             s[k] = ord(chr(s[k]).lower())
         s[rng.randrange(length)] = ord("R")

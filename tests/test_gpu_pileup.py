@@ -1,0 +1,140 @@
+"""GPU parity (through the C ABI): T>C pileup kernels vs the CPU oracle.  Bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+import py_oracle as po
+from helpers import kat_records, random_genome, random_records, to_py
+from kat_vectors import PILEUP_READS, PILEUP_REF
+from parasuite_b200 import PackedReference, ReadBatch, abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from parasuite_b200.runtime import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+CL_FIELDS = ("first_read", "running_id", "contig", "start", "end", "num_reads", "num_t2c", "minus_after_first",
+             "first_reverse", "combined_strand", "mask51", "site_begin", "site_end")
+SITE_FIELDS = ("pos", "t2c", "cov", "order_key")
+
+
+def assert_pileup_equal(got, exp, what=""):
+    assert got["counters"] == exp["counters"], (what, got["counters"], exp["counters"])
+    for f in CL_FIELDS:
+        if not np.array_equal(got["clusters"][f], exp["clusters"][f]):
+            k = int(np.argwhere(got["clusters"][f] != exp["clusters"][f])[0][0])
+            raise AssertionError(f"{what}: cluster field {f} differs first at {k}: "
+                                 f"{got['clusters'][k]} vs {exp['clusters'][k]}")
+    for f in SITE_FIELDS:
+        if not np.array_equal(got["sites"][f], exp["sites"][f]):
+            k = int(np.argwhere(got["sites"][f] != exp["sites"][f])[0][0])
+            raise AssertionError(f"{what}: site field {f} differs first at {k}: {got['sites'][k]} vs {exp['sites'][k]}")
+    if exp["open_cluster"] is None:
+        assert got["open_cluster"] is None
+    else:
+        for f in CL_FIELDS:
+            assert got["open_cluster"][f] == exp["open_cluster"][f], (what, "open", f)
+        for f in SITE_FIELDS:
+            assert np.array_equal(got["open_sites"][f], exp["open_sites"][f]), (what, "open sites", f)
+
+
+def test_kat(ctx, oracle):
+    ref = PackedReference.from_contigs([("chr1", PILEUP_REF.encode())])
+    batch = ReadBatch.from_records(kat_records(PILEUP_READS), ref)
+    ctx.upload_reference(ref)
+    got = ctx.pileup(batch)
+    assert_pileup_equal(got, oracle.pileup(ref, batch), "KAT")
+    assert got["counters"]["double_stranded"] == 2 and len(got["clusters"]) == 3
+    assert int(got["clusters"][0]["running_id"]) == 2          # first cluster is cl_2 (PileupClusters.java:355)
+
+
+def test_empty_and_single(ctx, oracle):
+    ref = PackedReference.from_contigs([("chr1", PILEUP_REF.encode())])
+    ctx.upload_reference(ref)
+    got = ctx.pileup(ReadBatch.from_records([], ref))
+    assert len(got["clusters"]) == 0 and got["open_cluster"] is None
+    one = ReadBatch.from_records(kat_records(PILEUP_READS[:1]), ref)
+    assert_pileup_equal(ctx.pileup(one), oracle.pileup(ref, one), "single read")
+
+
+@pytest.mark.parametrize("seed,kinds", [(11, ("M",)), (12, ("M", "clip", "indel")), (13, ("wild", "splice", "M")),
+                                        (14, ("indel", "clip"))])
+def test_random_records(ctx, oracle, seed, kinds):
+    rng = random.Random(seed)
+    contigs = random_genome(rng, n_contigs=3, length=8000, n_frac=0.003, lower_frac=0.05)
+    recs = random_records(rng, contigs, 2500, kinds=kinds, Lrange=(15, 30), flags_special=0.05)
+    recs = [r for r in recs if r.pos > 0]
+    ref = PackedReference.from_contigs(contigs)
+    g = po.Genome(dict(contigs))
+    ok, bad = [], []
+    for r in recs:
+        try:
+            po.pileup(to_py([r]), g, po.SnpDb([]), 1)
+            ok.append(r)
+        except po.ReferenceWouldThrow:
+            bad.append(r)
+    batch = ReadBatch.from_records(ok, ref)
+    ctx.upload_reference(ref)
+    got = ctx.pileup(batch)
+    exp = oracle.pileup(ref, batch)
+    assert_pileup_equal(got, exp, f"seed {seed}")
+    assert len(got["clusters"]) > 50
+    if bad:
+        mixed = ok[:500] + [bad[0]] + ok[500:]
+        mb = ReadBatch.from_records(mixed, ref)
+        with pytest.raises(oracle.OracleFault) as eo:
+            oracle.pileup(ref, mb)
+        with pytest.raises(abi.ReferenceWouldThrow) as eg:
+            ctx.pileup(mb)
+        assert eg.value.fault == (eo.value.code, eo.value.ordinal)
+
+
+@pytest.mark.parametrize("L,n,ppm", [(36, 400_000, 0), (50, 300_000, 2000), (21, 100_003, 0)])
+def test_synthetic(ctx, oracle, L, n, ppm):
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import DeviceBatch
+    ref = synth.synth_reference(21 + L, [4_000_000, 3_000_000], n_run=3000)
+    batch = synth.synth_reads(ref, n, L, seed=200 + L, special_ppm=ppm)
+    if ppm:   # POS==0 on a mapped record kills the JVM in the pileup loop: drop those for the parity run
+        keep = ((batch.meta >> 24) & abi.PS_RF_POS_ZERO) == 0
+        batch.meta[~keep] |= np.uint32(abi.PS_RF_UNMAPPED << 24)
+    ctx.upload_reference(ref)
+    exp = oracle.pileup(ref, batch)
+    assert_pileup_equal(ctx.pileup(batch), exp, f"synthetic L {L} host")
+    assert_pileup_equal(ctx.pileup(DeviceBatch(batch, "cuda:0")), exp, f"synthetic L {L} device")
+
+
+def test_dense_overlapping_clusters(ctx, oracle):
+    """Reads packed so densely that clusters chain and overlap by < 5 positions; deep pileups."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(77, [200_000], n_run=0)
+    batch = synth.synth_reads(ref, 150_000, 36, seed=5)      # ~27 reads per 36 bp: long chained clusters
+    ctx.upload_reference(ref)
+    assert_pileup_equal(ctx.pileup(batch), oracle.pileup(ref, batch), "dense")
+
+
+def test_region_sharding_halo_merge(ctx, oracle):
+    """Two shards cut at an arbitrary read index; carry-in + head partial merge equals the whole-stream result."""
+    from parasuite_b200 import synth
+    from parasuite_b200.sharding import merge_pileup_shards, slice_batch
+    ref = synth.synth_reference(31, [3_000_000, 1_000_000], n_run=2000)
+    batch = synth.synth_reads(ref, 200_000, 36, seed=6)
+    ctx.upload_reference(ref)
+    whole = oracle.pileup(ref, batch)
+    for cut in (100_000, 100_007, 65_536, 199_999, 1):
+        parts = [slice_batch(batch, 0, cut), slice_batch(batch, cut, batch.n_reads)]
+        shard_results = []
+        carry = None
+        for p in parts:
+            res = ctx.pileup(p, carry=carry)
+            shard_results.append(res)
+            carry = merge_pileup_shards.carry_after(shard_results, carry)
+        merged = merge_pileup_shards(shard_results, [0, cut])
+        assert_pileup_equal(merged, whole, f"cut {cut}")
