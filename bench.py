@@ -194,6 +194,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    pile = {}
+
     def step_resident():
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
@@ -201,7 +203,11 @@ def main():
             dist.all_reduce(ctx.profile_acc_tensor())
 
     def finish():
-        return ctx.profile_end()
+        res = ctx.profile_end()
+        # T>C pileup of the same reads (region shard of this rank; the halo exchange is 2 scalars per cut and is
+        # done by parasuite_b200.sharding when shards are merged -- not part of the per-shard step)
+        pile["res"] = ctx.pileup(dbatch, stream=stream.cuda_stream)
+        return res
 
     # ---- warm-up + parity of the timed configuration against the oracle on a prefix ---------------
     for _ in range(args.warmup):
@@ -236,46 +242,68 @@ def main():
     # ---- end-to-end leg: pinned HOST buffers through the C ABI, copies inside the timed region -------
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     pinned = PinnedBatch(batch)
-    for _ in range(2):
-        ctx.profile_begin(max_len)
-        ctx.profile_batch(pinned)
-        finish()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    def step_e2e():
         ctx.profile_begin(max_len)
         ctx.profile_batch(pinned)
         if world > 1:
             torch.cuda.synchronize()
             dist.all_reduce(ctx.profile_acc_tensor())
-        res_e2e = finish()
+        r = ctx.profile_end()
+        pile["res_e2e"] = ctx.pileup(pinned)
+        return r
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_e2e = step_e2e()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_reads * e2e_steps / (float(t.item()) * 1e-3)
-    d2h = int(res_e2e["wide"].nbytes + 8)
+    pr = pile["res_e2e"]
+    d2h = int(res_e2e["wide"].nbytes + 8 + pr["clusters"].nbytes + pr["sites"].nbytes)
+    h2d = 2 * pinned.h2d_bytes      # each stage takes the host batch through the C ABI
 
     if rank == 0:
         peak, peak_src = peaks()
-        kms = float(np.mean(ktimes)) if len(ktimes) else float("nan")
-        achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms == kms else None
+        # timer ring order per step: profile kernel, pileup pipeline
+        k_prof = float(np.mean(ktimes[0::2])) if len(ktimes) >= 2 else float("nan")
+        k_pile = float(np.mean(ktimes[1::2])) if len(ktimes) >= 2 else float("nan")
+        cl = pile["res"]["clusters"]
+        pile_bytes = (batch.algorithmic_bytes(with_qual=False)
+                      + 8 * int((cl["end"].astype(np.int64) - cl["start"].astype(np.int64) + 1).sum())
+                      + 32 * len(cl))
+        if k_prof >= k_pile or k_pile != k_pile:
+            kname, kms, kbytes = "profile_generic_kernel", k_prof, alg_bytes
+        else:
+            kname, kms, kbytes = "pileup pipeline (pl_read/flag/cluster/site + scans + sort)", k_pile, pile_bytes
+        achieved = kbytes / (kms * 1e-3) / 1e9 if kms == kms else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": name, "stages": ["profile"], "reads_per_gpu": batch.n_reads,
+            "config": {"workload": name, "stages": ["profile", "pileup"], "reads_per_gpu": batch.n_reads,
+                       "stage_ms": {"profile_kernel": k_prof, "pileup_device": k_pile},
+                       "pileup": {"clusters": int(len(cl)), "sites": int(len(pile["res"]["sites"]))},
                        "max_read_length": max_len, "l2": "inputs larger than L2 (%.0f MB per pass)" % (alg_bytes / 1e6),
                        "parallelism": f"read-batch sharded x{world}"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pinned.h2d_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "profile_generic_kernel", "kernel_ms": kms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+                         "kernel": kname, "kernel_ms": kms,
+                         "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
+                         "per_stage": {
+                             "profile": {"ms": k_prof, "bytes": alg_bytes,
+                                         "frac": alg_bytes / (k_prof * 1e-3) / 1e9 / peak if k_prof == k_prof else None},
+                             "pileup": {"ms": k_pile, "bytes": pile_bytes,
+                                        "frac": pile_bytes / (k_pile * 1e-3) / 1e9 / peak if k_pile == k_pile else None}}},
         }
         if not args.no_cpu_baseline:
             import oracle_lib

@@ -243,6 +243,10 @@ int ps_pileup_open_cluster(ps_pileup* h, ps_cluster* cluster, ps_site* sites, ui
 /* with opts->carry_valid: the leading reads that continue the preceding shard's open cluster (returns 1 and the
  * partial sums to merge into it, or 0).  first_read/start/first_reverse describe the first such read only. */
 int ps_pileup_head_partial(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites);
+/* baseCoveredMap of a boundary cluster as a dense array: cov[k] = coverage at position *first_pos + k.
+ * which = 0: head partial, 1: open cluster.  cov == NULL just returns the length.  A T>C site seen on one side
+ * of a shard cut is also covered by reads on the other side; the merge adds this in. */
+int64_t ps_pileup_boundary_coverage(ps_pileup* h, int which, int32_t* first_pos, uint32_t* cov, uint64_t max);
 int ps_pileup_fault(const ps_pileup* h, ps_fault* out);
 void ps_pileup_close(ps_pileup* h);
 int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);

@@ -52,6 +52,10 @@ def load() -> C.CDLL:
         lib.or_pileup_open.restype = C.c_int64
         lib.or_pileup_open.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.or_pileup_free.argtypes = [C.c_void_p]
+        lib.or_pileup_head.restype = C.c_int64
+        lib.or_pileup_head.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.or_pileup_boundary_cov.restype = C.c_int64
+        lib.or_pileup_boundary_cov.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_uint64]
         _lib = lib
     return _lib
 
@@ -115,11 +119,15 @@ def profile(ref, batch, max_len: int, infer_q: bool = False, threads: int = 1) -
     return split_acc(profile_acc(ref, batch, max_len, infer_q, threads), max_len, infer_q)
 
 
-def pileup(ref, batch, first_running_id: int = 1) -> dict:
+def pileup(ref, batch, first_running_id: int = 1, carry=None) -> dict:
+    """carry=(contig, cluster_end): sharding emulation for the CPU tests of the halo merge (not reference
+    behaviour); parity runs always pass the whole stream with carry=None."""
     lib = load()
     rs = ref.as_struct()
     bs = batch.as_struct()
     opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+    if carry is not None:
+        opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
     h = lib.or_pileup_run(C.byref(rs), C.byref(bs), C.byref(opts))
     try:
         fault = abi.ps_fault()
@@ -137,8 +145,20 @@ def pileup(ref, batch, first_running_id: int = 1) -> dict:
         k = lib.or_pileup_open(h, open_c.ctypes.data, open_s.ctypes.data, open_s.size)
         if k < 0:
             raise RuntimeError("open cluster has too many sites")
+        head_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
+        head_s = np.zeros(4096, dtype=abi.SITE_DTYPE)
+        kh = lib.or_pileup_head(h, head_c.ctypes.data, head_s.ctypes.data, head_s.size)
+        cov = {}
+        for which, name in ((0, "head_cov"), (1, "open_cov")):
+            p0 = C.c_int32()
+            ln = lib.or_pileup_boundary_cov(h, which, C.byref(p0), None, 0)
+            a = np.zeros(max(int(ln), 0), dtype=np.uint32)
+            if ln > 0:
+                lib.or_pileup_boundary_cov(h, which, C.byref(p0), a.ctypes.data, a.size)
+            cov[name] = (int(p0.value), a)
         return {
-            "clusters": clusters, "sites": sites,
+            "clusters": clusters, "sites": sites, **cov,
+            "head_partial": head_c[0] if kh > 0 else None, "head_sites": head_s[:max(0, kh - 1)].copy(),
             "open_cluster": open_c[0] if k > 0 else None, "open_sites": open_s[:max(0, k - 1)].copy(),
             "counters": {f: getattr(ctr, f) for f, _ in abi.ps_pileup_counters._fields_},
         }

@@ -346,6 +346,12 @@ struct or_pileup_result {
   std::vector<ps_site> sites;
   ps_cluster open_cluster;
   std::vector<ps_site> open_sites;
+  // sharding emulation only (not reference behaviour): the records at the head of a shard that continue the
+  // cluster the preceding shard left open, and baseCoveredMap of the two boundary clusters
+  ps_cluster head_partial;
+  std::vector<ps_site> head_sites;
+  bool has_head = false;
+  std::map<int32_t, uint32_t> open_cov, head_cov;
   ps_pileup_counters counters;
   ps_fault fault;
 };
@@ -361,7 +367,13 @@ or_pileup_result* or_pileup_run(const ps_reference* ref, const ps_read_batch* b,
   int64_t tempClusterChr = -1;  // "" : equals no contig
   uint32_t numReadsPerCluster = 0, numT2C = 0;
   uint32_t runningID = opts ? opts->first_running_id : 1;
-  // (opts->carry_* is a product-side sharding device; the oracle always sees the whole stream)
+  // opts->carry_*: sharding emulation for the CPU tests of the halo merge -- start as if the preceding shard had
+  // left a cluster open with this (chr, end).  The whole-stream runs that pin parity never set it.
+  bool in_head = opts && opts->carry_valid;
+  if (in_head) {
+    tempClusterChr = opts->carry_contig;
+    tempClusterEnd = opts->carry_cluster_end;
+  }
   int isReverse = 0;  // 0 false, 1 true, 2 null (StrandOrientation)
   bool tempIsReverse = false;
   uint64_t mask51 = 0;
@@ -430,13 +442,21 @@ or_pileup_result* or_pileup_run(const ps_reference* ref, const ps_read_batch* b,
         ps_cluster c;
         snapshot(c, R->sites);
         R->clusters.push_back(c);
+      } else if (in_head && numReadsPerCluster) {
+        snapshot(R->head_partial, R->head_sites);
+        R->head_partial.running_id = 0;
+        R->head_partial.minus_after_first = minusAfterFirst;
+        R->head_cov = baseCoveredMap;
+        R->has_head = true;
       }
+      in_head = false;
       tempClusterStart = start; tempClusterEnd = end; tempClusterChr = contig;   // :346-357
       numReadsPerCluster = 1; numT2C = 0; isReverse = 0;
       mutationMap.clear(); baseCoveredMap.clear();
       runningID++;
       mask51 = 0; minusAfterFirst = 0; firstRead = ord; have = true;
     } else {
+      if (in_head && numReadsPerCluster == 0) { tempClusterStart = start; firstRead = ord; tempIsReverse = (v.flags & PS_RF_REVERSE) != 0; }
       if (end > tempClusterEnd) tempClusterEnd = end;                     // :421,:480
       numReadsPerCluster++;                                               // :488
     }
@@ -490,7 +510,7 @@ or_pileup_result* or_pileup_run(const ps_reference* ref, const ps_read_batch* b,
       baseCoveredMap[checkPosition]++;                                    // :662-667
     }
     if (newCluster) tempIsReverse = isReverse == 1;                       // :364
-    else if (isReverse != 2 && tempIsReverse != (isReverse == 1)) {       // :494-498
+    else if (!in_head && isReverse != 2 && tempIsReverse != (isReverse == 1)) {       // :494-498
       R->counters.double_stranded++;
       isReverse = 2;
     }
@@ -498,7 +518,14 @@ or_pileup_result* or_pileup_run(const ps_reference* ref, const ps_read_batch* b,
   }
   if (have) {
     snapshot(R->open_cluster, R->open_sites);
+    R->open_cov = baseCoveredMap;
     R->counters.has_open_cluster = 1;
+  } else if (in_head && numReadsPerCluster) {
+    snapshot(R->head_partial, R->head_sites);
+    R->head_partial.running_id = 0;
+    R->head_partial.minus_after_first = minusAfterFirst;
+    R->head_cov = baseCoveredMap;
+    R->has_head = true;
   }
   R->counters.n_clusters = R->clusters.size();
   R->counters.n_sites = R->sites.size();
@@ -520,6 +547,26 @@ int64_t or_pileup_open(const or_pileup_result* r, ps_cluster* c, ps_site* sites,
   *c = r->open_cluster;
   std::copy(r->open_sites.begin(), r->open_sites.end(), sites);
   return 1 + (int64_t)r->open_sites.size();
+}
+int64_t or_pileup_head(const or_pileup_result* r, ps_cluster* c, ps_site* sites, uint64_t max_sites) {
+  if (!r->has_head) return 0;
+  if (r->head_sites.size() > max_sites) return PS_ERR_INVALID_ARG;
+  *c = r->head_partial;
+  std::copy(r->head_sites.begin(), r->head_sites.end(), sites);
+  return 1 + (int64_t)r->head_sites.size();
+}
+// dense baseCoveredMap of a boundary cluster (which: 0 head partial, 1 open cluster)
+int64_t or_pileup_boundary_cov(const or_pileup_result* r, int which, int32_t* first_pos, uint32_t* cov, uint64_t max) {
+  const std::map<int32_t, uint32_t>& m = which ? r->open_cov : r->head_cov;
+  if (m.empty()) { *first_pos = 0; return 0; }
+  int32_t lo = m.begin()->first, hi = m.rbegin()->first;
+  *first_pos = lo;
+  uint64_t n = (uint64_t)(hi - lo + 1);
+  if (!cov) return (int64_t)n;
+  if (n > max) return PS_ERR_INVALID_ARG;
+  std::fill(cov, cov + n, 0u);
+  for (auto& kv : m) cov[kv.first - lo] = kv.second;
+  return (int64_t)n;
 }
 void or_pileup_free(or_pileup_result* r) { delete r; }
 

@@ -31,6 +31,10 @@ struct ps_pileup {
   ps_cluster head_partial{};          // reads continuing the carry-in cluster (halo merge)
   std::vector<ps_site> head_sites;
   bool has_head = false;
+  // baseCoveredMap of the two boundary clusters as dense arrays (needed by the halo merge: a site seen on one
+  // side of a cut is also covered by reads on the other side)
+  std::vector<uint32_t> open_cov, head_cov;
+  int32_t open_cov_pos0 = 0, head_cov_pos0 = 0;
   ps_pileup_counters counters{};
   ps_fault fault{};
 };
@@ -528,6 +532,39 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
       H->counters.has_open_cluster = 1;
     }
   }
+  // dense coverage of the boundary clusters from the [lo,hi] intervals of their reads
+  {
+    auto dense = [&](uint64_t r0, uint64_t r1, uint32_t slot, std::vector<uint32_t>& cov, int32_t& pos0) -> int {
+      if (r1 <= r0) return PS_OK;
+      const uint64_t m = r1 - r0;
+      std::vector<int32_t> lo(m), hi(m);
+      std::vector<unsigned long long> ky(m);
+      std::vector<uint32_t> ci(m);
+      PS_CUDA(ctx, cudaMemcpy(lo.data(), rd.lo + r0, m * 4, cudaMemcpyDeviceToHost));
+      PS_CUDA(ctx, cudaMemcpy(hi.data(), rd.hi + r0, m * 4, cudaMemcpyDeviceToHost));
+      PS_CUDA(ctx, cudaMemcpy(ky.data(), rd.key + r0, m * 8, cudaMemcpyDeviceToHost));
+      PS_CUDA(ctx, cudaMemcpy(ci.data(), cidx + r0, m * 4, cudaMemcpyDeviceToHost));
+      int32_t mn = INT32_MAX, mx = INT32_MIN;
+      for (uint64_t k = 0; k < m; ++k)
+        if (ky[k] && ci[k] == slot && lo[k] <= hi[k]) { mn = std::min(mn, lo[k]); mx = std::max(mx, hi[k]); }
+      if (mn > mx) return PS_OK;
+      pos0 = mn;
+      cov.assign((size_t)(mx - mn + 1), 0);
+      for (uint64_t k = 0; k < m; ++k)
+        if (ky[k] && ci[k] == slot)
+          for (int32_t p = lo[k]; p <= hi[k]; ++p) cov[p - mn]++;
+      return PS_OK;
+    };
+    if (H->has_head) {
+      const uint64_t r1 = n_real ? h_cl[1].first_read : n;
+      int rc = dense(0, r1, 0, H->head_cov, H->head_cov_pos0);
+      if (rc) return rc;
+    }
+    if (H->counters.has_open_cluster) {
+      int rc = dense(h_cl[n_real].first_read, n, (uint32_t)n_real, H->open_cov, H->open_cov_pos0);
+      if (rc) return rc;
+    }
+  }
   H->counters.double_stranded = dstr;
   H->counters.n_clusters = H->clusters.size();
   H->counters.n_sites = H->sites.size();
@@ -611,6 +648,16 @@ int ps_pileup_head_partial(ps_pileup* h, ps_cluster* cluster, ps_site* sites, ui
   *cluster = h->head_partial;
   if (!h->head_sites.empty()) std::memcpy(sites, h->head_sites.data(), h->head_sites.size() * sizeof(ps_site));
   return 1;
+}
+
+int64_t ps_pileup_boundary_coverage(ps_pileup* h, int which, int32_t* first_pos, uint32_t* cov, uint64_t max) {
+  if (!h || !first_pos) return PS_ERR_INVALID_ARG;
+  const std::vector<uint32_t>& v = which ? h->open_cov : h->head_cov;
+  *first_pos = which ? h->open_cov_pos0 : h->head_cov_pos0;
+  if (!cov) return (int64_t)v.size();
+  if (v.size() > max) return PS_ERR_INVALID_ARG;
+  if (!v.empty()) std::memcpy(cov, v.data(), v.size() * 4);
+  return (int64_t)v.size();
 }
 
 int ps_pileup_fault(const ps_pileup* h, ps_fault* out) {

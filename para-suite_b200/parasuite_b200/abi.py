@@ -145,6 +145,7 @@ EXPORTS = {
     "ps_pileup_next": (C.c_int64, [VP, C.c_uint64, VP, C.c_uint64, VP, C.c_uint64]),
     "ps_pileup_open_cluster": (C.c_int, [VP, VP, VP, C.c_uint64]),
     "ps_pileup_head_partial": (C.c_int, [VP, VP, VP, C.c_uint64]),
+    "ps_pileup_boundary_coverage": (C.c_int64, [VP, C.c_int, C.POINTER(C.c_int32), VP, C.c_uint64]),
     "ps_pileup_fault": (C.c_int, [VP, C.POINTER(ps_fault)]),
     "ps_pileup_close": (None, [VP]),
     "ps_pileup_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_pileup_opts), C.POINTER(VP)]),

@@ -194,8 +194,16 @@ class Context:
             kh = self.lib.ps_pileup_head_partial(h, head_c.ctypes.data, head_s.ctypes.data, head_s.size)
             if kh < 0:
                 raise abi.PsError(kh, "head partial has too many sites")
+            cov = {}
+            for which, name in ((0, "head_cov"), (1, "open_cov")):
+                p0 = C.c_int32()
+                ln = self.lib.ps_pileup_boundary_coverage(h, which, C.byref(p0), None, 0)
+                a = np.zeros(max(int(ln), 0), dtype=np.uint32)
+                if ln > 0:
+                    self.lib.ps_pileup_boundary_coverage(h, which, C.byref(p0), a.ctypes.data, a.size)
+                cov[name] = (int(p0.value), a)
             return {
-                "clusters": clusters, "sites": sites,
+                "clusters": clusters, "sites": sites, **cov,
                 "open_cluster": open_c[0] if k > 0 else None,
                 "open_sites": open_s[:int(open_c[0]["site_end"])].copy() if k > 0 else open_s[:0],
                 "head_partial": head_c[0] if kh > 0 else None,

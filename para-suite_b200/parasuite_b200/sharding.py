@@ -80,6 +80,28 @@ def _strand(first_reverse: int, minus_after_first: int) -> int:
     return 1 if first_reverse else (2 if minus_after_first else 0)
 
 
+def _cov_at(cov, pos: np.ndarray) -> np.ndarray:
+    p0, a = cov
+    idx = pos.astype(np.int64) - p0
+    ok = (idx >= 0) & (idx < len(a))
+    out = np.zeros(len(pos), dtype=np.uint32)
+    out[ok] = a[idx[ok]]
+    return out
+
+
+def _cov_add(x, y):
+    (p0, a), (q0, b) = x, y
+    if len(a) == 0:
+        return q0, b.copy()
+    if len(b) == 0:
+        return p0, a.copy()
+    lo, hi = min(p0, q0), max(p0 + len(a), q0 + len(b))
+    out = np.zeros(hi - lo, dtype=np.uint32)
+    out[p0 - lo:p0 - lo + len(a)] += a
+    out[q0 - lo:q0 - lo + len(b)] += b
+    return lo, out
+
+
 def _merge_sites(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """Union of two site lists by position: counts add, first-insertion key is the smaller one."""
     if len(b) == 0:
@@ -108,6 +130,7 @@ class _Merger:
                         has_open_cluster=0)
         open_c: Optional[np.ndarray] = None     # running open cluster (a 1-element structured array copy)
         open_s = np.zeros(0, dtype=abi.SITE_DTYPE)
+        open_cov = (0, np.zeros(0, dtype=np.uint32))
         created = 0                              # clusters opened so far (closed + open)
 
         def close_open():
@@ -141,7 +164,11 @@ class _Merger:
                 if not int(open_c["first_reverse"]):
                     counters["double_stranded"] += int(hp["minus_after_first"])
                 open_c["combined_strand"] = _strand(int(open_c["first_reverse"]), int(open_c["minus_after_first"]))
+                # baseCoveredMap spans the cut: a site seen on one side is also covered by the other side's reads,
+                # so coverage is re-read from the summed dense map of the boundary cluster
+                open_cov = _cov_add(open_cov, res["head_cov"])
                 open_s = _merge_sites(open_s, hs)
+                open_s["cov"] = _cov_at(open_cov, open_s["pos"])
             n_new = len(res["clusters"]) + (1 if res["open_cluster"] is not None else 0)
             if n_new:
                 close_open()
@@ -164,6 +191,7 @@ class _Merger:
                 open_c = oc
                 open_s = res["open_sites"].copy()
                 open_s["order_key"] += np.uint64(off << 6)
+                open_cov = res["open_cov"]
             created += n_new
         out_c = np.concatenate(clusters) if clusters else np.zeros(0, dtype=abi.CLUSTER_DTYPE)
         out_s = np.concatenate(sites) if sites else np.zeros(0, dtype=abi.SITE_DTYPE)
