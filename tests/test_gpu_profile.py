@@ -133,8 +133,8 @@ def test_device_resident_and_multibatch(ctx, oracle):
 def test_int32_wrap(ctx, oracle):
     """Java int wrap-around: quality sums exceed 2^31 within a few million reads."""
     from parasuite_b200 import synth
-    ref = synth.synth_reference(3, [5_000_000], n_run=0)
-    batch = synth.synth_reads(ref, 3_000_000, 36, seed=3)
+    ref = synth.synth_reference(3, [20_000_000], n_run=0)
+    batch = synth.synth_reads(ref, 9_000_000, 36, seed=3)
     got = run_gpu(ctx, ref, batch, 51)
     exp = oracle.profile(ref, batch, 51, threads=8)
     assert_profile_equal(got, exp, "wrap")
