@@ -152,7 +152,7 @@ void ps_destroy(ps_ctx* ctx) {
     cudaEventDestroy(ctx->ev_stop[i]);
   }
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
-  ctx->acc.release(); ctx->fault.release();
+  ctx->acc.release(); ctx->fault.release(); ctx->deferred.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
     s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();
@@ -218,9 +218,10 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
   cudaSetDevice(ctx->device);
   ctx->layout = make_layout(opts->max_read_length, opts->infer_qualities ? 1 : 0);
   PS_CUDA(ctx, ctx->acc.reserve((size_t)ctx->layout.total * 8));
-  PS_CUDA(ctx, ctx->fault.reserve(8));
+  PS_CUDA(ctx, ctx->fault.reserve(64));
   PS_CUDA(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)ctx->layout.total * 8, ctx->stream));
   PS_CUDA(ctx, cudaMemsetAsync(ctx->fault.p, 0xFF, 8, ctx->stream));
+  PS_CUDA(ctx, cudaMemsetAsync((char*)ctx->fault.p + 8, 0, 56, ctx->stream));
   PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->reads_seen = 0;
   ctx->profile_open = true;
@@ -298,6 +299,15 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (out->quality_hist && l.infer_q) memcpy(out->quality_hist, &acc[l.qhist], (size_t)256 * m * 8);
   if (out->wide) memcpy(out->wide, acc.data(), (size_t)l.total * 8);
   return PS_OK;
+}
+
+// debug: words after the fault word ([1] = reads that took the fast path in the current run)
+unsigned long long ps_debug_word(ps_ctx* ctx, int idx) {
+  unsigned long long v = 0;
+  if (!ctx || !ctx->fault.p || idx < 0 || idx > 7) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(&v, (char*)ctx->fault.p + 8 * idx, 8, cudaMemcpyDeviceToHost);
+  return v;
 }
 
 // ---- instrumentation ---------------------------------------------------------------------------------

@@ -99,7 +99,8 @@ struct ps_ctx {
   bool profile_open = false;
   ProfileLayout layout{};
   DevBuf acc;        // int64[layout.total]
-  DevBuf fault;      // uint64
+  DevBuf fault;      // uint64 fault word + debug / deferred-count words (64 bytes)
+  DevBuf deferred;   // uint32 read indices the fast profile kernel hands to the generic routine
   uint64_t reads_seen = 0;
   // streams / staging
   cudaStream_t stream = nullptr;
