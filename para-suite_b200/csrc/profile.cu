@@ -194,7 +194,7 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
 
 // Shared memory: s_q[32] u64 | s_ctr[8] u64 | scan scratch[8] u64 | s_conv[max_len*16] u32
 __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const ProfileParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
   S.s_ctr = S.s_q + 32;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const
 // Reads the fast kernel could not take (flags, other cigars, contig edges): a dense list, so every thread of a
 // warp has work instead of 31 lanes waiting for one slow read.  Only uniform batches reach this kernel.
 __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(const ProfileParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
   S.s_ctr = S.s_q + 32;
@@ -295,26 +295,24 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   const uint32_t L = b.uniform_len;
   const bool fast_ok = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && !ctx->layout.infer_q && ctx->layout.max_len <= 256 &&
                        aligned16(b.meta) && aligned16(b.ref_start) && aligned16(b.cigar) && aligned16(b.bases2) &&
-                       aligned16(b.qual) && b.n_reads >= PS_TILE_READS && b.n_reads < 0xFFFFFFFFull;
+                       aligned16(b.qual) && b.n_reads < 0xFFFFFFFFull;
   if (fast_ok) {
     cudaError_t ee = ctx->deferred.reserve((size_t)b.n_reads * 4);
     if (ee != cudaSuccess) return ee;
     P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
     ee = cudaMemsetAsync(P.deferred_count, 0, 4, stream);
     if (ee != cudaSuccess) return ee;
-    const uint32_t n_super = (uint32_t)(b.n_reads / PS_TILE_READS) * (PS_TILE_READS / WT_READS);   // warp-tiles
+    const uint32_t n_wt = (uint32_t)((b.n_reads + WT_READS - 1) / WT_READS);   // the fast kernel takes every read
     const uint32_t nw = (L + 15) / 16;
     cudaError_t e;
-    switch (nw) {
-      case 1: e = launch_fast<1, 6>(ctx, P, n_super, stream); break;
-      case 2: e = launch_fast<2, 6>(ctx, P, n_super, stream); break;
-      case 3: e = launch_fast<3, 5>(ctx, P, n_super, stream); break;
-      default: e = launch_fast<4, 5>(ctx, P, n_super, stream); break;
-    }
+    if (L == 36) e = launch_fast<3, 6, 36>(ctx, P, n_wt, stream);
+    else if (L == 50) e = launch_fast<4, 5, 50>(ctx, P, n_wt, stream);
+    else if (nw == 1) e = launch_fast<1, 6, 0>(ctx, P, n_wt, stream);
+    else if (nw == 2) e = launch_fast<2, 6, 0>(ctx, P, n_wt, stream);
+    else if (nw == 3) e = launch_fast<3, 5, 0>(ctx, P, n_wt, stream);
+    else e = launch_fast<4, 5, 0>(ctx, P, n_wt, stream);
     if (e != cudaSuccess) return e;
-    e = launch_deferred(ctx, P, stream);
-    if (e != cudaSuccess) return e;
-    done = (uint64_t)n_super * WT_READS;
+    return launch_deferred(ctx, P, stream);
   }
   return launch_generic(ctx, P, done, stream);
 }

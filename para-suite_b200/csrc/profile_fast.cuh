@@ -96,12 +96,16 @@ __device__ __forceinline__ void vc_add2(uint32_t (&pl)[NPL], uint32_t x, uint32_
   }
 }
 
-// sum the bit-sliced counters of the 32 lanes; lane l ends up with the integer total of bit-lane l
 template <int NPL>
-__device__ __noinline__ uint32_t vc_warp_total(uint32_t (&pl)[NPL]) {
+struct Planes { uint32_t p[NPL]; };
+
+// sum the bit-sliced counters of the 32 lanes; lane l ends up with the integer total of bit-lane l
+// (passed by value so the caller's planes stay in registers across the call)
+template <int NPL>
+__device__ __noinline__ uint32_t vc_warp_total(Planes<NPL> pl) {
   uint32_t a[NPL + 5];
 #pragma unroll
-  for (int p = 0; p < NPL; ++p) { a[p] = pl[p]; pl[p] = 0; }
+  for (int p = 0; p < NPL; ++p) a[p] = pl.p[p];
 #pragma unroll
   for (int p = NPL; p < NPL + 5; ++p) a[p] = 0;
 #pragma unroll
@@ -132,14 +136,23 @@ struct FastSmem {
   uint32_t* s_fast;             // [max_len*4] match counts by (position, base)
 };
 
-// One read of the fast shape.  Produces the one-hot match words for the caller's bit-sliced counters.
-template <int NW>
-__device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& F, uint32_t L, uint32_t g0, bool rev,
+// number of bit-sliced counter words for NW 2-bit words: (A|C) and (G|T) per word; when the last word holds at
+// most 8 positions its two one-hot words share one counter word (A|C in the low half, G|T in the high half)
+__host__ __device__ constexpr int fast_nc(int NW, int LT) {
+  return (LT > 0 && LT - 16 * (NW - 1) <= 8) ? 2 * NW - 1 : 2 * NW;
+}
+
+// One read of the fast shape.  Produces the one-hot match words cw[] for the caller's bit-sliced counters.
+// LT > 0: the (uniform) read length is a compile-time constant.
+template <int NW, int LT>
+__device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& F, uint32_t Lrt, uint32_t g0, bool rev,
                                           const uint32_t* __restrict__ brow_w, uint32_t bshift,
                                           const uint32_t* __restrict__ qrow_w, uint32_t qshift,
                                           const unsigned char* __restrict__ qrow_b, const uint32_t (&lenmask)[NW],
-                                          uint32_t* __restrict__ inv_row, bool has_n, uint32_t (&ac)[NW],
-                                          uint32_t (&gt)[NW], int (&qacc)[4]) {
+                                          uint32_t* __restrict__ inv_row, bool has_n, const uint32_t (&tbl)[4],
+                                          uint32_t (&cw)[fast_nc(NW, LT)], int (&qacc)[4], int (&qinv)[4]) {
+  const uint32_t L = LT > 0 ? (uint32_t)LT : Lrt;
+  constexpr int NC = fast_nc(NW, LT);
   // ---- reference window: 2-bit codes and invalid bits -------------------------------------------------
   uint32_t rf[NW], rd[NW], ve[NW];   // ref codes, read codes, valid (even bit of each position)
   {
@@ -208,8 +221,10 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
     const uint32_t ne = (x | (x >> 1)) & 0x55555555u;
     const uint32_t m = ~ne & ve[k];
     const uint32_t lo = rd[k] & 0x55555555u, hi = (rd[k] >> 1) & 0x55555555u;
-    ac[k] = (m & ~hi & ~lo) | ((m & ~hi & lo) << 1);
-    gt[k] = (m & hi & ~lo) | ((m & hi & lo) << 1);
+    const uint32_t ac = (m & ~hi & ~lo) | ((m & ~hi & lo) << 1);
+    const uint32_t gt = (m & hi & ~lo) | ((m & hi & lo) << 1);
+    if (k == NW - 1 && NC == 2 * NW - 1) cw[2 * k] = ac | (gt << 16);
+    else { cw[2 * k] = ac; cw[2 * k + 1 < NC ? 2 * k + 1 : 0] = gt; }
     mm[k] = (lenmask[k] & 0x55555555u) & ~m;
   }
   // ---- quality sums by read base over ALL positions < L (corrected for mismatches / invalid at the end) ---
@@ -229,13 +244,16 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
       for (int j = 0; j < 2; ++j) {
         const int k = 2 * h + j;
         if (k < NQ && 4 * k < (int)L) {
-          const uint32_t q0 = qrow_w[k], q1 = (k + 1 <= nq) ? qrow_w[k + 1] : 0u;
-          const uint32_t q = __funnelshift_r(q0, q1, qshift);
+          uint32_t q = qrow_w[k];
+          if (LT == 0 || (LT & 3)) {     // rows start at any byte unless L is a multiple of 4
+            const uint32_t q1 = (k + 1 <= nq) ? qrow_w[k + 1] : 0u;
+            q = __funnelshift_r(q, q1, qshift);
+          }
           const uint32_t sel = j ? (s >> 16) : s;
-          qacc[0] = dp4a_ss(q, __byte_perm(0x000000FFu, 0u, sel), qacc[0]);
-          qacc[1] = dp4a_ss(q, __byte_perm(0x0000FF00u, 0u, sel), qacc[1]);
-          qacc[2] = dp4a_ss(q, __byte_perm(0x00FF0000u, 0u, sel), qacc[2]);
-          qacc[3] = dp4a_ss(q, __byte_perm(0xFF000000u, 0u, sel), qacc[3]);
+          qacc[0] = dp4a_ss(q, __byte_perm(tbl[0], 0u, sel), qacc[0]);
+          qacc[1] = dp4a_ss(q, __byte_perm(tbl[1], 0u, sel), qacc[1]);
+          qacc[2] = dp4a_ss(q, __byte_perm(tbl[2], 0u, sel), qacc[2]);
+          qacc[3] = dp4a_ss(q, __byte_perm(tbl[3], 0u, sel), qacc[3]);
         }
       }
     }
@@ -258,18 +276,19 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
       if ((vew >> sh) & 1u) {
         atomicAdd(&F.s_mm_cnt[i * 16 + a * 4 + bb], 1u);
         atomicAdd(&F.s_mm_q[i * 16 + a * 4 + bb], (uint32_t)q);
-      } else {
-        atomicAdd(&F.s_misc[4 + bb], (unsigned long long)(long long)q);
+      } else {   // invalid position: its quality went into the all-position sums, take it out again
+        qinv[0] += bb == 0u ? q : 0; qinv[1] += bb == 1u ? q : 0; qinv[2] += bb == 2u ? q : 0; qinv[3] += bb == 3u ? q : 0;
       }
     }
   }
 }
 
-template <int NW, int NPL>
+template <int NW, int NPL, int LT>
 __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NC = fast_nc(NW, LT);
   const uint32_t max_len = P.lay.max_len;
-  const uint32_t L = P.b.uniform_len;
+  const uint32_t L = LT > 0 ? (uint32_t)LT : P.b.uniform_len;
   const uint32_t bpr = (L + 3) >> 2;
   const FastStage lay = fast_stage_layout(L);
   const FastLayout fl = fast_layout(max_len, L, NW);
@@ -293,10 +312,13 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
   }
   __syncthreads();
 
-  const uint32_t n_wt = P.n_tiles;                       // warp-tiles in the batch
+  const uint64_t n_reads = P.b.n_reads;
+  const uint32_t n_wt = P.n_tiles;                       // warp-tiles in the batch (the last may be partial)
+  const uint32_t n_full = (uint32_t)(n_reads / WT_READS);
   const uint32_t gw = blockIdx.x * FAST_WARPS + warp;    // global warp id
   const uint32_t GW = gridDim.x * FAST_WARPS;
-  auto issue = [&](uint32_t wt, uint32_t slot) {         // lane 0 only
+  auto issue = [&](uint32_t wt, uint32_t slot) {         // lane 0 only; partial tiles are staged by the warp itself
+    if (wt >= n_full) return;
     unsigned char* dst = stage0 + (size_t)slot * lay.total;
     const uint64_t r0 = (uint64_t)wt * WT_READS;
     const uint32_t bb = WT_READS * bpr, qb = WT_READS * L;
@@ -321,31 +343,42 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
     const int rem = (int)L - 16 * k;
     lenmask[k] = rem >= 16 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << (2 * rem)) - 1u));
   }
-  uint32_t ac_pl[NW][NPL], gt_pl[NW][NPL];
-  uint32_t ac_tot[NW], gt_tot[NW];
+  // PRMT source tables (byte b = 0xFF): kept opaque so they live in registers instead of being re-materialised
+  uint32_t tbl[4];
+  asm volatile("mov.u32 %0, 0x000000FF;" : "=r"(tbl[0]));
+  asm volatile("mov.u32 %0, 0x0000FF00;" : "=r"(tbl[1]));
+  asm volatile("mov.u32 %0, 0x00FF0000;" : "=r"(tbl[2]));
+  asm volatile("mov.u32 %0, 0xFF000000;" : "=r"(tbl[3]));
+
+  Planes<NPL> pl[NC];
+  uint32_t tot[NC];
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    ac_tot[k] = gt_tot[k] = 0;
+  for (int c = 0; c < NC; ++c) {
+    tot[c] = 0;
 #pragma unroll
-    for (int p = 0; p < NPL; ++p) ac_pl[k][p] = gt_pl[k][p] = 0;
+    for (int p = 0; p < NPL; ++p) pl[c].p[p] = 0;
   }
-  int qacc[4] = {0, 0, 0, 0};
+  int qacc[4] = {0, 0, 0, 0}, qinv[4] = {0, 0, 0, 0};
   uint32_t n_fast = 0, since_flush = 0;
   constexpr uint32_t kFlushEvery = (1u << NPL) - 2u;   // reads a thread may add before a counter could overflow
   uint64_t c_lo = 1, c_hi = 0;                         // contig bounds cached from the previous warp-tile
 
   auto flush_vc = [&]() {
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      ac_tot[k] += vc_warp_total<NPL>(ac_pl[k]);
-      gt_tot[k] += vc_warp_total<NPL>(gt_pl[k]);
+    for (int c = 0; c < NC; ++c) {
+      tot[c] += vc_warp_total<NPL>(pl[c]);
+#pragma unroll
+      for (int p = 0; p < NPL; ++p) pl[c].p[p] = 0;
     }
     since_flush = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {        // dp4a accumulated -q; keep the int32 far from overflow
       const int t = __reduce_add_sync(0xFFFFFFFFu, qacc[b]);
+      const int u = __reduce_add_sync(0xFFFFFFFFu, qinv[b]);
       if (lane == 0 && t) atomicAdd(&F.s_misc[b], (unsigned long long)(long long)(-t));
+      if (lane == 0 && u) atomicAdd(&F.s_misc[4 + b], (unsigned long long)(long long)u);
       qacc[b] = 0;
+      qinv[b] = 0;
     }
   };
 
@@ -364,8 +397,27 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
       e_lo = __ldg(P.b.tile_exc_off + ((wt + GW) >> 2));
       e_hi = __ldg(P.b.tile_exc_off + ((wt + GW) >> 2) + 1);
     }
-    mbar_wait(&bars[slot], parity);
-    const unsigned char* sb = stage0 + (size_t)slot * lay.total;
+    unsigned char* sbw = stage0 + (size_t)slot * lay.total;
+    uint32_t n_here = WT_READS;
+    if (wt < n_full) {
+      mbar_wait(&bars[slot], parity);
+    } else {   // the batch's last, partial warp-tile: bounds-checked cooperative copy instead of TMA
+      const uint64_t r0 = (uint64_t)wt * WT_READS;
+      n_here = (uint32_t)(n_reads - r0);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(sbw);
+      for (uint32_t k = lane; k < WT_READS; k += 32) {
+        const bool in = k < n_here;
+        d32[lay.meta / 4 + k] = in ? __ldg(P.b.meta + r0 + k) : 0u;
+        d32[lay.start / 4 + k] = in ? __ldg(P.b.ref_start + r0 + k) : 0u;
+        d32[lay.cigar / 4 + k] = in ? __ldg(P.b.cigar + r0 + k) : 0u;
+      }
+      const uint32_t* gb = reinterpret_cast<const uint32_t*>(P.b.bases2 + r0 * bpr);   // r0*bpr is a multiple of 64
+      for (uint32_t k = lane; k < (n_here * bpr + 3) / 4; k += 32) d32[lay.bases / 4 + k] = __ldg(gb + k);
+      const uint32_t* gq = reinterpret_cast<const uint32_t*>(P.b.qual + r0 * L);
+      for (uint32_t k = lane; k < (n_here * L + 3) / 4; k += 32) d32[lay.qual / 4 + k] = __ldg(gq + k);
+      __syncwarp();
+    }
+    const unsigned char* sb = sbw;
     const uint32_t* s_meta = reinterpret_cast<const uint32_t*>(sb + lay.meta);
     const uint32_t* s_start = reinterpret_cast<const uint32_t*>(sb + lay.start);
     const uint32_t* s_cig = reinterpret_cast<const uint32_t*>(sb + lay.cigar);
@@ -381,7 +433,6 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
       }
     }
     // scatter this warp-tile's N calls into the per-read invalid map
-    bool exc_ok = true;
     {
       const uint32_t quarter = wt & 3u;
       uint32_t x = ex;
@@ -394,10 +445,9 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
       }
       __syncwarp();
     }
-    (void)exc_ok;
 
-    uint32_t xa[2][NW], xg[2][NW];
-#pragma unroll 1
+    uint32_t xw[2][NC];
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t rit = lane + h * 32;
       const uint32_t meta = s_meta[rit];
@@ -406,34 +456,27 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
       const uint32_t flags = PS_META_FLAGS(meta);
       const bool has_n = (flags & PS_RF_HAS_INVALID) != 0;
       const bool fast = (flags & ~(PS_RF_REVERSE | PS_RF_HAS_INVALID)) == 0 && op_is_match(cg & 15u) &&
-                        (cg >> 4) == L && L <= max_len && (uint64_t)g0 >= c_lo && (uint64_t)g0 + L <= c_hi;
-      uint32_t ta[NW], tg[NW];
+                        (cg >> 4) == L && L <= max_len && (uint64_t)g0 >= c_lo && (uint64_t)g0 + L <= c_hi &&
+                        rit < n_here;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) ta[k] = tg[k] = 0;
+      for (int c = 0; c < NC; ++c) xw[h][c] = 0;
       if (fast) {
         const uint32_t boff = rit * bpr, qoff = rit * L;
-        fast_read<NW>(P.ref, F, L, g0, (flags & PS_RF_REVERSE) != 0,
-                      reinterpret_cast<const uint32_t*>(sb + lay.bases + (boff & ~3u)), (boff & 3u) * 8u,
-                      reinterpret_cast<const uint32_t*>(sb + lay.qual + (qoff & ~3u)), (qoff & 3u) * 8u,
-                      sb + lay.qual + qoff, lenmask, s_inv + rit * NW, has_n, ta, tg, qacc);
+        fast_read<NW, LT>(P.ref, F, L, g0, (flags & PS_RF_REVERSE) != 0,
+                          reinterpret_cast<const uint32_t*>(sb + lay.bases + (boff & ~3u)), (boff & 3u) * 8u,
+                          reinterpret_cast<const uint32_t*>(sb + lay.qual + (qoff & ~3u)), (qoff & 3u) * 8u,
+                          sb + lay.qual + qoff, lenmask, s_inv + rit * NW, has_n, tbl, xw[h], qacc, qinv);
         ++n_fast;
-      } else {
+      } else if (rit < n_here) {
         if (has_n) {
 #pragma unroll
           for (int k = 0; k < NW; ++k) s_inv[rit * NW + k] = 0;
         }
         P.deferred[atomicAdd(P.deferred_count, 1u)] = (uint32_t)(P.first_read + (uint64_t)wt * WT_READS + rit);
       }
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        if (h == 0) { xa[0][k] = ta[k]; xg[0][k] = tg[k]; } else { xa[1][k] = ta[k]; xg[1][k] = tg[k]; }
-      }
     }
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      vc_add2<NPL>(ac_pl[k], xa[0][k], xa[1][k]);
-      vc_add2<NPL>(gt_pl[k], xg[0][k], xg[1][k]);
-    }
+    for (int c = 0; c < NC; ++c) vc_add2<NPL>(pl[c].p, xw[0][c], xw[1][c]);
     since_flush += 2;
     if (since_flush >= kFlushEvery) flush_vc();
 
@@ -447,12 +490,17 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
 
   // ---- per-thread totals -> shared histograms ----------------------------------------------------------------
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    const uint32_t i = 16u * k + (lane >> 1);
-    if (i < max_len) {
-      if (ac_tot[k]) atomicAdd(&F.s_fast[i * 4 + (lane & 1u)], ac_tot[k]);
-      if (gt_tot[k]) atomicAdd(&F.s_fast[i * 4 + 2 + (lane & 1u)], gt_tot[k]);
+  for (int c = 0; c < NC; ++c) {
+    if (tot[c] == 0) continue;
+    uint32_t i, base;
+    if (c == 2 * (NW - 1) && NC == 2 * NW - 1) {      // packed last word: A|C in lanes 0..15, G|T in 16..31
+      i = 16u * (NW - 1) + ((lane & 15u) >> 1);
+      base = (lane & 1u) + 2u * (lane >> 4);
+    } else {
+      i = 16u * (c >> 1) + (lane >> 1);
+      base = (lane & 1u) + 2u * (c & 1u);
     }
+    if (i < max_len) atomicAdd(&F.s_fast[i * 4 + base], tot[c]);
   }
   {
     const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, n_fast);
@@ -463,17 +511,23 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
   for (uint32_t k = threadIdx.x; k < max_len * 16; k += blockDim.x) {
     const uint32_t a = (k >> 2) & 3u, b = k & 3u, i = k >> 4;
     const unsigned long long cnt = a == b ? F.s_fast[i * 4 + a] : F.s_mm_cnt[k];
+    if (cnt) atomicAdd(P.acc + P.lay.conv + k, cnt);
+  }
+  if (threadIdx.x < 16) {   // per (ref, read) pair: counts and mismatch quality over all positions
+    const uint32_t a = threadIdx.x >> 2, b = threadIdx.x & 3u;
+    unsigned long long cnt = 0;
+    long long qs = 0;
+    for (uint32_t i = 0; i < max_len; ++i) {
+      cnt += a == b ? F.s_fast[i * 4 + a] : F.s_mm_cnt[i * 16 + threadIdx.x];
+      if (a != b) qs += (long long)(int)F.s_mm_q[i * 16 + threadIdx.x];
+    }
     if (cnt) {
-      atomicAdd(P.acc + P.lay.conv + k, cnt);
-      atomicAdd(P.acc + P.lay.qcnt + (k & 15u), cnt);   // fast reads never hold I/D: every counted base has a quality
+      atomicAdd(P.acc + P.lay.qcnt + threadIdx.x, cnt);   // fast reads never hold I/D: every counted base has a quality
       atomicAdd(P.acc + P.lay.ctr + PS_PC_TOTAL_BASES_CHECKED, cnt);
     }
-    if (a != b) {
-      const long long qs = (long long)(int)F.s_mm_q[k];
-      if (qs) {
-        atomicAdd(P.acc + P.lay.qsum + (k & 15u), (unsigned long long)qs);
-        atomicAdd(&F.s_misc[12 + b], (unsigned long long)qs);           // mismatch quality by read base
-      }
+    if (a != b && qs) {
+      atomicAdd(P.acc + P.lay.qsum + threadIdx.x, (unsigned long long)qs);
+      atomicAdd(&F.s_misc[12 + b], (unsigned long long)qs);             // mismatch quality by read base
     }
   }
   __syncthreads();
@@ -491,10 +545,10 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
 // a block may add this many reads before the 32-bit shared mismatch-quality cells could overflow
 #define FAST_MAX_READS_PER_BLOCK (1u << 18)
 
-template <int NW, int NPL>
+template <int NW, int NPL, int LT>
 cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cudaStream_t stream) {
   const size_t smem = fast_layout(P.lay.max_len, P.b.uniform_len, NW).total + 128;
-  auto kern = profile_fast_kernel<NW, NPL>;
+  auto kern = profile_fast_kernel<NW, NPL, LT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -515,6 +569,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
     Q.b.bases2 += r0 * ((P.b.uniform_len + 3) / 4);
     Q.b.qual += r0 * P.b.uniform_len;
     Q.b.tile_exc_off += r0 / PS_TILE_READS;
+    Q.b.n_reads = std::min<uint64_t>(P.b.n_reads - r0, cnt * WT_READS);
     Q.first_read = r0;    // offset added to deferred read indices
     kern<<<grid, PS_BLOCK_THREADS, smem, stream>>>(Q);
     ctx->launches++;
