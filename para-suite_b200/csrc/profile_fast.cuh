@@ -136,6 +136,12 @@ struct FastSmem {
   uint32_t* s_fast;             // [max_len*4] match counts by (position, base)
 };
 
+// match count of base a at one position from the four counted lanes E0..E3 (see fast_read)
+__device__ __forceinline__ uint32_t fast_base_count(const uint32_t* e, uint32_t a) {
+  const uint32_t e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+  return a == 0 ? e0 - e1 - e2 + e3 : (a == 1 ? e1 - e3 : (a == 2 ? e2 - e3 : e3));
+}
+
 // number of bit-sliced counter words for NW 2-bit words: (A|C) and (G|T) per word; when the last word holds at
 // most 8 positions its two one-hot words share one counter word (A|C in the low half, G|T in the high half)
 __host__ __device__ constexpr int fast_nc(int NW, int LT) {
@@ -155,6 +161,7 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
   constexpr int NC = fast_nc(NW, LT);
   // ---- reference window: 2-bit codes and invalid bits -------------------------------------------------
   uint32_t rf[NW], rd[NW], ve[NW];   // ref codes, read codes, valid (even bit of each position)
+  bool ve_dirty;                     // some position < L is invalid (else ve is the plain length mask)
   {
     const uint32_t wi = g0 >> 4, sh = (g0 & 15u) * 2u;
     uint32_t w[NW + 1];
@@ -170,6 +177,7 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
     const uint32_t any = (iv[0] & mask0) | (iv[1] & mask1);
 #pragma unroll
     for (int k = 0; k < NW; ++k) ve[k] = lenmask[k] & 0x55555555u;
+    ve_dirty = any != 0;
     if (any) {   // rare: N / IUPAC in the window -> clear those positions
 #pragma unroll
       for (int k = 0; k < NW; ++k) {
@@ -184,6 +192,7 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
   }
   // ---- N / IUPAC calls of this read: the warp has OR-ed them into this read's row of the invalid map --------
   if (has_n) {
+    ve_dirty = true;
 #pragma unroll
     for (int k = 0; k < NW; ++k) { ve[k] &= ~inv_row[k]; inv_row[k] = 0; }
   }
@@ -198,19 +207,28 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
   // ---- minus strand: reverse-complement both arrays (qualities stay forward, Q10) ------------------------
   if (rev) {
     const uint32_t s = 2u * (16u * NW - L);   // < 32
-    uint32_t a[NW], b[NW], v[NW];
+    uint32_t a[NW], b[NW];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) { a[k] = __brev(rf[NW - 1 - k]); b[k] = __brev(rd[NW - 1 - k]); v[k] = __brev(ve[NW - 1 - k]); }
+    for (int k = 0; k < NW; ++k) { a[k] = __brev(rf[NW - 1 - k]); b[k] = __brev(rd[NW - 1 - k]); }
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
-      const uint32_t an = k + 1 < NW ? a[k + 1] : 0u, bn = k + 1 < NW ? b[k + 1] : 0u, vn = k + 1 < NW ? v[k + 1] : 0u;
-      uint32_t x = __funnelshift_r(a[k], an, s), y = __funnelshift_r(b[k], bn, s), z = __funnelshift_r(v[k], vn, s);
+      const uint32_t an = k + 1 < NW ? a[k + 1] : 0u, bn = k + 1 < NW ? b[k + 1] : 0u;
+      uint32_t x = __funnelshift_r(a[k], an, s), y = __funnelshift_r(b[k], bn, s);
       // brev swapped the two bits of every code: swap back, then complement (A<->T, C<->G is bitwise NOT)
       x = ~(((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u));
       y = ~(((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u));
       rf[k] = x & lenmask[k];
       rd[k] = y & lenmask[k];
-      ve[k] = (z >> 1) & 0x55555555u;   // the valid bit sat on the even bit: brev moved it to the odd one
+    }
+    if (ve_dirty) {   // the plain length mask is its own mirror image; only a punctured one needs reversing
+      uint32_t v[NW];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) v[k] = __brev(ve[NW - 1 - k]);
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t vn = k + 1 < NW ? v[k + 1] : 0u;
+        ve[k] = (__funnelshift_r(v[k], vn, s) >> 1) & 0x55555555u;   // brev moved the even (valid) bit to the odd one
+      }
     }
   }
   // ---- match / mismatch masks and one-hot match words ---------------------------------------------------
@@ -220,9 +238,13 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
     const uint32_t x = rf[k] ^ rd[k];
     const uint32_t ne = (x | (x >> 1)) & 0x55555555u;
     const uint32_t m = ~ne & ve[k];
-    const uint32_t lo = rd[k] & 0x55555555u, hi = (rd[k] >> 1) & 0x55555555u;
-    const uint32_t ac = (m & ~hi & ~lo) | ((m & ~hi & lo) << 1);
-    const uint32_t gt = (m & hi & ~lo) | ((m & hi & lo) << 1);
+    // counted lanes per position (c1 c0 = read code of a matching base):
+    //   U: even bit E0 = match,        odd bit E2 = match & c1      (G or T)
+    //   V: even bit E1 = match & c0,   odd bit E3 = match & c1 & c0 (T)      (C or T)
+    // A = E0-E1-E2+E3, C = E1-E3, G = E2-E3, T = E3 are formed once, at the block flush.
+    const uint32_t ms = m << 1, rds = rd[k] << 1;
+    const uint32_t ac = m | (ms & rd[k]);
+    const uint32_t gt = rd[k] & (m | (ms & rds));
     if (k == NW - 1 && NC == 2 * NW - 1) cw[2 * k] = ac | (gt << 16);
     else { cw[2 * k] = ac; cw[2 * k + 1 < NC ? 2 * k + 1 : 0] = gt; }
     mm[k] = (lenmask[k] & 0x55555555u) & ~m;
@@ -250,7 +272,8 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
             q = __funnelshift_r(q, q1, qshift);
           }
           const uint32_t sel = j ? (s >> 16) : s;
-          qacc[0] = dp4a_ss(q, __byte_perm(tbl[0], 0u, sel), qacc[0]);
+          // qacc[0] collects the sum over all bases (A = total - C - G - T at the flush)
+          qacc[0] = dp4a_ss(q, (4 * k + 4 <= (int)L) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 * k + 4 - (int)L))), qacc[0]);
           qacc[1] = dp4a_ss(q, __byte_perm(tbl[1], 0u, sel), qacc[1]);
           qacc[2] = dp4a_ss(q, __byte_perm(tbl[2], 0u, sel), qacc[2]);
           qacc[3] = dp4a_ss(q, __byte_perm(tbl[3], 0u, sel), qacc[3]);
@@ -258,19 +281,23 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
       }
     }
   }
-  // ---- mismatching / invalid positions, one at a time (two words share one loop: even/odd bits) ------------
-#pragma unroll
-  for (int k = 0; k < NW; k += 2) {
-    const bool two = k + 1 < NW;
-    uint32_t word = mm[k] | (two ? (mm[k + 1] << 1) : 0u);
-    while (word) {
+  // ---- mismatching / invalid positions, one at a time.  Words 0,1 share the even/odd bits of w0, words 2,3 of w1;
+  //      one loop drains both so a warp pays max-over-lanes iterations once ------------------------------------
+  {
+    uint32_t w0 = mm[0] | (NW > 1 ? (mm[NW > 1 ? 1 : 0] << 1) : 0u);
+    uint32_t w1 = NW > 2 ? (mm[NW > 2 ? 2 : 0] | (NW > 3 ? (mm[NW > 3 ? 3 : 0] << 1) : 0u)) : 0u;
+    while (w0 | w1) {
+      const bool first = w0 != 0;
+      const uint32_t word = first ? w0 : w1;
       const int b = __ffs((int)word) - 1;
-      word &= word - 1;
-      const bool odd = two && (b & 1);
+      if (first) w0 &= w0 - 1; else w1 &= w1 - 1;
+      const int k = (first ? 0 : 2) + (b & 1);
       const int sh = b & ~1;
-      const uint32_t rfw = odd ? rf[two ? k + 1 : k] : rf[k], rdw = odd ? rd[two ? k + 1 : k] : rd[k];
-      const uint32_t vew = odd ? ve[two ? k + 1 : k] : ve[k];
-      const uint32_t i = 16u * (k + (odd ? 1 : 0)) + (sh >> 1);
+      uint32_t rfw = rf[0], rdw = rd[0], vew = ve[0];
+#pragma unroll
+      for (int j = 1; j < NW; ++j)
+        if (k == j) { rfw = rf[j]; rdw = rd[j]; vew = ve[j]; }
+      const uint32_t i = 16u * k + (sh >> 1);
       const uint32_t a = (rfw >> sh) & 3u, bb = (rdw >> sh) & 3u;
       const int q = (int)(signed char)qrow_b[i];
       if ((vew >> sh) & 1u) {
@@ -371,6 +398,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
       for (int p = 0; p < NPL; ++p) pl[c].p[p] = 0;
     }
     since_flush = 0;
+    qacc[0] -= qacc[1] + qacc[2] + qacc[3];   // qacc[0] held the all-base total
 #pragma unroll
     for (int b = 0; b < 4; ++b) {        // dp4a accumulated -q; keep the int32 far from overflow
       const int t = __reduce_add_sync(0xFFFFFFFFu, qacc[b]);
@@ -495,10 +523,10 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
     uint32_t i, base;
     if (c == 2 * (NW - 1) && NC == 2 * NW - 1) {      // packed last word: A|C in lanes 0..15, G|T in 16..31
       i = 16u * (NW - 1) + ((lane & 15u) >> 1);
-      base = (lane & 1u) + 2u * (lane >> 4);
+      base = 2u * (lane & 1u) + (lane >> 4);        // U half: E0/E2, V half: E1/E3
     } else {
       i = 16u * (c >> 1) + (lane >> 1);
-      base = (lane & 1u) + 2u * (c & 1u);
+      base = 2u * (lane & 1u) + (c & 1u);
     }
     if (i < max_len) atomicAdd(&F.s_fast[i * 4 + base], tot[c]);
   }
@@ -510,7 +538,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
   // ---- block flush ---------------------------------------------------------------------------------------------
   for (uint32_t k = threadIdx.x; k < max_len * 16; k += blockDim.x) {
     const uint32_t a = (k >> 2) & 3u, b = k & 3u, i = k >> 4;
-    const unsigned long long cnt = a == b ? F.s_fast[i * 4 + a] : F.s_mm_cnt[k];
+    const unsigned long long cnt = a == b ? fast_base_count(F.s_fast + i * 4, a) : F.s_mm_cnt[k];
     if (cnt) atomicAdd(P.acc + P.lay.conv + k, cnt);
   }
   if (threadIdx.x < 16) {   // per (ref, read) pair: counts and mismatch quality over all positions
@@ -518,7 +546,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const
     unsigned long long cnt = 0;
     long long qs = 0;
     for (uint32_t i = 0; i < max_len; ++i) {
-      cnt += a == b ? F.s_fast[i * 4 + a] : F.s_mm_cnt[i * 16 + threadIdx.x];
+      cnt += a == b ? fast_base_count(F.s_fast + i * 4, a) : F.s_mm_cnt[i * 16 + threadIdx.x];
       if (a != b) qs += (long long)(int)F.s_mm_q[i * 16 + threadIdx.x];
     }
     if (cnt) {
