@@ -1,5 +1,5 @@
 import sys, os, time, ctypes as C
-sys.path.insert(0, "para-suite_b200"); sys.path.insert(0, "oracle")
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(R, "para-suite_b200")); sys.path.insert(0, os.path.join(R, "oracle"))
 import numpy as np, torch
 from parasuite_b200 import synth
 from parasuite_b200.runtime import Context, DeviceBatch
@@ -9,12 +9,10 @@ ref = synth.synth_reference(0x5EED0001, [100_000_000])
 b = synth.synth_reads(ref, n, L, seed=0x5EED0002)
 ctx = Context(0); ctx.upload_reference(ref)
 d = DeviceBatch(b, "cuda:0")
-ctx.lib.ps_debug_word.restype = C.c_uint64
-ctx.lib.ps_debug_word.argtypes = [C.c_void_p, C.c_int]
 for it in range(3):
-    ctx.profile_begin(51)
     ctx.kernel_times_reset(True)
-    ctx.profile_batch_device(d, torch.cuda.current_stream().cuda_stream)
+    t0 = time.perf_counter()
+    res = ctx.pileup(d, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    print("kernel ms", ctx.kernel_times_ms(), "fast reads", ctx.lib.ps_debug_word(ctx.h, 1), "of", n)
-    ctx.profile_end()
+    dt = time.perf_counter() - t0
+    print("device ms", ctx.kernel_times_ms(), "wall ms", dt * 1e3, "clusters", len(res["clusters"]), "sites", len(res["sites"]))
