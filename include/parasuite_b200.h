@@ -208,6 +208,13 @@ int ps_reference_load_fasta(ps_ctx* ctx, const char* fasta_path); /* needs <fast
 /* adopt device-resident arrays (no copy; caller keeps them alive) */
 int ps_reference_adopt_device(ps_ctx* ctx, const ps_reference* dev_ref, const uint64_t* host_contig_off);
 
+/* ---- batches -----------------------------------------------------------------------------------
+ * Copy a host batch (pinned or pageable) into device memory owned by the context, asynchronously on the context's
+ * stream, and return a device-resident view of it for the *_batch_device calls (pass stream = NULL so they run on
+ * the same stream, after the copy).  The view stays valid until the second-next ps_batch_upload / ps_*_batch call on
+ * this context (two staging slots).  Lets the two tools share one upload of the same records. */
+int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* host_batch, ps_read_batch* dev_view);
+
 /* ---- error profile: replaces the loop ErrorProfiling.java:146-409 ---------------------------- */
 int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts);
 /* host-resident batch: staged through pinned memory, H2D, kernels; asynchronous, returns when queued */

@@ -46,7 +46,7 @@ static int check_batch(ps_ctx* ctx, const ps_read_batch* b) {
 }
 
 // H2D copy of a host batch into one of the two staging slots (async on ctx->stream)
-int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, StagedBatch** out) {
+int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatch** out) {
   const int slot = ctx->staged_next;
   ctx->staged_next ^= 1;
   StagedBatch& s = ctx->staged[slot];
@@ -58,7 +58,7 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, StagedBatch** out) {
       {&s.meta, hb->meta, n * 4},
       {&s.ref_start, hb->ref_start, n * 4},
       {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
-      {&s.qual, hb->qual, (size_t)hb->qual_bytes},
+      {&s.qual, hb->qual, with_qual ? (size_t)hb->qual_bytes : 0},   // the pileup never reads qualities
       {&s.cigar, hb->cigar, (size_t)hb->cigar_count * 4},
       {&s.tbo, hb->tile_base_off, hb->tile_base_off ? (nt + 1) * 8 : 0},
       {&s.tqo, hb->tile_qual_off, hb->tile_qual_off ? (nt + 1) * 8 : 0},
@@ -138,6 +138,14 @@ int ps_create(ps_ctx** out, int device) {
   for (int i = 0; i < PS_TIMER_RING; ++i) {
     cudaEventCreate(&ctx->ev_start[i]);
     cudaEventCreate(&ctx->ev_stop[i]);
+  }
+  {   // result buffers are stream-ordered allocations: keep freed blocks in the pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
   }
   *out = ctx;
   return PS_OK;
@@ -250,12 +258,28 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
   if (hb->n_reads == 0) return PS_OK;
   cudaSetDevice(ctx->device);
   StagedBatch* sb = nullptr;
-  st = stage_batch(ctx, hb, &sb);
+  st = stage_batch(ctx, hb, true, &sb);
   if (st) return st;
   timer_begin(ctx, ctx->stream);
   PS_CUDA(ctx, launch_profile(ctx, sb->view, ctx->reads_seen, ctx->stream));
   timer_end(ctx, ctx->stream);
   ctx->reads_seen += hb->n_reads;
+  return PS_OK;
+}
+
+int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* hb, ps_read_batch* dev_view) {
+  if (!ctx || !dev_view) return PS_ERR_INVALID_ARG;
+  int st = check_batch(ctx, hb);
+  if (st) return st;
+  cudaSetDevice(ctx->device);
+  StagedBatch* sb = nullptr;
+  st = stage_batch(ctx, hb, true, &sb);
+  if (st) return st;
+  *dev_view = *hb;
+  const DeviceBatch& v = sb->view;
+  dev_view->meta = v.meta; dev_view->ref_start = v.ref_start; dev_view->bases2 = v.bases2; dev_view->qual = v.qual;
+  dev_view->cigar = v.cigar; dev_view->tile_base_off = v.tile_base_off; dev_view->tile_qual_off = v.tile_qual_off;
+  dev_view->tile_cigar_off = v.tile_cigar_off; dev_view->tile_exc_off = v.tile_exc_off; dev_view->exc = v.exc;
   return PS_OK;
 }
 

@@ -113,8 +113,11 @@ struct ps_ctx {
   cudaEvent_t ev_stop[PS_TIMER_RING];
   uint32_t ev_count = 0;   // pairs recorded since reset
   bool timers_on = true;
-  // pileup scratch
+  // pileup scratch (pileup.cu): run state, read intervals, look-back descriptors, slot tables, events
   DevBuf pl_scratch[12];
+  uint64_t pl_generation = 0;   // pileup calls so far (a result handle's view of the scratch is valid while equal)
+  unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)
+  uint64_t pl_cap_cl = 0, pl_cap_ev = 0;   // cluster-slot / event capacities learnt from earlier batches
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------------

@@ -193,7 +193,7 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
 }
 
 // Shared memory: s_q[32] u64 | s_ctr[8] u64 | scan scratch[8] u64 | s_conv[max_len*16] u32
-__global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const ProfileParams P) {
+__global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const
 
 // Reads the fast kernel could not take (flags, other cigars, contig edges): a dense list, so every thread of a
 // warp has work instead of 31 lanes waiting for one slow read.  Only uniform batches reach this kernel.
-__global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(const ProfileParams P) {
+__global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);

@@ -131,6 +131,7 @@ EXPORTS = {
     "ps_reference_upload": (C.c_int, [VP, C.POINTER(ps_reference)]),
     "ps_reference_load_fasta": (C.c_int, [VP, C.c_char_p]),
     "ps_reference_adopt_device": (C.c_int, [VP, C.POINTER(ps_reference), VP]),
+    "ps_batch_upload": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_read_batch)]),
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "ps_profile_begin": (C.c_int, [VP, C.POINTER(ps_profile_opts)]),
     "ps_profile_batch": (C.c_int, [VP, C.POINTER(ps_read_batch)]),

@@ -46,6 +46,15 @@ class DeviceBatch:
         self.nbytes = sum(t.numel() for t in self._t.values() if t is not None)
 
 
+class UploadedBatch:
+    """Device-resident view returned by ps_batch_upload (memory owned by the context's staging slots)."""
+
+    def __init__(self, struct, n_reads, source):
+        self.struct = struct
+        self.n_reads = n_reads
+        self._source = source        # keeps the host buffers alive until the copy has completed
+
+
 class PinnedBatch:
     """A ReadBatch copied into page-locked host memory (what the native batcher fills)."""
 
@@ -97,6 +106,15 @@ class Context:
         _check(self.lib, self.h, self.lib.ps_reference_upload(self.h, C.byref(s)))
         self.ref = ref
 
+    # ---- batches ---------------------------------------------------------------------------------
+    def upload(self, batch) -> UploadedBatch:
+        """One H2D copy of a host batch (ReadBatch / PinnedBatch); both tools can then run on the device view
+        (pass stream=0 so they are ordered after the copy on the context's stream)."""
+        s = batch.struct if hasattr(batch, "struct") else batch.as_struct()
+        v = abi.ps_read_batch()
+        _check(self.lib, self.h, self.lib.ps_batch_upload(self.h, C.byref(s), C.byref(v)))
+        return UploadedBatch(v, batch.n_reads, batch)
+
     # ---- error profile (ErrorProfiling.java:146-409) ---------------------------------------------
     def profile_begin(self, max_read_length: int, infer_qualities: bool = False):
         o = abi.ps_profile_opts(max_read_length, int(infer_qualities))
@@ -110,7 +128,7 @@ class Context:
         self._keep.append(batch)
         _check(self.lib, self.h, self.lib.ps_profile_batch(self.h, C.byref(s)))
 
-    def profile_batch_device(self, dbatch: DeviceBatch, stream: int = 0):
+    def profile_batch_device(self, dbatch, stream: int = 0):
         _check(self.lib, self.h, self.lib.ps_profile_batch_device(self.h, C.byref(dbatch.struct), stream or None))
 
     def profile_acc_tensor(self):
@@ -165,7 +183,7 @@ class Context:
         if carry is not None:
             opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
         h = C.c_void_p()
-        if isinstance(batch, DeviceBatch):
+        if isinstance(batch, (DeviceBatch, UploadedBatch)):
             st = self.lib.ps_pileup_batch_device(self.h, C.byref(batch.struct), C.byref(opts), stream or None,
                                                  C.byref(h))
         else:

@@ -68,6 +68,24 @@ def slice_batch(b: ReadBatch, lo: int, hi: int) -> ReadBatch:
         exc_count=len(exc))
 
 
+def take_uniform(b: ReadBatch, idx: np.ndarray) -> ReadBatch:
+    """Reads `idx` (ascending) of a uniform batch (one length, one cigar op per read, no N calls) as a new batch."""
+    if not (b.uniform_len and b.uniform_ncigar == 1) or b.exc_count:
+        raise ValueError("take_uniform needs a uniform batch without N calls")
+    T = abi.PS_TILE_READS
+    L, bb, n = b.uniform_len, (b.uniform_len + 3) // 4, len(idx)
+    n_tiles = (n + T - 1) // T
+    edges = np.minimum(np.arange(0, n_tiles + 1, dtype=np.uint64) * np.uint64(T), np.uint64(n))
+    pad8, pad32 = np.zeros(64, dtype=np.uint8), np.zeros(16, dtype=np.uint32)
+    bases = b.bases2[: b.n_reads * bb].reshape(b.n_reads, bb)[idx].reshape(-1)
+    qual = b.qual[: b.n_reads * L].reshape(b.n_reads, L)[idx].reshape(-1)
+    return ReadBatch(
+        n, np.ascontiguousarray(b.meta[idx]), np.ascontiguousarray(b.ref_start[idx]), np.concatenate((bases, pad8)),
+        np.concatenate((qual, pad8)), np.concatenate((b.cigar[: b.n_reads][idx], pad32)), edges * np.uint64(bb),
+        edges * np.uint64(L), edges.copy(), np.zeros(n_tiles + 1, dtype=np.uint32), pad32.copy(), uniform_len=L,
+        uniform_ncigar=1, bases_bytes=n * bb, qual_bytes=n * L, cigar_count=n, exc_count=0)
+
+
 def shard_ranges(n_reads: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous, tile-aligned read ranges per rank."""
     T = abi.PS_TILE_READS

@@ -120,6 +120,41 @@ def test_dense_overlapping_clusters(ctx, oracle):
     assert_pileup_equal(ctx.pileup(batch), oracle.pileup(ref, batch), "dense")
 
 
+def test_sparse_reads_capacity_retry(ctx, oracle):
+    """Nearly every read is its own cluster: more cluster slots than the first-guess capacity (n/8) -> the scan
+    kernel is re-run once with exact capacities; results must not depend on that."""
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context
+    from parasuite_b200.sharding import take_uniform
+    ref = synth.synth_reference(78, [30_000_000], n_run=0)
+    dense = synth.synth_reads(ref, 640_000, 36, seed=9, n_ppm=0)
+    batch = take_uniform(dense, np.arange(0, dense.n_reads, 16))      # ~1 read per cluster, 40 000 reads
+    fresh = Context(0)                     # capacities are learnt per context: use one that has seen nothing
+    try:
+        fresh.upload_reference(ref)
+        exp = oracle.pileup(ref, batch)
+        got = fresh.pileup(batch)
+        assert_pileup_equal(got, exp, "sparse")
+        assert len(got["clusters"]) > 40_000 // 8
+        assert_pileup_equal(fresh.pileup(batch), exp, "sparse, second call")
+    finally:
+        fresh.close()
+
+
+def test_shared_upload(ctx, oracle):
+    """ps_batch_upload: one H2D copy, both tools on the device view."""
+    from helpers import assert_profile_equal
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(79, [2_000_000], n_run=1000)
+    batch = synth.synth_reads(ref, 120_000, 36, seed=10)
+    ctx.upload_reference(ref)
+    view = ctx.upload(batch)
+    ctx.profile_begin(51)
+    ctx.profile_batch_device(view)
+    assert_profile_equal(ctx.profile_end(), oracle.profile(ref, batch, 51, threads=4), "shared upload profile")
+    assert_pileup_equal(ctx.pileup(view), oracle.pileup(ref, batch), "shared upload pileup")
+
+
 def test_region_sharding_halo_merge(ctx, oracle):
     """Two shards cut at an arbitrary read index; carry-in + head partial merge equals the whole-stream result."""
     from parasuite_b200 import synth
