@@ -49,6 +49,7 @@ static int check_batch(ps_ctx* ctx, const ps_read_batch* b) {
 int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatch** out) {
   const int slot = ctx->staged_next;
   ctx->staged_next ^= 1;
+  ctx->stage_serial++;
   StagedBatch& s = ctx->staged[slot];
   // the slot may still be read by a kernel queued two batches ago: same stream, so ordering is implicit
   const uint64_t n = hb->n_reads;

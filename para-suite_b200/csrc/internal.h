@@ -107,17 +107,17 @@ struct ps_ctx {
   StagedBatch staged[2];
   cudaEvent_t staged_done[2] = {nullptr, nullptr};
   int staged_next = 0;
+  uint64_t stage_serial = 0;   // uploads so far (a staged batch stays valid until the second-next one)
   // instrumentation
   uint64_t launches = 0;
   cudaEvent_t ev_start[PS_TIMER_RING];
   cudaEvent_t ev_stop[PS_TIMER_RING];
   uint32_t ev_count = 0;   // pairs recorded since reset
   bool timers_on = true;
-  // pileup scratch (pileup.cu): run state, read intervals, look-back descriptors, slot tables, events
+  // pileup scratch (pileup.cu): run state, look-back descriptors
   DevBuf pl_scratch[12];
-  uint64_t pl_generation = 0;   // pileup calls so far (a result handle's view of the scratch is valid while equal)
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)
-  uint64_t pl_cap_cl = 0, pl_cap_ev = 0;   // cluster-slot / event capacities learnt from earlier batches
+  uint64_t pl_cap_cl = 0, pl_cap_ev = 0;   // cluster-slot / site capacities learnt from earlier batches
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------------

@@ -1,23 +1,23 @@
 // K2/K3: T>C conversion pileup.  Replaces the loop PileupClusters.java:137-500 and
 // calculateClusterInformation :585-673 (reference: /root/reference/src/src/utils/pileupclusters/).
 //
-// Two kernels over one coordinate-sorted SoA batch, every record assembled on the device:
+// Two kernels over one coordinate-sorted SoA batch; every output record is assembled on the device:
 //
-//   pl_scan_kernel   ONE pass over the reads (tiles of 1024 reads, tile numbers from an atomic counter):
-//       per read      filter (P1), contig/start/end, T>C bit mask over the concatenated alignment blocks (P3) --
-//                     bit-parallel on 2-bit packed words for the PAR-CLIP shape (uniform length, one M op),
-//                     a literal CIGAR walk otherwise
-//       look-back #1  running max of (contig, end) over all earlier reads = the cluster end the Java loop holds
-//                     (tempClusterEnd) -> boundary flag (clusterEnd - start) < 5 or contig changed (P2)
-//       look-back #2  segmented reduction keyed by the flags: cluster number, event offset and the running
-//                     aggregate of the open cluster (reads, T>C count, end, 51-bit mask, strand state P6)
-//       output        the read that opens cluster c+1 writes the finished sums of cluster c (one writer per field,
-//                     no atomics, no zero-initialised accumulators); T>C events (position, insertion key) are
-//                     appended at the scanned offset, i.e. in read order
-//   pl_site_kernel   one warp per cluster: mutationMap keys = distinct event positions, their counts, the
-//                     first-insertion key and baseCoveredMap at those keys (difference array over the cluster's
-//                     read intervals), in windows of 128 positions of shared memory; site slots come from a third
-//                     look-back so the site array is compact and ordered by (cluster, position)
+//   pl_flag_kernel     the only ORDERED step, kept as light as possible (12 B/read: meta, ref_start, cigar):
+//       per read       filter (P1), (contig, start, end)
+//       look-back #1   running max of (contig, end) over all earlier reads = the cluster end the Java loop holds
+//                      (tempClusterEnd) -> boundary flag (clusterEnd - start) < 5 or contig changed (P2)
+//       look-back #2   prefix sum of the flags = cluster slot; the opening read writes cl_first[slot]
+//   pl_cluster_kernel  one WARP per cluster (a contiguous run of reads), lanes = reads, no inter-block dependency except
+//                      the prefix of site counts:
+//       per read       T>C bit mask over the concatenated alignment blocks (P3): bit-parallel on 2-bit packed words
+//                      for the PAR-CLIP shape (uniform length, one M op), a literal CIGAR walk otherwise
+//       per cluster    reads, T>C count, end, 51-bit position mask, strand state (P4, P6) by warp reductions;
+//                      mutationMap keys/values, first-insertion key and baseCoveredMap at those keys (P3, P7) by warp
+//                      ballots over a 128-position window -- clusters of more than 32 reads or longer than the window
+//                      go through per-warp shared-memory tables instead
+//       output         cluster records staged in shared memory and written as one coalesced 4 KB run per block; site
+//                      slots come from look-back #3, so the site array is compact and ordered by (cluster, position)
 //
 // The flush-time logic (SNP filter, anchor site, text rows: :178-344) stays on the host side of the boundary.
 #include <algorithm>
@@ -33,98 +33,251 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
 namespace {
 
 constexpr int PL_THREADS = 256;
-constexpr int PL_SITE_CLUSTERS = 64;     // clusters per block of pl_site_kernel
-constexpr int PL_WINDOW = 128;           // positions per shared-memory window
+constexpr int PL_WARPS = PL_THREADS / 32;
+constexpr int CB_PER_WARP = 8;                        // clusters per warp of pl_cluster_kernel
+constexpr int CB_CLUSTERS = PL_WARPS * CB_PER_WARP;   // clusters per block
+constexpr int CB_SITE_CAP = 40;                       // sites a warp can stage in shared memory
+constexpr int PL_WINDOW = 128;                        // positions per window
 
 struct PlState {                  // device-side run state (one per call)
   unsigned long long fault;       // min over (ordinal << 8 | code); ~0 = none
   unsigned long long skipped;     // skippedDueIndel (:156)
   unsigned long long dstr;        // doubleStranded (:496)
-  unsigned long long n_ev;        // T>C events
   unsigned long long n_sites;     // distinct (cluster, position)
   unsigned int n_flags;           // clusters opened
   unsigned int unsorted;
-  unsigned int tile_ctr_scan;
-  unsigned int tile_ctr_site;
+  unsigned int tile_ctr_flag;
+  unsigned int tile_ctr_cluster;
 };
 
-// running aggregate of the cluster that is open after a prefix of the reads
-struct Seg {
-  uint32_t nflags;      // boundary flags in the prefix
-  uint32_t reads;       // numReadsPerCluster
-  uint32_t t2c;         // numT2CMutationPerCluster
-  uint32_t minus;       // minus-strand reads of the cluster
-  int32_t end;          // tempClusterEnd
-  uint32_t first_rev;   // tempIsReverse (strand of the first read)
-  unsigned long long nev;    // events in the prefix
-  unsigned long long mask;   // alleleFrequencyPositionsTemp
-};
-__device__ __forceinline__ Seg seg_identity() {
-  Seg s;
-  s.nflags = 0; s.reads = 0; s.t2c = 0; s.minus = 0; s.end = INT32_MIN; s.first_rev = 0; s.nev = 0; s.mask = 0;
-  return s;
-}
-struct SegOp {
-  __device__ __forceinline__ Seg operator()(const Seg& a, const Seg& b) const {
-    Seg r;
-    r.nflags = a.nflags + b.nflags;
-    r.nev = a.nev + b.nev;
-    if (b.nflags) {
-      r.reads = b.reads; r.t2c = b.t2c; r.minus = b.minus; r.end = b.end; r.first_rev = b.first_rev; r.mask = b.mask;
-    } else {
-      r.reads = a.reads + b.reads; r.t2c = a.t2c + b.t2c; r.minus = a.minus + b.minus;
-      r.end = a.end > b.end ? a.end : b.end;
-      r.first_rev = a.reads ? a.first_rev : b.first_rev;
-      r.mask = a.mask | b.mask;
-    }
-    return r;
-  }
-};
-struct MaxOp {
-  __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
-    return a > b ? a : b;
-  }
-};
-struct SumOp {
-  __device__ __forceinline__ unsigned long long operator()(unsigned long long a, unsigned long long b) const {
-    return a + b;
-  }
-};
-
-struct PlItem {          // what the pileup needs from one read
-  unsigned long long key;    // (contig+1) << 32 | end; 0 = record not kept
+struct PlRead {              // what the pileup needs from one read
   unsigned long long mask;   // T>C by index i over the strand-oriented concatenated blocks
-  int32_t start, end, lo, hi;
-  bool rev;
+  int32_t start, end;        // alignment start / end (1-based, contig coordinates)
+  int32_t lo, hi;            // checkPosition interval (baseCoveredMap support)
+  uint32_t contig;
+  bool kept, rev;
 };
 
-struct ScanParams {
+struct ContigCache {         // contig bounds of the last read looked up by this thread
+  uint64_t lo = 1, hi = 0;
+  uint32_t idx = 0;
+};
+__device__ __forceinline__ bool contig_lookup(const DeviceRef& ref, uint64_t g0, ContigCache& c) {
+  if (g0 >= c.lo && g0 < c.hi) return true;
+  if (g0 >= ref.n_bases) return false;
+  c.idx = contig_of(ref, g0);
+  c.lo = __ldg(ref.contig_off + c.idx);
+  c.hi = __ldg(ref.contig_off + c.idx + 1);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pl_flag_kernel
+// ---------------------------------------------------------------------------------------------------------
+struct FlagParams {
   DeviceBatch b;
   DeviceRef ref;
   PlState* st;
-  LbDesc<unsigned long long>* d_max;
-  LbDesc<Seg>* d_seg;
+  LbDesc* d_max;
+  LbDesc* d_cnt;
   unsigned int epoch;
   uint32_t n_tiles;
   unsigned long long carry_key;
-  uint32_t first_id;
-  // outputs
-  int2* iv;                 // [n] checkPosition interval of every read (empty for records not kept)
-  ps_cluster* cl;           // [cap_cl] slot 0 = reads continuing the carry-in cluster
-  uint32_t* cl_first;       // [cap_cl+1] first read of each slot
-  uint32_t* cl_ev;          // [cap_cl+1] first event of each slot
-  int32_t* ev_pos;          // [cap_ev]
-  unsigned long long* ev_key;   // [cap_ev] (read ordinal << 6) | i
-  uint64_t cap_cl, cap_ev;
+  uint32_t* cl_first;       // [cap_cl + 2] first read of each slot; slot 0 = reads continuing the carry-in cluster
+  uint64_t cap_cl;
 };
 
+// (contig+1) << 32 | end of a kept record, 0 otherwise (PileupClusters.java:146-158)
+__device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64_t r, uint32_t meta, const uint32_t* cig,
+                                                     uint32_t g0, ContigCache& cc, int32_t& start) {
+  const uint32_t flags = PS_META_FLAGS(meta), ncig = PS_META_NCIGAR(meta);
+  start = 0;
+  if (flags & PS_RF_UNMAPPED) return 0;                                      // :146
+  uint32_t R = 0;
+  bool hasI = false, hasD = false, hasN = false;
+  for (uint32_t e = 0; e < ncig; ++e) {
+    const uint32_t c = __ldg(cig + e), op = c & 15u;
+    hasI |= op == 1u; hasD |= op == 2u; hasN |= op == 3u;
+    if (op_consumes_ref(op)) R += c >> 4;
+  }
+  if ((hasI || hasD) && hasN) {                                              // :152-157
+    atomicAdd(&P.st->skipped, 1ull);
+    return 0;
+  }
+  if (flags & PS_RF_POS_ZERO) return 0;           // the JVM dies on this record: pl_cluster_kernel raises the fault
+  if (!contig_lookup(P.ref, g0, cc)) return 0;    // likewise
+  start = (int32_t)((uint64_t)g0 - cc.lo) + 1;
+  const int32_t end = start + (int32_t)R - 1;
+  return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)end;
+}
+
+// block-wide exclusive scan over one 64-bit value per thread (PL_THREADS threads); also returns the block total
+template <typename Op>
+__device__ __forceinline__ unsigned long long block_exclusive(unsigned long long v, Op op, unsigned long long identity,
+                                                              unsigned long long* warp_tot /* [8] smem */,
+                                                              unsigned long long& total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    if (lane >= (uint32_t)d) x = op(y, x);
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  unsigned long long prefix = identity, tot = identity;
+#pragma unroll
+  for (uint32_t w = 0; w < PL_WARPS; ++w) {
+    const unsigned long long t = warp_tot[w];
+    if (w < warp) prefix = op(prefix, t);
+    tot = op(tot, t);
+  }
+  total = tot;
+  unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+  if (lane == 0) up = identity;
+  __syncthreads();
+  return op(prefix, up);
+}
+
+// ITEMS == 4: every read has one cigar op and the three streams are 16-byte aligned (vector loads);
+// ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
+template <int ITEMS>
+__global__ void __launch_bounds__(PL_THREADS) pl_flag_kernel(const __grid_constant__ FlagParams P) {
+  constexpr int TILE = PL_THREADS * ITEMS;
+  __shared__ unsigned long long s_wtot[PL_WARPS];
+  __shared__ uint64_t s_scan[8];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_pre;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_flag, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t n = P.b.n_reads;
+  const uint64_t r0 = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  unsigned long long key[ITEMS];
+  int32_t start[ITEMS];
+  ContigCache cc;
+  if constexpr (ITEMS == 4) {
+    uint32_t metas[4], starts[4];
+    if (r0 + 4 <= n) {
+      const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(P.b.meta + r0));
+      const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(P.b.ref_start + r0));
+      metas[0] = m4.x; metas[1] = m4.y; metas[2] = m4.z; metas[3] = m4.w;
+      starts[0] = s4.x; starts[1] = s4.y; starts[2] = s4.z; starts[3] = s4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = r0 + j < n;
+        metas[j] = in ? __ldg(P.b.meta + r0 + j) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
+        starts[j] = in ? __ldg(P.b.ref_start + r0 + j) : 0u;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) key[j] = pl_key(P, r0 + j, metas[j], P.b.cigar + r0 + j, starts[j], cc, start[j]);
+  } else {
+    const bool in_range = r0 < n;
+    const uint32_t meta = in_range ? __ldg(P.b.meta + r0) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
+    const ReadOffsets off = read_offsets(P.b, tile, r0, meta, in_range, s_scan);
+    key[0] = in_range ? pl_key(P, r0, meta, P.b.cigar + off.cigar, __ldg(P.b.ref_start + r0), cc, start[0]) : 0ull;
+    if (!in_range) start[0] = 0;
+  }
+
+  // ---- look-back #1: running max of (contig, end) -----------------------------------------------------------
+  unsigned long long tmax = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) tmax = key[j] > tmax ? key[j] : tmax;
+  unsigned long long block_max;
+  const unsigned long long ex_max = block_exclusive(tmax, LbMax(), 0ull, s_wtot, block_max);
+  if (warp == 0) {
+    if (tile == 0) {
+      if (lane == 0) { lb_publish(&P.d_max[0], block_max, 2u, P.epoch); s_pre = 0; }
+    } else {
+      if (lane == 0) lb_publish(&P.d_max[tile], block_max, 1u, P.epoch);
+      const unsigned long long pre = lb_exclusive_prefix(P.d_max, (int)tile, P.epoch, LbMax(), 0ull);
+      if (lane == 0) {
+        lb_publish(&P.d_max[tile], pre > block_max ? pre : block_max, 2u, P.epoch);
+        s_pre = pre;
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long E = s_pre > ex_max ? s_pre : ex_max;
+  E = E > P.carry_key ? E : P.carry_key;
+
+  // ---- boundary flags (:175-176) ---------------------------------------------------------------------------------
+  uint32_t fl = 0, nfl = 0;
+  bool unsorted = false;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned long long my = key[j];
+    if (my) {
+      const uint32_t pc = (uint32_t)(E >> 32), mc = (uint32_t)(my >> 32);
+      bool f;
+      if (E == 0) f = true;                             // tempClusterEnd = 0, tempClusterChr = "" (:118-120)
+      else if (pc != mc) f = true;
+      else f = ((int64_t)(int32_t)(uint32_t)E - (int64_t)start[j]) < 5;
+      unsorted |= pc > mc;                              // contig order went backwards: not coordinate sorted
+      E = my > E ? my : E;
+      if (f) { fl |= 1u << j; ++nfl; }
+    }
+  }
+  if (unsorted) P.st->unsorted = 1u;
+  __syncthreads();   // s_pre is reused below
+
+  // ---- look-back #2: cluster slots ---------------------------------------------------------------------------------
+  unsigned long long block_cnt;
+  const unsigned long long ex_cnt = block_exclusive((unsigned long long)nfl, LbSum(), 0ull, s_wtot, block_cnt);
+  if (warp == 0) {
+    if (tile == 0) {
+      if (lane == 0) { lb_publish(&P.d_cnt[0], block_cnt, 2u, P.epoch); s_pre = 0; }
+    } else {
+      if (lane == 0) lb_publish(&P.d_cnt[tile], block_cnt, 1u, P.epoch);
+      const unsigned long long pre = lb_exclusive_prefix(P.d_cnt, (int)tile, P.epoch, LbSum(), 0ull);
+      if (lane == 0) {
+        lb_publish(&P.d_cnt[tile], pre + block_cnt, 2u, P.epoch);
+        s_pre = pre;
+      }
+    }
+  }
+  __syncthreads();
+  uint64_t slot = s_pre + ex_cnt;     // flags before this thread's first read
+  if (tile == 0 && threadIdx.x == 0) P.cl_first[0] = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    if ((fl >> j) & 1u) {
+      ++slot;
+      if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
+    }
+  if (tile == P.n_tiles - 1 && threadIdx.x == PL_THREADS - 1) {
+    if (slot + 1 <= P.cap_cl) P.cl_first[slot + 1] = (uint32_t)n;   // slots 0 .. n_flags, the last one is the open cluster
+    P.st->n_flags = (unsigned int)slot;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
+// per-read decode for pl_cluster_kernel
+// ---------------------------------------------------------------------------------------------------------
+struct ClusterParams {
+  DeviceBatch b;
+  DeviceRef ref;
+  PlState* st;
+  LbDesc* d_cnt;
+  unsigned int epoch;
+  uint32_t first_id;
+  const uint32_t* cl_first;
+  ps_cluster* cl;
+  ps_site* sites;
+  uint64_t cap_cl, cap_sites;
+};
+
 // Literal per-read routine (any CIGAR, any flag): PileupClusters.java:146-158, :585-673
-// ---------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void pl_decode_generic(const ScanParams& P, uint64_t r, uint32_t meta, ReadOffsets off, PlItem& it) {
+__device__ __noinline__ void pl_decode_generic(const ClusterParams& P, uint64_t r, uint32_t meta, uint64_t off_base,
+                                               uint64_t off_cigar, PlRead& x) {
   const uint32_t flags = PS_META_FLAGS(meta), L = PS_META_LEN(meta), ncig = PS_META_NCIGAR(meta);
-  const uint32_t* cig = P.b.cigar + off.cigar;
-  it.key = 0; it.mask = 0; it.start = 0; it.end = 0; it.lo = 1; it.hi = 0; it.rev = false;
+  const uint32_t* cig = P.b.cigar + off_cigar;
+  x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
   if (flags & PS_RF_UNMAPPED) return;                                        // :146
   uint32_t R = 0, alen = 0;
   bool hasI = false, hasD = false, hasN = false;
@@ -134,19 +287,20 @@ __device__ __noinline__ void pl_decode_generic(const ScanParams& P, uint64_t r, 
     if (op_consumes_ref(op)) R += c >> 4;
     if (op_is_match(op)) alen += c >> 4;
   }
-  if ((hasI || hasD) && hasN) {                                              // :152-157
-    atomicAdd(&P.st->skipped, 1ull);
-    return;
-  }
+  if ((hasI || hasD) && hasN) return;                                        // :152-157 (counted by pl_flag_kernel)
   if (flags & PS_RF_POS_ZERO) { raise_fault(&P.st->fault, r, PS_THROW_REF_RANGE); return; }
   const uint64_t g0 = __ldg(P.b.ref_start + r);
-  const uint32_t contig = g0 < P.ref.n_bases ? contig_of(P.ref, g0) : P.ref.n_contigs - 1;
+  if (g0 >= P.ref.n_bases) { raise_fault(&P.st->fault, r, PS_THROW_REF_RANGE); return; }
+  const uint32_t contig = contig_of(P.ref, g0);
   const uint64_t c_lo = __ldg(P.ref.contig_off + contig), c_hi = __ldg(P.ref.contig_off + contig + 1);
   const int32_t start = (int32_t)(g0 - c_lo) + 1;
   const int32_t end = start + (int32_t)R - 1;
   const bool rev = flags & PS_RF_REVERSE;
   const bool has_inv = flags & PS_RF_HAS_INVALID;
-  const uint8_t* rb = P.b.bases2 + off.base;
+  const uint8_t* rb = P.b.bases2 + off_base;
+  x.kept = true; x.start = start; x.end = end; x.rev = rev; x.contig = contig;
+  if (rev) { x.hi = end; x.lo = end - (int32_t)alen + 1; }
+  else { x.lo = start; x.hi = start + (int32_t)alen - 1; }
   // alignment blocks (SAMUtils.getAlignmentBlocks): S,I advance the read; D,N the reference; H,P nothing.
   // The reference slices every block (read bases, then FASTA) before it looks at a single base (:593-604).
   int64_t rdp = 0, rfp = 0;
@@ -157,7 +311,7 @@ __device__ __noinline__ void pl_decode_generic(const ScanParams& P, uint64_t r, 
     else if (op == 2u || op == 3u) rfp += n;
     else if (op_is_match(op)) {
       if (rdp + n > (int64_t)L) { raise_fault(&P.st->fault, r, PS_THROW_BLOCK_RANGE); return; }
-      if ((flags & PS_RF_REF_RANGE) || g0 + (uint64_t)(rfp + n) > c_hi || g0 >= P.ref.n_bases) {
+      if ((flags & PS_RF_REF_RANGE) || g0 + (uint64_t)(rfp + n) > c_hi) {
         raise_fault(&P.st->fault, r, PS_THROW_REF_RANGE); return;
       }
       rdp += n; rfp += n;
@@ -188,16 +342,10 @@ __device__ __noinline__ void pl_decode_generic(const ScanParams& P, uint64_t r, 
       rdp += n; rfp += n;
     }
   }
-  it.key = ((unsigned long long)(contig + 1) << 32) | (uint32_t)end;
-  it.mask = mask;
-  it.start = start; it.end = end; it.rev = rev;
-  if (rev) { it.hi = end; it.lo = end - (int32_t)alen + 1; }
-  else { it.lo = start; it.hi = start + (int32_t)alen - 1; }
+  x.mask = mask;
 }
 
-// ---------------------------------------------------------------------------------------------------------
 // PAR-CLIP shape: uniform length L <= 64, one M/=/X op of length L, no N call in the read.
-// ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t compress_even(uint32_t c) {   // even bits of c -> low 16 bits
   c = (c | (c >> 1)) & 0x33333333u;
   c = (c | (c >> 2)) & 0x0F0F0F0Fu;
@@ -212,7 +360,7 @@ __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref
   const uint32_t wi = g0 >> 4, sh = (g0 & 15u) * 2u;
   uint32_t w[NW + 1], bw[NW + 1];
 #pragma unroll
-  for (int k = 0; k <= NW; ++k) { w[k] = __ldg(ref.seq2 + wi + k); bw[k] = brow_w[k]; }
+  for (int k = 0; k <= NW; ++k) { w[k] = __ldg(ref.seq2 + wi + k); bw[k] = __ldg(brow_w + k); }
   const uint32_t ii = g0 >> 5, s1 = g0 & 31u;
   const uint32_t i0 = __ldg(ref.inv + ii), i1 = __ldg(ref.inv + ii + 1), i2 = NW > 2 ? __ldg(ref.inv + ii + 2) : 0u;
   unsigned long long m = 0;
@@ -232,344 +380,214 @@ __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref
   return m;
 }
 
-// block-wide exclusive scans over one value per thread (PL_THREADS threads); also return the block total
-template <typename T, typename Op>
-__device__ __forceinline__ T block_exclusive(const T& v, Op op, const T& identity, T* warp_tot /* [8] smem */, T& total) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T x = v;
+// stream offsets of the reads of one warp chunk [q, q+32) in a batch of non-uniform records
+// (tile tables + the metas between the tile start and the read)
+__device__ __forceinline__ void chunk_offsets(const DeviceBatch& b, uint64_t q, uint64_t r, bool in, uint32_t meta,
+                                              uint64_t& off_base, uint64_t& off_cigar) {
+  if (b.uniform_len && b.uniform_ncigar) {
+    off_base = r * (uint64_t)((b.uniform_len + 3) >> 2);
+    off_cigar = r * (uint64_t)b.uniform_ncigar;
+    return;
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t t0 = q / PS_TILE_READS;
+  // bytes in the low half, cigar ops in the high half (a tile holds 256 reads: neither can overflow 32 bits)
+  unsigned long long pre = 0;
+  for (uint64_t j = t0 * PS_TILE_READS + lane; j < q; j += 32) {
+    const uint32_t m = __ldg(b.meta + j);
+    pre += (unsigned long long)((PS_META_LEN(m) + 3) >> 2) | ((unsigned long long)PS_META_NCIGAR(m) << 32);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) pre += __shfl_xor_sync(0xFFFFFFFFu, pre, d);
+  const unsigned long long mine = in ? ((unsigned long long)((PS_META_LEN(meta) + 3) >> 2) | ((unsigned long long)PS_META_NCIGAR(meta) << 32)) : 0ull;
+  unsigned long long inc = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const T y = lb_shfl_up(x, d);
-    if (lane >= (uint32_t)d) x = op(y, x);
+    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
   }
-  if (lane == 31) warp_tot[warp] = x;
-  __syncthreads();
-  T prefix = identity;
-  T tot = identity;
-#pragma unroll
-  for (uint32_t w = 0; w < PL_THREADS / 32; ++w) {
-    const T t = warp_tot[w];
-    if (w < warp) prefix = op(prefix, t);
-    tot = op(tot, t);
-  }
-  total = tot;
-  // exclusive value of this thread: prefix of earlier warps, then the lanes before it
-  T up = lb_shfl_up(x, 1);
-  if (lane == 0) up = identity;
-  __syncthreads();
-  return op(prefix, up);
+  unsigned long long ex = inc - mine;
+  const uint64_t my_tile = r / PS_TILE_READS;
+  const uint32_t crossed = __ballot_sync(0xFFFFFFFFu, my_tile != t0);
+  unsigned long long rel;
+  uint64_t tile = t0;
+  if (crossed) {
+    const int bl = __ffs((int)crossed) - 1;            // first lane of the next tile
+    const unsigned long long exb = __shfl_sync(0xFFFFFFFFu, ex, bl);
+    if (my_tile != t0) { rel = ex - exb; tile = t0 + 1; } else rel = pre + ex;
+  } else rel = pre + ex;
+  if (!in) { off_base = 0; off_cigar = 0; return; }
+  off_base = b.uniform_len ? r * (uint64_t)((b.uniform_len + 3) >> 2) : __ldg(b.tile_base_off + tile) + (rel & 0xFFFFFFFFull);
+  off_cigar = b.uniform_ncigar ? r * (uint64_t)b.uniform_ncigar : __ldg(b.tile_cigar_off + tile) + (rel >> 32);
 }
 
-template <int ITEMS, int NW>   // NW > 0: PAR-CLIP fast decode; NW == 0: generic batch (ITEMS == 1)
-__global__ void __launch_bounds__(PL_THREADS) pl_scan_kernel(const __grid_constant__ ScanParams P) {
-  constexpr int TILE = PL_THREADS * ITEMS;
-  __shared__ unsigned long long s_wmax[PL_THREADS / 32];
-  __shared__ Seg s_wseg[PL_THREADS / 32];
-  __shared__ uint64_t s_scan[8];
-  __shared__ unsigned int s_tile;
-  __shared__ unsigned long long s_pmax;
-  __shared__ Seg s_pseg;
-  __shared__ __align__(16) uint32_t s_bases[NW > 0 ? (TILE * NW + 16) : 4];
-
-  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_scan, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  const uint64_t n = P.b.n_reads;
-  const uint64_t r0 = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  PlItem it[ITEMS];
+// one lane decodes read r (r < n); NW > 0: the batch has the PAR-CLIP shape and most reads take the bit-parallel path
+template <int NW>
+__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, ContigCache& cc, PlRead& x) {
+  x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
+  const uint32_t meta = in ? __ldg(P.b.meta + r) : 0u;
   if constexpr (NW > 0) {
-    // ---- stage the tile's packed bases (contiguous, 16-byte aligned) ----
+    if (!in) return;
     const uint32_t L = P.b.uniform_len, bpr = (L + 3) >> 2;
-    const uint64_t t0 = (uint64_t)tile * TILE;
-    const uint32_t n_here = (uint32_t)min((uint64_t)TILE, n - t0);
-    const uint32_t nbytes = n_here * bpr;
-    const uint4* src = reinterpret_cast<const uint4*>(P.b.bases2 + t0 * bpr);
-    uint4* dst = reinterpret_cast<uint4*>(s_bases);
-    for (uint32_t k = threadIdx.x; k < (nbytes + 15) / 16; k += PL_THREADS) dst[k] = __ldg(src + k);   // batch is padded
-    uint32_t metas[ITEMS], starts[ITEMS], cigs[ITEMS];
-    static_assert(ITEMS == 4, "the fast decode takes 4 reads per thread");
-    if (r0 + 4 <= n) {
-      const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(P.b.meta + r0));
-      const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(P.b.ref_start + r0));
-      const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(P.b.cigar + r0));
-      metas[0] = m4.x; metas[1] = m4.y; metas[2] = m4.z; metas[3] = m4.w;
-      starts[0] = s4.x; starts[1] = s4.y; starts[2] = s4.z; starts[3] = s4.w;
-      cigs[0] = c4.x; cigs[1] = c4.y; cigs[2] = c4.z; cigs[3] = c4.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < ITEMS; ++j) {
-        const bool in = r0 + j < n;
-        metas[j] = in ? __ldg(P.b.meta + r0 + j) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
-        starts[j] = in ? __ldg(P.b.ref_start + r0 + j) : 0u;
-        cigs[j] = in ? __ldg(P.b.cigar + r0 + j) : 0u;
-      }
+    const uint32_t flags = PS_META_FLAGS(meta), g0 = __ldg(P.b.ref_start + r), cg = __ldg(P.b.cigar + r);
+    // N calls are stored as code 0 (A): never read C (forward T>C) nor read G (reverse), so such reads need no
+    // look at the exception list; duplicates are not filtered by this tool and qualities are never read
+    constexpr uint32_t kHarmless = PS_RF_REVERSE | PS_RF_HAS_INVALID | PS_RF_DUPLICATE | PS_RF_QUAL_MISSING;
+    bool fast = (flags & ~kHarmless) == 0 && op_is_match(cg & 15u) && (cg >> 4) == L && PS_META_LEN(meta) == L;
+    fast = fast && contig_lookup(P.ref, g0, cc) && (uint64_t)g0 + L <= cc.hi;
+    if (fast) {
+      const bool rev = (flags & PS_RF_REVERSE) != 0;
+      const uint64_t boff = r * (uint64_t)bpr;
+      unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, reinterpret_cast<const uint32_t*>(P.b.bases2 + (boff & ~3ull)),
+                                               (uint32_t)(boff & 3u) * 8u);
+      const int32_t start = (int32_t)((uint64_t)g0 - cc.lo) + 1, end = start + (int32_t)L - 1;
+      if (L > 51u && (m >> 51)) { raise_fault(&P.st->fault, r, PS_THROW_MASK51); return; }
+      x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = rev; x.contig = cc.idx;
+      return;
     }
-    // contig bounds of the thread's first read, reused while the reads stay inside
-    uint64_t c_lo = 1, c_hi = 0;
-    uint32_t contig = 0;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const uint32_t meta = metas[j], flags = PS_META_FLAGS(meta), g0 = starts[j], cg = cigs[j];
-      bool fast = (flags & ~PS_RF_REVERSE) == 0 && op_is_match(cg & 15u) && (cg >> 4) == L && PS_META_LEN(meta) == L;
-      if (fast && !((uint64_t)g0 >= c_lo && (uint64_t)g0 < c_hi)) {
-        if ((uint64_t)g0 < P.ref.n_bases) {
-          contig = contig_of(P.ref, g0);
-          c_lo = __ldg(P.ref.contig_off + contig);
-          c_hi = __ldg(P.ref.contig_off + contig + 1);
-        } else fast = false;
-      }
-      fast = fast && (uint64_t)g0 + L <= c_hi;
-      if (fast) {
-        const bool rev = (flags & PS_RF_REVERSE) != 0;
-        const uint32_t q = threadIdx.x * ITEMS + j, boff = q * bpr;
-        unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, s_bases + (boff >> 2), (boff & 3u) * 8u);
-        const int32_t start = (int32_t)((uint64_t)g0 - c_lo) + 1, end = start + (int32_t)L - 1;
-        if (L > 51u && (m >> 51)) { raise_fault(&P.st->fault, r0 + j, PS_THROW_MASK51); m = 0; it[j].key = 0; it[j].lo = 1; it[j].hi = 0; }
-        else { it[j].key = ((unsigned long long)(contig + 1) << 32) | (uint32_t)end; it[j].lo = start; it[j].hi = end; }
-        it[j].mask = m; it[j].start = start; it[j].end = end; it[j].rev = rev;
-      } else if (r0 + j < n) {
-        ReadOffsets off;
-        off.base = (r0 + j) * (uint64_t)bpr; off.qual = (r0 + j) * (uint64_t)L; off.cigar = r0 + j;
-        PlItem tmp;                       // the out-of-line routine gets an addressable copy; it[] stays in registers
-        pl_decode_generic(P, r0 + j, meta, off, tmp);
-        it[j] = tmp;
-      } else {
-        it[j].key = 0; it[j].mask = 0; it[j].start = 0; it[j].end = 0; it[j].lo = 1; it[j].hi = 0; it[j].rev = false;
-      }
-    }
+    pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, x);
   } else {
-    const bool in_range = r0 < n;
-    const uint32_t meta = in_range ? __ldg(P.b.meta + r0) : 0;
-    const ReadOffsets off = read_offsets(P.b, tile, r0, meta, in_range, s_scan);
-    if (in_range) {
-      PlItem tmp;
-      pl_decode_generic(P, r0, meta, off, tmp);
-      it[0] = tmp;
-    } else { it[0].key = 0; it[0].mask = 0; it[0].start = 0; it[0].end = 0; it[0].lo = 1; it[0].hi = 0; it[0].rev = false; }
+    uint64_t ob, oc;
+    chunk_offsets(P.b, q, r, in, meta, ob, oc);    // warp-collective
+    if (in) pl_decode_generic(P, r, meta, ob, oc, x);
   }
-  // checkPosition intervals (baseCoveredMap support) for the site kernel
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-    if (r0 + j < n) P.iv[r0 + j] = make_int2(it[j].lo, it[j].hi);
+}
 
-  // ---- look-back #1: running max of (contig, end) -----------------------------------------------------------
-  unsigned long long tmax = 0;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) tmax = it[j].key > tmax ? it[j].key : tmax;
-  unsigned long long block_max;
-  const unsigned long long ex_max = block_exclusive<unsigned long long>(tmax, MaxOp(), 0ull, s_wmax, block_max);
-  if (warp == 0) {
-    if (tile == 0) {
-      if (lane == 0) { lb_publish(&P.d_max[0], block_max, 2u, P.epoch); s_pmax = 0; }
-    } else {
-      if (lane == 0) lb_publish(&P.d_max[tile], block_max, 1u, P.epoch);
-      const unsigned long long pre = lb_exclusive_prefix(P.d_max, (int)tile, P.epoch, MaxOp(), 0ull);
-      if (lane == 0) {
-        lb_publish(&P.d_max[tile], pre > block_max ? pre : block_max, 2u, P.epoch);
-        s_pmax = pre;
-      }
+// ---------------------------------------------------------------------------------------------------------
+// pl_cluster_kernel
+// ---------------------------------------------------------------------------------------------------------
+struct WarpTables {     // one window of PL_WINDOW positions
+  int32_t diff[PL_WINDOW];            // +1 at lo, -1 after hi  -> prefix sum = baseCoveredMap
+  uint32_t cnt[PL_WINDOW];            // mutationMap
+  unsigned long long first[PL_WINDOW];   // min over events of (read << 6 | i) = first insertion
+};
+
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
+
+// One cluster = reads [f, fe) (slot `slot`), whole warp.  Fills *rec (shared memory) when `fill`, writes up to `cap`
+// sites to `dest` in position order and returns the number of sites the cluster has.
+template <int NW>
+__device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slot, uint32_t f, uint32_t fe, WarpTables& T,
+                                            ps_cluster* rec, bool fill, ps_site* dest, uint32_t cap, unsigned long long& dstr) {
+  const uint32_t lane = threadIdx.x & 31;
+  ContigCache cc;
+  PlRead x;
+  // ---- aggregates (P3 counters, P4, P6) ----------------------------------------------------------------------
+  uint32_t reads = 0, t2c = 0, minus = 0, first_rev = 0, contig = 0;
+  int32_t end = INT32_MIN, cstart = 0, ev_min = INT32_MAX, ev_max = INT32_MIN;
+  unsigned long long mask = 0, first_read = f;
+  bool have_first = false;
+  for (uint32_t q = f; q < fe; q += 32) {
+    const uint32_t r = q + lane;
+    pl_decode<NW>(P, q, r, r < fe, cc, x);
+    const uint32_t kb = __ballot_sync(0xFFFFFFFFu, x.kept);
+    if (kb == 0) continue;
+    if (!have_first) {
+      const int fl = __ffs((int)kb) - 1;
+      first_read = q + fl;
+      cstart = __shfl_sync(0xFFFFFFFFu, x.start, fl);
+      contig = __shfl_sync(0xFFFFFFFFu, x.contig, fl);
+      first_rev = __shfl_sync(0xFFFFFFFFu, (uint32_t)x.rev, fl);
+      have_first = true;
     }
-  }
-  __syncthreads();
-  unsigned long long E = s_pmax > ex_max ? s_pmax : ex_max;
-  E = E > P.carry_key ? E : P.carry_key;
-
-  // ---- boundary flags (:175-176) and this thread's segment aggregate --------------------------------------------
-  bool flag[ITEMS];
-  Seg tseg = seg_identity();
-  bool unsorted = false;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    flag[j] = false;
-    const unsigned long long my = it[j].key;
-    if (my) {
-      const uint32_t pc = (uint32_t)(E >> 32), mc = (uint32_t)(my >> 32);
-      if (E == 0) flag[j] = true;                       // tempClusterEnd = 0, tempClusterChr = "" (:118-120)
-      else if (pc != mc) flag[j] = true;
-      else flag[j] = ((int64_t)(int32_t)(uint32_t)E - (int64_t)it[j].start) < 5;
-      unsorted |= pc > mc;                              // contig order went backwards: not coordinate sorted
-      E = my > E ? my : E;
-      Seg e;
-      e.nflags = flag[j] ? 1u : 0u; e.reads = 1; e.t2c = __popcll(it[j].mask); e.minus = it[j].rev ? 1u : 0u;
-      e.end = it[j].end; e.first_rev = it[j].rev ? 1u : 0u; e.nev = e.t2c; e.mask = it[j].mask;
-      tseg = SegOp()(tseg, e);
-    }
-  }
-  if (unsorted) P.st->unsorted = 1u;
-
-  // ---- look-back #2: segmented aggregate ------------------------------------------------------------------------
-  Seg block_seg;
-  const Seg ex_seg = block_exclusive<Seg>(tseg, SegOp(), seg_identity(), s_wseg, block_seg);
-  if (warp == 0) {
-    if (tile == 0) {
-      if (lane == 0) { lb_publish(&P.d_seg[0], block_seg, 2u, P.epoch); s_pseg = seg_identity(); }
-    } else {
-      if (lane == 0) lb_publish(&P.d_seg[tile], block_seg, 1u, P.epoch);
-      const Seg pre = lb_exclusive_prefix(P.d_seg, (int)tile, P.epoch, SegOp(), seg_identity());
-      if (lane == 0) {
-        lb_publish(&P.d_seg[tile], SegOp()(pre, block_seg), 2u, P.epoch);
-        s_pseg = pre;
+    reads += __popc(kb);
+    minus += __popc(__ballot_sync(0xFFFFFFFFu, x.kept && x.rev));
+    end = max(end, __reduce_max_sync(0xFFFFFFFFu, x.kept ? x.end : INT32_MIN));
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, x.mask != 0);
+    if (any) {
+      t2c += __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popcll(x.mask));
+      mask |= (unsigned long long)warp_or((uint32_t)x.mask) | ((unsigned long long)warp_or((uint32_t)(x.mask >> 32)) << 32);
+      int32_t lo_e = INT32_MAX, hi_e = INT32_MIN;
+      if (x.mask) {
+        const int ia = __ffsll((long long)x.mask) - 1, ib = 63 - __clzll((long long)x.mask);
+        lo_e = x.rev ? x.hi - ib : x.lo + ia;
+        hi_e = x.rev ? x.hi - ia : x.lo + ib;
       }
+      ev_min = min(ev_min, __reduce_min_sync(0xFFFFFFFFu, lo_e));
+      ev_max = max(ev_max, __reduce_max_sync(0xFFFFFFFFu, hi_e));
     }
   }
-  __syncthreads();
-  Seg run = SegOp()(s_pseg, ex_seg);   // state left by every read before this thread's first
+  if (fill && lane == 0) {
+    const uint32_t maf = slot ? minus - first_rev : minus;   // slot 0 continues a cluster opened by the preceding shard
+    rec->first_read = first_read;
+    rec->running_id = slot ? P.first_id + slot : 0;          // runningID++ then "cl_<id>_<chr>" (:355): first cluster is cl_2
+    rec->contig = contig;
+    rec->start = cstart;
+    rec->end = reads ? end : 0;
+    rec->num_reads = reads;
+    rec->num_t2c = t2c;
+    rec->minus_after_first = maf;
+    rec->first_reverse = (uint8_t)first_rev;
+    // StrandOrientation state at flush (P6): minus-first -> "-"; plus-first -> "+/-" once a minus member came
+    rec->combined_strand = first_rev ? 1 : (maf ? 2 : 0);
+    rec->reserved = 0;
+    rec->mask51 = mask;
+    rec->site_begin = 0;
+    rec->site_end = 0;
+    if (slot && !first_rev) dstr += maf;                     // doubleStranded++ (:494-498), incl. the never-flushed last cluster
+  }
+  if (t2c == 0) return 0;
 
-  // ---- records: the opener of a cluster closes the previous one ------------------------------------------------
-  unsigned long long dstr = 0;
-  auto close_slot = [&](const Seg& s) {
-    const uint32_t slot = s.nflags;
-    const uint32_t maf = slot ? s.minus - s.first_rev : s.minus;
-    if (slot < P.cap_cl) {
-      ps_cluster* c = P.cl + slot;
-      c->end = s.reads ? s.end : 0;
-      c->num_reads = s.reads;
-      c->num_t2c = s.t2c;
-      c->minus_after_first = maf;
-      c->first_reverse = (uint8_t)s.first_rev;
-      // StrandOrientation state at flush (P6): minus-first -> "-"; plus-first -> "+/-" once a minus member came
-      c->combined_strand = s.first_rev ? 1 : (maf ? 2 : 0);
-      c->reserved = 0;
-      c->mask51 = s.mask;
-    }
-    if (slot && !s.first_rev) dstr += maf;              // doubleStranded++ (:494-498), incl. the never-flushed last cluster
-  };
-  if (tile == 0 && threadIdx.x == 0) { P.cl_first[0] = 0; P.cl_ev[0] = 0; }
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    if (!it[j].key) continue;
-    const uint64_t r = r0 + j;
-    const uint32_t t2c = __popcll(it[j].mask);
-    if (flag[j]) {
-      close_slot(run);
-      const uint32_t slot = run.nflags + 1;
-      if (slot < P.cap_cl) {
-        ps_cluster* c = P.cl + slot;
-        c->first_read = r;
-        c->running_id = P.first_id + slot;               // runningID++ then "cl_<id>_<chr>" (:355): first cluster is cl_2
-        c->contig = (uint32_t)(it[j].key >> 32) - 1;
-        c->start = it[j].start;
-        P.cl_first[slot] = (uint32_t)r;
-        P.cl_ev[slot] = (uint32_t)run.nev;
-      }
-      run.nflags = slot; run.reads = 1; run.t2c = t2c; run.minus = it[j].rev ? 1u : 0u; run.end = it[j].end;
-      run.first_rev = it[j].rev ? 1u : 0u; run.mask = it[j].mask;
-    } else {
-      if (run.nflags == 0 && run.reads == 0) {           // first read continuing the carry-in cluster (halo merge)
-        ps_cluster* c = P.cl;
-        c->first_read = r; c->running_id = 0; c->contig = (uint32_t)(it[j].key >> 32) - 1; c->start = it[j].start;
-        run.first_rev = it[j].rev ? 1u : 0u;
-      }
-      run.reads += 1; run.t2c += t2c; run.minus += it[j].rev ? 1u : 0u;
-      run.end = it[j].end > run.end ? it[j].end : run.end;
-      run.mask |= it[j].mask;
-    }
-    unsigned long long m = it[j].mask;
-    unsigned long long o = run.nev;
+  // ---- sites: one chunk of reads, all events inside one window -> warp ballots, no shared memory ----------------
+  if (fe - f <= 32 && (int64_t)ev_max - (int64_t)ev_min < PL_WINDOW) {
+    // x still holds this lane's read
+    uint32_t pm[4] = {0, 0, 0, 0};
+    unsigned long long m = x.mask;
     while (m) {
       const int i = __ffsll((long long)m) - 1;
       m &= m - 1;
-      if (o < P.cap_ev) {
-        P.ev_pos[o] = it[j].rev ? it[j].end - i : it[j].start + i;      // checkPosition (:638-643)
-        P.ev_key[o] = (r << 6) | (unsigned)i;
-      }
-      ++o;
+      const uint32_t rel = (uint32_t)((x.rev ? x.hi - i : x.lo + i) - ev_min);   // checkPosition (:638-643)
+      const uint32_t bit = 1u << (rel & 31u);
+      const uint32_t w = rel >> 5;
+      pm[0] |= w == 0 ? bit : 0u; pm[1] |= w == 1 ? bit : 0u; pm[2] |= w == 2 ? bit : 0u; pm[3] |= w == 3 ? bit : 0u;
     }
-    run.nev = o;
-  }
-  if (tile == P.n_tiles - 1 && threadIdx.x == PL_THREADS - 1) {     // state after the last read: the open cluster
-    close_slot(run);
-    const uint64_t n_slots = (uint64_t)run.nflags + 1;
-    if (n_slots <= P.cap_cl) { P.cl_first[n_slots] = (uint32_t)n; P.cl_ev[n_slots] = (uint32_t)run.nev; }
-    P.st->n_flags = run.nflags;
-    P.st->n_ev = run.nev;
-  }
-  // warp-reduce doubleStranded
+    uint32_t n_sites = 0;
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) dstr += __shfl_down_sync(0xFFFFFFFFu, dstr, d);
-  if (lane == 0 && dstr) atomicAdd(&P.st->dstr, dstr);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Sites
-// ---------------------------------------------------------------------------------------------------------
-struct SiteParams {
-  PlState* st;
-  LbDesc<unsigned long long>* d_cnt;
-  unsigned int epoch;
-  uint32_t n_slots;
-  uint32_t n_tiles;
-  const int2* iv;
-  ps_cluster* cl;
-  const uint32_t* cl_first;
-  const uint32_t* cl_ev;
-  const int32_t* ev_pos;
-  const unsigned long long* ev_key;
-  ps_site* sites;
-};
-
-struct WarpTables {     // one window of PL_WINDOW positions
-  int32_t diff[PL_WINDOW];       // +1 at lo, -1 after hi  -> prefix sum = baseCoveredMap
-  uint32_t cnt[PL_WINDOW];       // mutationMap
-  uint32_t first[PL_WINDOW];     // first event (index inside the cluster) = first insertion
-};
-
-// distinct event positions of one cluster (whole warp)
-__device__ __forceinline__ uint32_t site_count(const SiteParams& P, uint32_t e0, uint32_t e1, WarpTables& T) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ne = e1 - e0;
-  if (ne == 0) return 0;
-  if (ne <= 32) {
-    const bool have = lane < ne;
-    const int32_t pos = have ? __ldg(P.ev_pos + e0 + lane) : INT32_MIN + (int32_t)lane;   // dummies are all different
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, pos);
-    const bool leader = have && (uint32_t)(__ffs((int)peers) - 1) == lane;
-    return __popc(__ballot_sync(0xFFFFFFFFu, leader));
-  }
-  int32_t mn = INT32_MAX, mx = INT32_MIN;
-  for (uint32_t e = e0 + lane; e < e1; e += 32) { const int32_t p = __ldg(P.ev_pos + e); mn = min(mn, p); mx = max(mx, p); }
-  mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-  uint32_t total = 0;
-  for (int64_t w0 = mn; w0 <= mx; w0 += PL_WINDOW) {
-    for (uint32_t k = lane; k < PL_WINDOW; k += 32) T.cnt[k] = 0;
-    __syncwarp();
-    for (uint32_t e = e0 + lane; e < e1; e += 32) {
-      const int64_t d = (int64_t)__ldg(P.ev_pos + e) - w0;
-      if (d >= 0 && d < PL_WINDOW) T.cnt[d] = 1;
+    for (int w = 0; w < 4; ++w) {
+      uint32_t u = warp_or(pm[w]);
+      while (u) {
+        const int b = __ffs((int)u) - 1;
+        u &= u - 1;
+        const int32_t pos = ev_min + 32 * w + b;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (pm[w] >> b) & 1u);
+        const int fl = __ffs((int)bal) - 1;
+        const uint32_t cov = __popc(__ballot_sync(0xFFFFFFFFu, x.kept && x.lo <= pos && pos <= x.hi));
+        const uint32_t i_me = (uint32_t)(x.rev ? x.hi - pos : pos - x.lo);
+        const uint32_t i_first = __shfl_sync(0xFFFFFFFFu, i_me, fl);
+        if (lane == 0 && n_sites < cap) {
+          ps_site s;
+          s.pos = pos; s.t2c = __popc(bal); s.cov = cov; s.reserved = 0;
+          s.order_key = ((unsigned long long)(f + fl) << 6) | i_first;
+          dest[n_sites] = s;
+        }
+        ++n_sites;
+      }
     }
-    __syncwarp();
-    for (uint32_t k = lane; k < PL_WINDOW; k += 32) total += __popc(__ballot_sync(0xFFFFFFFFu, T.cnt[k] != 0));
-    __syncwarp();
+    return n_sites;
   }
-  return total;
-}
 
-// full tables of one cluster, sites written in position order from `out`
-__device__ __forceinline__ void site_emit(const SiteParams& P, uint32_t r_lo, uint32_t r_hi, uint32_t e0, uint32_t e1,
-                                          WarpTables& T, ps_site* out) {
-  const uint32_t lane = threadIdx.x & 31;
-  int32_t mn = INT32_MAX, mx = INT32_MIN;
-  for (uint32_t e = e0 + lane; e < e1; e += 32) { const int32_t p = __ldg(P.ev_pos + e); mn = min(mn, p); mx = max(mx, p); }
-  mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  // ---- sites: per-warp tables, one window of positions at a time -------------------------------------------------
   uint32_t written = 0;
-  for (int64_t w0 = mn; w0 <= mx; w0 += PL_WINDOW) {
+  for (int64_t w0 = ev_min; w0 <= ev_max; w0 += PL_WINDOW) {
     const int64_t w1 = w0 + PL_WINDOW - 1;
-    for (uint32_t k = lane; k < PL_WINDOW; k += 32) { T.diff[k] = 0; T.cnt[k] = 0; T.first[k] = 0xFFFFFFFFu; }
+    for (uint32_t k = lane; k < PL_WINDOW; k += 32) { T.diff[k] = 0; T.cnt[k] = 0; T.first[k] = ~0ull; }
     __syncwarp();
-    for (uint32_t e = e0 + lane; e < e1; e += 32) {
-      const int64_t d = (int64_t)__ldg(P.ev_pos + e) - w0;
-      if (d >= 0 && d < PL_WINDOW) { atomicAdd(&T.cnt[d], 1u); atomicMin(&T.first[d], e - e0); }
-    }
-    for (uint32_t r = r_lo + lane; r < r_hi; r += 32) {
-      const int2 v = __ldg(P.iv + r);
-      if (v.x > v.y || (int64_t)v.y < w0 || (int64_t)v.x > w1) continue;
-      atomicAdd(&T.diff[(int64_t)v.x > w0 ? (int64_t)v.x - w0 : 0], 1);
-      if ((int64_t)v.y < w1) atomicAdd(&T.diff[(int64_t)v.y + 1 - w0], -1);
+    for (uint32_t q = f; q < fe; q += 32) {
+      const uint32_t r = q + lane;
+      pl_decode<NW>(P, q, r, r < fe, cc, x);
+      if (!x.kept || (int64_t)x.hi < w0 || (int64_t)x.lo > w1) continue;
+      unsigned long long m = x.mask;
+      while (m) {
+        const int i = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int64_t d = (int64_t)(x.rev ? x.hi - i : x.lo + i) - w0;
+        if (d >= 0 && d < PL_WINDOW) {
+          atomicAdd(&T.cnt[d], 1u);
+          atomicMin(&T.first[d], ((unsigned long long)r << 6) | (unsigned)i);
+        }
+      }
+      atomicAdd(&T.diff[(int64_t)x.lo > w0 ? (int64_t)x.lo - w0 : 0], 1);
+      if ((int64_t)x.hi < w1) atomicAdd(&T.diff[(int64_t)x.hi + 1 - w0], -1);
     }
     __syncwarp();
     int32_t carry = 0;
@@ -584,38 +602,54 @@ __device__ __forceinline__ void site_emit(const SiteParams& P, uint32_t r_lo, ui
       carry = __shfl_sync(0xFFFFFFFFu, c, 31);
       const uint32_t n = T.cnt[k0 + lane];
       const uint32_t bal = __ballot_sync(0xFFFFFFFFu, n != 0);
-      if (n) {
+      const uint32_t at = written + __popc(bal & ((1u << lane) - 1u));
+      if (n && at < cap) {
         ps_site s;
         s.pos = (int32_t)(w0 + k0 + lane);
         s.t2c = n;
         s.cov = (uint32_t)c;
         s.reserved = 0;
-        s.order_key = __ldg(P.ev_key + e0 + T.first[k0 + lane]);
-        out[written + __popc(bal & ((1u << lane) - 1u))] = s;
+        s.order_key = T.first[k0 + lane];
+        dest[at] = s;
       }
       written += __popc(bal);
     }
     __syncwarp();
   }
+  return written;
 }
 
-__global__ void __launch_bounds__(PL_THREADS) pl_site_kernel(const __grid_constant__ SiteParams P) {
-  __shared__ WarpTables s_tab[PL_THREADS / 32];
-  __shared__ uint32_t s_cnt[PL_SITE_CLUSTERS], s_off[PL_SITE_CLUSTERS];
+template <int NW>
+__global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
+  __shared__ __align__(16) ps_cluster s_cl[CB_CLUSTERS];
+  __shared__ __align__(16) ps_site s_sites[PL_WARPS][CB_SITE_CAP];
+  __shared__ WarpTables s_tab[PL_WARPS];
+  __shared__ uint32_t s_cnt[CB_CLUSTERS], s_off[CB_CLUSTERS], s_stage[CB_CLUSTERS];   // s_stage: offset in the warp's staging area, ~0 = not staged
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_tile;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_site, 1u);
+  const uint32_t n_slots = P.st->n_flags + 1;          // written by pl_flag_kernel
+  if (n_slots > P.cap_cl) return;                       // the host re-runs both kernels with larger arrays
+  const uint32_t n_tiles = (n_slots + CB_CLUSTERS - 1) / CB_CLUSTERS;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_cluster, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
+  if (tile >= n_tiles) return;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t c0 = tile * PL_SITE_CLUSTERS;
+  const uint32_t c0 = tile * CB_CLUSTERS;
   WarpTables& T = s_tab[warp];
-  for (uint32_t k = warp; k < PL_SITE_CLUSTERS; k += PL_THREADS / 32) {
-    const uint32_t c = c0 + k;
-    uint32_t cnt = 0;
-    if (c < P.n_slots) cnt = site_count(P, __ldg(P.cl_ev + c), __ldg(P.cl_ev + c + 1), T);
-    if (lane == 0) s_cnt[k] = cnt;
+  unsigned long long dstr = 0;
+  uint32_t staged = 0;
+  for (uint32_t j = 0; j < CB_PER_WARP; ++j) {
+    const uint32_t k = warp * CB_PER_WARP + j, c = c0 + k;
+    uint32_t cnt = 0, st = ~0u;
+    if (c < n_slots) {
+      cnt = pl_cluster<NW>(P, c, __ldg(P.cl_first + c), __ldg(P.cl_first + c + 1), T, &s_cl[k], true,
+                           &s_sites[warp][staged], CB_SITE_CAP - staged, dstr);
+      if (cnt <= CB_SITE_CAP - staged) { st = staged; staged += cnt; }
+    }
+    if (lane == 0) { s_cnt[k] = cnt; s_stage[k] = st; }
   }
+  if (lane == 0 && dstr) atomicAdd(&P.st->dstr, dstr);
   __syncthreads();
   if (warp == 0) {
     // exclusive prefix of the 64 counts (2 per lane) and the tile's base from the look-back
@@ -634,30 +668,58 @@ __global__ void __launch_bounds__(PL_THREADS) pl_site_kernel(const __grid_consta
       if (lane == 0) lb_publish(&P.d_cnt[0], total, 2u, P.epoch);
     } else {
       if (lane == 0) lb_publish(&P.d_cnt[tile], total, 1u, P.epoch);
-      pre = lb_exclusive_prefix(P.d_cnt, (int)tile, P.epoch, SumOp(), 0ull);
+      pre = lb_exclusive_prefix(P.d_cnt, (int)tile, P.epoch, LbSum(), 0ull);
       if (lane == 0) lb_publish(&P.d_cnt[tile], pre + total, 2u, P.epoch);
     }
     if (lane == 0) {
       s_base = pre;
-      if (tile == P.n_tiles - 1) P.st->n_sites = pre + total;
+      if (tile == n_tiles - 1) P.st->n_sites = pre + total;
     }
   }
   __syncthreads();
   const unsigned long long base = s_base;
-  for (uint32_t k = warp; k < PL_SITE_CLUSTERS; k += PL_THREADS / 32) {
-    const uint32_t c = c0 + k;
-    if (c >= P.n_slots) break;
+  for (uint32_t j = 0; j < CB_PER_WARP; ++j) {
+    const uint32_t k = warp * CB_PER_WARP + j, c = c0 + k;
+    if (c >= n_slots) break;
     const unsigned long long b = base + s_off[k];
     const uint32_t cnt = s_cnt[k];
-    if (cnt) site_emit(P, __ldg(P.cl_first + c), __ldg(P.cl_first + c + 1), __ldg(P.cl_ev + c), __ldg(P.cl_ev + c + 1), T, P.sites + b);
-    if (lane == 0) { P.cl[c].site_begin = b; P.cl[c].site_end = b + cnt; }
+    if (lane == 0) { s_cl[k].site_begin = b; s_cl[k].site_end = b + cnt; }
+    if (cnt == 0 || b >= P.cap_sites) continue;
+    const uint32_t room = (uint32_t)min((unsigned long long)cnt, P.cap_sites - b);
+    if (s_stage[k] != ~0u) {
+      // a site is 24 bytes = 3 x 8
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_sites[warp][s_stage[k]]);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.sites + b);
+      for (uint32_t e = lane; e < room * 3; e += 32) dst[e] = src[e];
+    } else {
+      unsigned long long unused = 0;
+      pl_cluster<NW>(P, c, __ldg(P.cl_first + c), __ldg(P.cl_first + c + 1), T, nullptr, false, P.sites + b, room, unused);
+    }
+  }
+  __syncthreads();
+  {   // cluster records: one coalesced run per block
+    const uint32_t k = threadIdx.x >> 2;
+    if (c0 + k < n_slots)
+      reinterpret_cast<uint4*>(P.cl + c0)[threadIdx.x] = reinterpret_cast<const uint4*>(s_cl)[threadIdx.x];
+  }
+}
+
+// checkPosition interval of reads [r0, r1) (halo merge: dense coverage of a boundary cluster)
+template <int NW>
+__global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint32_t r0, uint32_t r1, int2* out) {
+  ContigCache cc;
+  PlRead x;
+  for (uint32_t q = r0 + blockIdx.x * blockDim.x; q < r1; q += gridDim.x * blockDim.x) {
+    const uint32_t qw = q + (threadIdx.x & ~31u), r = q + threadIdx.x;
+    pl_decode<NW>(P, qw, r, r < r1, cc, x);
+    if (r < r1) out[r - r0] = x.kept ? make_int2(x.lo, x.hi) : make_int2(1, 0);
   }
 }
 
 __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
-    st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_ev = 0; st->n_sites = 0; st->n_flags = 0;
-    st->unsorted = 0; st->tile_ctr_scan = 0; st->tile_ctr_site = 0;
+    st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_flags = 0;
+    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_cluster = 0;
   }
 }
 
@@ -665,11 +727,14 @@ __global__ void pl_init_state(PlState* st) {
 
 struct ps_pileup {
   ps_ctx* ctx = nullptr;
-  uint64_t generation = 0;           // ctx->pl_generation at creation: scratch (iv, cl_first) is valid while equal
   cudaStream_t stream = nullptr;
+  DeviceBatch batch{};               // the records (device pointers): needed again only for the halo-merge coverage
+  uint64_t stage_serial = 0;         // != 0: the batch lives in a staging slot of the context (valid for two uploads)
+  int nw = 0;                        // kernel flavour the batch was run with
   // device results, owned by the handle (stream-ordered allocations)
   ps_cluster* d_cl = nullptr;        // slot 0 = head partial, 1..n_flags-1 closed, n_flags = open
   ps_site* d_sites = nullptr;
+  uint32_t* d_first = nullptr;       // [n_slots + 1] first read of each slot
   uint64_t n_slots = 0, n_reads = 0;
   ps_cluster head{}, open{};
   bool has_head = false;
@@ -692,33 +757,47 @@ static T* scratch(ps_ctx* ctx, int slot, size_t count, cudaError_t& err, bool ze
 
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+static int flavour_of(const DeviceBatch& b) {   // 0 = generic decode, 1..4 = PAR-CLIP shape with that many 2-bit words
+  const uint32_t L = b.uniform_len;
+  const bool fast = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && (reinterpret_cast<uintptr_t>(b.bases2) & 3u) == 0;
+  return fast ? (int)((L + 15) / 16) : 0;
+}
+
+static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
+  switch (nw) {
+    case 1: pl_cluster_kernel<1><<<grid, PL_THREADS, 0, st>>>(Q); break;
+    case 2: pl_cluster_kernel<2><<<grid, PL_THREADS, 0, st>>>(Q); break;
+    case 3: pl_cluster_kernel<3><<<grid, PL_THREADS, 0, st>>>(Q); break;
+    case 4: pl_cluster_kernel<4><<<grid, PL_THREADS, 0, st>>>(Q); break;
+    default: pl_cluster_kernel<0><<<grid, PL_THREADS, 0, st>>>(Q); break;
+  }
+}
+
 static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out) {
   ps_pileup* H = new ps_pileup();
   *out = H;
   H->ctx = ctx;
   H->stream = st;
+  H->batch = b;
   const uint64_t n = b.n_reads;
   H->n_reads = n;
   H->counters.num_reads_processed = n;
-  H->generation = ++ctx->pl_generation;
   if (n == 0) return PS_OK;
   if (n >= 0xFFFFFFFFull) return set_error(ctx, PS_ERR_UNSUPPORTED, "pileup batch of >= 2^32 reads");
 
-  const uint32_t L = b.uniform_len;
-  const bool fast = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start) &&
-                    aligned16p(b.cigar) && aligned16p(b.bases2);
-  const uint32_t items = fast ? 4u : 1u;
-  const uint32_t tile_reads = PL_THREADS * items;
+  const bool vec = b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start);
+  const uint32_t tile_reads = PL_THREADS * (vec ? 4u : 1u);
   const uint32_t n_tiles = (uint32_t)((n + tile_reads - 1) / tile_reads);
+  const int nw = flavour_of(b);
+  H->nw = nw;
 
   cudaError_t err = cudaSuccess;
   PlState* d_state = scratch<PlState>(ctx, 0, 1, err);
-  int2* iv = scratch<int2>(ctx, 1, n, err);
-  auto* d_max = scratch<LbDesc<unsigned long long>>(ctx, 2, n_tiles, err, true);
-  auto* d_seg = scratch<LbDesc<Seg>>(ctx, 3, n_tiles, err, true);
+  LbDesc* d_max = scratch<LbDesc>(ctx, 2, n_tiles, err, true);
+  LbDesc* d_cnt = scratch<LbDesc>(ctx, 3, n_tiles, err, true);
   if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
   if (ctx->pl_cap_cl < 1024) ctx->pl_cap_cl = std::max<uint64_t>(1024, n / 8);
-  if (ctx->pl_cap_ev < 1024) ctx->pl_cap_ev = std::max<uint64_t>(1024, n);
+  if (ctx->pl_cap_ev < 1024) ctx->pl_cap_ev = std::max<uint64_t>(1024, n / 4);   // site capacity
 
   unsigned long long carry_key = 0;
   if (opts && opts->carry_valid)
@@ -727,63 +806,52 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   PlState hs{};
   timer_begin(ctx, st);
   for (int attempt = 0;; ++attempt) {
-    const uint64_t cap_cl = std::min<uint64_t>(ctx->pl_cap_cl, n + 2), cap_ev = ctx->pl_cap_ev;
-    uint32_t* cl_first = scratch<uint32_t>(ctx, 4, cap_cl + 2, err);
-    uint32_t* cl_ev = scratch<uint32_t>(ctx, 5, cap_cl + 2, err);
-    int32_t* ev_pos = scratch<int32_t>(ctx, 6, cap_ev, err);
-    unsigned long long* ev_key = scratch<unsigned long long>(ctx, 7, cap_ev, err);
+    const uint64_t cap_cl = std::min<uint64_t>(ctx->pl_cap_cl, n + 2), cap_sites = ctx->pl_cap_ev;
+    const uint32_t c_tiles = (uint32_t)((cap_cl + CB_CLUSTERS - 1) / CB_CLUSTERS);
+    LbDesc* d_sc = scratch<LbDesc>(ctx, 8, c_tiles, err, true);
     if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
     if (H->d_cl) { cudaFreeAsync(H->d_cl, st); H->d_cl = nullptr; }
+    if (H->d_sites) { cudaFreeAsync(H->d_sites, st); H->d_sites = nullptr; }
+    if (H->d_first) { cudaFreeAsync(H->d_first, st); H->d_first = nullptr; }
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_cl, cap_cl * sizeof(ps_cluster), st));
+    PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (cap_sites + 1) * sizeof(ps_site), st));
+    PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_first, (cap_cl + 2) * sizeof(uint32_t), st));
 
-    ScanParams P;
-    P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_seg = d_seg; P.epoch = ++ctx->pl_epoch;
-    P.n_tiles = n_tiles; P.carry_key = carry_key; P.first_id = opts ? opts->first_running_id : 1;
-    P.iv = iv; P.cl = H->d_cl; P.cl_first = cl_first; P.cl_ev = cl_ev; P.ev_pos = ev_pos; P.ev_key = ev_key;
-    P.cap_cl = cap_cl; P.cap_ev = cap_ev;
+    FlagParams P;
+    P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
+    P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = H->d_first; P.cap_cl = cap_cl;
     pl_init_state<<<1, 32, 0, st>>>(d_state);
-    if (!fast) pl_scan_kernel<1, 0><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    else if (L <= 16) pl_scan_kernel<4, 1><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    else if (L <= 32) pl_scan_kernel<4, 2><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    else if (L <= 48) pl_scan_kernel<4, 3><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    else pl_scan_kernel<4, 4><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    ctx->launches += 2;
+    if (vec) pl_flag_kernel<4><<<n_tiles, PL_THREADS, 0, st>>>(P);
+    else pl_flag_kernel<1><<<n_tiles, PL_THREADS, 0, st>>>(P);
+    ClusterParams Q;
+    Q.b = b; Q.ref = ctx->ref; Q.st = d_state; Q.d_cnt = d_sc; Q.epoch = ++ctx->pl_epoch;
+    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = H->d_first; Q.cl = H->d_cl; Q.sites = H->d_sites;
+    Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
+    launch_cluster(nw, c_tiles, st, Q);
+    ctx->launches += 3;
     PS_CUDA(ctx, cudaGetLastError());
     PS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));
-    const uint64_t need_cl = (uint64_t)hs.n_flags + 2, need_ev = hs.n_ev;
-    if (need_cl <= cap_cl && need_ev <= cap_ev) break;
-    if (attempt >= 1) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }
-    // totals do not depend on the capacities (dropped writes only): size exactly and run once more
-    ctx->pl_cap_cl = std::max(ctx->pl_cap_cl, need_cl + need_cl / 16);
-    ctx->pl_cap_ev = std::max(ctx->pl_cap_ev, need_ev + need_ev / 16);
+    const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
+    if (need_cl <= cap_cl && need_sites <= cap_sites) break;
+    if (attempt >= 2) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }
+    // the totals do not depend on the capacities (dropped writes only); the site total is only known once the
+    // cluster slots fit, so a batch may need two more passes the first time a context sees its shape
+    ctx->pl_cap_cl = std::max(ctx->pl_cap_cl, need_cl + need_cl / 16 + 2);
+    ctx->pl_cap_ev = std::max(ctx->pl_cap_ev, need_sites + need_sites / 16);
   }
+  timer_end(ctx, st);
   H->counters.skipped_due_indel = hs.skipped;
   if (hs.fault != PS_FAULT_NONE) {
     H->fault.code = (int32_t)(hs.fault & 0xFF);
     H->fault.read_ordinal = hs.fault >> 8;
-    timer_end(ctx, st);
     return set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, "pileup: the JVM would die on a record of this batch");
   }
-  if (hs.unsorted) { timer_end(ctx, st); return set_error(ctx, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED)); }
+  if (hs.unsorted) return set_error(ctx, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED));
 
   const uint64_t n_slots = (uint64_t)hs.n_flags + 1;
   H->n_slots = n_slots;
-  const uint32_t s_tiles = (uint32_t)((n_slots + PL_SITE_CLUSTERS - 1) / PL_SITE_CLUSTERS);
-  auto* d_cnt = scratch<LbDesc<unsigned long long>>(ctx, 8, s_tiles, err, true);
-  if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-  PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (hs.n_ev + 1) * sizeof(ps_site), st));
-  SiteParams Q;
-  Q.st = d_state; Q.d_cnt = d_cnt; Q.epoch = ++ctx->pl_epoch; Q.n_slots = (uint32_t)n_slots; Q.n_tiles = s_tiles;
-  Q.iv = iv; Q.cl = H->d_cl; Q.cl_first = (const uint32_t*)ctx->pl_scratch[4].p; Q.cl_ev = (const uint32_t*)ctx->pl_scratch[5].p;
-  Q.ev_pos = (const int32_t*)ctx->pl_scratch[6].p; Q.ev_key = (const unsigned long long*)ctx->pl_scratch[7].p;
-  Q.sites = H->d_sites;
-  pl_site_kernel<<<s_tiles, PL_THREADS, 0, st>>>(Q);
-  ctx->launches += 1;
-  PS_CUDA(ctx, cudaGetLastError());
-  timer_end(ctx, st);
-  // summary: state, head partial (slot 0), open cluster (last slot)
-  PS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
+  // summary: head partial (slot 0), open cluster (last slot)
   PS_CUDA(ctx, cudaMemcpyAsync(&H->head, H->d_cl, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
   if (hs.n_flags) PS_CUDA(ctx, cudaMemcpyAsync(&H->open, H->d_cl + hs.n_flags, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
   PS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -810,6 +878,7 @@ static void free_handle(ps_pileup* h) {
   if (h->ctx) cudaSetDevice(h->ctx->device);
   if (h->d_cl) cudaFreeAsync(h->d_cl, h->stream);
   if (h->d_sites) cudaFreeAsync(h->d_sites, h->stream);
+  if (h->d_first) cudaFreeAsync(h->d_first, h->stream);
   delete h;
 }
 
@@ -818,15 +887,28 @@ static int boundary_coverage(ps_pileup* h) {
   if (h->cov_done) return PS_OK;
   ps_ctx* ctx = h->ctx;
   if (!ctx || h->n_reads == 0) { h->cov_done = true; return PS_OK; }
-  if (ctx->pl_generation != h->generation)
-    return set_error(ctx, PS_ERR_STATE, "boundary coverage must be read before the next pileup call on this context");
+  if (h->stage_serial && ctx->stage_serial - h->stage_serial >= 2)
+    return set_error(ctx, PS_ERR_STATE, "boundary coverage must be read before the second-next upload on this context");
   cudaSetDevice(ctx->device);
-  const int2* iv = (const int2*)ctx->pl_scratch[1].p;
-  const uint32_t* cl_first = (const uint32_t*)ctx->pl_scratch[4].p;
+  ClusterParams Q{};
+  Q.b = h->batch; Q.ref = ctx->ref; Q.st = (PlState*)ctx->pl_scratch[0].p;
   auto dense = [&](uint64_t r0, uint64_t r1, std::vector<uint32_t>& cov, int32_t& pos0) -> int {
     if (r1 <= r0) return PS_OK;
+    int2* d_iv = nullptr;
+    PS_CUDA(ctx, cudaMallocAsync((void**)&d_iv, (r1 - r0) * sizeof(int2), h->stream));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((r1 - r0 + 255) / 256, 1024);
+    switch (h->nw) {
+      case 1: pl_interval_kernel<1><<<grid, 256, 0, h->stream>>>(Q, (uint32_t)r0, (uint32_t)r1, d_iv); break;
+      case 2: pl_interval_kernel<2><<<grid, 256, 0, h->stream>>>(Q, (uint32_t)r0, (uint32_t)r1, d_iv); break;
+      case 3: pl_interval_kernel<3><<<grid, 256, 0, h->stream>>>(Q, (uint32_t)r0, (uint32_t)r1, d_iv); break;
+      case 4: pl_interval_kernel<4><<<grid, 256, 0, h->stream>>>(Q, (uint32_t)r0, (uint32_t)r1, d_iv); break;
+      default: pl_interval_kernel<0><<<grid, 256, 0, h->stream>>>(Q, (uint32_t)r0, (uint32_t)r1, d_iv); break;
+    }
+    ctx->launches++;
     std::vector<int2> v(r1 - r0);
-    PS_CUDA(ctx, cudaMemcpy(v.data(), iv + r0, (r1 - r0) * sizeof(int2), cudaMemcpyDeviceToHost));
+    PS_CUDA(ctx, cudaMemcpyAsync(v.data(), d_iv, (r1 - r0) * sizeof(int2), cudaMemcpyDeviceToHost, h->stream));
+    PS_CUDA(ctx, cudaStreamSynchronize(h->stream));
+    cudaFreeAsync(d_iv, h->stream);
     int32_t mn = INT32_MAX, mx = INT32_MIN;
     for (const int2& x : v)
       if (x.x <= x.y) { mn = std::min(mn, x.x); mx = std::max(mx, x.y); }
@@ -840,7 +922,7 @@ static int boundary_coverage(ps_pileup* h) {
   const uint64_t n_flags = h->n_slots - 1;
   if (h->has_head) {
     uint32_t r1 = (uint32_t)h->n_reads;
-    if (n_flags) PS_CUDA(ctx, cudaMemcpy(&r1, cl_first + 1, 4, cudaMemcpyDeviceToHost));
+    if (n_flags) PS_CUDA(ctx, cudaMemcpy(&r1, h->d_first + 1, 4, cudaMemcpyDeviceToHost));
     int rc = dense(0, r1, h->head_cov, h->head_cov_pos0);
     if (rc) return rc;
   }
@@ -876,6 +958,7 @@ int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* hb, const ps_pileup_opts* 
   int rc = stage_batch(ctx, hb, /*with_qual=*/false, &sb);
   if (rc) return rc;
   rc = run_pileup(ctx, sb->view, opts, ctx->stream, out);
+  if (*out) (*out)->stage_serial = ctx->stage_serial;
   if (rc != PS_OK && rc != PS_ERR_REFERENCE_WOULD_THROW) { free_handle(*out); *out = nullptr; }
   return rc;
 }
