@@ -34,9 +34,9 @@ namespace {
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int CB_PER_WARP = 8;                        // clusters per warp of pl_cluster_kernel
-constexpr int CB_CLUSTERS = PL_WARPS * CB_PER_WARP;   // clusters per block
-constexpr int CB_SITE_CAP = 40;                       // sites a warp can stage in shared memory
+constexpr int CB_CLUSTERS = 128;                      // clusters per block of pl_cluster_kernel (thread per cluster)
+constexpr int CB_CHUNK = 2048;                        // reads decoded into shared memory at a time
+constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
 constexpr int PL_WINDOW = 128;                        // positions per window
 
 struct PlState {                  // device-side run state (one per call)
@@ -47,7 +47,7 @@ struct PlState {                  // device-side run state (one per call)
   unsigned int n_flags;           // clusters opened
   unsigned int unsorted;
   unsigned int tile_ctr_flag;
-  unsigned int tile_ctr_cluster;
+  unsigned int tile_ctr_compact;
 };
 
 struct PlRead {              // what the pileup needs from one read
@@ -263,12 +263,10 @@ struct ClusterParams {
   DeviceBatch b;
   DeviceRef ref;
   PlState* st;
-  LbDesc* d_cnt;
-  unsigned int epoch;
   uint32_t first_id;
   const uint32_t* cl_first;
   ps_cluster* cl;
-  ps_site* sites;
+  ps_site* sites;           // pl_cluster_kernel: sites grouped by block in completion order; pl_compact_kernel orders them
   uint64_t cap_cl, cap_sites;
 };
 
@@ -619,50 +617,300 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
   return written;
 }
 
+// Shared-memory plan of pl_cluster_kernel (dynamic): decoded reads of one chunk, per-cluster site tables
+struct ClusterSmem {
+  unsigned long long* mask;   // [CB_CHUNK] T>C mask | rev << 62 | kept << 63
+  int32_t *lo, *hi, *start, *end;   // [CB_CHUNK]
+  uint32_t* contig;           // [CB_CHUNK]
+  unsigned long long* umask;  // [CB_CLUSTERS] mutationMap key set: bit p = position base + p holds a T>C
+  uint32_t *scnt, *scov, *skey;   // [CB_SITES * CB_CLUSTERS] site s of cluster k at [s * CB_CLUSTERS + k]
+  int32_t* base;              // [CB_CLUSTERS] position of bit 0 of umask
+  uint32_t* ovf;              // [CB_CLUSTERS] != 0: the cluster does not fit the tables
+  uint32_t* first;            // [CB_CLUSTERS + 1] cl_first of the block's clusters
+  uint32_t* fb;               // [CB_CLUSTERS] clusters left to the warp routine
+  uint8_t* cid;               // [CB_CHUNK] cluster (index inside the block) of each read
+};
+constexpr size_t kClusterSmemBytes = (size_t)CB_CHUNK * (8 + 5 * 4 + 1) + (size_t)CB_CLUSTERS * (8 + CB_SITES * 12 + 4 * 4) + 64;
+static_assert((size_t)CB_CHUNK * 28 >= PL_WARPS * (sizeof(WarpTables) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
+static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is one byte / one thread per cluster");
+
+// One block = CB_CLUSTERS consecutive clusters = one contiguous run of reads, taken in chunks of CB_CHUNK reads.
+//   A   thread per READ:    decode (T>C mask, interval, strand) into shared memory -- full lanes whatever the cluster
+//                           sizes are
+//   B0  thread per CLUSTER: counters over the cluster's decoded reads (P3 counters, P4, P6)
+//   B1  thread per READ:    OR the read's T>C positions into its cluster's 64-position key set (shared atomics)
+//   B2  thread per READ:    per key: mutationMap count, first-insertion key (min), and baseCoveredMap -- every read adds
+//                           itself to the keys its interval covers.  A key's slot is its rank in the key set, so the
+//                           sites come out in position order.
+//   B3  thread per CLUSTER: record (64 contiguous bytes per thread) and sites; the block's sites go to one run of
+//                           slots taken with a single atomic, pl_compact_kernel orders the runs afterwards
+// Clusters that do not fit (more than CB_CHUNK reads, T>C positions more than 64 apart, more than CB_SITES of them)
+// are left to the warp-per-cluster routine above at the end of the block.
 template <int NW>
 __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
-  __shared__ __align__(16) ps_cluster s_cl[CB_CLUSTERS];
-  __shared__ __align__(16) ps_site s_sites[PL_WARPS][CB_SITE_CAP];
-  __shared__ WarpTables s_tab[PL_WARPS];
-  __shared__ uint32_t s_cnt[CB_CLUSTERS], s_off[CB_CLUSTERS], s_stage[CB_CLUSTERS];   // s_stage: offset in the warp's staging area, ~0 = not staged
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long s_wtot[PL_WARPS];
   __shared__ unsigned long long s_base;
-  __shared__ unsigned int s_tile;
+  __shared__ uint32_t s_nfb;
+  ClusterSmem S;
+  S.mask = reinterpret_cast<unsigned long long*>(smem_raw);
+  S.lo = reinterpret_cast<int32_t*>(S.mask + CB_CHUNK);
+  S.hi = S.lo + CB_CHUNK; S.start = S.hi + CB_CHUNK; S.end = S.start + CB_CHUNK;
+  S.contig = reinterpret_cast<uint32_t*>(S.end + CB_CHUNK);
+  S.umask = reinterpret_cast<unsigned long long*>(S.contig + CB_CHUNK);
+  S.scnt = reinterpret_cast<uint32_t*>(S.umask + CB_CLUSTERS);
+  S.scov = S.scnt + CB_SITES * CB_CLUSTERS;
+  S.skey = S.scov + CB_SITES * CB_CLUSTERS;
+  S.base = reinterpret_cast<int32_t*>(S.skey + CB_SITES * CB_CLUSTERS);
+  S.ovf = reinterpret_cast<uint32_t*>(S.base + CB_CLUSTERS);
+  S.first = S.ovf + CB_CLUSTERS;
+  S.fb = S.first + CB_CLUSTERS + 1;
+  S.cid = reinterpret_cast<uint8_t*>(S.fb + CB_CLUSTERS);
+
   const uint32_t n_slots = P.st->n_flags + 1;          // written by pl_flag_kernel
-  if (n_slots > P.cap_cl) return;                       // the host re-runs both kernels with larger arrays
-  const uint32_t n_tiles = (n_slots + CB_CLUSTERS - 1) / CB_CLUSTERS;
-  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_cluster, 1u);
+  if (n_slots > P.cap_cl) return;                       // the host re-runs the kernels with larger arrays
+  const uint32_t c0 = blockIdx.x * CB_CLUSTERS;
+  if (c0 >= n_slots) return;
+  const uint32_t ncl = min((uint32_t)CB_CLUSTERS, n_slots - c0);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t k = tid; k <= ncl; k += PL_THREADS) S.first[k] = __ldg(P.cl_first + c0 + k);
+  if (tid == 0) s_nfb = 0;
+  __syncthreads();
+
+  unsigned long long dstr = 0;
+  ContigCache cc;
+  uint32_t cur = 0;
+  while (cur < ncl) {
+    const uint32_t rs = S.first[cur];
+    // clusters cur .. cur+ncomp-1 lie completely inside the chunk [rs, rs + CB_CHUNK)
+    const bool complete = cur + tid < ncl && S.first[cur + tid + 1] - rs <= (uint32_t)CB_CHUNK;
+    const uint32_t ncomp = (uint32_t)__syncthreads_count(complete);
+    if (ncomp == 0) {           // a single cluster larger than the chunk
+      if (tid == 0) S.fb[s_nfb++] = cur;
+      ++cur;
+      __syncthreads();
+      continue;
+    }
+    const uint32_t re = S.first[cur + ncomp], nrd = re - rs;
+    // ---- A ------------------------------------------------------------------------------------------------------
+    for (uint32_t q = rs + warp * 32; q < re; q += PL_THREADS) {
+      const uint32_t r = q + lane;
+      PlRead x;
+      pl_decode<NW>(P, q, r, r < re, cc, x);
+      if (r < re) {
+        const uint32_t i = r - rs;
+        S.mask[i] = x.mask | ((unsigned long long)x.rev << 62) | ((unsigned long long)x.kept << 63);
+        S.lo[i] = x.lo; S.hi[i] = x.hi; S.start[i] = x.start; S.end[i] = x.end; S.contig[i] = x.contig;
+      }
+    }
+    __syncthreads();
+    // ---- B0 -----------------------------------------------------------------------------------------------------
+    const bool mine = tid < ncomp;
+    uint32_t reads = 0, t2c = 0, minus = 0, first_rev = 0, contig = 0;
+    int32_t end = INT32_MIN, cstart = 0;
+    unsigned long long mask = 0, first_read = 0;
+    if (mine) {
+      const uint32_t k = cur + tid;
+      const uint32_t a = S.first[k] - rs, b = S.first[k + 1] - rs;
+      first_read = S.first[k];
+      for (uint32_t i = a; i < b; ++i) {
+        S.cid[i] = (uint8_t)tid;
+        unsigned long long m = S.mask[i];
+        if (!(m >> 63)) continue;
+        const uint32_t rev = (uint32_t)(m >> 62) & 1u;
+        m &= (1ull << 51) - 1ull;
+        if (reads == 0) { first_read = rs + i; cstart = S.start[i]; contig = S.contig[i]; first_rev = rev; }
+        ++reads; minus += rev;
+        end = max(end, S.end[i]);
+        t2c += __popcll(m);
+        mask |= m;
+      }
+      S.base[tid] = cstart;      // sorted input: no position of the cluster lies before the start of its first read
+      S.umask[tid] = 0;
+      S.ovf[tid] = 0;
+#pragma unroll
+      for (int u = 0; u < CB_SITES; ++u) {
+        S.scnt[u * CB_CLUSTERS + tid] = 0; S.scov[u * CB_CLUSTERS + tid] = 0; S.skey[u * CB_CLUSTERS + tid] = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
+    // ---- B1 -----------------------------------------------------------------------------------------------------
+    for (uint32_t i = tid; i < nrd; i += PL_THREADS) {
+      unsigned long long m = S.mask[i];
+      if (!(m >> 63)) continue;
+      const bool rev = (m >> 62) & 1ull;
+      m &= (1ull << 51) - 1ull;
+      if (!m) continue;
+      const uint32_t k = S.cid[i];
+      const int32_t lo = S.lo[i], hi = S.hi[i], base = S.base[k];
+      unsigned long long bits = 0;
+      bool bad = false;
+      while (m) {
+        const int ib = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int32_t rel = (rev ? hi - ib : lo + ib) - base;               // checkPosition (:638-643)
+        if ((uint32_t)rel >= 64u) bad = true; else bits |= 1ull << rel;
+      }
+      if (bad) S.ovf[k] = 1u;
+      if (bits) atomicOr(&S.umask[k], bits);
+    }
+    __syncthreads();
+    // ---- B2 -----------------------------------------------------------------------------------------------------
+    for (uint32_t i = tid; i < nrd; i += PL_THREADS) {
+      unsigned long long m = S.mask[i];
+      if (!(m >> 63)) continue;
+      const uint32_t k = S.cid[i];
+      const unsigned long long um = S.umask[k];
+      if (um == 0 || S.ovf[k] || __popcll(um) > CB_SITES) continue;
+      const bool rev = (m >> 62) & 1ull;
+      m &= (1ull << 51) - 1ull;
+      const int32_t lo = S.lo[i], hi = S.hi[i], base = S.base[k];
+      while (m) {
+        const int ib = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int32_t rel = (rev ? hi - ib : lo + ib) - base;
+        const uint32_t slot = __popcll(um & ((1ull << rel) - 1ull));
+        atomicAdd(&S.scnt[slot * CB_CLUSTERS + k], 1u);                   // mutationMap.put(pos, old + 1)
+        atomicMin(&S.skey[slot * CB_CLUSTERS + k], (i << 6) | (uint32_t)ib);   // first insertion = earliest read
+      }
+      const int32_t l = max(lo - base, 0), h = min(hi - base, 63);       // baseCoveredMap (:662-667) at the keys
+      if (l <= h) {
+        unsigned long long cov = um & (~0ull << l) & (~0ull >> (63 - h));
+        while (cov) {
+          const int bit = __ffsll((long long)cov) - 1;
+          cov &= cov - 1;
+          atomicAdd(&S.scov[__popcll(um & ((1ull << bit) - 1ull)) * CB_CLUSTERS + k], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- B3 -----------------------------------------------------------------------------------------------------
+    uint32_t ns = 0;
+    bool left = false;
+    unsigned long long um = 0;
+    if (mine) {
+      um = S.umask[tid];
+      ns = __popcll(um);
+      left = S.ovf[tid] != 0 || ns > (uint32_t)CB_SITES;
+      if (left) { S.fb[atomicAdd(&s_nfb, 1u)] = cur + tid; ns = 0; }
+    }
+    unsigned long long total;
+    const unsigned long long ex = block_exclusive((unsigned long long)ns, LbSum(), 0ull, s_wtot, total);
+    if (tid == 0) s_base = total ? atomicAdd(&P.st->n_sites, total) : 0ull;
+    __syncthreads();
+    if (mine && !left) {
+      const uint32_t slot = c0 + cur + tid;
+      const unsigned long long sb = s_base + ex;
+      const uint32_t maf = slot ? minus - first_rev : minus;   // slot 0 continues a cluster opened by the preceding shard
+      ps_cluster rec;
+      rec.first_read = first_read;
+      rec.running_id = slot ? P.first_id + slot : 0;           // runningID++ then "cl_<id>_<chr>" (:355): first cluster is cl_2
+      rec.contig = contig;
+      rec.start = cstart;
+      rec.end = reads ? end : 0;
+      rec.num_reads = reads;
+      rec.num_t2c = t2c;
+      rec.minus_after_first = maf;
+      rec.first_reverse = (uint8_t)first_rev;
+      rec.combined_strand = first_rev ? 1 : (maf ? 2 : 0);     // StrandOrientation state at flush (P6)
+      rec.reserved = 0;
+      rec.mask51 = mask;
+      rec.site_begin = sb;
+      rec.site_end = sb + ns;
+      if (slot && !first_rev) dstr += maf;                     // doubleStranded++ (:494-498)
+      const uint4* src = reinterpret_cast<const uint4*>(&rec);
+      uint4* dst = reinterpret_cast<uint4*>(P.cl + slot);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) dst[w] = src[w];
+      const int32_t base = S.base[tid];
+      for (uint32_t u = 0; u < ns; ++u) {
+        const int bit = __ffsll((long long)um) - 1;
+        um &= um - 1;
+        if (sb + u >= P.cap_sites) break;
+        ps_site o;
+        o.pos = base + bit; o.t2c = S.scnt[u * CB_CLUSTERS + tid]; o.cov = S.scov[u * CB_CLUSTERS + tid];
+        o.reserved = 0;
+        const uint32_t key = S.skey[u * CB_CLUSTERS + tid];
+        o.order_key = ((unsigned long long)(rs + (key >> 6)) << 6) | (key & 63u);
+        P.sites[sb + u] = o;
+      }
+    }
+    __syncthreads();            // the next chunk overwrites the shared arrays
+    cur += ncomp;
+  }
+
+  // ---- clusters left to the warp routine (tables alias the read arrays, which are free now) ---------------------------
+  __syncthreads();
+  {
+    WarpTables* T = reinterpret_cast<WarpTables*>(smem_raw) + warp;
+    ps_cluster* wrec = reinterpret_cast<ps_cluster*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + warp;
+    const uint32_t nfb = s_nfb;
+    for (uint32_t e = warp; e < nfb; e += PL_WARPS) {
+      const uint32_t k = S.fb[e], slot = c0 + k;
+      const uint32_t f = S.first[k], fe = S.first[k + 1];
+      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, wrec, true, nullptr, 0, dstr);
+      unsigned long long sb = 0;
+      if (lane == 0 && cnt) sb = atomicAdd(&P.st->n_sites, (unsigned long long)cnt);
+      sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+      if (cnt && sb < P.cap_sites) {
+        unsigned long long unused = 0;
+        pl_cluster<NW>(P, slot, f, fe, *T, nullptr, false, P.sites + sb, (uint32_t)min((unsigned long long)cnt, P.cap_sites - sb), unused);
+      }
+      __syncwarp();
+      if (lane == 0) { wrec->site_begin = sb; wrec->site_end = sb + cnt; }
+      __syncwarp();
+      if (lane < 4) reinterpret_cast<uint4*>(P.cl + slot)[lane] = reinterpret_cast<const uint4*>(wrec)[lane];
+      __syncwarp();
+    }
+  }
+  // doubleStranded of the block
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) dstr += __shfl_xor_sync(0xFFFFFFFFu, dstr, d);
+  if (lane == 0 && dstr) atomicAdd(&P.st->dstr, dstr);
+}
+
+// Orders the site runs: exclusive prefix of the per-cluster site counts (look-back #3) = final site_begin; every
+// cluster's sites move from the completion-ordered array to their place, so the site array ends up compact and
+// sorted by (cluster, position) whatever order the blocks of pl_cluster_kernel finished in.
+struct CompactParams {
+  PlState* st;
+  LbDesc* d_cnt;
+  unsigned int epoch;
+  ps_cluster* cl;
+  const ps_site* src;
+  ps_site* dst;
+  uint64_t cap_cl, cap_sites;
+};
+
+__global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_constant__ CompactParams P) {
+  constexpr int ITEMS = 4;
+  __shared__ unsigned long long s_wtot[PL_WARPS];
+  __shared__ unsigned long long s_pre;
+  __shared__ unsigned int s_tile;
+  const uint32_t n_slots = P.st->n_flags + 1;
+  if (n_slots > P.cap_cl || P.st->n_sites > P.cap_sites) return;
+  const uint32_t n_tiles = (n_slots + PL_THREADS * ITEMS - 1) / (PL_THREADS * ITEMS);
+  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_compact, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
   if (tile >= n_tiles) return;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t c0 = tile * CB_CLUSTERS;
-  WarpTables& T = s_tab[warp];
-  unsigned long long dstr = 0;
-  uint32_t staged = 0;
-  for (uint32_t j = 0; j < CB_PER_WARP; ++j) {
-    const uint32_t k = warp * CB_PER_WARP + j, c = c0 + k;
-    uint32_t cnt = 0, st = ~0u;
-    if (c < n_slots) {
-      cnt = pl_cluster<NW>(P, c, __ldg(P.cl_first + c), __ldg(P.cl_first + c + 1), T, &s_cl[k], true,
-                           &s_sites[warp][staged], CB_SITE_CAP - staged, dstr);
-      if (cnt <= CB_SITE_CAP - staged) { st = staged; staged += cnt; }
-    }
-    if (lane == 0) { s_cnt[k] = cnt; s_stage[k] = st; }
-  }
-  if (lane == 0 && dstr) atomicAdd(&P.st->dstr, dstr);
-  __syncthreads();
-  if (warp == 0) {
-    // exclusive prefix of the 64 counts (2 per lane) and the tile's base from the look-back
-    const uint32_t a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
-    uint32_t x = a + b;
+  const uint32_t c0 = tile * PL_THREADS * ITEMS + threadIdx.x * ITEMS;
+  unsigned long long from[ITEMS];
+  uint32_t cnt[ITEMS];
+  uint32_t mine = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-      if (lane >= (uint32_t)d) x += y;
+  for (int j = 0; j < ITEMS; ++j) {
+    from[j] = 0; cnt[j] = 0;
+    if (c0 + j < n_slots) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&P.cl[c0 + j].site_begin);
+      from[j] = v.x; cnt[j] = (uint32_t)(v.y - v.x);
     }
-    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, x, 31);
-    s_off[2 * lane] = x - a - b;
-    s_off[2 * lane + 1] = x - b;
+    mine += cnt[j];
+  }
+  unsigned long long total;
+  const unsigned long long ex = block_exclusive((unsigned long long)mine, LbSum(), 0ull, s_wtot, total);
+  if (warp == 0) {
     unsigned long long pre = 0;
     if (tile == 0) {
       if (lane == 0) lb_publish(&P.d_cnt[0], total, 2u, P.epoch);
@@ -671,36 +919,18 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
       pre = lb_exclusive_prefix(P.d_cnt, (int)tile, P.epoch, LbSum(), 0ull);
       if (lane == 0) lb_publish(&P.d_cnt[tile], pre + total, 2u, P.epoch);
     }
-    if (lane == 0) {
-      s_base = pre;
-      if (tile == n_tiles - 1) P.st->n_sites = pre + total;
-    }
+    if (lane == 0) s_pre = pre;
   }
   __syncthreads();
-  const unsigned long long base = s_base;
-  for (uint32_t j = 0; j < CB_PER_WARP; ++j) {
-    const uint32_t k = warp * CB_PER_WARP + j, c = c0 + k;
-    if (c >= n_slots) break;
-    const unsigned long long b = base + s_off[k];
-    const uint32_t cnt = s_cnt[k];
-    if (lane == 0) { s_cl[k].site_begin = b; s_cl[k].site_end = b + cnt; }
-    if (cnt == 0 || b >= P.cap_sites) continue;
-    const uint32_t room = (uint32_t)min((unsigned long long)cnt, P.cap_sites - b);
-    if (s_stage[k] != ~0u) {
-      // a site is 24 bytes = 3 x 8
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_sites[warp][s_stage[k]]);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.sites + b);
-      for (uint32_t e = lane; e < room * 3; e += 32) dst[e] = src[e];
-    } else {
-      unsigned long long unused = 0;
-      pl_cluster<NW>(P, c, __ldg(P.cl_first + c), __ldg(P.cl_first + c + 1), T, nullptr, false, P.sites + b, room, unused);
-    }
-  }
-  __syncthreads();
-  {   // cluster records: one coalesced run per block
-    const uint32_t k = threadIdx.x >> 2;
-    if (c0 + k < n_slots)
-      reinterpret_cast<uint4*>(P.cl + c0)[threadIdx.x] = reinterpret_cast<const uint4*>(s_cl)[threadIdx.x];
+  unsigned long long to = s_pre + ex;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (c0 + j >= n_slots) break;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.src + from[j]);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.dst + to);
+    for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];     // a site is 24 bytes
+    *reinterpret_cast<ulonglong2*>(&P.cl[c0 + j].site_begin) = make_ulonglong2(to, to + cnt[j]);
+    to += cnt[j];
   }
 }
 
@@ -719,7 +949,7 @@ __global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint
 __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
     st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_flags = 0;
-    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_cluster = 0;
+    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0;
   }
 }
 
@@ -763,13 +993,22 @@ static int flavour_of(const DeviceBatch& b) {   // 0 = generic decode, 1..4 = PA
   return fast ? (int)((L + 15) / 16) : 0;
 }
 
+template <int NW>
+static void launch_cluster_nw(uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pl_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
+    configured = true;
+  }
+  pl_cluster_kernel<NW><<<grid, PL_THREADS, kClusterSmemBytes, st>>>(Q);
+}
 static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
   switch (nw) {
-    case 1: pl_cluster_kernel<1><<<grid, PL_THREADS, 0, st>>>(Q); break;
-    case 2: pl_cluster_kernel<2><<<grid, PL_THREADS, 0, st>>>(Q); break;
-    case 3: pl_cluster_kernel<3><<<grid, PL_THREADS, 0, st>>>(Q); break;
-    case 4: pl_cluster_kernel<4><<<grid, PL_THREADS, 0, st>>>(Q); break;
-    default: pl_cluster_kernel<0><<<grid, PL_THREADS, 0, st>>>(Q); break;
+    case 1: launch_cluster_nw<1>(grid, st, Q); break;
+    case 2: launch_cluster_nw<2>(grid, st, Q); break;
+    case 3: launch_cluster_nw<3>(grid, st, Q); break;
+    case 4: launch_cluster_nw<4>(grid, st, Q); break;
+    default: launch_cluster_nw<0>(grid, st, Q); break;
   }
 }
 
@@ -815,6 +1054,8 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     if (H->d_first) { cudaFreeAsync(H->d_first, st); H->d_first = nullptr; }
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_cl, cap_cl * sizeof(ps_cluster), st));
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (cap_sites + 1) * sizeof(ps_site), st));
+    ps_site* d_tmp = nullptr;
+    PS_CUDA(ctx, cudaMallocAsync((void**)&d_tmp, (cap_sites + 1) * sizeof(ps_site), st));
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_first, (cap_cl + 2) * sizeof(uint32_t), st));
 
     FlagParams P;
@@ -824,11 +1065,16 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     if (vec) pl_flag_kernel<4><<<n_tiles, PL_THREADS, 0, st>>>(P);
     else pl_flag_kernel<1><<<n_tiles, PL_THREADS, 0, st>>>(P);
     ClusterParams Q;
-    Q.b = b; Q.ref = ctx->ref; Q.st = d_state; Q.d_cnt = d_sc; Q.epoch = ++ctx->pl_epoch;
-    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = H->d_first; Q.cl = H->d_cl; Q.sites = H->d_sites;
+    Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
+    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = H->d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
     Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
     launch_cluster(nw, c_tiles, st, Q);
-    ctx->launches += 3;
+    CompactParams R;
+    R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
+    R.cap_cl = cap_cl; R.cap_sites = cap_sites;
+    pl_compact_kernel<<<(uint32_t)((cap_cl + PL_THREADS * 4 - 1) / (PL_THREADS * 4)), PL_THREADS, 0, st>>>(R);
+    cudaFreeAsync(d_tmp, st);
+    ctx->launches += 4;
     PS_CUDA(ctx, cudaGetLastError());
     PS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));
