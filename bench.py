@@ -197,35 +197,34 @@ def main():
     pile = {}
 
     def step_resident():
+        # the whole hot path on a batch that is already in HBM: profile kernel (+ the tiny all-reduce), read-back of
+        # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
+        # their counters come back to the host
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
         if world > 1:
             dist.all_reduce(ctx.profile_acc_tensor())
-
-    def finish():
         res = ctx.profile_end()
-        # T>C pileup of the same reads (region shard of this rank; the halo exchange is 2 scalars per cut and is
-        # done by parasuite_b200.sharding when shards are merged -- not part of the per-shard step)
-        pile["res"] = ctx.pileup(dbatch, stream=stream.cuda_stream)
+        with ctx.pileup_run(dbatch, stream=stream.cuda_stream) as h:
+            pile["counters"] = h.counters
         return res
 
-    # ---- warm-up + parity of the timed configuration against the oracle on a prefix ---------------
+    # ---- warm-up ------------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        step_resident()
-        res = finish()
+        res = step_resident()
     # ---- device-resident timed region ---------------------------------------------------------------
     sampler = ClockSampler(visible_physical_index(local_rank))
     ctx.kernel_times_reset(True)
     launches0 = ctx.kernel_launches()
+    stage_ms = []
     barrier()
     sampler.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        step_resident()
-        # profile_end() synchronises and reads back < 10 KB of counts: part of the step
-        res = finish()
+        res = step_resident()
+        stage_ms.append(ctx.pileup_stage_ms())       # events of the step just finished (already synchronised)
     e1.record(stream)
     barrier()
     sampler.stop_flag = True
@@ -240,16 +239,21 @@ def main():
     value = total_reads * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end leg: pinned HOST buffers through the C ABI, copies inside the timed region -------
+    # one upload of the records serves both tools; every cluster and site record comes back to (pinned) host memory
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     pinned = PinnedBatch(batch)
+
     def step_e2e():
+        view = ctx.upload(pinned)
         ctx.profile_begin(max_len)
-        ctx.profile_batch(pinned)
+        ctx.profile_batch_device(view)
         if world > 1:
             torch.cuda.synchronize()
             dist.all_reduce(ctx.profile_acc_tensor())
+            torch.cuda.current_stream().synchronize()
         r = ctx.profile_end()
-        pile["res_e2e"] = ctx.pileup(pinned)
+        with ctx.pileup_run(view) as h:
+            pile["res_e2e"] = h.fetch(pinned=True, boundary=False)
         return r
 
     for _ in range(2):
@@ -266,31 +270,44 @@ def main():
     e2e_value = total_reads * e2e_steps / (float(t.item()) * 1e-3)
     pr = pile["res_e2e"]
     d2h = int(res_e2e["wide"].nbytes + 8 + pr["clusters"].nbytes + pr["sites"].nbytes)
-    h2d = 2 * pinned.h2d_bytes      # each stage takes the host batch through the C ABI
+    h2d = pinned.h2d_bytes
 
     if rank == 0:
         peak, peak_src = peaks()
-        # timer ring order per step: profile kernel, pileup pipeline
+        # timer ring order per step: profile kernel(s), pileup pipeline
         k_prof = float(np.mean(ktimes[0::2])) if len(ktimes) >= 2 else float("nan")
         k_pile = float(np.mean(ktimes[1::2])) if len(ktimes) >= 2 else float("nan")
-        cl = pile["res"]["clusters"]
-        pile_bytes = (batch.algorithmic_bytes(with_qual=False)
-                      + 8 * int((cl["end"].astype(np.int64) - cl["start"].astype(np.int64) + 1).sum())
-                      + 32 * len(cl))
-        if k_prof >= k_pile or k_pile != k_pile:
-            kname, kms, kbytes = "profile_generic_kernel", k_prof, alg_bytes
-        else:
-            kname, kms, kbytes = "pileup pipeline (pl_read/flag/cluster/site + scans + sort)", k_pile, pile_bytes
-        achieved = kbytes / (kms * 1e-3) / 1e9 if kms == kms else None
+        k_flag, k_cluster, k_compact = (float(x) for x in np.mean(np.asarray(stage_ms, dtype=np.float64), axis=0))
+        cl = pr["clusters"]
+        n_cl, n_sites = int(len(cl)), int(len(pr["sites"]))
+        covered = int((cl["end"].astype(np.int64) - cl["start"].astype(np.int64) + 1).sum())
+        pile_bytes = batch.algorithmic_bytes(with_qual=False) + 8 * covered + 32 * n_cl
+        flag_bytes = 12 * batch.n_reads + 4 * n_cl            # meta + ref_start + cigar in, one opener index per cluster out
+        compact_bytes = 2 * 24 * n_sites + 2 * 16 * n_cl      # every site moved once, site range of every record rewritten
+
+        def frac(nbytes, kms):
+            return nbytes / (kms * 1e-3) / 1e9 / peak if kms == kms and kms > 0 else None
+
+        kernels = {
+            "profile_fast_kernel": (k_prof, alg_bytes),
+            "pl_flag_kernel": (k_flag, flag_bytes),
+            "pl_cluster_kernel": (k_cluster, pile_bytes),
+            "pl_compact_kernel": (k_compact, compact_bytes),
+        }
+        kname = max(kernels, key=lambda k: kernels[k][0] if kernels[k][0] == kernels[k][0] else -1.0)
+        kms, kbytes = kernels[kname]
+        achieved = kbytes / (kms * 1e-3) / 1e9 if kms == kms and kms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": name, "stages": ["profile", "pileup"], "reads_per_gpu": batch.n_reads,
-                       "stage_ms": {"profile_kernel": k_prof, "pileup_device": k_pile},
-                       "pileup": {"clusters": int(len(cl)), "sites": int(len(pile["res"]["sites"]))},
+                       "stage_ms": {"profile_kernel": k_prof, "pileup_device_incl_sync": k_pile, "pl_flag_kernel": k_flag,
+                                    "pl_cluster_kernel": k_cluster, "pl_compact_kernel": k_compact},
+                       "pileup": {"clusters": n_cl, "sites": n_sites, "covered_loci": covered},
                        "max_read_length": max_len, "l2": "inputs larger than L2 (%.0f MB per pass)" % (alg_bytes / 1e6),
-                       "parallelism": f"read-batch sharded x{world}"},
+                       "parallelism": f"profile: read-batch sharded x{world} + all-reduce of the count vector; "
+                                      f"pileup: region sharded x{world}, halo merge on the host"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
@@ -299,11 +316,7 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "kernel": kname, "kernel_ms": kms,
                          "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
-                         "per_stage": {
-                             "profile": {"ms": k_prof, "bytes": alg_bytes,
-                                         "frac": alg_bytes / (k_prof * 1e-3) / 1e9 / peak if k_prof == k_prof else None},
-                             "pileup": {"ms": k_pile, "bytes": pile_bytes,
-                                        "frac": pile_bytes / (k_pile * 1e-3) / 1e9 / peak if k_pile == k_pile else None}}},
+                         "per_kernel": {k: {"ms": v[0], "bytes": v[1], "frac": frac(v[1], v[0])} for k, v in kernels.items()}},
         }
         if not args.no_cpu_baseline:
             import oracle_lib
@@ -319,7 +332,7 @@ def main():
                                     "sample": f"first {sample} reads of the workload, error-profile loop, {cores} "
                                               "threads (C++ restatement of the Java loop; no JVM in this image)"}
             if sample == batch.n_reads and world == 1:
-                line["parity"] = bool(np.array_equal(acc, res["wide"]))
+                line["parity"] = bool(np.array_equal(acc, res["wide"]) and np.array_equal(acc, res_e2e["wide"]))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

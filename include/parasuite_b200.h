@@ -267,6 +267,8 @@ float ps_last_kernel_ms(const ps_ctx* ctx);
  * order (at most 512 are kept); returns how many were written.  reset(enabled=0) switches the event pairs off. */
 int ps_kernel_times(ps_ctx* ctx, float* ms, int max);
 void ps_kernel_times_reset(ps_ctx* ctx, int enabled);
+/* device times (ms) of the three kernels of the last pileup call: flag scan, cluster kernel, site compaction */
+int ps_pileup_stage_times(ps_ctx* ctx, float* ms3);
 
 #ifdef __cplusplus
 }

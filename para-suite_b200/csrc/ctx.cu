@@ -140,6 +140,9 @@ int ps_create(ps_ctx** out, int device) {
     cudaEventCreate(&ctx->ev_start[i]);
     cudaEventCreate(&ctx->ev_stop[i]);
   }
+  for (auto& e : ctx->pl_ev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&ctx->reset_ev, cudaEventDisableTiming);
+  if (cudaHostAlloc(&ctx->h_pinned, 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->h_pinned = nullptr; }
   {   // result buffers are stream-ordered allocations: keep freed blocks in the pool instead of returning them to the OS
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -160,6 +163,9 @@ void ps_destroy(ps_ctx* ctx) {
     cudaEventDestroy(ctx->ev_start[i]);
     cudaEventDestroy(ctx->ev_stop[i]);
   }
+  for (auto& e : ctx->pl_ev) cudaEventDestroy(e);
+  cudaEventDestroy(ctx->reset_ev);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release();
   for (auto& s : ctx->staged) {
@@ -231,7 +237,8 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
   PS_CUDA(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)ctx->layout.total * 8, ctx->stream));
   PS_CUDA(ctx, cudaMemsetAsync(ctx->fault.p, 0xFF, 8, ctx->stream));
   PS_CUDA(ctx, cudaMemsetAsync((char*)ctx->fault.p + 8, 0, 56, ctx->stream));
-  PS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // kernels of this run may be queued on a caller's stream: order them after the resets
+  PS_CUDA(ctx, cudaEventRecord(ctx->reset_ev, ctx->stream));
   ctx->reads_seen = 0;
   ctx->profile_open = true;
   return PS_OK;
@@ -244,6 +251,8 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
   if (st) return st;
   cudaSetDevice(ctx->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  if (s != ctx->stream) PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));
+  ctx->profile_stream = s;
   timer_begin(ctx, s);
   PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s));
   timer_end(ctx, s);
@@ -261,6 +270,7 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
   StagedBatch* sb = nullptr;
   st = stage_batch(ctx, hb, true, &sb);
   if (st) return st;
+  ctx->profile_stream = ctx->stream;
   timer_begin(ctx, ctx->stream);
   PS_CUDA(ctx, launch_profile(ctx, sb->view, ctx->reads_seen, ctx->stream));
   timer_end(ctx, ctx->stream);
@@ -296,12 +306,14 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (!ctx || !out) return PS_ERR_INVALID_ARG;
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
   cudaSetDevice(ctx->device);
-  PS_CUDA(ctx, cudaDeviceSynchronize());   // kernels may have run on caller streams
   const ProfileLayout& l = ctx->layout;
   std::vector<int64_t> acc(l.total);
   unsigned long long fw = 0;
-  PS_CUDA(ctx, cudaMemcpy(acc.data(), ctx->acc.p, (size_t)l.total * 8, cudaMemcpyDeviceToHost));
-  PS_CUDA(ctx, cudaMemcpy(&fw, ctx->fault.p, 8, cudaMemcpyDeviceToHost));
+  // the last batch's stream (the context's or the caller's); earlier batches on other streams are the caller's to order
+  cudaStream_t ps = ctx->profile_stream ? ctx->profile_stream : ctx->stream;
+  PS_CUDA(ctx, cudaMemcpyAsync(acc.data(), ctx->acc.p, (size_t)l.total * 8, cudaMemcpyDeviceToHost, ps));
+  PS_CUDA(ctx, cudaMemcpyAsync(&fw, ctx->fault.p, 8, cudaMemcpyDeviceToHost, ps));
+  PS_CUDA(ctx, cudaStreamSynchronize(ps));
   ctx->profile_open = false;
   out->fault.code = 0;
   out->fault.read_ordinal = 0;
@@ -354,6 +366,14 @@ int ps_kernel_times(ps_ctx* ctx, float* ms, int max) {
     cudaEventElapsedTime(&ms[i], ctx->ev_start[i], ctx->ev_stop[i]);
   }
   return n;
+}
+
+int ps_pileup_stage_times(ps_ctx* ctx, float* ms3) {
+  if (!ctx || !ms3) return PS_ERR_INVALID_ARG;
+  if (!ctx->pl_ev_valid) return PS_ERR_STATE;
+  cudaEventSynchronize(ctx->pl_ev[3]);
+  for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms3[i], ctx->pl_ev[i], ctx->pl_ev[i + 1]);
+  return PS_OK;
 }
 
 void ps_kernel_times_reset(ps_ctx* ctx, int enabled) {

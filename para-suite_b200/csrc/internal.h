@@ -102,6 +102,7 @@ struct ps_ctx {
   DevBuf fault;      // uint64 fault word + debug / deferred-count words (64 bytes)
   DevBuf deferred;   // uint32 read indices the fast profile kernel hands to the generic routine
   uint64_t reads_seen = 0;
+  cudaStream_t profile_stream = nullptr;   // stream of the last profile batch
   // streams / staging
   cudaStream_t stream = nullptr;
   StagedBatch staged[2];
@@ -114,6 +115,10 @@ struct ps_ctx {
   cudaEvent_t ev_stop[PS_TIMER_RING];
   uint32_t ev_count = 0;   // pairs recorded since reset
   bool timers_on = true;
+  cudaEvent_t pl_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the three pileup kernels of the last call
+  cudaEvent_t reset_ev = nullptr;   // accumulators of the current profile run have been cleared
+  bool pl_ev_valid = false;
+  void* h_pinned = nullptr;   // 4 KB of page-locked host memory for small read-backs
   // pileup scratch (pileup.cu): run state, look-back descriptors
   DevBuf pl_scratch[12];
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)

@@ -752,7 +752,10 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
         if ((uint32_t)rel >= 64u) bad = true; else bits |= 1ull << rel;
       }
       if (bad) S.ovf[k] = 1u;
-      if (bits) atomicOr(&S.umask[k], bits);
+      // two native 32-bit atomics (a 64-bit OR on shared memory is a compare-and-swap loop)
+      uint32_t* um32 = reinterpret_cast<uint32_t*>(&S.umask[k]);
+      if ((uint32_t)bits) atomicOr(um32, (uint32_t)bits);
+      if ((uint32_t)(bits >> 32)) atomicOr(um32 + 1, (uint32_t)(bits >> 32));
     }
     __syncthreads();
     // ---- B2 -----------------------------------------------------------------------------------------------------
@@ -1062,22 +1065,33 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
     P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = H->d_first; P.cap_cl = cap_cl;
     pl_init_state<<<1, 32, 0, st>>>(d_state);
+    const bool ev = ctx->timers_on;
+    if (ev) cudaEventRecord(ctx->pl_ev[0], st);
     if (vec) pl_flag_kernel<4><<<n_tiles, PL_THREADS, 0, st>>>(P);
     else pl_flag_kernel<1><<<n_tiles, PL_THREADS, 0, st>>>(P);
+    if (ev) cudaEventRecord(ctx->pl_ev[1], st);
     ClusterParams Q;
     Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
     Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = H->d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
     Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
     launch_cluster(nw, c_tiles, st, Q);
+    if (ev) cudaEventRecord(ctx->pl_ev[2], st);
     CompactParams R;
     R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
     R.cap_cl = cap_cl; R.cap_sites = cap_sites;
     pl_compact_kernel<<<(uint32_t)((cap_cl + PL_THREADS * 4 - 1) / (PL_THREADS * 4)), PL_THREADS, 0, st>>>(R);
+    if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
     cudaFreeAsync(d_tmp, st);
     ctx->launches += 4;
     PS_CUDA(ctx, cudaGetLastError());
-    PS_CUDA(ctx, cudaMemcpyAsync(&hs, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
+    PlState* hsp = ctx->h_pinned ? static_cast<PlState*>(ctx->h_pinned) : &hs;
+    PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
+    // head partial (slot 0) rides along; the open cluster's slot is only known once the state is here
+    ps_cluster* hhead = ctx->h_pinned ? reinterpret_cast<ps_cluster*>(static_cast<char*>(ctx->h_pinned) + 256) : &H->head;
+    PS_CUDA(ctx, cudaMemcpyAsync(hhead, H->d_cl, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));
+    hs = *hsp;
+    H->head = *hhead;
     const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
     if (need_cl <= cap_cl && need_sites <= cap_sites) break;
     if (attempt >= 2) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }
@@ -1098,9 +1112,12 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   const uint64_t n_slots = (uint64_t)hs.n_flags + 1;
   H->n_slots = n_slots;
   // summary: head partial (slot 0), open cluster (last slot)
-  PS_CUDA(ctx, cudaMemcpyAsync(&H->head, H->d_cl, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
-  if (hs.n_flags) PS_CUDA(ctx, cudaMemcpyAsync(&H->open, H->d_cl + hs.n_flags, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
-  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (hs.n_flags) {
+    ps_cluster* hopen = ctx->h_pinned ? reinterpret_cast<ps_cluster*>(static_cast<char*>(ctx->h_pinned) + 512) : &H->open;
+    PS_CUDA(ctx, cudaMemcpyAsync(hopen, H->d_cl + hs.n_flags, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
+    PS_CUDA(ctx, cudaStreamSynchronize(st));
+    H->open = *hopen;
+  }
   H->has_head = H->head.num_reads != 0;
   H->counters.has_open_cluster = hs.n_flags ? 1 : 0;
   H->counters.double_stranded = hs.dstr;

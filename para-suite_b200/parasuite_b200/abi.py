@@ -154,6 +154,7 @@ EXPORTS = {
     "ps_last_kernel_ms": (C.c_float, [VP]),
     "ps_kernel_times": (C.c_int, [VP, VP, C.c_int]),
     "ps_kernel_times_reset": (None, [VP, C.c_int]),
+    "ps_pileup_stage_times": (C.c_int, [VP, VP]),
 }
 
 LIB_NAME = "libparasuite_b200.so"

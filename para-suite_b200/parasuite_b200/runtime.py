@@ -88,6 +88,7 @@ class Context:
         self._max_len = 0
         self._infer_q = False
         self._keep = []
+        self._pinned_bufs = {}
 
     def close(self):
         if self.h:
@@ -176,8 +177,9 @@ class Context:
         return self.profile_end()
 
     # ---- T>C pileup (PileupClusters.java:137-500, 585-673) ----------------------------------------
-    def pileup(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> dict:
-        """batch: ReadBatch / PinnedBatch (host buffers, H2D inside) or DeviceBatch (resident).
+    def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> "PileupResult":
+        """Run the pileup kernels; the cluster and site records stay in HBM behind the returned handle.
+        batch: ReadBatch / PinnedBatch (host buffers, H2D inside) or DeviceBatch / UploadedBatch (resident).
         carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None."""
         opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
         if carry is not None:
@@ -189,48 +191,31 @@ class Context:
         else:
             s = batch.struct if hasattr(batch, "struct") else batch.as_struct()
             st = self.lib.ps_pileup_batch(self.h, C.byref(s), C.byref(opts), C.byref(h))
+        res = PileupResult(self, h, batch)
         try:
             if st == abi.PS_ERR_REFERENCE_WOULD_THROW and h:
                 f = abi.ps_fault()
                 self.lib.ps_pileup_fault(h, C.byref(f))
                 _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
             _check(self.lib, self.h, st)
-            ctr = abi.ps_pileup_counters()
-            self.lib.ps_pileup_counters_get(h, C.byref(ctr))
-            clusters = np.zeros(ctr.n_clusters, dtype=abi.CLUSTER_DTYPE)
-            sites = np.zeros(ctr.n_sites, dtype=abi.SITE_DTYPE)
-            got = self.lib.ps_pileup_next(h, 0, clusters.ctypes.data, ctr.n_clusters, sites.ctypes.data, ctr.n_sites)
-            if got != ctr.n_clusters:
-                raise abi.PsError(int(got), "ps_pileup_next returned fewer clusters than announced")
-            open_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
-            open_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
-            k = self.lib.ps_pileup_open_cluster(h, open_c.ctypes.data, open_s.ctypes.data, open_s.size)
-            if k < 0:
-                raise abi.PsError(k, "open cluster has too many sites")
-            head_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
-            head_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
-            kh = self.lib.ps_pileup_head_partial(h, head_c.ctypes.data, head_s.ctypes.data, head_s.size)
-            if kh < 0:
-                raise abi.PsError(kh, "head partial has too many sites")
-            cov = {}
-            for which, name in ((0, "head_cov"), (1, "open_cov")):
-                p0 = C.c_int32()
-                ln = self.lib.ps_pileup_boundary_coverage(h, which, C.byref(p0), None, 0)
-                a = np.zeros(max(int(ln), 0), dtype=np.uint32)
-                if ln > 0:
-                    self.lib.ps_pileup_boundary_coverage(h, which, C.byref(p0), a.ctypes.data, a.size)
-                cov[name] = (int(p0.value), a)
-            return {
-                "clusters": clusters, "sites": sites, **cov,
-                "open_cluster": open_c[0] if k > 0 else None,
-                "open_sites": open_s[:int(open_c[0]["site_end"])].copy() if k > 0 else open_s[:0],
-                "head_partial": head_c[0] if kh > 0 else None,
-                "head_sites": head_s[:int(head_c[0]["site_end"])].copy() if kh > 0 else head_s[:0],
-                "counters": {f: getattr(ctr, f) for f, _ in abi.ps_pileup_counters._fields_},
-            }
-        finally:
-            if h:
-                self.lib.ps_pileup_close(h)
+        except Exception:
+            res.close()
+            raise
+        return res
+
+    def pileup(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> dict:
+        """pileup_run + fetch of every record into host arrays."""
+        with self.pileup_run(batch, first_running_id, carry, stream) as res:
+            return res.fetch()
+
+    def _pinned(self, key: str, nbytes: int) -> np.ndarray:
+        """Reusable page-locked host buffer (grown on demand) viewed as uint8."""
+        import torch
+        t = self._pinned_bufs.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes + nbytes // 8, 4096), dtype=torch.uint8).pin_memory()
+            self._pinned_bufs[key] = t
+        return t.numpy()[:nbytes]
 
     # ---- instrumentation -------------------------------------------------------------------------
     def kernel_launches(self) -> int:
@@ -239,7 +224,88 @@ class Context:
     def kernel_times_reset(self, enabled: bool = True):
         self.lib.ps_kernel_times_reset(self.h, int(enabled))
 
+    def pileup_stage_ms(self) -> np.ndarray:
+        """Device times of the last pileup call's kernels: flag scan, cluster kernel, site compaction."""
+        buf = np.zeros(3, dtype=np.float32)
+        st = self.lib.ps_pileup_stage_times(self.h, buf.ctypes.data)
+        return buf if st == abi.PS_OK else np.full(3, np.nan, dtype=np.float32)
+
     def kernel_times_ms(self) -> np.ndarray:
         buf = np.zeros(512, dtype=np.float32)
         n = self.lib.ps_kernel_times(self.h, buf.ctypes.data, buf.size)
         return buf[:max(n, 0)].copy()
+
+
+class PileupResult:
+    """Handle of one pileup call: counters on the host, cluster / site records resident in HBM until fetched."""
+
+    def __init__(self, ctx: Context, h, batch):
+        self.ctx = ctx
+        self.h = h
+        self._batch = batch            # the records must outlive the halo-merge coverage query
+        self._counters = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ps_pileup_close(self.h)
+            self.h = None
+
+    @property
+    def counters(self) -> dict:
+        if self._counters is None:
+            ctr = abi.ps_pileup_counters()
+            self.ctx.lib.ps_pileup_counters_get(self.h, C.byref(ctr))
+            self._counters = {f: getattr(ctr, f) for f, _ in abi.ps_pileup_counters._fields_}
+        return self._counters
+
+    def fetch(self, pinned: bool = False, boundary: bool = True) -> dict:
+        """Copy the records to the host.  pinned=True: into page-locked buffers owned by the context and REUSED by the
+        next pinned fetch (what a streaming caller does); otherwise into fresh arrays."""
+        lib, ctx = self.ctx.lib, self.ctx
+        c = self.counters
+        nc, ns = c["n_clusters"], c["n_sites"]
+        csz, ssz = np.dtype(abi.CLUSTER_DTYPE).itemsize, np.dtype(abi.SITE_DTYPE).itemsize
+        if pinned:
+            clusters = ctx._pinned("clusters", nc * csz).view(abi.CLUSTER_DTYPE)
+            sites = ctx._pinned("sites", ns * ssz).view(abi.SITE_DTYPE)
+        else:
+            clusters = np.zeros(nc, dtype=abi.CLUSTER_DTYPE)
+            sites = np.zeros(ns, dtype=abi.SITE_DTYPE)
+        got = lib.ps_pileup_next(self.h, 0, clusters.ctypes.data, nc, sites.ctypes.data, ns)
+        if got != nc:
+            raise abi.PsError(int(got), "ps_pileup_next returned fewer clusters than announced")
+        out = {"clusters": clusters, "sites": sites, "counters": dict(c)}
+        if not boundary:
+            return out
+        open_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
+        open_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
+        k = lib.ps_pileup_open_cluster(self.h, open_c.ctypes.data, open_s.ctypes.data, open_s.size)
+        if k < 0:
+            raise abi.PsError(k, "open cluster has too many sites")
+        head_c = np.zeros(1, dtype=abi.CLUSTER_DTYPE)
+        head_s = np.zeros(1 << 16, dtype=abi.SITE_DTYPE)
+        kh = lib.ps_pileup_head_partial(self.h, head_c.ctypes.data, head_s.ctypes.data, head_s.size)
+        if kh < 0:
+            raise abi.PsError(kh, "head partial has too many sites")
+        for which, name in ((0, "head_cov"), (1, "open_cov")):
+            p0 = C.c_int32()
+            ln = lib.ps_pileup_boundary_coverage(self.h, which, C.byref(p0), None, 0)
+            if ln < 0:
+                raise abi.PsError(int(ln), lib.ps_last_error(ctx.h).decode())
+            a = np.zeros(max(int(ln), 0), dtype=np.uint32)
+            if ln > 0:
+                lib.ps_pileup_boundary_coverage(self.h, which, C.byref(p0), a.ctypes.data, a.size)
+            out[name] = (int(p0.value), a)
+        out.update({
+            "open_cluster": open_c[0] if k > 0 else None,
+            "open_sites": open_s[:int(open_c[0]["site_end"])].copy() if k > 0 else open_s[:0],
+            "head_partial": head_c[0] if kh > 0 else None,
+            "head_sites": head_s[:int(head_c[0]["site_end"])].copy() if kh > 0 else head_s[:0],
+        })
+        return out
