@@ -1,0 +1,156 @@
+/*
+ * parasuite_jni.c -- thin JNI shim over libparasuite_b200.so (no logic of its own).
+ *
+ * Binds the two native classes a maintainer adds to PARA-suite (INTEGRATION.md shows the Java side):
+ *
+ *   utils.errorprofile.NativeErrorProfile   replaces the loop ErrorProfiling.java:146-409
+ *   utils.pileupclusters.NativePileup       replaces the loop PileupClusters.java:137-500 (+ :585-673)
+ *
+ * Build (needs a JDK; none exists in the build image of this repo, so it is compiled only when jni.h is found):
+ *   cc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
+ *      jni/parasuite_jni.c -Lpara-suite_b200/lib -lparasuite_b200 -o libparasuite_jni.so
+ *
+ * Error convention: every non-zero status becomes a java.lang.RuntimeException carrying ps_last_error();
+ * PS_ERR_UNSORTED keeps the reference's message (ErrorProfiling.java:128-131) so the Java caller can log it and exit.
+ */
+#include <jni.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "parasuite_b200.h"
+
+static void throw_status(JNIEnv* env, ps_ctx* ctx, int status) {
+  jclass cls = (*env)->FindClass(env, "java/lang/RuntimeException");
+  const char* msg = ctx ? ps_last_error(ctx) : ps_strerror(status);
+  if (!msg || !*msg) msg = ps_strerror(status);
+  if (cls) (*env)->ThrowNew(env, cls, msg);
+}
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+
+/* static native long create(int device); */
+JNIEXPORT jlong JNICALL Java_utils_errorprofile_NativeErrorProfile_create(JNIEnv* env, jclass c, jint device) {
+  (void)c;
+  ps_ctx* ctx = NULL;
+  int st = ps_create(&ctx, (int)device);
+  if (st != PS_OK) { throw_status(env, NULL, st); return 0; }
+  return (jlong)(intptr_t)ctx;
+}
+
+/* static native void destroy(long ctx); */
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_destroy(JNIEnv* env, jclass c, jlong ctx) {
+  (void)env; (void)c;
+  ps_destroy((ps_ctx*)(intptr_t)ctx);
+}
+
+/* static native void loadReference(long ctx, String fasta);   -- new IndexedFastaSequenceFile(fasta), :109-110 */
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_loadReference(JNIEnv* env, jclass c, jlong h, jstring fasta) {
+  (void)c;
+  ps_ctx* ctx = (ps_ctx*)(intptr_t)h;
+  const char* path = (*env)->GetStringUTFChars(env, fasta, NULL);
+  if (!path) return;
+  int st = ps_reference_load_fasta(ctx, path);
+  (*env)->ReleaseStringUTFChars(env, fasta, path);
+  if (st != PS_OK) throw_status(env, ctx, st);
+}
+
+/* ---- error profile --------------------------------------------------------------------------------------
+ * static native void profileBam(long ctx, String bam, int maxReadLength, boolean inferQualities,
+ *     int[] positionConversions (maxLen*16, [i][ref][read]), int[] qualityPerMismatch (16),
+ *     int[] qualityPerMismatchCounts (16), double[] insertionsPerPos (maxLen), double[] deletionsPerPos (maxLen),
+ *     long[] qualityHist (maxLen*256 or null), int[] counters (8: numReadsProcessed, unmapped, duplicates,
+ *     startZero, indelRead, skippedReads, longerIndels, totalBasesChecked));
+ * The arrays are the Java fields themselves (ErrorProfiling.java:41-55); the loop's post-processing (:410-621)
+ * runs unchanged on them. */
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
+    JNIEnv* env, jclass c, jlong h, jstring bam, jint maxReadLength, jboolean inferQualities, jintArray positionConversions,
+    jintArray qualityPerMismatch, jintArray qualityPerMismatchCounts, jdoubleArray insertionsPerPos,
+    jdoubleArray deletionsPerPos, jlongArray qualityHist, jintArray counters) {
+  (void)c;
+  ps_ctx* ctx = (ps_ctx*)(intptr_t)h;
+  const char* path = (*env)->GetStringUTFChars(env, bam, NULL);
+  if (!path) return;
+  ps_profile_opts opts;
+  opts.max_read_length = (uint32_t)maxReadLength;
+  opts.infer_qualities = inferQualities ? 1u : 0u;
+  ps_profile_result r;
+  memset(&r, 0, sizeof r);
+  /* plain Get/Release (not Critical): the call runs for a while and must not block the collector */
+  r.position_conversions = (int32_t*)(*env)->GetIntArrayElements(env, positionConversions, NULL);
+  r.quality_per_mismatch = (int32_t*)(*env)->GetIntArrayElements(env, qualityPerMismatch, NULL);
+  r.quality_per_mismatch_counts = (int32_t*)(*env)->GetIntArrayElements(env, qualityPerMismatchCounts, NULL);
+  r.insertions_per_pos = (double*)(*env)->GetDoubleArrayElements(env, insertionsPerPos, NULL);
+  r.deletions_per_pos = (double*)(*env)->GetDoubleArrayElements(env, deletionsPerPos, NULL);
+  r.counters = (int32_t*)(*env)->GetIntArrayElements(env, counters, NULL);
+  r.quality_hist = qualityHist ? (int64_t*)(*env)->GetLongArrayElements(env, qualityHist, NULL) : NULL;
+  int st = ps_profile_bam(ctx, path, &opts, &r);
+  (*env)->ReleaseIntArrayElements(env, positionConversions, (jint*)r.position_conversions, 0);
+  (*env)->ReleaseIntArrayElements(env, qualityPerMismatch, (jint*)r.quality_per_mismatch, 0);
+  (*env)->ReleaseIntArrayElements(env, qualityPerMismatchCounts, (jint*)r.quality_per_mismatch_counts, 0);
+  (*env)->ReleaseDoubleArrayElements(env, insertionsPerPos, (jdouble*)r.insertions_per_pos, 0);
+  (*env)->ReleaseDoubleArrayElements(env, deletionsPerPos, (jdouble*)r.deletions_per_pos, 0);
+  (*env)->ReleaseIntArrayElements(env, counters, (jint*)r.counters, 0);
+  if (qualityHist) (*env)->ReleaseLongArrayElements(env, qualityHist, (jlong*)r.quality_hist, 0);
+  (*env)->ReleaseStringUTFChars(env, bam, path);
+  if (st != PS_OK) throw_status(env, ctx, st);
+}
+
+/* ---- T>C pileup ------------------------------------------------------------------------------------------
+ * static native long pileupBam(long ctx, String bam);        -> handle
+ * static native long[] counters(long handle);                -> numReadsProcessed, skippedDueIndel, doubleStranded,
+ *                                                               nClusters, nSites, hasOpenCluster
+ * static native int nextClusters(long handle, long first, long[] cluster64 (8 per cluster), int maxClusters,
+ *                                long[] site64 (3 per site), int maxSites);   -> clusters copied
+ * static native void close(long handle);
+ * Cluster and site records cross as their raw 64-bit words (ps_cluster = 8 words, ps_site = 3 words); the Java
+ * side unpacks them with shifts. */
+JNIEXPORT jlong JNICALL Java_utils_pileupclusters_NativePileup_pileupBam(JNIEnv* env, jclass c, jlong h, jstring bam) {
+  (void)c;
+  ps_ctx* ctx = (ps_ctx*)(intptr_t)h;
+  const char* path = (*env)->GetStringUTFChars(env, bam, NULL);
+  if (!path) return 0;
+  ps_pileup_opts opts;
+  memset(&opts, 0, sizeof opts);
+  opts.first_running_id = 1; /* runningID = 1 (PileupClusters.java:133) */
+  ps_pileup* out = NULL;
+  int st = ps_pileup_bam(ctx, path, &opts, &out);
+  (*env)->ReleaseStringUTFChars(env, bam, path);
+  if (st != PS_OK) {
+    if (out) ps_pileup_close(out);
+    throw_status(env, ctx, st);
+    return 0;
+  }
+  return (jlong)(intptr_t)out;
+}
+
+JNIEXPORT jlongArray JNICALL Java_utils_pileupclusters_NativePileup_counters(JNIEnv* env, jclass c, jlong handle) {
+  (void)c;
+  ps_pileup_counters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  ps_pileup_counters_get((ps_pileup*)(intptr_t)handle, &ctr);
+  jlong v[6] = {(jlong)ctr.num_reads_processed, (jlong)ctr.skipped_due_indel, (jlong)ctr.double_stranded,
+                (jlong)ctr.n_clusters, (jlong)ctr.n_sites, (jlong)ctr.has_open_cluster};
+  jlongArray a = (*env)->NewLongArray(env, 6);
+  if (a) (*env)->SetLongArrayRegion(env, a, 0, 6, v);
+  return a;
+}
+
+JNIEXPORT jint JNICALL Java_utils_pileupclusters_NativePileup_nextClusters(JNIEnv* env, jclass c, jlong handle, jlong first,
+                                                                             jlongArray cluster64, jint maxClusters,
+                                                                             jlongArray site64, jint maxSites) {
+  (void)c;
+  jlong* cl = (*env)->GetLongArrayElements(env, cluster64, NULL);
+  jlong* si = (*env)->GetLongArrayElements(env, site64, NULL);
+  int64_t n = ps_pileup_next((ps_pileup*)(intptr_t)handle, (uint64_t)first, (ps_cluster*)cl, (uint64_t)maxClusters,
+                             (ps_site*)si, (uint64_t)maxSites);
+  (*env)->ReleaseLongArrayElements(env, cluster64, cl, 0);
+  (*env)->ReleaseLongArrayElements(env, site64, si, 0);
+  if (n < 0) { throw_status(env, NULL, (int)n); return 0; }
+  return (jint)n;
+}
+
+JNIEXPORT void JNICALL Java_utils_pileupclusters_NativePileup_close(JNIEnv* env, jclass c, jlong handle) {
+  (void)env; (void)c;
+  ps_pileup_close((ps_pileup*)(intptr_t)handle);
+}
