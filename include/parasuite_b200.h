@@ -258,6 +258,26 @@ int ps_pileup_fault(const ps_pileup* h, ps_fault* out);
 void ps_pileup_close(ps_pileup* h);
 int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);
 
+/* ---- host batcher (usable without a GPU) --------------------------------------------------------
+ * What htsjdk does for the two loops, as a library: FASTA(+.fai) -> packed reference; BGZF/BAM -> SoA batches in
+ * page-locked host memory (pageable when no CUDA device is present), records in file order, presented exactly as
+ * SAMRecord presents them to ErrorProfiling.java:146-409 / PileupClusters.java:137-500. */
+typedef struct ps_packed_fasta ps_packed_fasta;
+typedef struct ps_bam ps_bam;
+/* *out is set even on failure (read ps_fasta_error / ps_bam_error, then free / close it) */
+int ps_fasta_pack(const char* fasta_path, ps_packed_fasta** out);           /* needs <fasta>.fai */
+const ps_reference* ps_fasta_reference(const ps_packed_fasta* f);            /* host arrays owned by f */
+const char* ps_fasta_contig_name(const ps_packed_fasta* f, uint32_t i);
+const char* ps_fasta_error(const ps_packed_fasta* f);
+void ps_fasta_free(ps_packed_fasta* f);
+/* Opens a coordinate-sorted BAM (PS_ERR_UNSORTED otherwise: ErrorProfiling.java:124-132).  Contigs are matched to the
+ * FASTA by name; max_batch_reads = 0 picks a default; threads <= 0 uses the host cores. */
+int ps_bam_open(ps_bam** out, const char* bam_path, const ps_packed_fasta* ref, uint64_t max_batch_reads, int threads);
+/* 1: *batch filled (host pointers, valid until the second-next call); 0: end of file; < 0: status */
+int ps_bam_next(ps_bam* b, ps_read_batch* batch);
+const char* ps_bam_error(const ps_bam* b);
+void ps_bam_close(ps_bam* b);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 uint64_t ps_kernel_launches(const ps_ctx* ctx);

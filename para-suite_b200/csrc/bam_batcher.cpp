@@ -1,0 +1,627 @@
+// Host batcher: FASTA(+.fai) -> packed reference, BGZF/BAM -> SoA read batches in page-locked memory.
+//
+// Stands in for what htsjdk does for the two Java loops (reference: /root/reference/src/src/utils/errorprofile/
+// ErrorProfiling.java:104-110 opens the BAM with SamReaderFactory and the FASTA with IndexedFastaSequenceFile; the
+// loops then see SAMRecord objects in file order).  The record view presented to the kernels is the one SURVEY.md 8(b)
+// lists: POS+1 (0 when POS = -1), flags 0x4 / 0x10 / 0x400, cigar ops 0..8 = MIDNSHP=X, bases from 4-bit nibbles via
+// "=ACMGRSVTWYHKDBN" (only A, C, G, T are countable), raw phred bytes (first byte 0xFF = missing), header sort order.
+//
+// BGZF blocks are independent deflate streams: the block table is scanned once (sequential, 18 bytes per block), the
+// blocks of a window are inflated by a pool of threads straight into their place of one contiguous buffer, records are
+// located with a cheap sequential hop over block_size fields, and the SoA arrays are filled by the same pool
+// (thread ranges are multiples of the 256-read tile so the per-tile offset tables fall out of one prefix sum).
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "internal.h"
+
+namespace {
+
+struct MappedFile {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  int fd = -1;
+  bool open(const char* path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); fd = -1; return false; }
+    n = (size_t)st.st_size;
+    if (n == 0) { p = nullptr; return true; }
+    void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { ::close(fd); fd = -1; return false; }
+    p = static_cast<const uint8_t*>(m);
+    return true;
+  }
+  ~MappedFile() {
+    if (p) munmap(const_cast<uint8_t*>(p), n);
+    if (fd >= 0) ::close(fd);
+  }
+};
+
+template <typename F>
+void parallel_for(int threads, uint64_t n, F f) {   // f(thread, lo, hi) over [0, n) in contiguous ranges
+  if (threads < 1) threads = 1;
+  if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+  if (threads == 1) { f(0, (uint64_t)0, n); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) {
+    const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+    pool.emplace_back([=] { f(t, lo, hi); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// FASTA
+// ---------------------------------------------------------------------------------------------------------
+struct ps_packed_fasta {
+  std::vector<std::string> names;
+  std::vector<uint64_t> off;          // [n+1]
+  std::vector<uint32_t> seq2, inv;
+  std::vector<const char*> name_ptrs;
+  ps_reference view{};
+  std::string err;
+};
+
+static int fasta_pack(const char* path, ps_packed_fasta* F, int threads) {
+  struct Fai { std::string name; uint64_t len, offset, linebases, linewidth; };
+  std::vector<Fai> fai;
+  {
+    const std::string fp = std::string(path) + ".fai";
+    FILE* f = fopen(fp.c_str(), "r");
+    if (!f) { F->err = "cannot open " + fp + " (the FASTA index is required, as for htsjdk's IndexedFastaSequenceFile)"; return PS_ERR_IO; }
+    char line[4096];
+    while (fgets(line, sizeof line, f)) {
+      char name[2048];
+      unsigned long long a, b, c, d;
+      if (sscanf(line, "%2047[^\t]\t%llu\t%llu\t%llu\t%llu", name, &a, &b, &c, &d) != 5) continue;
+      if (c == 0 || d < c) { fclose(f); F->err = "malformed .fai line"; return PS_ERR_FORMAT; }
+      fai.push_back({name, a, b, c, d});
+    }
+    fclose(f);
+  }
+  if (fai.empty()) { F->err = "empty FASTA index"; return PS_ERR_FORMAT; }
+  MappedFile mf;
+  if (!mf.open(path)) { F->err = std::string("cannot open ") + path; return PS_ERR_IO; }
+  F->off.assign(1, 0);
+  for (auto& e : fai) { F->names.push_back(e.name); F->off.push_back(F->off.back() + e.len); }
+  const uint64_t n = F->off.back();
+  if (n >= (1ull << 32)) { F->err = "reference >= 2^32 bases"; return PS_ERR_UNSUPPORTED; }
+  for (size_t c = 0; c < fai.size(); ++c) {
+    const Fai& e = fai[c];
+    const uint64_t bytes = e.len ? (e.len - 1) / e.linebases * e.linewidth + (e.len - 1) % e.linebases + 1 : 0;
+    if (e.offset + bytes > mf.n) { F->err = "FASTA shorter than its index says (" + e.name + ")"; return PS_ERR_FORMAT; }
+  }
+  F->seq2.assign((n + 15) / 16 + 8, 0);
+  F->inv.assign((n + 31) / 32 + 8, 0);
+  uint8_t code[256];
+  memset(code, 4, sizeof code);
+  code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2; code['T'] = code['t'] = 3;
+  // chunks of 2^20 bases aligned to 32: threads never share a word
+  const uint64_t chunk = 1u << 20, n_chunks = (n + chunk - 1) / chunk;
+  uint32_t* seq2 = F->seq2.data();
+  uint32_t* inv = F->inv.data();
+  const std::vector<uint64_t>& off = F->off;
+  parallel_for(threads, n_chunks, [&](int, uint64_t lo, uint64_t hi) {
+    for (uint64_t ch = lo; ch < hi; ++ch) {
+      uint64_t g = ch * chunk;
+      const uint64_t gend = std::min(n, g + chunk);
+      size_t c = std::upper_bound(off.begin(), off.end(), g) - off.begin() - 1;
+      while (g < gend) {
+        while (off[c + 1] <= g) ++c;
+        const Fai& e = fai[c];
+        const uint64_t in = g - off[c];                                   // position inside the contig
+        const uint64_t stop = std::min(gend, off[c + 1]);
+        uint64_t line = in / e.linebases, col = in % e.linebases;
+        const uint8_t* src = mf.p + e.offset + line * e.linewidth + col;
+        while (g < stop) {
+          const uint64_t take = std::min<uint64_t>(e.linebases - col, stop - g);
+          for (uint64_t k = 0; k < take; ++k, ++g) {
+            const uint8_t cd = code[src[k]];
+            if (cd == 4) inv[g >> 5] |= 1u << (g & 31);
+            else seq2[g >> 4] |= (uint32_t)cd << (2 * (g & 15));
+          }
+          src += take + (e.linewidth - e.linebases);
+          if (col + take < e.linebases) src -= (e.linewidth - e.linebases);   // stopped inside a line
+          col = 0;
+        }
+      }
+    }
+  });
+  for (auto& s : F->names) F->name_ptrs.push_back(s.c_str());
+  F->view.n_bases = n;
+  F->view.seq2 = F->seq2.data();
+  F->view.inv = F->inv.data();
+  F->view.n_contigs = (uint32_t)F->names.size();
+  F->view.contig_off = F->off.data();
+  return PS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BAM
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Slab {            // one SoA batch in a single (page-locked when possible) allocation
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  void release() {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+    p = nullptr; cap = 0;
+  }
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    release();
+    const size_t want = n + n / 8 + 4096;
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocDefault) == cudaSuccess) { p = (uint8_t*)q; pinned = true; }
+    else { cudaGetLastError(); p = (uint8_t*)malloc(want); pinned = false; }
+    if (!p) return false;
+    cap = want;
+    return true;
+  }
+};
+
+struct Block { uint64_t coff; uint32_t clen, isize; };
+
+}  // namespace
+
+struct ps_bam {
+  MappedFile mf;
+  std::vector<Block> blocks;
+  size_t next_block = 0;
+  std::vector<uint8_t> buf;        // inflated bytes not yet consumed
+  size_t head = 0;
+  bool header_done = false;
+  bool sorted = false;
+  std::vector<std::string> ref_names;
+  std::vector<int64_t> ref_to_contig;   // BAM refID -> FASTA contig (-1: absent from the FASTA)
+  const ps_packed_fasta* fa = nullptr;
+  uint64_t max_batch = 0;
+  int threads = 1;
+  Slab slab[2];
+  int cur = 0;
+  uint64_t ordinal = 0;
+  std::string err;
+  std::vector<uint64_t> rec_off;   // scratch: offsets of the records of the batch being built
+};
+
+static int bam_fail(ps_bam* B, int st, const std::string& m) { B->err = m; return st; }
+
+static int bam_scan_blocks(ps_bam* B) {
+  const uint8_t* p = B->mf.p;
+  const size_t n = B->mf.n;
+  size_t o = 0;
+  while (o < n) {
+    if (o + 18 > n || p[o] != 0x1f || p[o + 1] != 0x8b || p[o + 2] != 8 || !(p[o + 3] & 4))
+      return bam_fail(B, PS_ERR_FORMAT, "not a BGZF file (bad block header)");
+    const uint32_t xlen = rd16(p + o + 10);
+    uint32_t bsize = 0;
+    size_t x = o + 12;
+    const size_t xend = x + xlen;
+    if (xend > n) return bam_fail(B, PS_ERR_FORMAT, "truncated BGZF block");
+    while (x + 4 <= xend) {
+      const uint32_t slen = rd16(p + x + 2);
+      if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2) bsize = (uint32_t)rd16(p + x + 4) + 1;
+      x += 4 + slen;
+    }
+    if (bsize < xlen + 20 || o + bsize > n) return bam_fail(B, PS_ERR_FORMAT, "truncated BGZF block");
+    const uint32_t isize = rd32(p + o + bsize - 4);
+    if (isize) B->blocks.push_back({o + 12 + xlen, bsize - xlen - 20, isize});
+    o += bsize;
+  }
+  return PS_OK;
+}
+
+// inflate blocks until at least `want` unconsumed bytes are buffered (or the file ends)
+static int bam_fill(ps_bam* B, size_t want) {
+  while (B->buf.size() - B->head < want && B->next_block < B->blocks.size()) {
+    // a window of blocks: enough for `want`, at least 64 MB when a big batch is being assembled
+    size_t b1 = B->next_block, total = 0;
+    const size_t target = std::max<size_t>(want - (B->buf.size() - B->head), (size_t)16 << 20);
+    std::vector<size_t> at;
+    while (b1 < B->blocks.size() && total < target) { at.push_back(total); total += B->blocks[b1].isize; ++b1; }
+    const size_t base = B->buf.size();
+    B->buf.resize(base + total);
+    std::atomic<int> bad{0};
+    const size_t b0 = B->next_block;
+    parallel_for(B->threads, b1 - b0, [&](int, uint64_t lo, uint64_t hi) {
+      z_stream zs;
+      memset(&zs, 0, sizeof zs);
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+      for (uint64_t k = lo; k < hi; ++k) {
+        const Block& bl = B->blocks[b0 + k];
+        inflateReset(&zs);
+        zs.next_in = const_cast<Bytef*>(B->mf.p + bl.coff);
+        zs.avail_in = bl.clen;
+        zs.next_out = B->buf.data() + base + at[k];
+        zs.avail_out = bl.isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+      }
+      inflateEnd(&zs);
+    });
+    if (bad) return bam_fail(B, PS_ERR_FORMAT, "corrupt BGZF block (inflate failed)");
+    B->next_block = b1;
+  }
+  return PS_OK;
+}
+
+static int bam_header(ps_bam* B) {
+  int st = bam_fill(B, 12);
+  if (st) return st;
+  auto avail = [&] { return B->buf.size() - B->head; };
+  if (avail() < 12 || memcmp(B->buf.data() + B->head, "BAM\1", 4) != 0) return bam_fail(B, PS_ERR_FORMAT, "not a BAM file");
+  const uint32_t l_text = rd32(B->buf.data() + B->head + 4);
+  st = bam_fill(B, 12 + (size_t)l_text);
+  if (st) return st;
+  if (avail() < 12 + (size_t)l_text) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM header");
+  const std::string text((const char*)B->buf.data() + B->head + 8, l_text);
+  // @HD ... SO:coordinate  (SAMFileHeader.getSortOrder; ErrorProfiling.java:124-132)
+  {
+    size_t hd = text.rfind("@HD", 0) == 0 ? 0 : text.find("\n@HD");
+    if (hd != std::string::npos) {
+      const size_t eol = text.find('\n', hd + 1);
+      const std::string line = text.substr(hd, eol == std::string::npos ? std::string::npos : eol - hd);
+      B->sorted = line.find("\tSO:coordinate") != std::string::npos;
+    }
+  }
+  size_t o = B->head + 8 + l_text;
+  const uint32_t n_ref = rd32(B->buf.data() + o);
+  o += 4;
+  for (uint32_t r = 0; r < n_ref; ++r) {
+    st = bam_fill(B, o - B->head + 4);
+    if (st) return st;
+    if (B->buf.size() < o + 4) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM header");
+    const uint32_t l_name = rd32(B->buf.data() + o);
+    st = bam_fill(B, o - B->head + 8 + (size_t)l_name);
+    if (st) return st;
+    if (B->buf.size() < o + 8 + (size_t)l_name) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM header");
+    std::string name((const char*)B->buf.data() + o + 4, l_name ? l_name - 1 : 0);
+    B->ref_names.push_back(name);
+    o += 8 + (size_t)l_name;
+  }
+  B->head = o;
+  std::unordered_map<std::string, int64_t> idx;
+  for (size_t c = 0; c < B->fa->names.size(); ++c) idx.emplace(B->fa->names[c], (int64_t)c);
+  int64_t last = -1;
+  for (auto& nm : B->ref_names) {
+    auto it = idx.find(nm);
+    const int64_t c = it == idx.end() ? -1 : it->second;
+    B->ref_to_contig.push_back(c);
+    if (c >= 0) {
+      if (c < last)
+        return bam_fail(B, PS_ERR_UNSUPPORTED, "the BAM header lists contigs in a different order than the FASTA index: "
+                                               "coordinate order of the reads would not follow the packed reference");
+      last = c;
+    }
+  }
+  B->header_done = true;
+  return PS_OK;
+}
+
+extern "C" {
+
+int ps_fasta_pack(const char* fasta_path, ps_packed_fasta** out) {
+  if (!fasta_path || !out) return PS_ERR_INVALID_ARG;
+  ps_packed_fasta* F = new ps_packed_fasta();
+  *out = F;      // returned even on failure so the caller can read ps_fasta_error
+  unsigned hc = std::thread::hardware_concurrency();
+  return fasta_pack(fasta_path, F, hc ? (int)std::min(hc, 32u) : 4);
+}
+const ps_reference* ps_fasta_reference(const ps_packed_fasta* f) { return f ? &f->view : nullptr; }
+const char* ps_fasta_contig_name(const ps_packed_fasta* f, uint32_t i) {
+  return f && i < f->names.size() ? f->names[i].c_str() : nullptr;
+}
+const char* ps_fasta_error(const ps_packed_fasta* f) { return f ? f->err.c_str() : "no object"; }
+void ps_fasta_free(ps_packed_fasta* f) { delete f; }
+
+int ps_bam_open(ps_bam** out, const char* bam_path, const ps_packed_fasta* ref, uint64_t max_batch_reads, int threads) {
+  if (!out || !bam_path || !ref) return PS_ERR_INVALID_ARG;
+  ps_bam* B = new ps_bam();
+  *out = B;      // returned even on failure so the caller can read ps_bam_error
+  B->fa = ref;
+  B->max_batch = max_batch_reads ? max_batch_reads : (1ull << 22);
+  if (B->max_batch >= 0xFFFFFF00ull) B->max_batch = 0xFFFFFF00ull;
+  if (threads <= 0) {
+    unsigned hc = std::thread::hardware_concurrency();
+    threads = hc ? (int)std::min(hc, 32u) : 4;
+  }
+  B->threads = threads;
+  if (!B->mf.open(bam_path)) return bam_fail(B, PS_ERR_IO, std::string("cannot open ") + bam_path);
+  int st = bam_scan_blocks(B);
+  if (st) return st;
+  st = bam_header(B);
+  if (st) return st;
+  // SamReader header check of both tools (ErrorProfiling.java:124-132, PileupClusters.java:85-92)
+  if (!B->sorted) return bam_fail(B, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED));
+  return PS_OK;
+}
+
+const char* ps_bam_error(const ps_bam* b) { return b ? b->err.c_str() : "no object"; }
+
+void ps_bam_close(ps_bam* b) {
+  if (!b) return;
+  b->slab[0].release();
+  b->slab[1].release();
+  delete b;
+}
+
+// Next batch of at most max_batch_reads records, in file order.  Returns 1 (batch filled; its arrays stay valid until
+// the second-next call), 0 at end of file, or a negative status.
+int ps_bam_next(ps_bam* B, ps_read_batch* out) {
+  if (!B || !out) return PS_ERR_INVALID_ARG;
+  if (!B->header_done) return bam_fail(B, PS_ERR_STATE, "BAM not open");
+  // drop consumed bytes (offsets below are relative to the new start)
+  if (B->head) {
+    B->buf.erase(B->buf.begin(), B->buf.begin() + (ptrdiff_t)B->head);
+    B->head = 0;
+  }
+  // ---- locate records -------------------------------------------------------------------------------------
+  std::vector<uint64_t>& ro = B->rec_off;
+  ro.clear();
+  size_t o = 0;
+  while (ro.size() < B->max_batch) {
+    if (B->buf.size() - o < 4) {
+      int st = bam_fill(B, o + 4);
+      if (st) return st;
+      if (B->buf.size() - o < 4) {
+        if (B->buf.size() != o) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM record");
+        break;
+      }
+    }
+    const uint32_t bs = rd32(B->buf.data() + o);
+    if (bs < 32) return bam_fail(B, PS_ERR_FORMAT, "malformed BAM record (block_size < 32)");
+    if (B->buf.size() - o < 4 + (size_t)bs) {
+      int st = bam_fill(B, o + 4 + (size_t)bs);
+      if (st) return st;
+      if (B->buf.size() - o < 4 + (size_t)bs) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM record");
+    }
+    ro.push_back(o);
+    o += 4 + (size_t)bs;
+  }
+  B->head = o;
+  const uint64_t n = ro.size();
+  memset(out, 0, sizeof *out);
+  if (n == 0) return 0;
+  const uint8_t* buf = B->buf.data();
+  const uint64_t n_tiles = (n + PS_TILE_READS - 1) / PS_TILE_READS;
+
+  // ---- pass 1: sizes, per tile ----------------------------------------------------------------------------
+  std::vector<uint64_t> tb(n_tiles + 1, 0), tq(n_tiles + 1, 0), tc(n_tiles + 1, 0);
+  std::vector<uint32_t> te(n_tiles + 1, 0);
+  std::atomic<int> bad{0};
+  std::atomic<uint32_t> lens_min{0xFFFFFFFFu}, lens_max{0}, nc_min{0xFFFFFFFFu}, nc_max{0};
+  auto amin = [](std::atomic<uint32_t>& a, uint32_t v) { uint32_t c = a.load(); while (v < c && !a.compare_exchange_weak(c, v)) {} };
+  auto amax = [](std::atomic<uint32_t>& a, uint32_t v) { uint32_t c = a.load(); while (v > c && !a.compare_exchange_weak(c, v)) {} };
+  parallel_for(B->threads, n_tiles, [&](int, uint64_t lo, uint64_t hi) {
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0, cmin = 0xFFFFFFFFu, cmax = 0;
+    for (uint64_t t = lo; t < hi; ++t) {
+      uint64_t sb = 0, sq = 0, sc = 0;
+      uint32_t se = 0;
+      const uint64_t r1 = std::min(n, (t + 1) * PS_TILE_READS);
+      for (uint64_t r = t * PS_TILE_READS; r < r1; ++r) {
+        const uint8_t* p = buf + ro[r] + 4;
+        const uint32_t bs = rd32(p - 4);
+        const uint32_t l_name = p[8], n_cig = rd16(p + 12), l_seq = rd32(p + 16);
+        if (32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > bs || l_seq > 0xFFFFu) { bad = 1; return; }
+        const uint32_t nc = n_cig > 255 ? 0 : n_cig;
+        sb += (l_seq + 3) / 4; sq += l_seq; sc += nc;
+        const uint8_t* sq4 = p + 32 + l_name + 4ull * n_cig;
+        for (uint32_t k = 0; k < l_seq; ++k) {
+          const uint32_t nib = (sq4[k >> 1] >> ((~k & 1) * 4)) & 15u;
+          se += !(nib == 1 || nib == 2 || nib == 4 || nib == 8);
+        }
+        lmin = std::min(lmin, l_seq); lmax = std::max(lmax, l_seq); cmin = std::min(cmin, nc); cmax = std::max(cmax, nc);
+      }
+      tb[t + 1] = sb; tq[t + 1] = sq; tc[t + 1] = sc; te[t + 1] = se;
+    }
+    amin(lens_min, lmin); amax(lens_max, lmax); amin(nc_min, cmin); amax(nc_max, cmax);
+  });
+  if (bad) return bam_fail(B, PS_ERR_FORMAT, "malformed BAM record (lengths exceed block_size, or read longer than 65535)");
+  for (uint64_t t = 0; t < n_tiles; ++t) { tb[t + 1] += tb[t]; tq[t + 1] += tq[t]; tc[t + 1] += tc[t]; te[t + 1] += te[t]; }
+  const uint64_t bases_bytes = tb[n_tiles], qual_bytes = tq[n_tiles], cigar_count = tc[n_tiles], exc_count = te[n_tiles];
+
+  // ---- slab layout ----------------------------------------------------------------------------------------------
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off_meta = 0, off_start = up(off_meta + n * 4), off_bases = up(off_start + n * 4);
+  size_t off_qual = up(off_bases + bases_bytes + 64), off_cigar = up(off_qual + qual_bytes + 64);
+  size_t off_exc = up(off_cigar + (cigar_count + 16) * 4), off_tb = up(off_exc + (exc_count + 16) * 4);
+  size_t off_tq = up(off_tb + (n_tiles + 1) * 8), off_tc = up(off_tq + (n_tiles + 1) * 8), off_te = up(off_tc + (n_tiles + 1) * 8);
+  const size_t total = up(off_te + (n_tiles + 1) * 4);
+  Slab& S = B->slab[B->cur];
+  B->cur ^= 1;
+  if (!S.reserve(total)) return bam_fail(B, PS_ERR_OOM, "out of host memory for the batch");
+  uint32_t* meta = (uint32_t*)(S.p + off_meta);
+  uint32_t* ref_start = (uint32_t*)(S.p + off_start);
+  uint8_t* bases2 = S.p + off_bases;
+  uint8_t* qual = S.p + off_qual;
+  uint32_t* cigar = (uint32_t*)(S.p + off_cigar);
+  uint32_t* exc = (uint32_t*)(S.p + off_exc);
+  memcpy(S.p + off_tb, tb.data(), (n_tiles + 1) * 8);
+  memcpy(S.p + off_tq, tq.data(), (n_tiles + 1) * 8);
+  memcpy(S.p + off_tc, tc.data(), (n_tiles + 1) * 8);
+  memcpy(S.p + off_te, te.data(), (n_tiles + 1) * 4);
+  memset(bases2 + bases_bytes, 0, 64);
+  memset(qual + qual_bytes, 0, 64);
+  memset(cigar + cigar_count, 0, 64);
+  memset(exc + exc_count, 0, 64);
+
+  // ---- pass 2: fill ---------------------------------------------------------------------------------------------
+  static const int8_t kNib[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};   // "=ACMGRSVTWYHKDBN"
+  const ps_packed_fasta* fa = B->fa;
+  parallel_for(B->threads, n_tiles, [&](int, uint64_t lo, uint64_t hi) {
+    for (uint64_t t = lo; t < hi; ++t) {
+      uint64_t ob = tb[t], oq = tq[t], oc = tc[t];
+      uint32_t oe = te[t];
+      const uint64_t r1 = std::min(n, (t + 1) * PS_TILE_READS);
+      for (uint64_t r = t * PS_TILE_READS; r < r1; ++r) {
+        const uint8_t* p = buf + ro[r] + 4;
+        const int32_t refID = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
+        const uint32_t l_name = p[8], n_cig = rd16(p + 12), flag = rd16(p + 14), l_seq = rd32(p + 16);
+        const uint8_t* cg = p + 32 + l_name;
+        const uint8_t* sq4 = cg + 4ull * n_cig;
+        const uint8_t* ql = sq4 + (l_seq + 1) / 2;
+        uint32_t fl = 0;
+        if (flag & 0x4) fl |= PS_RF_UNMAPPED;
+        if (flag & 0x10) fl |= PS_RF_REVERSE;
+        if (flag & 0x400) fl |= PS_RF_DUPLICATE;
+        if (pos < 0) fl |= PS_RF_POS_ZERO;                       // getAlignmentStart() == 0
+        if (l_seq == 0 || ql[0] == 0xFF) fl |= PS_RF_QUAL_MISSING;
+        uint32_t nc = n_cig;
+        if (n_cig > 255) { fl |= PS_RF_CIGAR_OVERFLOW; nc = 0; }
+        uint64_t R = 0;
+        for (uint32_t e = 0; e < nc; ++e) {
+          const uint32_t c = rd32(cg + 4 * e), op = c & 15u;
+          cigar[oc + e] = c;
+          if ((0x18Du >> op) & 1u) R += c >> 4;                  // M, D, N, =, X consume the reference
+        }
+        // bases: 2-bit codes, 4 per byte; everything that is not A, C, G, T goes to the exception list as code 0
+        for (uint32_t k = 0; k < (l_seq + 3) / 4; ++k) bases2[ob + k] = 0;
+        bool any_inv = false;
+        for (uint32_t k = 0; k < l_seq; ++k) {
+          const int8_t cd = kNib[(sq4[k >> 1] >> ((~k & 1) * 4)) & 15u];
+          if (cd < 0) { any_inv = true; exc[oe++] = ((uint32_t)(r % PS_TILE_READS) << 16) | k; }
+          else bases2[ob + (k >> 2)] |= (uint8_t)(cd << (2 * (k & 3)));
+        }
+        if (any_inv) fl |= PS_RF_HAS_INVALID;
+        memcpy(qual + oq, ql, l_seq);
+        uint32_t g32 = 0;
+        if (!(fl & (PS_RF_UNMAPPED | PS_RF_POS_ZERO))) {
+          const int64_t c = (refID >= 0 && (size_t)refID < B->ref_to_contig.size()) ? B->ref_to_contig[refID] : -1;
+          if (c < 0) fl |= PS_RF_REF_RANGE;                       // getSubsequenceAt on an unknown contig: SAMException
+          else {
+            const uint64_t clen = fa->off[c + 1] - fa->off[c];
+            if ((uint64_t)pos + R > clen) fl |= PS_RF_REF_RANGE;  // stop > contig length: SAMException
+            const uint64_t g = fa->off[c] + (uint64_t)pos;
+            g32 = g > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)g;
+          }
+        }
+        ref_start[r] = g32;
+        meta[r] = PS_MAKE_META(l_seq, nc, fl);
+        ob += (l_seq + 3) / 4; oq += l_seq; oc += nc;
+      }
+    }
+  });
+
+  out->n_reads = n;
+  out->meta = meta;
+  out->ref_start = ref_start;
+  out->bases2 = bases2;
+  out->qual = qual;
+  out->cigar = cigar;
+  out->tile_base_off = (const uint64_t*)(S.p + off_tb);
+  out->tile_qual_off = (const uint64_t*)(S.p + off_tq);
+  out->tile_cigar_off = (const uint64_t*)(S.p + off_tc);
+  out->tile_exc_off = (const uint32_t*)(S.p + off_te);
+  out->exc = exc;
+  out->uniform_len = lens_min.load() == lens_max.load() ? lens_max.load() : 0;
+  out->uniform_ncigar = nc_min.load() == nc_max.load() ? nc_max.load() : 0;
+  out->bases_bytes = bases_bytes;
+  out->qual_bytes = qual_bytes;
+  out->cigar_count = cigar_count;
+  out->exc_count = exc_count;
+  B->ordinal += n;
+  return 1;
+}
+
+// ---- whole-tool entry points -------------------------------------------------------------------------------------
+int ps_reference_load_fasta(ps_ctx* ctx, const char* fasta_path) {
+  if (!ctx || !fasta_path) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
+  ps_packed_fasta* F = nullptr;
+  int st = ps_fasta_pack(fasta_path, &F);
+  if (st != PS_OK) {
+    st = set_error(ctx, st, F ? F->err : "FASTA pack failed");
+    ps_fasta_free(F);
+    return st;
+  }
+  st = ps_reference_upload(ctx, &F->view);
+  if (st != PS_OK) { ps_fasta_free(F); return st; }
+  if (ctx->fasta) ps_fasta_free(ctx->fasta);
+  ctx->fasta = F;      // contig names for the BAM header; the packed words stay on the host for later uploads
+  return PS_OK;
+}
+
+static int open_for_ctx(ps_ctx* ctx, const char* bam_path, uint64_t max_batch, ps_bam** B) {
+  if (!ctx->fasta) return set_error(ctx, PS_ERR_STATE, "ps_reference_load_fasta must come first (contig names are needed)");
+  int st = ps_bam_open(B, bam_path, ctx->fasta, max_batch, 0);
+  if (st != PS_OK) {
+    st = set_error(ctx, st, *B ? (*B)->err : "cannot open BAM");
+    ps_bam_close(*B);
+    *B = nullptr;
+  }
+  return st;
+}
+
+// ErrorProfiling.inferErrorProfile up to the end of the record loop (:104-409), streaming in batches
+int ps_profile_bam(ps_ctx* ctx, const char* bam_path, const ps_profile_opts* opts, ps_profile_result* out) {
+  if (!ctx || !bam_path || !opts || !out) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
+  ps_bam* B = nullptr;
+  uint64_t batch_reads = 1ull << 22;     // ~280 MB of SoA per batch at 36 nt; two slabs + two staging slots in flight
+  if (const char* e = getenv("PARASUITE_B200_BATCH_READS")) { const long long v = atoll(e); if (v > 0) batch_reads = (uint64_t)v; }
+  int st = open_for_ctx(ctx, bam_path, batch_reads, &B);
+  if (st) return st;
+  st = ps_profile_begin(ctx, opts);
+  ps_read_batch hb;
+  while (st == PS_OK) {
+    // the slab ps_bam_next is about to fill was handed to the batch before last: wait for its copy (staging slots
+    // and slabs alternate in lock-step)
+    if (ctx->staged_done[ctx->staged_next]) cudaEventSynchronize(ctx->staged_done[ctx->staged_next]);
+    const int k = ps_bam_next(B, &hb);
+    if (k < 0) { st = set_error(ctx, k, B->err); break; }
+    if (k == 0) break;
+    st = ps_profile_batch(ctx, &hb);      // staged asynchronously; the slab stays valid until the second-next batch
+  }
+  if (st == PS_OK) st = ps_profile_end(ctx, out);
+  else if (ctx->profile_open) { ps_profile_result dump; memset(&dump, 0, sizeof dump); ps_profile_end(ctx, &dump); }
+  ps_bam_close(B);
+  return st;
+}
+
+// PileupClusters.calculateReadPileups up to the end of the record loop (:62-500).  The file is taken as ONE batch
+// (the cluster chain is a prefix scan over all reads); callers that need to stream use ps_pileup_batch with
+// ps_pileup_opts.carry_* per window and merge the boundary clusters (parasuite_b200/sharding.py).
+int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out) {
+  if (!ctx || !bam_path || !out) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  ps_bam* B = nullptr;
+  int st = open_for_ctx(ctx, bam_path, 0xFFFFFF00ull, &B);
+  if (st) return st;
+  ps_read_batch hb;
+  const int k = ps_bam_next(B, &hb);
+  if (k < 0) st = set_error(ctx, k, B->err);
+  else {
+    if (k == 0) memset(&hb, 0, sizeof hb);
+    st = ps_pileup_batch(ctx, &hb, opts, out);
+    if (st == PS_OK && k == 1) {
+      ps_read_batch more;
+      if (ps_bam_next(B, &more) != 0) st = set_error(ctx, PS_ERR_UNSUPPORTED, "BAM holds more than 2^32-256 records");
+    }
+  }
+  ps_bam_close(B);
+  return st;
+}
+
+}  // extern "C"

@@ -71,6 +71,8 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
     PS_CUDA(ctx, it.d->reserve(it.bytes + 64));   // +64: kernels may read a few bytes past the last read
     if (it.bytes) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (!ctx->staged_done[slot]) cudaEventCreateWithFlags(&ctx->staged_done[slot], cudaEventDisableTiming);
+  cudaEventRecord(ctx->staged_done[slot], ctx->stream);   // host buffers of this batch may be reused once it has fired
   DeviceBatch& v = s.view;
   v.n_reads = n;
   v.meta = (const uint32_t*)s.meta.p;
@@ -166,6 +168,8 @@ void ps_destroy(ps_ctx* ctx) {
   for (auto& e : ctx->pl_ev) cudaEventDestroy(e);
   cudaEventDestroy(ctx->reset_ev);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->fasta) ps_fasta_free(ctx->fasta);
+  for (auto& e : ctx->staged_done) if (e) cudaEventDestroy(e);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release();
   for (auto& s : ctx->staged) {

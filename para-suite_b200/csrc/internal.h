@@ -86,6 +86,8 @@ struct StagedBatch {   // device copy of a host batch
 
 #define PS_TIMER_RING 512
 
+struct ps_packed_fasta;
+
 struct ps_ctx {
   int device = 0;
   int sm_count = 148;
@@ -95,6 +97,7 @@ struct ps_ctx {
   DevBuf ref_seq2, ref_inv, ref_contig;
   std::vector<uint64_t> contig_off;  // host copy
   bool ref_loaded = false;
+  ps_packed_fasta* fasta = nullptr;   // set by ps_reference_load_fasta: contig names for BAM headers
   // profile state
   bool profile_open = false;
   ProfileLayout layout{};

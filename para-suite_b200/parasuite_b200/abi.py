@@ -150,6 +150,15 @@ EXPORTS = {
     "ps_pileup_fault": (C.c_int, [VP, C.POINTER(ps_fault)]),
     "ps_pileup_close": (None, [VP]),
     "ps_pileup_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_pileup_opts), C.POINTER(VP)]),
+    "ps_fasta_pack": (C.c_int, [C.c_char_p, C.POINTER(VP)]),
+    "ps_fasta_reference": (C.POINTER(ps_reference), [VP]),
+    "ps_fasta_contig_name": (C.c_char_p, [VP, C.c_uint32]),
+    "ps_fasta_error": (C.c_char_p, [VP]),
+    "ps_fasta_free": (None, [VP]),
+    "ps_bam_open": (C.c_int, [C.POINTER(VP), C.c_char_p, VP, C.c_uint64, C.c_int]),
+    "ps_bam_next": (C.c_int, [VP, C.POINTER(ps_read_batch)]),
+    "ps_bam_error": (C.c_char_p, [VP]),
+    "ps_bam_close": (None, [VP]),
     "ps_kernel_launches": (C.c_uint64, [VP]),
     "ps_last_kernel_ms": (C.c_float, [VP]),
     "ps_kernel_times": (C.c_int, [VP, VP, C.c_int]),

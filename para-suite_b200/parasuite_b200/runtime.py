@@ -107,6 +107,38 @@ class Context:
         _check(self.lib, self.h, self.lib.ps_reference_upload(self.h, C.byref(s)))
         self.ref = ref
 
+    def load_fasta(self, path: str):
+        """FASTA + .fai -> packed reference resident in HBM (replaces IndexedFastaSequenceFile, ErrorProfiling.java:109)."""
+        _check(self.lib, self.h, self.lib.ps_reference_load_fasta(self.h, path.encode()))
+        self.ref = None
+
+    # ---- whole-tool loops from files ------------------------------------------------------------------
+    def profile_bam(self, bam_path: str, max_read_length: int, infer_qualities: bool = False) -> dict:
+        """The record loop of the `error` tool (ErrorProfiling.java:104-409) on a coordinate-sorted BAM."""
+        self._max_len, self._infer_q = max_read_length, infer_qualities
+        out, r = self._profile_result_arrays()
+        o = abi.ps_profile_opts(max_read_length, int(infer_qualities))
+        st = self.lib.ps_profile_bam(self.h, bam_path.encode(), C.byref(o), C.byref(r))
+        _check(self.lib, self.h, st, fault=(r.fault.code, r.fault.read_ordinal))
+        return out
+
+    def pileup_bam(self, bam_path: str, first_running_id: int = 1) -> "PileupResult":
+        """The record loop of the `clust` tool (PileupClusters.java:62-500) on a coordinate-sorted BAM."""
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+        h = C.c_void_p()
+        st = self.lib.ps_pileup_bam(self.h, bam_path.encode(), C.byref(opts), C.byref(h))
+        res = PileupResult(self, h, None)
+        try:
+            if st == abi.PS_ERR_REFERENCE_WOULD_THROW and h:
+                f = abi.ps_fault()
+                self.lib.ps_pileup_fault(h, C.byref(f))
+                _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
+            _check(self.lib, self.h, st)
+        except Exception:
+            res.close()
+            raise
+        return res
+
     # ---- batches ---------------------------------------------------------------------------------
     def upload(self, batch) -> UploadedBatch:
         """One H2D copy of a host batch (ReadBatch / PinnedBatch); both tools can then run on the device view
@@ -144,7 +176,7 @@ class Context:
 
         return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
 
-    def profile_end(self) -> dict:
+    def _profile_result_arrays(self):
         m = self._max_len
         out = {
             "position_conversions": np.zeros((m, 4, 4), dtype=np.int32),
@@ -166,6 +198,10 @@ class Context:
         r.counters = out["counters"].ctypes.data
         r.quality_hist = out["quality_hist"].ctypes.data if self._infer_q else None
         r.wide = out["wide"].ctypes.data
+        return out, r
+
+    def profile_end(self) -> dict:
+        out, r = self._profile_result_arrays()
         st = self.lib.ps_profile_end(self.h, C.byref(r))
         self._keep.clear()
         _check(self.lib, self.h, st, fault=(r.fault.code, r.fault.read_ordinal))

@@ -1,0 +1,165 @@
+"""CPU: the native host batcher (FASTA -> packed reference, BGZF/BAM -> SoA batches) against the record-by-record
+Python packers, on files written by the pure-Python writers.  No GPU needed (the batcher is host code)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import random_genome, random_records
+from parasuite_b200 import PackedReference, ReadBatch, Record, abi
+from parasuite_b200.bamio import BamBatcher, PackedFasta, batch_to_records, write_bam, write_fasta
+
+pytestmark = pytest.mark.skipif(not os.path.exists(abi.lib_path()), reason="library not built")
+
+STREAMS = ("meta", "ref_start", "tile_base_off", "tile_qual_off", "tile_cigar_off", "tile_exc_off")
+
+
+def assert_batch_equal(a: ReadBatch, b: ReadBatch, what=""):
+    assert a.n_reads == b.n_reads, what
+    for f in ("uniform_len", "uniform_ncigar", "bases_bytes", "qual_bytes", "cigar_count", "exc_count"):
+        assert getattr(a, f) == getattr(b, f), (what, f, getattr(a, f), getattr(b, f))
+    for f in STREAMS:
+        assert np.array_equal(getattr(a, f), getattr(b, f)), (what, f)
+    assert np.array_equal(a.bases2[:a.bases_bytes], b.bases2[:b.bases_bytes]), (what, "bases2")
+    assert np.array_equal(a.qual[:a.qual_bytes], b.qual[:b.qual_bytes]), (what, "qual")
+    assert np.array_equal(a.cigar[:a.cigar_count], b.cigar[:b.cigar_count]), (what, "cigar")
+    assert np.array_equal(a.exc[:a.exc_count], b.exc[:b.exc_count]), (what, "exc")
+
+
+@pytest.mark.parametrize("width", [60, 7, 1000])
+def test_fasta_pack_matches_python_packer(tmp_path, width):
+    rng = random.Random(width)
+    contigs = random_genome(rng, n_contigs=4, length=3000 + width, n_frac=0.05, lower_frac=0.2)
+    contigs.append(("tiny", b"ACGTN"))
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, contigs, line_width=width)
+    pf = PackedFasta(fa)
+    got, exp = pf.reference(), PackedReference.from_contigs(contigs)
+    assert got.names == exp.names and got.lengths == exp.lengths
+    assert np.array_equal(got.contig_off, exp.contig_off)
+    assert np.array_equal(got.seq2, exp.seq2) and np.array_equal(got.inv, exp.inv)
+    pf.close()
+
+
+def test_fasta_errors(tmp_path):
+    fa = str(tmp_path / "x.fa")
+    with open(fa, "w") as f:
+        f.write(">a\nACGT\n")
+    with pytest.raises(abi.PsError) as e:
+        PackedFasta(fa)                       # no .fai
+    assert e.value.status == abi.PS_ERR_IO
+    with open(fa + ".fai", "w") as f:
+        f.write("a\t400\t3\t60\t61\n")        # index claims more than the file holds
+    with pytest.raises(abi.PsError) as e:
+        PackedFasta(fa)
+    assert e.value.status == abi.PS_ERR_FORMAT
+
+
+@pytest.mark.parametrize("seed,kinds,max_batch", [(1, ("M",), 0), (2, ("M", "clip", "indel", "splice", "wild"), 700),
+                                                  (3, ("wild", "indel"), 256), (4, ("M",), 1)])
+def test_bam_batches_match_python_packer(tmp_path, seed, kinds, max_batch):
+    rng = random.Random(seed)
+    contigs = random_genome(rng, n_contigs=3, length=5000, n_frac=0.01, lower_frac=0.1)
+    recs = random_records(rng, contigs, 1800 if max_batch != 1 else 40, kinds=kinds, Lrange=(1, 60), flags_special=0.08)
+    # a record on a contig the FASTA does not hold, one without sequence, one with missing qualities
+    recs.append(Record(0, "chrUn", 5, "4M", b"ACGT", bytes([30] * 4)))
+    recs.append(Record(4, "*", 0, "*", b"", b""))
+    recs.append(Record(16, contigs[2][0], 10, "3M", b"ACN", b"\xff\xff\xff"))
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "x.bam")
+    write_fasta(fa, contigs)
+    write_bam(bam, [(n, len(s)) for n, s in contigs] + [("chrUn", 1000)], recs, block_bytes=3000)
+    pf = PackedFasta(fa)
+    ref = pf.reference()
+    got = list(BamBatcher(bam, pf, max_batch_reads=max_batch, threads=3))
+    step = max_batch or len(recs)
+    assert sum(b.n_reads for b in got) == len(recs)
+    assert len(got) == (len(recs) + step - 1) // step
+    for k, b in enumerate(got):
+        assert_batch_equal(b, ReadBatch.from_records(recs[k * step:(k + 1) * step], ref), f"batch {k}")
+
+
+def test_bam_header_checks(tmp_path):
+    rng = random.Random(9)
+    contigs = random_genome(rng, n_contigs=2, length=500)
+    recs = random_records(rng, contigs, 20)
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, contigs)
+    pf = PackedFasta(fa)
+    sq = [(n, len(s)) for n, s in contigs]
+    bam = str(tmp_path / "u.bam")
+    write_bam(bam, sq, recs, sort_order="unsorted")
+    with pytest.raises(abi.PsError) as e:
+        BamBatcher(bam, pf)
+    assert e.value.status == abi.PS_ERR_UNSORTED and "sorted" in str(e.value)      # ErrorProfiling.java:128-131
+    write_bam(bam, sq[::-1], recs)                                                   # @SQ order != FASTA order
+    with pytest.raises(abi.PsError) as e:
+        BamBatcher(bam, pf)
+    assert e.value.status == abi.PS_ERR_UNSUPPORTED
+    write_bam(bam, sq, recs)
+    data = open(bam, "rb").read()
+    open(bam, "wb").write(data[:len(data) // 2])                                     # truncated file
+    with pytest.raises(abi.PsError) as e:
+        list(BamBatcher(bam, pf))
+    assert e.value.status == abi.PS_ERR_FORMAT
+    open(bam, "wb").write(b"not a bam")
+    with pytest.raises(abi.PsError):
+        BamBatcher(bam, pf)
+    with pytest.raises(abi.PsError) as e:
+        BamBatcher(str(tmp_path / "missing.bam"), pf)
+    assert e.value.status == abi.PS_ERR_IO
+
+
+def test_empty_bam(tmp_path):
+    contigs = [("chr1", b"ACGT" * 50)]
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "e.bam")
+    write_fasta(fa, contigs)
+    write_bam(bam, [("chr1", 200)], [])
+    assert list(BamBatcher(bam, PackedFasta(fa))) == []
+
+
+def test_synthetic_batch_round_trip(tmp_path):
+    """synthetic SoA batch -> records -> BAM -> native batcher gives the batch back."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(5, [300_000, 200_000], n_run=500)
+    batch = synth.synth_reads(ref, 3000, 36, seed=3, special_ppm=20000)
+    # the BAM carries contig names: give the packed reference a FASTA twin
+    codes = np.zeros(ref.n_bases, dtype=np.uint8)
+    for k in range(16):
+        codes[k::16] = ((ref.seq2[: (ref.n_bases + 15) // 16] >> (2 * k)) & 3)[: len(codes[k::16])]
+    ascii_ = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+    invbits = np.unpackbits(ref.inv.view(np.uint8), bitorder="little")[: ref.n_bases].astype(bool)
+    ascii_[invbits] = ord("N")
+    contigs = [(n, ascii_[int(ref.contig_off[i]):int(ref.contig_off[i + 1])].tobytes()) for i, n in enumerate(ref.names)]
+    fa, bam = str(tmp_path / "s.fa"), str(tmp_path / "s.bam")
+    write_fasta(fa, contigs)
+    recs = batch_to_records(batch, ref)
+    write_bam(bam, [(n, len(s)) for n, s in contigs], recs)
+    pf = PackedFasta(fa)
+    assert np.array_equal(pf.reference().seq2, ref.seq2) and np.array_equal(pf.reference().inv, ref.inv)
+    got = list(BamBatcher(bam, pf))
+    assert len(got) == 1
+    assert_batch_equal(got[0], ReadBatch.from_records(recs, ref), "synthetic via records")
+    # and against the generator's own arrays (unmapped / POS==0 records lose their coordinates in a BAM)
+    g = got[0]
+    assert np.array_equal(g.bases2[:g.bases_bytes], batch.bases2[:batch.bases_bytes])
+    assert np.array_equal(g.qual[:g.qual_bytes], batch.qual[:batch.qual_bytes])
+
+
+REF_FIXTURE = "/root/reference/examples/references/reference_chr1.fa"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FIXTURE), reason="reference checkout not mounted (build container only)")
+def test_reference_fixture_fasta(tmp_path):
+    """The reference's own example genome (chr1, 483 300 bp, N runs, soft-masked): native pack == Python pack."""
+    raw = open(REF_FIXTURE, "rb").read().split(b"\n")
+    name = raw[0][1:].split()[0].decode()
+    seq = b"".join(raw[1:])
+    fa = str(tmp_path / "chr1.fa")
+    write_fasta(fa, [(name, seq)], line_width=len(raw[1]))
+    assert open(fa, "rb").read().rstrip(b"\n") == open(REF_FIXTURE, "rb").read().rstrip(b"\n")   # same bytes as the fixture
+    pf = PackedFasta(fa)
+    got, exp = pf.reference(), PackedReference.from_contigs([(name, seq)])
+    assert got.lengths == [483300]
+    assert np.array_equal(got.seq2, exp.seq2) and np.array_equal(got.inv, exp.inv)
+    assert int(np.unpackbits(got.inv.view(np.uint8)).sum()) == seq.upper().count(b"N")
