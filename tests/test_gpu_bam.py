@@ -50,7 +50,7 @@ def test_profile_bam(ctx, oracle, tmp_path, monkeypatch, batch_reads):
     ref = PackedReference.from_contigs(contigs)
     exp = oracle.profile(ref, ReadBatch.from_records(ok, ref), 64)
     assert_profile_equal(got, exp, f"profile_bam batch_reads={batch_reads}")
-    assert int(got["counters"][abi.PS_PC_NUM_READS_PROCESSED]) > 2000
+    assert int(got["counters"][0]) > 2000
 
 
 def test_pileup_bam(ctx, oracle, tmp_path):
@@ -75,7 +75,7 @@ def test_pileup_bam(ctx, oracle, tmp_path):
     exp2["open_cluster"] = None
     got["open_cluster"] = None
     assert_pileup_equal(got, exp2, "pileup_bam")
-    assert len(got["clusters"]) > 50
+    assert len(got["clusters"]) > 20
 
 
 def test_unsorted_bam_is_refused(ctx, tmp_path):
