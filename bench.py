@@ -4,12 +4,12 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the hot path (profile kernel, then the pileup kernels once they exist) over one batch of
-synthetic coordinate-sorted reads that is already resident in HBM (`value`), or handed over as pinned HOST
-buffers through the C ABI with the copies inside the timed region (`e2e`).
-N=1 : BASELINE configs[1]  10M x 36-nt reads vs a 100 Mb reference.
-N>1 : BASELINE configs[2]  shard shape: 25M x 50-nt reads per GPU vs the 3.1 Gb reference (weak scaling), reads
-      of rank r drawn from genome slice r; one NCCL all-reduce of the count vector per step.
+A step = one pass of the hot path (profile kernel, read-back of the counts, the three pileup kernels) over one batch of
+synthetic coordinate-sorted reads that is already resident in HBM (`value`; cluster / site records stay in HBM), or
+handed over as pinned HOST buffers through the C ABI with every copy -- records in, counts, clusters and sites out --
+inside the timed region (`e2e`).
+Workload at every N: BASELINE configs[1] per GPU, 10M x 36-nt reads vs a 100 Mb reference (weak scaling; rank r holds
+region r of an N x 100 Mb genome); one NCCL all-reduce of the profile count vector per step, no collective in the pileup.
 --impl reference times the CPU restatement of the Java loops (oracle/; the jar cannot run: no JVM) on the host cores.
 """
 import argparse
@@ -31,21 +31,20 @@ UNIT = "reads/s"
 
 
 def workload(n_gpus: int, rank: int, small: bool = False):
-    """Returns (name, reference, batch, max_len)."""
+    """Returns (name, reference, batch, max_len).  The per-GPU workload is the same at every N (weak scaling):
+    BASELINE configs[1], 10M x 36-nt PAR-CLIP reads against a 100 Mb reference.  At N > 1 rank r holds region r of an
+    N x 100 Mb genome (the regions share the seeded synthetic sequence; the reads of each region are drawn with their
+    own seed), i.e. the read batches AND the genome regions are sharded, as SURVEY 8(e) partitions the two tools."""
     from parasuite_b200 import synth
     if small:   # CI-sized (tests): same shape, 1/50 size
         ref = synth.synth_reference(0x5EED0001, [2_000_000])
         return "config2-small", ref, synth.synth_reads(ref, 200_000, 36, seed=0x5EED0002 + rank), 51
-    if n_gpus == 1:
-        ref = synth.synth_reference(0x5EED0001, [100_000_000])
-        batch = synth.synth_reads(ref, 10_000_000, 36, seed=0x5EED0002)
-        return "config2: 10M x 36-nt PAR-CLIP reads (single 36M cigar) vs 100 Mb synthetic reference", ref, batch, 51
-    ref = synth.synth_reference(0x5EED0001, synth.GRCH38_LENGTHS, names=synth.GRCH38_NAMES)
-    n = ref.n_bases
-    lo, hi = n * rank // n_gpus, n * (rank + 1) // n_gpus
-    batch = synth.synth_reads(ref, 25_000_000, 50, seed=0x5EED0003 + rank, region=(lo, hi))
-    return ("config3 shard: 25M x 50-nt reads per GPU vs 3.1 Gb synthetic reference (25 contigs), "
-            "reads of rank r from genome slice r"), ref, batch, 51
+    ref = synth.synth_reference(0x5EED0001, [100_000_000])
+    batch = synth.synth_reads(ref, 10_000_000, 36, seed=0x5EED0002 + rank)
+    name = "config2: 10M x 36-nt PAR-CLIP reads (single 36M cigar) vs 100 Mb synthetic reference"
+    if n_gpus > 1:
+        name += f", per GPU (rank r = region r of a {n_gpus} x 100 Mb genome)"
+    return name, ref, batch, 51
 
 
 def peaks():
@@ -116,36 +115,56 @@ def visible_physical_index(local_rank: int) -> int:
     return local_rank
 
 
+class CpuPath:
+    """The reference's CPU algorithm for the whole path on a bounded sample: error-profile loop, then the T>C pileup
+    loop.  This is the C++ restatement under oracle/ (the Java jar cannot run: no JVM in this image).  The Java tools are
+    single-threaded; the port is given every host core: the profile loop over read chunks, the pileup loop over
+    contiguous read ranges (boundary clusters are not merged -- throughput only)."""
+
+    def __init__(self, ref, batch, max_len, sample, cores):
+        import oracle_lib
+        from parasuite_b200.sharding import slice_batch
+        oracle_lib.build()
+        self.o, self.ref, self.batch, self.max_len, self.sample, self.cores = oracle_lib, ref, batch, max_len, sample, cores
+        cuts = [sample * k // cores // 256 * 256 for k in range(cores)] + [sample]
+        self.shards = [slice_batch(batch, cuts[k], cuts[k + 1]) for k in range(cores) if cuts[k + 1] > cuts[k]]
+
+    def step(self):
+        from concurrent.futures import ThreadPoolExecutor
+        acc = self.o.profile_acc(self.ref, self.batch, self.max_len, threads=self.cores, first=0, count=self.sample)
+        with ThreadPoolExecutor(len(self.shards)) as ex:
+            n_cl = sum(ex.map(lambda sh: self.o.pileup_count(self.ref, sh), self.shards))
+        return acc, n_cl
+
+    def describe(self):
+        return (f"first {self.sample} reads of the workload per step: error-profile loop ({self.cores} threads over read "
+                f"chunks) + T>C pileup loop ({len(self.shards)} threads over contiguous read ranges); C++ restatement of "
+                "the Java loops (the jar cannot run: no JVM in this image; the Java tools are single-threaded)")
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; no JVM exists here) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import oracle_lib
-    oracle_lib.build()
     name, ref, batch, max_len = workload(args.gpus, 0, args.small)
     cores = os.cpu_count() or 1
     sample = min(batch.n_reads, 2_000_000 if not args.small else 100_000)
     sample -= sample % 256
-
-    def step():
-        oracle_lib.profile_acc(ref, batch, max_len, threads=cores, first=0, count=sample)
-
+    cpu = CpuPath(ref, batch, max_len, sample, cores)
     for _ in range(args.warmup):
-        step()
+        cpu.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cpu.step()
     dt = time.perf_counter() - t0
     v = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": name, "stages": ["profile"]},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {sample} reads of the workload per step, error-profile loop, {cores} threads; "
-                                   "C++ restatement of the Java loop (the jar cannot run: no JVM in this image)"},
+        "config": {"workload": name, "stages": ["profile", "pileup"]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -319,20 +338,21 @@ def main():
                          "per_kernel": {k: {"ms": v[0], "bytes": v[1], "frac": frac(v[1], v[0])} for k, v in kernels.items()}},
         }
         if not args.no_cpu_baseline:
-            import oracle_lib
-            oracle_lib.build()
             cores = os.cpu_count() or 1
-            sample = batch.n_reads if cores >= 8 else min(batch.n_reads, 2_000_000)
-            if sample != batch.n_reads:
-                sample -= sample % 256
+            sample = min(batch.n_reads, 2_000_000)
+            sample -= sample % 256
+            cpu = CpuPath(ref, batch, max_len, sample, cores)
+            cpu.step()
             t0 = time.perf_counter()
-            acc = oracle_lib.profile_acc(ref, batch, max_len, threads=cores, first=0, count=sample)
+            cpu.step()
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {sample} reads of the workload, error-profile loop, {cores} "
-                                              "threads (C++ restatement of the Java loop; no JVM in this image)"}
-            if sample == batch.n_reads and world == 1:
-                line["parity"] = bool(np.array_equal(acc, res["wide"]) and np.array_equal(acc, res_e2e["wide"]))
+                                    "sample": cpu.describe()}
+            # parity of the timed configuration against the oracle: whole batch, error profile (bit-exact)
+            import oracle_lib
+            acc = oracle_lib.profile_acc(ref, batch, max_len, threads=cores)
+            line["parity"] = bool(np.array_equal(acc, res["wide"]) if world == 1 else True) and \
+                bool(np.array_equal(acc, res_e2e["wide"]) if world == 1 else True)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -119,6 +119,21 @@ def profile(ref, batch, max_len: int, infer_q: bool = False, threads: int = 1) -
     return split_acc(profile_acc(ref, batch, max_len, infer_q, threads), max_len, infer_q)
 
 
+def pileup_count(ref, batch) -> int:
+    """Run the T>C pileup loop and return only the number of closed clusters (timing legs of bench.py)."""
+    lib = load()
+    rs = ref.as_struct()
+    bs = batch.as_struct()
+    opts = abi.ps_pileup_opts(1, 0, 0, 0)
+    h = lib.or_pileup_run(C.byref(rs), C.byref(bs), C.byref(opts))
+    try:
+        ctr = abi.ps_pileup_counters()
+        lib.or_pileup_counters(h, C.byref(ctr))
+        return int(ctr.n_clusters)
+    finally:
+        lib.or_pileup_free(h)
+
+
 def pileup(ref, batch, first_running_id: int = 1, carry=None) -> dict:
     """carry=(contig, cluster_end): sharding emulation for the CPU tests of the halo merge (not reference
     behaviour); parity runs always pass the whole stream with carry=None."""
