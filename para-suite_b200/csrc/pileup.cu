@@ -37,6 +37,7 @@ constexpr int PL_WARPS = PL_THREADS / 32;
 constexpr int CB_CLUSTERS = 128;                      // clusters per block of pl_cluster_kernel (thread per cluster)
 constexpr int CB_CHUNK = 2048;                        // reads decoded into shared memory at a time
 constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
+constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
 constexpr int PL_WINDOW = 128;                        // positions per window
 
 struct PlState {                  // device-side run state (one per call)
@@ -111,6 +112,18 @@ __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64
   return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)end;
 }
 
+// same for a record with exactly one cigar op `cg` (a lone I or D next to no N is kept: :152-157 needs both)
+__device__ __forceinline__ unsigned long long pl_key1(const FlagParams& P, uint32_t meta, uint32_t cg, uint32_t g0,
+                                                      ContigCache& cc, int32_t& start) {
+  const uint32_t flags = PS_META_FLAGS(meta);
+  start = 0;
+  if (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) return 0;
+  if (!contig_lookup(P.ref, g0, cc)) return 0;
+  const uint32_t R = op_consumes_ref(cg & 15u) ? cg >> 4 : 0u;
+  start = (int32_t)((uint64_t)g0 - cc.lo) + 1;
+  return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(start + (int32_t)R - 1);
+}
+
 // block-wide exclusive scan over one 64-bit value per thread (PL_THREADS threads); also returns the block total
 template <typename Op>
 __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long v, Op op, unsigned long long identity,
@@ -139,7 +152,7 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
   return op(prefix, up);
 }
 
-// ITEMS == 4: every read has one cigar op and the three streams are 16-byte aligned (vector loads);
+// ITEMS == PL_FLAG_ITEMS: every read has one cigar op and the streams are 16-byte aligned (vector loads);
 // ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
 template <int ITEMS>
 __global__ void __launch_bounds__(PL_THREADS) pl_flag_kernel(const __grid_constant__ FlagParams P) {
@@ -159,23 +172,31 @@ __global__ void __launch_bounds__(PL_THREADS) pl_flag_kernel(const __grid_consta
   unsigned long long key[ITEMS];
   int32_t start[ITEMS];
   ContigCache cc;
-  if constexpr (ITEMS == 4) {
-    uint32_t metas[4], starts[4];
-    if (r0 + 4 <= n) {
-      const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(P.b.meta + r0));
-      const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(P.b.ref_start + r0));
-      metas[0] = m4.x; metas[1] = m4.y; metas[2] = m4.z; metas[3] = m4.w;
-      starts[0] = s4.x; starts[1] = s4.y; starts[2] = s4.z; starts[3] = s4.w;
-    } else {
+  if constexpr (ITEMS > 1) {
+    static_assert(ITEMS % 4 == 0, "vector loads take 4 reads at a time");
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool in = r0 + j < n;
-        metas[j] = in ? __ldg(P.b.meta + r0 + j) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
-        starts[j] = in ? __ldg(P.b.ref_start + r0 + j) : 0u;
+    for (int g = 0; g < ITEMS; g += 4) {
+      uint32_t metas[4], starts[4], cigs[4];
+      const uint64_t rg = r0 + g;
+      if (rg + 4 <= n) {
+        const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(P.b.meta + rg));
+        const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(P.b.ref_start + rg));
+        const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(P.b.cigar + rg));
+        metas[0] = m4.x; metas[1] = m4.y; metas[2] = m4.z; metas[3] = m4.w;
+        starts[0] = s4.x; starts[1] = s4.y; starts[2] = s4.z; starts[3] = s4.w;
+        cigs[0] = c4.x; cigs[1] = c4.y; cigs[2] = c4.z; cigs[3] = c4.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool in = rg + j < n;
+          metas[j] = in ? __ldg(P.b.meta + rg + j) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
+          starts[j] = in ? __ldg(P.b.ref_start + rg + j) : 0u;
+          cigs[j] = in ? __ldg(P.b.cigar + rg + j) : 0u;
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) key[j] = pl_key(P, r0 + j, metas[j], P.b.cigar + r0 + j, starts[j], cc, start[j]);
+      for (int j = 0; j < 4; ++j) key[g + j] = pl_key1(P, metas[j], cigs[j], starts[j], cc, start[g + j]);
+    }
   } else {
     const bool in_range = r0 < n;
     const uint32_t meta = in_range ? __ldg(P.b.meta + r0) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
@@ -637,8 +658,8 @@ static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is
 // One block = CB_CLUSTERS consecutive clusters = one contiguous run of reads, taken in chunks of CB_CHUNK reads.
 //   A   thread per READ:    decode (T>C mask, interval, strand) into shared memory -- full lanes whatever the cluster
 //                           sizes are
+//       (and ORs the read's T>C positions into its cluster's 64-position key set: shared atomics)
 //   B0  thread per CLUSTER: counters over the cluster's decoded reads (P3 counters, P4, P6)
-//   B1  thread per READ:    OR the read's T>C positions into its cluster's 64-position key set (shared atomics)
 //   B2  thread per READ:    per key: mutationMap count, first-insertion key (min), and baseCoveredMap -- every read adds
 //                           itself to the keys its interval covers.  A key's slot is its rank in the key set, so the
 //                           sites come out in position order.
@@ -692,7 +713,27 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
       continue;
     }
     const uint32_t re = S.first[cur + ncomp], nrd = re - rs;
-    // ---- A ------------------------------------------------------------------------------------------------------
+    const bool mine = tid < ncomp;
+    // ---- pre-pass, thread per cluster: cluster of every read, origin of the key set ----------------------------------
+    if (mine) {
+      const uint32_t k = cur + tid;
+      const uint32_t a = S.first[k] - rs, b = S.first[k + 1] - rs;
+      for (uint32_t i = a; i < b; ++i) S.cid[i] = (uint8_t)tid;
+      // sorted input: no position of a cluster lies before the start of the read that opened it (slot 0, the reads
+      // continuing the preceding shard's cluster, has no opener: it is left to the warp routine)
+      int32_t base = 0;
+      const uint32_t g0 = __ldg(P.b.ref_start + S.first[k]);
+      if (c0 + k != 0 && contig_lookup(P.ref, g0, cc)) base = (int32_t)((uint64_t)g0 - cc.lo) + 1;
+      S.base[tid] = base;
+      S.umask[tid] = 0;
+      S.ovf[tid] = (c0 + k == 0 && b > a) ? 1u : 0u;
+#pragma unroll
+      for (int u = 0; u < CB_SITES; ++u) {
+        S.scnt[u * CB_CLUSTERS + tid] = 0; S.scov[u * CB_CLUSTERS + tid] = 0; S.skey[u * CB_CLUSTERS + tid] = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
+    // ---- A, thread per read: decode; T>C positions into the cluster's key set -------------------------------------
     for (uint32_t q = rs + warp * 32; q < re; q += PL_THREADS) {
       const uint32_t r = q + lane;
       PlRead x;
@@ -701,11 +742,27 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
         const uint32_t i = r - rs;
         S.mask[i] = x.mask | ((unsigned long long)x.rev << 62) | ((unsigned long long)x.kept << 63);
         S.lo[i] = x.lo; S.hi[i] = x.hi; S.start[i] = x.start; S.end[i] = x.end; S.contig[i] = x.contig;
+        if (x.mask) {
+          const uint32_t k = S.cid[i];
+          const int32_t base = S.base[k];
+          unsigned long long m = x.mask, bits = 0;
+          bool bad = false;
+          while (m) {
+            const int ib = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int32_t rel = (x.rev ? x.hi - ib : x.lo + ib) - base;           // checkPosition (:638-643)
+            if ((uint32_t)rel >= 64u) bad = true; else bits |= 1ull << rel;
+          }
+          if (bad) S.ovf[k] = 1u;
+          // two native 32-bit atomics (a 64-bit OR on shared memory is a compare-and-swap loop)
+          uint32_t* um32 = reinterpret_cast<uint32_t*>(&S.umask[k]);
+          if ((uint32_t)bits) atomicOr(um32, (uint32_t)bits);
+          if ((uint32_t)(bits >> 32)) atomicOr(um32 + 1, (uint32_t)(bits >> 32));
+        }
       }
     }
     __syncthreads();
-    // ---- B0 -----------------------------------------------------------------------------------------------------
-    const bool mine = tid < ncomp;
+    // ---- B0, thread per cluster: counters ---------------------------------------------------------------------------
     uint32_t reads = 0, t2c = 0, minus = 0, first_rev = 0, contig = 0;
     int32_t end = INT32_MIN, cstart = 0;
     unsigned long long mask = 0, first_read = 0;
@@ -714,7 +771,6 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
       const uint32_t a = S.first[k] - rs, b = S.first[k + 1] - rs;
       first_read = S.first[k];
       for (uint32_t i = a; i < b; ++i) {
-        S.cid[i] = (uint8_t)tid;
         unsigned long long m = S.mask[i];
         if (!(m >> 63)) continue;
         const uint32_t rev = (uint32_t)(m >> 62) & 1u;
@@ -725,39 +781,7 @@ __global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_con
         t2c += __popcll(m);
         mask |= m;
       }
-      S.base[tid] = cstart;      // sorted input: no position of the cluster lies before the start of its first read
-      S.umask[tid] = 0;
-      S.ovf[tid] = 0;
-#pragma unroll
-      for (int u = 0; u < CB_SITES; ++u) {
-        S.scnt[u * CB_CLUSTERS + tid] = 0; S.scov[u * CB_CLUSTERS + tid] = 0; S.skey[u * CB_CLUSTERS + tid] = 0xFFFFFFFFu;
-      }
     }
-    __syncthreads();
-    // ---- B1 -----------------------------------------------------------------------------------------------------
-    for (uint32_t i = tid; i < nrd; i += PL_THREADS) {
-      unsigned long long m = S.mask[i];
-      if (!(m >> 63)) continue;
-      const bool rev = (m >> 62) & 1ull;
-      m &= (1ull << 51) - 1ull;
-      if (!m) continue;
-      const uint32_t k = S.cid[i];
-      const int32_t lo = S.lo[i], hi = S.hi[i], base = S.base[k];
-      unsigned long long bits = 0;
-      bool bad = false;
-      while (m) {
-        const int ib = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int32_t rel = (rev ? hi - ib : lo + ib) - base;               // checkPosition (:638-643)
-        if ((uint32_t)rel >= 64u) bad = true; else bits |= 1ull << rel;
-      }
-      if (bad) S.ovf[k] = 1u;
-      // two native 32-bit atomics (a 64-bit OR on shared memory is a compare-and-swap loop)
-      uint32_t* um32 = reinterpret_cast<uint32_t*>(&S.umask[k]);
-      if ((uint32_t)bits) atomicOr(um32, (uint32_t)bits);
-      if ((uint32_t)(bits >> 32)) atomicOr(um32 + 1, (uint32_t)(bits >> 32));
-    }
-    __syncthreads();
     // ---- B2 -----------------------------------------------------------------------------------------------------
     for (uint32_t i = tid; i < nrd; i += PL_THREADS) {
       unsigned long long m = S.mask[i];
@@ -1027,8 +1051,8 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   if (n == 0) return PS_OK;
   if (n >= 0xFFFFFFFFull) return set_error(ctx, PS_ERR_UNSUPPORTED, "pileup batch of >= 2^32 reads");
 
-  const bool vec = b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start);
-  const uint32_t tile_reads = PL_THREADS * (vec ? 4u : 1u);
+  const bool vec = b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start) && aligned16p(b.cigar);
+  const uint32_t tile_reads = PL_THREADS * (vec ? (uint32_t)PL_FLAG_ITEMS : 1u);
   const uint32_t n_tiles = (uint32_t)((n + tile_reads - 1) / tile_reads);
   const int nw = flavour_of(b);
   H->nw = nw;
@@ -1067,7 +1091,7 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     pl_init_state<<<1, 32, 0, st>>>(d_state);
     const bool ev = ctx->timers_on;
     if (ev) cudaEventRecord(ctx->pl_ev[0], st);
-    if (vec) pl_flag_kernel<4><<<n_tiles, PL_THREADS, 0, st>>>(P);
+    if (vec) pl_flag_kernel<PL_FLAG_ITEMS><<<n_tiles, PL_THREADS, 0, st>>>(P);
     else pl_flag_kernel<1><<<n_tiles, PL_THREADS, 0, st>>>(P);
     if (ev) cudaEventRecord(ctx->pl_ev[1], st);
     ClusterParams Q;
