@@ -278,6 +278,37 @@ int ps_bam_next(ps_bam* b, ps_read_batch* batch);
 const char* ps_bam_error(const ps_bam* b);
 void ps_bam_close(ps_bam* b);
 
+/* ---- cluster flush (host code, usable without a GPU) ----------------------------------------------
+ * What PileupClusters.java does with every closed cluster before it writes its rows (:178-260: SNP filter,
+ * anchor site, sorted T>C fractions, allele statistics) and the run totals (:502-545), on the records ps_pileup_next
+ * returns.  The anchor tie-break follows java.util.HashMap (JDK 8+) iteration order; SNPs as SNPCalling.java:49-69. */
+typedef struct ps_flush ps_flush;
+typedef struct ps_flush_row {
+  uint8_t emitted;           /* numReadsPerCluster >= minReadCoverage: the cluster row is written (:180, :317-343) */
+  uint8_t has_ccr;           /* tempBestMutationPos > 0: CCR FASTA + row are written (:262-315) */
+  uint16_t reserved;
+  uint32_t num_t2c_sites;    /* numT2CSitesPerCluster = mutationMap.size() before the SNP filter (:181) */
+  int32_t best_pos;          /* tempBestMutationPos, -1 if none */
+  uint32_t best_count;       /* mutationMap.get(tempBestMutationPos) */
+  double best_value;         /* tempBestMutationValue */
+  double fraction;           /* fractionT2CMutationPerCluster */
+} ps_flush_row;
+typedef struct ps_flush_totals {
+  uint64_t snp_hit;                    /* :193 */
+  uint64_t high_frequent_error;        /* :196 */
+  uint64_t num_crosslinked_clusters;   /* :250 */
+  uint64_t num_allele_positions;       /* :254 */
+  uint64_t allele_positions[51];       /* :253 */
+  uint64_t n_allele_frequency;         /* alleleFrequencyInformation.size() */
+} ps_flush_totals;
+int ps_flush_create(ps_flush** out, uint32_t min_read_coverage, uint32_t n_contigs, const char* const* contig_names);
+int ps_flush_add_snp(ps_flush* f, const char* chrom, int32_t pos, const char* ref, const char* alt0);
+int ps_flush_load_vcf(ps_flush* f, const char* vcf_path);     /* plain, gzip or bgzip */
+int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const ps_site* sites, ps_flush_row* rows);
+int ps_flush_totals_get(const ps_flush* f, ps_flush_totals* out, double* allele_frequency_information, uint64_t max);
+const char* ps_flush_error(const ps_flush* f);
+void ps_flush_destroy(ps_flush* f);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 uint64_t ps_kernel_launches(const ps_ctx* ctx);

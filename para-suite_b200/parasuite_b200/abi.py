@@ -113,6 +113,15 @@ class ps_pileup_opts(C.Structure):
                 ("carry_cluster_end", C.c_int32)]
 
 
+class ps_flush_totals(C.Structure):
+    _fields_ = [("snp_hit", C.c_uint64), ("high_frequent_error", C.c_uint64), ("num_crosslinked_clusters", C.c_uint64),
+                ("num_allele_positions", C.c_uint64), ("allele_positions", C.c_uint64 * 51),
+                ("n_allele_frequency", C.c_uint64)]
+
+
+FLUSH_ROW_DTYPE = [("emitted", "u1"), ("has_ccr", "u1"), ("reserved", "<u2"), ("num_t2c_sites", "<u4"),
+                   ("best_pos", "<i4"), ("best_count", "<u4"), ("best_value", "<f8"), ("fraction", "<f8")]
+
 # numpy dtypes with the same layout as ps_cluster / ps_site (checked in tests against ctypes.sizeof)
 CLUSTER_DTYPE = [("first_read", "<u8"), ("running_id", "<u4"), ("contig", "<u4"), ("start", "<i4"), ("end", "<i4"),
                  ("num_reads", "<u4"), ("num_t2c", "<u4"), ("minus_after_first", "<u4"), ("first_reverse", "u1"),
@@ -159,6 +168,13 @@ EXPORTS = {
     "ps_bam_next": (C.c_int, [VP, C.POINTER(ps_read_batch)]),
     "ps_bam_error": (C.c_char_p, [VP]),
     "ps_bam_close": (None, [VP]),
+    "ps_flush_create": (C.c_int, [C.POINTER(VP), C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p)]),
+    "ps_flush_add_snp": (C.c_int, [VP, C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p]),
+    "ps_flush_load_vcf": (C.c_int, [VP, C.c_char_p]),
+    "ps_flush_clusters": (C.c_int, [VP, VP, C.c_uint64, VP, VP]),
+    "ps_flush_totals_get": (C.c_int, [VP, C.POINTER(ps_flush_totals), VP, C.c_uint64]),
+    "ps_flush_error": (C.c_char_p, [VP]),
+    "ps_flush_destroy": (None, [VP]),
     "ps_kernel_launches": (C.c_uint64, [VP]),
     "ps_last_kernel_ms": (C.c_float, [VP]),
     "ps_kernel_times": (C.c_int, [VP, VP, C.c_int]),
