@@ -84,11 +84,26 @@ __device__ __forceinline__ ReadOffsets read_offsets(const DeviceBatch& b, uint64
   return o;
 }
 
-// is position p of read `rit` (index inside its tile) listed as an invalid (non-ACGT) base?
-__device__ __forceinline__ bool read_pos_invalid(const DeviceBatch& b, uint64_t tile, uint32_t rit, uint32_t p) {
+// Exception list (non-ACGT base calls) of one read: the tile's list is sorted by (read_in_tile << 16 | position), so a
+// read's entries are one contiguous run [e0, e1), found once per read with two binary searches.
+struct ExcRange { uint32_t e0, e1; };
+__device__ __forceinline__ uint32_t exc_lower_bound(const uint32_t* exc, uint32_t lo, uint32_t hi, uint32_t key) {
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(exc + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ ExcRange read_exc_range(const DeviceBatch& b, uint64_t tile, uint32_t rit) {
   const uint32_t lo = __ldg(b.tile_exc_off + tile), hi = __ldg(b.tile_exc_off + tile + 1);
-  const uint32_t key = (rit << 16) | p;
-  for (uint32_t e = lo; e < hi; ++e)
-    if (__ldg(b.exc + e) == key) return true;
+  ExcRange r;
+  r.e0 = exc_lower_bound(b.exc, lo, hi, rit << 16);
+  r.e1 = exc_lower_bound(b.exc, r.e0, hi, (rit + 1u) << 16);
+  return r;
+}
+// is position p of the read listed as an invalid base?  (a read holds a handful of entries at most)
+__device__ __forceinline__ bool read_pos_invalid(const DeviceBatch& b, ExcRange r, uint32_t p) {
+  for (uint32_t e = r.e0; e < r.e1; ++e)
+    if ((__ldg(b.exc + e) & 0xFFFFu) == p) return true;
   return false;
 }

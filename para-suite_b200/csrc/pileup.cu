@@ -353,7 +353,7 @@ __device__ __noinline__ void pl_decode_generic(const ClusterParams& P, uint64_t 
         // minus strand: both arrays are reverse-complemented, so ref T & read C there is ref A & read G here
         const bool hit = rev ? (a == 0u && bb == 2u) : (a == 3u && bb == 1u);
         if (!hit) continue;
-        if (has_inv && read_pos_invalid(P.b, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS), p)) continue;
+        if (has_inv && read_pos_invalid(P.b, read_exc_range(P.b, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS)), p)) continue;
         const uint32_t i = rev ? alen - 1 - j : j;
         if (i >= 51u) { raise_fault(&P.st->fault, r, PS_THROW_MASK51); return; }   // boolean[51] (:654)
         mask |= 1ull << i;

@@ -39,6 +39,7 @@ struct GenericSmem {
   unsigned long long* s_q;    // [32] qualityPerMismatch sums | counts
   unsigned long long* s_ctr;  // [8]
   uint32_t* s_conv;           // [max_len*16]
+  uint32_t* s_indel;          // [2*max_len] insertionsPerPos | deletionsPerPos (hot addresses: never global atomics)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -92,10 +93,10 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
         if (n > 0 && pm + n > (int64_t)ml) { raise_fault(P.fault, ordinal, PS_THROW_INDEL_FILL); return; }
         pm += n;
         if (op == 1u) pq += n; else pr += n;
-        unsigned long long* arr = P.acc + (op == 1u ? P.lay.ins : P.lay.del);
+        uint32_t* arr = S.s_indel + (op == 1u ? 0u : max_len);
         for (int64_t q = 1; q <= n; ++q) {
           if (pm + q >= (int64_t)max_len) { raise_fault(P.fault, ordinal, PS_THROW_INDEL_POS); return; }
-          atomicAdd(arr + (pm + q), 1ull);
+          atomicAdd(arr + (pm + q), 1u);
         }
         if (n > 1) atomicAdd(&S.s_ctr[PS_PC_LONGER_INDELS], 1ull);
       }
@@ -107,6 +108,8 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   // count loop :349-408 over the (virtual) temp arrays
   const bool rev = flags & PS_RF_REVERSE;
   const bool has_inv = flags & PS_RF_HAS_INVALID;
+  ExcRange xr{0, 0};
+  if (has_inv) xr = read_exc_range(P.b, tile, rit);
   const uint32_t qual_len = (flags & PS_RF_QUAL_MISSING) ? 0u : L;
   const uint8_t* rb = P.b.bases2 + off.base;
   const uint8_t* rq = P.b.qual + off.qual;
@@ -145,7 +148,7 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
       const uint64_t g = g0 + (uint64_t)(seg_ref + z);
       const uint32_t p = (uint32_t)(seg_read + z);
       bool ok = !ref_invalid_at(P.ref, g);
-      if (ok && has_inv) ok = !read_pos_invalid(P.b, tile, rit, p);
+      if (ok && has_inv) ok = !read_pos_invalid(P.b, xr, p);
       if (!ok) continue;
       uint32_t a = ref_code_at(P.ref, g), b = read_code_at(rb, p);
       if (rev) { a = 3u - a; b = 3u - b; }
@@ -187,12 +190,14 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
 __device__ __forceinline__ void flush_generic(const ProfileParams& P, const GenericSmem& S) {
   for (uint32_t k = threadIdx.x; k < P.lay.max_len * 16; k += blockDim.x)
     if (S.s_conv[k]) atomicAdd(P.acc + P.lay.conv + k, (unsigned long long)S.s_conv[k]);
+  for (uint32_t k = threadIdx.x; k < 2 * P.lay.max_len; k += blockDim.x)   // ins and del are adjacent in the layout
+    if (S.s_indel[k]) atomicAdd(P.acc + P.lay.ins + k, (unsigned long long)S.s_indel[k]);
   if (threadIdx.x < 32 && S.s_q[threadIdx.x]) atomicAdd(P.acc + P.lay.qsum + threadIdx.x, S.s_q[threadIdx.x]);
   if (threadIdx.x < PS_PC_COUNT && S.s_ctr[threadIdx.x])
     atomicAdd(P.acc + P.lay.ctr + threadIdx.x, S.s_ctr[threadIdx.x]);
 }
 
-// Shared memory: s_q[32] u64 | s_ctr[8] u64 | scan scratch[8] u64 | s_conv[max_len*16] u32
+// Shared memory: s_q[32] u64 | s_ctr[8] u64 | scan scratch[8] u64 | s_conv[max_len*16] u32 | s_indel[2*max_len] u32
 __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
@@ -200,7 +205,8 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const
   S.s_ctr = S.s_q + 32;
   uint64_t* s_scan = reinterpret_cast<uint64_t*>(S.s_ctr + 8);
   S.s_conv = reinterpret_cast<uint32_t*>(s_scan + 8);
-  for (uint32_t k = threadIdx.x; k < P.lay.max_len * 16; k += blockDim.x) S.s_conv[k] = 0;
+  S.s_indel = S.s_conv + P.lay.max_len * 16;
+  for (uint32_t k = threadIdx.x; k < P.lay.max_len * 18; k += blockDim.x) S.s_conv[k] = 0;   // s_conv and s_indel
   if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q, s_ctr, s_scan are contiguous
   __syncthreads();
   const uint64_t tile0 = P.first_read / PS_TILE_READS;   // first_read is tile aligned
@@ -224,7 +230,8 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(cons
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
   S.s_ctr = S.s_q + 32;
   S.s_conv = reinterpret_cast<uint32_t*>(S.s_ctr + 16);
-  for (uint32_t k = threadIdx.x; k < P.lay.max_len * 16; k += blockDim.x) S.s_conv[k] = 0;
+  S.s_indel = S.s_conv + P.lay.max_len * 16;
+  for (uint32_t k = threadIdx.x; k < P.lay.max_len * 18; k += blockDim.x) S.s_conv[k] = 0;
   if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;
   __syncthreads();
   const unsigned int n = *P.deferred_count;
@@ -249,7 +256,7 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   if (first_read >= P.b.n_reads) return cudaSuccess;
   P.first_read = first_read;
   P.n_tiles = (uint32_t)((P.b.n_reads - first_read + PS_TILE_READS - 1) / PS_TILE_READS);
-  size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 16 * 4;
+  size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 18 * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -268,7 +275,7 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
 }
 
 static cudaError_t launch_deferred(ps_ctx* ctx, const ProfileParams& P, cudaStream_t stream) {
-  size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 16 * 4;
+  size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 18 * 4;
   cudaError_t e = cudaFuncSetAttribute(profile_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   profile_deferred_kernel<<<(uint32_t)ctx->sm_count, PS_BLOCK_THREADS, smem, stream>>>(P);
