@@ -399,47 +399,6 @@ __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref
   return m;
 }
 
-// stream offsets of the reads of one warp chunk [q, q+32) in a batch of non-uniform records
-// (tile tables + the metas between the tile start and the read)
-__device__ __forceinline__ void chunk_offsets(const DeviceBatch& b, uint64_t q, uint64_t r, bool in, uint32_t meta,
-                                              uint64_t& off_base, uint64_t& off_cigar) {
-  if (b.uniform_len && b.uniform_ncigar) {
-    off_base = r * (uint64_t)((b.uniform_len + 3) >> 2);
-    off_cigar = r * (uint64_t)b.uniform_ncigar;
-    return;
-  }
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t t0 = q / PS_TILE_READS;
-  // bytes in the low half, cigar ops in the high half (a tile holds 256 reads: neither can overflow 32 bits)
-  unsigned long long pre = 0;
-  for (uint64_t j = t0 * PS_TILE_READS + lane; j < q; j += 32) {
-    const uint32_t m = __ldg(b.meta + j);
-    pre += (unsigned long long)((PS_META_LEN(m) + 3) >> 2) | ((unsigned long long)PS_META_NCIGAR(m) << 32);
-  }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) pre += __shfl_xor_sync(0xFFFFFFFFu, pre, d);
-  const unsigned long long mine = in ? ((unsigned long long)((PS_META_LEN(meta) + 3) >> 2) | ((unsigned long long)PS_META_NCIGAR(meta) << 32)) : 0ull;
-  unsigned long long inc = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-    if (lane >= (uint32_t)d) inc += y;
-  }
-  unsigned long long ex = inc - mine;
-  const uint64_t my_tile = r / PS_TILE_READS;
-  const uint32_t crossed = __ballot_sync(0xFFFFFFFFu, my_tile != t0);
-  unsigned long long rel;
-  uint64_t tile = t0;
-  if (crossed) {
-    const int bl = __ffs((int)crossed) - 1;            // first lane of the next tile
-    const unsigned long long exb = __shfl_sync(0xFFFFFFFFu, ex, bl);
-    if (my_tile != t0) { rel = ex - exb; tile = t0 + 1; } else rel = pre + ex;
-  } else rel = pre + ex;
-  if (!in) { off_base = 0; off_cigar = 0; return; }
-  off_base = b.uniform_len ? r * (uint64_t)((b.uniform_len + 3) >> 2) : __ldg(b.tile_base_off + tile) + (rel & 0xFFFFFFFFull);
-  off_cigar = b.uniform_ncigar ? r * (uint64_t)b.uniform_ncigar : __ldg(b.tile_cigar_off + tile) + (rel >> 32);
-}
-
 // one lane decodes read r (r < n); NW > 0: the batch has the PAR-CLIP shape and most reads take the bit-parallel path
 template <int NW>
 __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, ContigCache& cc, PlRead& x) {
@@ -466,9 +425,8 @@ __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, ui
     }
     pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, x);
   } else {
-    uint64_t ob, oc;
-    chunk_offsets(P.b, q, r, in, meta, ob, oc);    // warp-collective
-    if (in) pl_decode_generic(P, r, meta, ob, oc, x);
+    const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);    // warp-collective
+    if (in) pl_decode_generic(P, r, meta, off.base, off.cigar, x);
   }
 }
 

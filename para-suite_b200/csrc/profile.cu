@@ -105,7 +105,9 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   }
   if (skip) { atomicAdd(&S.s_ctr[PS_PC_SKIPPED_READS], 1ull); return; }        // :303-306
 
-  // count loop :349-408 over the (virtual) temp arrays
+  // count loop :349-408 over the (virtual) temp arrays.  Every effect is a commutative sum, so the M/=/X blocks are
+  // taken in cigar order on either strand (minus strand: i = ml-1-column, both bases complemented) and 16 bases at a
+  // time: one funnel shift each for the reference codes, the invalid bits and the read codes.
   const bool rev = flags & PS_RF_REVERSE;
   const bool has_inv = flags & PS_RF_HAS_INVALID;
   ExcRange xr{0, 0};
@@ -113,61 +115,69 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   const uint32_t qual_len = (flags & PS_RF_QUAL_MISSING) ? 0u : L;
   const uint8_t* rb = P.b.bases2 + off.base;
   const uint8_t* rq = P.b.qual + off.qual;
-  long long q_acc0 = 0, q_acc1 = 0, q_acc2 = 0, q_acc3 = 0;
+  int q_acc0 = 0, q_acc1 = 0, q_acc2 = 0, q_acc3 = 0;          // |q| <= 128, <= 65535 bases: no overflow
   uint32_t q_cnt0 = 0, q_cnt1 = 0, q_cnt2 = 0, q_cnt3 = 0;
   uint32_t checked = 0;
-  uint32_t f_i = 0xFFFFFFFFu, f_code = 0;   // first uncaught exception of the count loop (by position i)
-  bool live = true;
-  // forward strand: columns ascend with the cigar; reverse strand: i = ml-1-col, so iterate ops backwards.
-  const uint32_t n_ops = walked ? ncig : 1u;
-  for (uint32_t step = 0; step < n_ops && live; ++step) {
-    int64_t seg_col, seg_ref, seg_read, seg_len;
-    if (!walked) {
-      seg_col = 0; seg_ref = 0; seg_read = 0; seg_len = L;   // L == R: ungapped compare (Q1)
-    } else {
-      const uint32_t e_target = rev ? ncig - 1 - step : step;
-      int64_t pr = 0, pq = 0, pm = 0;
-      uint32_t c = 0;
-      for (uint32_t e = 0; e <= e_target; ++e) {
-        c = __ldg(cig + e);
-        if (e == e_target) break;
-        const uint32_t op = c & 15u;
-        const int64_t n = c >> 4;
-        if (op_is_match(op)) { pm += n; pr += n; pq += n; }
-        else if (op == 3u) { pr += n; pq += n; }
-        else if (op == 1u) { pm += n; pq += n; }
-        else if (op == 2u) { pm += n; pr += n; }
+  uint32_t f_key = 0xFFFFFFFFu;   // first uncaught exception of the count loop: min over (i << 1 | QUAL_RANGE)
+  {
+    int64_t pr = 0, pq = 0, pm = 0;
+    const uint32_t n_ops = walked ? ncig : 1u;
+    for (uint32_t e = 0; e < n_ops; ++e) {
+      int64_t n;
+      if (!walked) n = L;                                      // L == R: ungapped compare (Q1)
+      else {
+        const uint32_t c = __ldg(cig + e), op = c & 15u;
+        n = c >> 4;
+        if (op == 3u) { pr += n; pq += n; continue; }
+        if (op == 1u) { pm += n; pq += n; continue; }
+        if (op == 2u) { pm += n; pr += n; continue; }
+        if (!op_is_match(op)) continue;
       }
-      if (!op_is_match(c & 15u)) continue;
-      seg_col = pm; seg_ref = pr; seg_read = pq; seg_len = c >> 4;
-    }
-    for (int64_t zz = 0; zz < seg_len; ++zz) {
-      const int64_t z = rev ? seg_len - 1 - zz : zz;
-      const int64_t col = seg_col + z;
-      const uint32_t i = (uint32_t)(rev ? (int64_t)ml - 1 - col : col);
-      const uint64_t g = g0 + (uint64_t)(seg_ref + z);
-      const uint32_t p = (uint32_t)(seg_read + z);
-      bool ok = !ref_invalid_at(P.ref, g);
-      if (ok && has_inv) ok = !read_pos_invalid(P.b, xr, p);
-      if (!ok) continue;
-      uint32_t a = ref_code_at(P.ref, g), b = read_code_at(rb, p);
-      if (rev) { a = 3u - a; b = 3u - b; }
-      if (i >= max_len) { f_i = i; f_code = PS_THROW_POS_MAXLEN; live = false; break; }
-      atomicAdd(&S.s_conv[i * 16 + a * 4 + b], 1u);
-      ++checked;
-      if (!has_indel) {
-        if (i >= qual_len) { f_i = i; f_code = PS_THROW_QUAL_RANGE; live = false; break; }
-        const long long qv = (long long)(signed char)__ldg(rq + i);   // qualities are NOT reversed (Q10)
-        if (a == b) {
-          if (a == 0) { q_acc0 += qv; q_cnt0++; } else if (a == 1) { q_acc1 += qv; q_cnt1++; }
-          else if (a == 2) { q_acc2 += qv; q_cnt2++; } else { q_acc3 += qv; q_cnt3++; }
-        } else {
-          atomicAdd(&S.s_q[a * 4 + b], (unsigned long long)qv);
-          atomicAdd(&S.s_q[16 + a * 4 + b], 1ull);
+      for (int64_t z0 = 0; z0 < n; z0 += 16) {
+        const uint32_t cnt = (uint32_t)(n - z0 < 16 ? n - z0 : 16);
+        const uint64_t g = g0 + (uint64_t)(pr + z0);
+        const uint32_t p = (uint32_t)(pq + z0);
+        const uint32_t rw = __funnelshift_r(__ldg(P.ref.seq2 + (g >> 4)), __ldg(P.ref.seq2 + (g >> 4) + 1), (uint32_t)(g & 15u) * 2u);
+        const uint32_t iw = __funnelshift_r(__ldg(P.ref.inv + (g >> 5)), __ldg(P.ref.inv + (g >> 5) + 1), (uint32_t)(g & 31u));
+        const uintptr_t ba = reinterpret_cast<uintptr_t>(rb + (p >> 2));
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(ba & ~(uintptr_t)3);
+        const uint32_t rdw = __funnelshift_r(__ldg(bw), __ldg(bw + 1), (uint32_t)(ba & 3u) * 8u + (p & 3u) * 2u);
+        uint32_t valid = (cnt == 16 ? 0x55555555u : ((1u << (2u * cnt)) - 1u) & 0x55555555u) & ~spread16_even(iw);
+        if (has_inv)
+          for (uint32_t x = xr.e0; x < xr.e1; ++x) {
+            const uint32_t d = (__ldg(P.b.exc + x) & 0xFFFFu) - p;
+            if (d < cnt) valid &= ~(1u << (2u * d));
+          }
+        const int64_t col0 = pm + z0;
+        while (valid) {
+          const uint32_t k2 = (uint32_t)__ffs((int)valid) - 1u;
+          valid &= valid - 1u;
+          uint32_t a = (rw >> k2) & 3u, b = (rdw >> k2) & 3u;
+          const int64_t col = col0 + (k2 >> 1);
+          const uint32_t i = (uint32_t)(rev ? (int64_t)ml - 1 - col : col);
+          if (rev) { a = 3u - a; b = 3u - b; }
+          if (i >= max_len) { f_key = min(f_key, i << 1); continue; }                 // :377
+          atomicAdd(&S.s_conv[i * 16 + a * 4 + b], 1u);
+          ++checked;
+          if (!has_indel) {
+            if (i >= qual_len) { f_key = min(f_key, (i << 1) | 1u); continue; }       // :388
+            const int qv = (int)(signed char)__ldg(rq + i);   // qualities are NOT reversed (Q10)
+            if (a == b) {
+              if (a == 0) { q_acc0 += qv; q_cnt0++; } else if (a == 1) { q_acc1 += qv; q_cnt1++; }
+              else if (a == 2) { q_acc2 += qv; q_cnt2++; } else { q_acc3 += qv; q_cnt3++; }
+            } else {
+              atomicAdd(&S.s_q[a * 4 + b], (unsigned long long)(long long)qv);
+              atomicAdd(&S.s_q[16 + a * 4 + b], 1ull);
+            }
+          }
         }
       }
+      pm += n; pr += n; pq += n;
     }
   }
+  uint32_t f_i = f_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : f_key >> 1;
+  uint32_t f_code = (f_key & 1u) ? PS_THROW_QUAL_RANGE : PS_THROW_POS_MAXLEN;
+  bool live = f_key == 0xFFFFFFFFu;
   if (P.lay.infer_q) {   // :402-407 touches baseQualitiesPerPos[i] / readQualities[i] for EVERY i < ml
     const uint32_t iq = max_len < qual_len ? max_len : qual_len;
     if (ml > iq && iq < f_i) {
@@ -178,10 +188,10 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   }
   if (f_i != 0xFFFFFFFFu) raise_fault(P.fault, ordinal, f_code);
   if (!live) return;
-  if (q_cnt0) { atomicAdd(&S.s_q[0], (unsigned long long)q_acc0); atomicAdd(&S.s_q[16], (unsigned long long)q_cnt0); }
-  if (q_cnt1) { atomicAdd(&S.s_q[5], (unsigned long long)q_acc1); atomicAdd(&S.s_q[21], (unsigned long long)q_cnt1); }
-  if (q_cnt2) { atomicAdd(&S.s_q[10], (unsigned long long)q_acc2); atomicAdd(&S.s_q[26], (unsigned long long)q_cnt2); }
-  if (q_cnt3) { atomicAdd(&S.s_q[15], (unsigned long long)q_acc3); atomicAdd(&S.s_q[31], (unsigned long long)q_cnt3); }
+  if (q_cnt0) { atomicAdd(&S.s_q[0], (unsigned long long)(long long)q_acc0); atomicAdd(&S.s_q[16], (unsigned long long)q_cnt0); }
+  if (q_cnt1) { atomicAdd(&S.s_q[5], (unsigned long long)(long long)q_acc1); atomicAdd(&S.s_q[21], (unsigned long long)q_cnt1); }
+  if (q_cnt2) { atomicAdd(&S.s_q[10], (unsigned long long)(long long)q_acc2); atomicAdd(&S.s_q[26], (unsigned long long)q_cnt2); }
+  if (q_cnt3) { atomicAdd(&S.s_q[15], (unsigned long long)(long long)q_acc3); atomicAdd(&S.s_q[31], (unsigned long long)q_cnt3); }
   atomicAdd(&S.s_ctr[PS_PC_TOTAL_BASES_CHECKED], (unsigned long long)checked);
   if (P.lay.infer_q)
     for (uint32_t i = 0; i < ml; ++i) atomicAdd(P.acc + P.lay.qhist + (size_t)i * 256 + __ldg(rq + i), 1ull);
@@ -197,26 +207,32 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
     atomicAdd(P.acc + P.lay.ctr + threadIdx.x, S.s_ctr[threadIdx.x]);
 }
 
-// Shared memory: s_q[32] u64 | s_ctr[8] u64 | scan scratch[8] u64 | s_conv[max_len*16] u32 | s_indel[2*max_len] u32
+// Shared memory: s_q[32] u64 | s_ctr[8] u64 | pad[8] u64 | s_conv[max_len*16] u32 | s_indel[2*max_len] u32
+// Work unit = a warp-tile of 32 consecutive reads, handed out by an atomic counter: no block barrier in the loop (read
+// lengths and cigars differ, so tiles take very different times), per-read stream offsets from a warp scan.
 __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
   S.s_ctr = S.s_q + 32;
-  uint64_t* s_scan = reinterpret_cast<uint64_t*>(S.s_ctr + 8);
-  S.s_conv = reinterpret_cast<uint32_t*>(s_scan + 8);
+  S.s_conv = reinterpret_cast<uint32_t*>(S.s_ctr + 16);
   S.s_indel = S.s_conv + P.lay.max_len * 16;
   for (uint32_t k = threadIdx.x; k < P.lay.max_len * 18; k += blockDim.x) S.s_conv[k] = 0;   // s_conv and s_indel
-  if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q, s_ctr, s_scan are contiguous
+  if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q, s_ctr, pad are contiguous
   __syncthreads();
-  const uint64_t tile0 = P.first_read / PS_TILE_READS;   // first_read is tile aligned
-  for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-    const uint64_t tile = tile0 + t;
-    const uint64_t r = tile * PS_TILE_READS + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(P.fault + 3);   // zeroed by the launcher
+  for (;;) {
+    unsigned int wt = 0;
+    if (lane == 0) wt = atomicAdd(counter, 1u);
+    wt = __shfl_sync(0xFFFFFFFFu, wt, 0);
+    if (wt >= P.n_tiles) break;
+    const uint64_t q = P.first_read + (uint64_t)wt * 32u, r = q + lane;
     const bool in_range = r < P.b.n_reads;
     const uint32_t meta = in_range ? __ldg(P.b.meta + r) : 0;
-    const ReadOffsets off = read_offsets(P.b, tile, r, meta, in_range, s_scan);
-    if (in_range) profile_read_generic(P, S, tile, threadIdx.x, r, meta, off);
+    const ReadOffsets off = warp_read_offsets(P.b, q, r, in_range, meta);
+    if (in_range) profile_read_generic(P, S, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS), r, meta, off);
+    __syncwarp();
   }
   __syncthreads();
   flush_generic(P, S);
@@ -255,7 +271,9 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(cons
 static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_read, cudaStream_t stream) {
   if (first_read >= P.b.n_reads) return cudaSuccess;
   P.first_read = first_read;
-  P.n_tiles = (uint32_t)((P.b.n_reads - first_read + PS_TILE_READS - 1) / PS_TILE_READS);
+  const uint64_t n_wt = (P.b.n_reads - first_read + 31) / 32;
+  if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
+  P.n_tiles = (uint32_t)n_wt;
   size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 18 * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -268,7 +286,10 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
-  if (grid > P.n_tiles) grid = P.n_tiles;
+  const uint32_t need = (P.n_tiles + PS_BLOCK_THREADS / 32 - 1) / (PS_BLOCK_THREADS / 32);
+  if (grid > need) grid = need;
+  e = cudaMemsetAsync(P.fault + 3, 0, 4, stream);     // warp-tile counter
+  if (e != cudaSuccess) return e;
   profile_generic_kernel<<<grid, PS_BLOCK_THREADS, smem, stream>>>(P);
   ctx->launches++;
   return cudaGetLastError();
