@@ -45,6 +45,10 @@ struct GenericSmem {
 // ---------------------------------------------------------------------------------------------------------
 // Generic per-read routine: literal restatement of ErrorProfiling.java:155-408 on packed data.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {   // native shared-memory reduction
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const GenericSmem& S, uint64_t tile,
                                                   uint32_t rit, uint64_t r, uint32_t meta, ReadOffsets off) {
   const uint32_t max_len = P.lay.max_len;
@@ -119,6 +123,7 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   uint32_t q_cnt0 = 0, q_cnt1 = 0, q_cnt2 = 0, q_cnt3 = 0;
   uint32_t checked = 0;
   uint32_t f_key = 0xFFFFFFFFu;   // first uncaught exception of the count loop: min over (i << 1 | QUAL_RANGE)
+  const uint32_t s_conv32 = (uint32_t)__cvta_generic_to_shared(S.s_conv);
   {
     int64_t pr = 0, pq = 0, pm = 0;
     const uint32_t n_ops = walked ? ncig : 1u;
@@ -148,26 +153,53 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
             const uint32_t d = (__ldg(P.b.exc + x) & 0xFFFFu) - p;
             if (d < cnt) valid &= ~(1u << (2u * d));
           }
-        const int64_t col0 = pm + z0;
-        while (valid) {
-          const uint32_t k2 = (uint32_t)__ffs((int)valid) - 1u;
-          valid &= valid - 1u;
-          uint32_t a = (rw >> k2) & 3u, b = (rdw >> k2) & 3u;
-          const int64_t col = col0 + (k2 >> 1);
-          const uint32_t i = (uint32_t)(rev ? (int64_t)ml - 1 - col : col);
-          if (rev) { a = 3u - a; b = 3u - b; }
-          if (i >= max_len) { f_key = min(f_key, i << 1); continue; }                 // :377
-          atomicAdd(&S.s_conv[i * 16 + a * 4 + b], 1u);
-          ++checked;
-          if (!has_indel) {
-            if (i >= qual_len) { f_key = min(f_key, (i << 1) | 1u); continue; }       // :388
-            const int qv = (int)(signed char)__ldg(rq + i);   // qualities are NOT reversed (Q10)
-            if (a == b) {
-              if (a == 0) { q_acc0 += qv; q_cnt0++; } else if (a == 1) { q_acc1 += qv; q_cnt1++; }
-              else if (a == 2) { q_acc2 += qv; q_cnt2++; } else { q_acc3 += qv; q_cnt3++; }
-            } else {
-              atomicAdd(&S.s_q[a * 4 + b], (unsigned long long)(long long)qv);
-              atomicAdd(&S.s_q[16 + a * 4 + b], 1ull);
+        const uint32_t col0 = (uint32_t)(pm + z0);                    // columns < ml <= 65535 + 65535
+        // positions of this chunk: i = ibase + istep * k, k = 0 .. cnt-1
+        const uint32_t ibase = rev ? ml - 1u - col0 : col0;
+        const int istep = rev ? -1 : 1;
+        const uint32_t i_max = rev ? ibase : ibase + cnt - 1u;
+        const uint32_t flip = rev ? 15u : 0u;                         // complementing both bases: pair -> 15 - pair
+        if (i_max < max_len && (has_indel || i_max < qual_len)) {     // no exception can be raised in this chunk
+          while (valid) {
+            const uint32_t k2 = (uint32_t)__ffs((int)valid) - 1u;
+            valid &= valid - 1u;
+            const uint32_t ra = (rw >> k2) & 3u, rb2 = (rdw >> k2) & 3u;
+            const uint32_t pair = (ra * 4u + rb2) ^ flip;             // 15 - x == x ^ 15 for x < 16
+            const uint32_t i = ibase + (uint32_t)(istep * (int)(k2 >> 1));
+            red_shared_add(s_conv32 + (i * 16u + pair) * 4u, 1u);
+            ++checked;
+            if (!has_indel) {
+              const int qv = (int)(signed char)__ldg(rq + i);   // qualities are NOT reversed (Q10)
+              if (ra == rb2) {
+                const uint32_t a = pair >> 2;
+                if (a == 0) { q_acc0 += qv; q_cnt0++; } else if (a == 1) { q_acc1 += qv; q_cnt1++; }
+                else if (a == 2) { q_acc2 += qv; q_cnt2++; } else { q_acc3 += qv; q_cnt3++; }
+              } else {
+                atomicAdd(&S.s_q[pair], (unsigned long long)(long long)qv);
+                atomicAdd(&S.s_q[16 + pair], 1ull);
+              }
+            }
+          }
+        } else {
+          while (valid) {
+            const uint32_t k2 = (uint32_t)__ffs((int)valid) - 1u;
+            valid &= valid - 1u;
+            const uint32_t pair = (((rw >> k2) & 3u) * 4u + ((rdw >> k2) & 3u)) ^ flip;
+            const uint32_t i = ibase + (uint32_t)(istep * (int)(k2 >> 1));
+            if (i >= max_len) { f_key = min(f_key, i << 1); continue; }                 // :377
+            red_shared_add(s_conv32 + (i * 16u + pair) * 4u, 1u);
+            ++checked;
+            if (!has_indel) {
+              if (i >= qual_len) { f_key = min(f_key, (i << 1) | 1u); continue; }       // :388
+              const int qv = (int)(signed char)__ldg(rq + i);
+              if ((pair >> 2) == (pair & 3u)) {
+                const uint32_t a = pair >> 2;
+                if (a == 0) { q_acc0 += qv; q_cnt0++; } else if (a == 1) { q_acc1 += qv; q_cnt1++; }
+                else if (a == 2) { q_acc2 += qv; q_cnt2++; } else { q_acc3 += qv; q_cnt3++; }
+              } else {
+                atomicAdd(&S.s_q[pair], (unsigned long long)(long long)qv);
+                atomicAdd(&S.s_q[16 + pair], 1ull);
+              }
             }
           }
         }
