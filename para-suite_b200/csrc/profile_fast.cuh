@@ -14,9 +14,10 @@
 // Reads outside the shape (flags, other cigars, contig edges) are appended to a dense list for
 // profile_deferred_kernel instead of being walked inline (one slow lane would stall the other 31).
 
-#define FAST_STAGES 3
+#define FAST_STAGES 2
 #define WT_READS 64            // reads per warp-tile
-#define FAST_WARPS (PS_BLOCK_THREADS / 32)
+#define FAST_THREADS 128
+#define FAST_WARPS (FAST_THREADS / 32)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -311,7 +312,7 @@ __device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& 
 }
 
 template <int NW, int NPL, int LT>
-__global__ void __launch_bounds__(PS_BLOCK_THREADS, 2) profile_fast_kernel(const ProfileParams P) {
+__global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NC = fast_nc(NW, LT);
   const uint32_t max_len = P.lay.max_len;
@@ -580,7 +581,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PS_BLOCK_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FAST_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
@@ -599,7 +600,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
     Q.b.tile_exc_off += r0 / PS_TILE_READS;
     Q.b.n_reads = std::min<uint64_t>(P.b.n_reads - r0, cnt * WT_READS);
     Q.first_read = r0;    // offset added to deferred read indices
-    kern<<<grid, PS_BLOCK_THREADS, smem, stream>>>(Q);
+    kern<<<grid, FAST_THREADS, smem, stream>>>(Q);
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
