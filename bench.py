@@ -33,17 +33,20 @@ UNIT = "reads/s"
 def workload(n_gpus: int, rank: int, small: bool = False):
     """Returns (name, reference, batch, max_len).  The per-GPU workload is the same at every N (weak scaling):
     BASELINE configs[1], 10M x 36-nt PAR-CLIP reads against a 100 Mb reference.  At N > 1 rank r holds region r of an
-    N x 100 Mb genome (the regions share the seeded synthetic sequence; the reads of each region are drawn with their
-    own seed), i.e. the read batches AND the genome regions are sharded, as SURVEY 8(e) partitions the two tools."""
+    N x 100 Mb genome, i.e. the read batches AND the genome regions are sharded, as SURVEY 8(e) partitions the two
+    tools: one all-reduce of the profile count vector, one all-gather of a (contig, end) pair per rank for the pileup."""
     from parasuite_b200 import synth
     if small:   # CI-sized (tests): same shape, 1/50 size
         ref = synth.synth_reference(0x5EED0001, [2_000_000])
         return "config2-small", ref, synth.synth_reads(ref, 200_000, 36, seed=0x5EED0002 + rank), 51
-    ref = synth.synth_reference(0x5EED0001, [100_000_000])
-    batch = synth.synth_reads(ref, 10_000_000, 36, seed=0x5EED0002 + rank)
+    # the N-GPU job: an N x 100 Mb genome (one contig per region), replicated on every GPU as the tools need it; rank r
+    # holds the 10M reads of region r
+    region = 100_000_000
+    ref = synth.synth_reference(0x5EED0001, [region] * n_gpus)
+    batch = synth.synth_reads(ref, 10_000_000, 36, seed=0x5EED0002 + rank, region=(rank * region, (rank + 1) * region))
     name = "config2: 10M x 36-nt PAR-CLIP reads (single 36M cigar) vs 100 Mb synthetic reference"
     if n_gpus > 1:
-        name += f", per GPU (rank r = region r of a {n_gpus} x 100 Mb genome)"
+        name += f", per GPU (rank r = region r of a {n_gpus} x 100 Mb genome, reference replicated)"
     return name, ref, batch, 51
 
 
@@ -188,6 +191,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from parasuite_b200.distributed import sharded_pileup_carry
     from parasuite_b200.runtime import Context, DeviceBatch, PinnedBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,7 +228,10 @@ def main():
         if world > 1:
             dist.all_reduce(ctx.profile_acc_tensor())
         res = ctx.profile_end()
-        with ctx.pileup_run(dbatch, stream=stream.cuda_stream) as h:
+        carry = None
+        if world > 1:   # region sharding: exclusive prefix-max of one (contig, end) pair per rank = this region's carry-in
+            carry = sharded_pileup_carry(ctx.pileup_max_key(dbatch, stream.cuda_stream), device=dev)
+        with ctx.pileup_run(dbatch, first_running_id=1, carry=carry, stream=stream.cuda_stream) as h:
             pile["counters"] = h.counters
         return res
 
@@ -271,7 +278,10 @@ def main():
             dist.all_reduce(ctx.profile_acc_tensor())
             torch.cuda.current_stream().synchronize()
         r = ctx.profile_end()
-        with ctx.pileup_run(view) as h:
+        carry = None
+        if world > 1:
+            carry = sharded_pileup_carry(ctx.pileup_max_key(view), device=dev)
+        with ctx.pileup_run(view, carry=carry) as h:
             pile["res_e2e"] = h.fetch(pinned=True, boundary=False)
         return r
 
@@ -313,6 +323,11 @@ def main():
             "pl_cluster_kernel": (k_cluster, pile_bytes),
             "pl_compact_kernel": (k_compact, compact_bytes),
         }
+        traffic = {}
+        try:    # DRAM bytes per launch from the committed ncu --set full capture of this command (tools/ncu_traffic.py)
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         kname = max(kernels, key=lambda k: kernels[k][0] if kernels[k][0] == kernels[k][0] else -1.0)
         kms, kbytes = kernels[kname]
         achieved = kbytes / (kms * 1e-3) / 1e9 if kms == kms and kms > 0 else None
@@ -332,10 +347,12 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic.get(kname) if world == 1 else None,
                          "kernel": kname, "kernel_ms": kms,
                          "algorithmic_bytes_per_launch": kbytes, "peak_source": peak_src,
-                         "per_kernel": {k: {"ms": v[0], "bytes": v[1], "frac": frac(v[1], v[0])} for k, v in kernels.items()}},
+                         "per_kernel": {k: {"ms": v[0], "bytes": v[1], "frac": frac(v[1], v[0]), "traffic": traffic.get(k)}
+                                        for k, v in kernels.items()}},
         }
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -240,6 +240,10 @@ typedef struct ps_pileup_opts {
 int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* host_batch, const ps_pileup_opts* opts, ps_pileup** out);
 int ps_pileup_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, const ps_pileup_opts* opts, void* stream,
                            ps_pileup** out);
+/* Region sharding: max over the batch's kept records of (contig, alignment end).  The exclusive prefix-max of these
+ * over the shards (one pair per shard: an all-gather of 8 scalars) is shard s's carry-in, so all shards run at once. */
+int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,
+                      int32_t* end);
 int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out);
 /* copy up to `max_clusters` closed clusters starting at `first` (and their sites) into caller arrays;
  * returns the number copied (>= 0) or a negative status */

@@ -89,6 +89,7 @@ struct FlagParams {
 };
 
 // (contig+1) << 32 | end of a kept record, 0 otherwise (PileupClusters.java:146-158)
+template <bool COUNT = true>
 __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64_t r, uint32_t meta, const uint32_t* cig,
                                                      uint32_t g0, ContigCache& cc, int32_t& start) {
   const uint32_t flags = PS_META_FLAGS(meta), ncig = PS_META_NCIGAR(meta);
@@ -102,7 +103,7 @@ __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64
     if (op_consumes_ref(op)) R += c >> 4;
   }
   if ((hasI || hasD) && hasN) {                                              // :152-157
-    atomicAdd(&P.st->skipped, 1ull);
+    if (COUNT) atomicAdd(&P.st->skipped, 1ull);
     return 0;
   }
   if (flags & PS_RF_POS_ZERO) return 0;           // the JVM dies on this record: pl_cluster_kernel raises the fault
@@ -122,6 +123,27 @@ __device__ __forceinline__ unsigned long long pl_key1(const FlagParams& P, uint3
   const uint32_t R = op_consumes_ref(cg & 15u) ? cg >> 4 : 0u;
   start = (int32_t)((uint64_t)g0 - cc.lo) + 1;
   return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(start + (int32_t)R - 1);
+}
+
+// max over the records of a batch of (contig, end): what a following shard needs as carry-in (region sharding: the
+// exclusive prefix-max of these keys over the shards replaces Java's (tempClusterChr, tempClusterEnd) at the cut)
+__global__ void __launch_bounds__(PL_THREADS) pl_maxkey_kernel(const __grid_constant__ FlagParams P, unsigned long long* out) {
+  ContigCache cc;
+  unsigned long long best = 0;
+  const uint64_t n = P.b.n_reads;
+  for (uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = q + (threadIdx.x & 31u);
+    const bool in = r < n;
+    const uint32_t meta = in ? __ldg(P.b.meta + r) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
+    const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);
+    if (!in) continue;
+    int32_t start;
+    const unsigned long long k = pl_key<false>(P, r, meta, P.b.cigar + off.cigar, __ldg(P.b.ref_start + r), cc, start);
+    best = k > best ? k : best;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, best, d); best = o > best ? o : best; }
+  if ((threadIdx.x & 31u) == 0 && best) atomicMax(out, best);
 }
 
 // block-wide exclusive scan over one 64-bit value per thread (PL_THREADS threads); also returns the block total
@@ -1206,6 +1228,33 @@ int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* hb, const ps_pileup_opts* 
   if (*out) (*out)->stage_serial = ctx->stage_serial;
   if (rc != PS_OK && rc != PS_ERR_REFERENCE_WOULD_THROW) { free_handle(*out); *out = nullptr; }
   return rc;
+}
+
+int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,
+                      int32_t* end) {
+  if (!ctx || !dev_batch || !valid || !contig || !end) return PS_ERR_INVALID_ARG;
+  if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  *valid = 0; *contig = 0; *end = 0;
+  if (dev_batch->n_reads == 0) return PS_OK;
+  cudaError_t err = cudaSuccess;
+  unsigned long long* d_key = scratch<unsigned long long>(ctx, 9, 1, err);
+  if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+  FlagParams P{};
+  P.b = pl_view_of(dev_batch); P.ref = ctx->ref;
+  PS_CUDA(ctx, cudaMemsetAsync(d_key, 0, 8, st));
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((dev_batch->n_reads + PL_THREADS - 1) / PL_THREADS, (uint64_t)ctx->sm_count * 8);
+  pl_maxkey_kernel<<<grid, PL_THREADS, 0, st>>>(P, d_key);
+  ctx->launches++;
+  PS_CUDA(ctx, cudaGetLastError());
+  unsigned long long* hk = ctx->h_pinned ? reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->h_pinned) + 1024) : nullptr;
+  unsigned long long tmp = 0;
+  PS_CUDA(ctx, cudaMemcpyAsync(hk ? hk : &tmp, d_key, 8, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(ctx, cudaStreamSynchronize(st));
+  const unsigned long long k = hk ? *hk : tmp;
+  if (k) { *valid = 1; *contig = (uint32_t)(k >> 32) - 1; *end = (int32_t)(uint32_t)k; }
+  return PS_OK;
 }
 
 int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out) {

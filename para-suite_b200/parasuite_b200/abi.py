@@ -151,6 +151,8 @@ EXPORTS = {
     "ps_pileup_batch": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_pileup_opts), C.POINTER(VP)]),
     "ps_pileup_batch_device": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_pileup_opts), VP,
                                          C.POINTER(VP)]),
+    "ps_pileup_max_key": (C.c_int, [VP, C.POINTER(ps_read_batch), VP, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                C.POINTER(C.c_int32)]),
     "ps_pileup_counters_get": (C.c_int, [VP, C.POINTER(ps_pileup_counters)]),
     "ps_pileup_next": (C.c_int64, [VP, C.c_uint64, VP, C.c_uint64, VP, C.c_uint64]),
     "ps_pileup_open_cluster": (C.c_int, [VP, VP, VP, C.c_uint64]),

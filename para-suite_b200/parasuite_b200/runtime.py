@@ -239,6 +239,13 @@ class Context:
             raise
         return res
 
+    def pileup_max_key(self, dbatch, stream: int = 0):
+        """(contig, end) maximum over the kept records of a device-resident batch, or None (region sharding carry)."""
+        v, c, e = C.c_uint32(), C.c_uint32(), C.c_int32()
+        _check(self.lib, self.h, self.lib.ps_pileup_max_key(self.h, C.byref(dbatch.struct), stream or None, C.byref(v),
+                                                             C.byref(c), C.byref(e)))
+        return (int(c.value), int(e.value)) if v.value else None
+
     def pileup(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> dict:
         """pileup_run + fetch of every record into host arrays."""
         with self.pileup_run(batch, first_running_id, carry, stream) as res:

@@ -139,3 +139,87 @@ def test_world2_gloo(oracle):
     while not q.empty():
         out.append(q.get())
     assert out and out[-1] is True, out
+
+
+# ---- parallel carry: exclusive prefix-max of one (contig, end) pair per shard (parasuite_b200.distributed) ----------
+def np_max_key(ref, batch):
+    """(contig, end) maximum over the kept records of a single-M-op batch (numpy stand-in for ps_pileup_max_key)."""
+    if batch.n_reads == 0:
+        return None
+    fl = batch.meta >> 24
+    kept = (fl & (abi.PS_RF_UNMAPPED | abi.PS_RF_POS_ZERO)) == 0
+    if not kept.any():
+        return None
+    g = batch.ref_start[kept].astype(np.int64)
+    contig = np.searchsorted(ref.contig_off.astype(np.int64), g, side="right") - 1
+    start = g - ref.contig_off.astype(np.int64)[contig] + 1
+    R = (batch.cigar[: batch.n_reads][kept] >> 4).astype(np.int64)
+    end = start + R - 1
+    k = int(np.lexsort((end, contig))[-1])
+    return int(contig[k]), int(end[k])
+
+
+def test_prefix_max_carry_equals_sequential_carry(oracle):
+    from parasuite_b200 import synth
+    from parasuite_b200.distributed import exclusive_prefix_max
+    assert exclusive_prefix_max([(0, 5), None, (0, 3), (1, 1)]) == [None, (0, 5), (0, 5), (0, 5)]
+    for ref, batch in ((synth.synth_reference(31, [2_000_000, 700_000], n_run=1000), None),
+                       (synth.synth_reference(32, [60_000], n_run=0), None)):
+        batch = synth.synth_reads(ref, 40_000, 36, seed=6, threads=2)
+        whole = oracle.pileup(ref, batch)
+        for cuts in ([20_000], [1], [39_999], [100, 150, 20_000], [256, 512, 30_000, 30_001]):
+            bounds = [0] + cuts + [batch.n_reads]
+            shards = [slice_batch(batch, lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:])]
+            carries = exclusive_prefix_max([np_max_key(ref, s) for s in shards])
+            results = [oracle.pileup(ref, s, carry=c) for s, c in zip(shards, carries)]     # all shards independent
+            assert_same(merge_pileup_shards(results, bounds[:-1]), whole, f"parallel carry {cuts}")
+
+
+def _worker_parallel(rank, world, port, q):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    repo = os.path.dirname(here)
+    for p in (os.path.join(repo, "para-suite_b200"), os.path.join(repo, "oracle"), here):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from parasuite_b200 import synth
+    from parasuite_b200.distributed import allreduce_profile, sharded_pileup
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ref = synth.synth_reference(43, [400_000, 300_000], n_run=500)
+    batch = synth.synth_reads(ref, 45_000, 36, seed=9, threads=1)
+    lo, hi = shard_ranges(batch.n_reads, world)[rank]
+    shard = slice_batch(batch, lo, hi)
+    acc = allreduce_profile(torch.from_numpy(oracle_lib.profile_acc(ref, batch, 51, first=lo, count=hi - lo, ordinal0=0)))
+    res, merged = sharded_pileup(shard, lambda b: np_max_key(ref, b), lambda b, c: oracle_lib.pileup(ref, b, carry=c), lo)
+    if rank == 0:
+        ok = bool(np.array_equal(acc.numpy(), oracle_lib.profile_acc(ref, batch, 51)))
+        try:
+            assert_same(merged, oracle_lib.pileup(ref, batch), "gloo parallel carry")
+        except AssertionError as e:
+            ok = False
+            q.put(repr(e))
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_world_gloo_parallel_carry(oracle, world):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_parallel, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    out = []
+    while not q.empty():
+        out.append(q.get())
+    assert out and out[-1] is True, out
