@@ -177,7 +177,7 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
 // ITEMS == PL_FLAG_ITEMS: every read has one cigar op and the streams are 16-byte aligned (vector loads);
 // ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
 template <int ITEMS>
-__global__ void __launch_bounds__(PL_THREADS) pl_flag_kernel(const __grid_constant__ FlagParams P) {
+__global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_constant__ FlagParams P) {
   constexpr int TILE = PL_THREADS * ITEMS;
   __shared__ unsigned long long s_wtot[PL_WARPS];
   __shared__ uint64_t s_scan[8];
@@ -648,7 +648,7 @@ static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is
 // Clusters that do not fit (more than CB_CHUNK reads, T>C positions more than 64 apart, more than CB_SITES of them)
 // are left to the warp-per-cluster routine above at the end of the block.
 template <int NW>
-__global__ void __launch_bounds__(PL_THREADS) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
+__global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_wtot[PL_WARPS];
   __shared__ unsigned long long s_base;
