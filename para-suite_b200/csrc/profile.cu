@@ -239,20 +239,190 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
     atomicAdd(P.acc + P.lay.ctr + threadIdx.x, S.s_ctr[threadIdx.x]);
 }
 
-// Shared memory: s_q[32] u64 | s_ctr[8] u64 | pad[8] u64 | s_conv[max_len*16] u32 | s_indel[2*max_len] u32
-// Work unit = a warp-tile of 32 consecutive reads, handed out by an atomic counter: no block barrier in the loop (read
-// lengths and cigars differ, so tiles take very different times), per-read stream offsets from a warp scan.
-__global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
+// ---------------------------------------------------------------------------------------------------------
+// General kernel: one WARP per read, lanes = alignment columns.
+// All lanes walk the cigar together (uniform control flow, broadcast loads); inside an M/=/X block lane l takes columns
+// l, l+32, ...: consecutive reference bases, read bases and qualities per lane, conflict-free native shared-memory
+// reductions into a [pair][position] histogram.  Matching-base quality sums and the base counter live in per-lane
+// registers for the whole kernel.  Same statements as profile_read_generic (ErrorProfiling.java:155-408).
+// ---------------------------------------------------------------------------------------------------------
+struct WarpAcc {
+  long long q_acc[4];
+  unsigned long long q_cnt[4];
+  unsigned long long checked;
+};
+
+// what the count loop needs to know about a read that reached it
+struct ReadPlan {
+  uint64_t g0;
+  uint32_t ml;          // 0: nothing to count (filtered, skipped, or the JVM died on this record)
+  uint32_t bits;        // bit 0: the cigar string holds I or D; bit 1: L != R (the read was walked)
+};
+
+// Prologue of one read by ONE lane (32 reads of a warp-tile at a time): filters, FASTA range, cigar bounds, indel side
+// effects, uncaught exceptions of the walk (ErrorProfiling.java:155-306).
+__device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P, const GenericSmem& S, uint64_t r, uint32_t meta,
+                                                          const ReadOffsets& off) {
+  ReadPlan plan;
+  plan.g0 = 0; plan.ml = 0; plan.bits = 0;
+  const uint32_t max_len = P.lay.max_len;
+  const uint32_t flags = PS_META_FLAGS(meta), L = PS_META_LEN(meta), ncig = PS_META_NCIGAR(meta);
+  const uint64_t ordinal = P.ordinal0 + r;
+  // filters :155-166 (first match wins)
+  if (flags & PS_RF_UNMAPPED) { atomicAdd(&S.s_ctr[PS_PC_UNMAPPED], 1ull); return plan; }
+  if (flags & PS_RF_DUPLICATE) { atomicAdd(&S.s_ctr[PS_PC_DUPLICATES], 1ull); return plan; }
+  if (flags & PS_RF_POS_ZERO) { atomicAdd(&S.s_ctr[PS_PC_START_ZERO], 1ull); return plan; }
+  const uint32_t* cig = P.b.cigar + off.cigar;
+  uint32_t R = 0;
+  bool has_indel = false;
+  for (uint32_t e = 0; e < ncig; ++e) {
+    const uint32_t c = __ldg(cig + e), op = c & 15u;
+    if (op_consumes_ref(op)) R += c >> 4;
+    has_indel |= (op == 1u) | (op == 2u);
+  }
+  const uint64_t g0 = __ldg(P.b.ref_start + r);
+  {  // :169-172 FASTA fetch range
+    bool bad = (flags & PS_RF_REF_RANGE) || g0 >= P.ref.n_bases;
+    if (!bad) {
+      const uint32_t c = contig_of(P.ref, g0);
+      bad = g0 + R > __ldg(P.ref.contig_off + c + 1);
+    }
+    if (bad) { raise_fault(P.fault, ordinal, PS_THROW_REF_RANGE); return plan; }
+  }
+  atomicAdd(&S.s_ctr[PS_PC_NUM_READS_PROCESSED], 1ull);                        // :174
+  if (R == 0) { raise_fault(P.fault, ordinal, PS_THROW_EMPTY_REF); return plan; }
+  const uint32_t ml = L > R ? L : R;
+  if (L != R) {   // :194-299, pass 1: bounds (skip), indel side effects, uncaught exceptions
+    bool skip = false;
+    int64_t pr = 0, pq = 0, pm = 0;
+    for (uint32_t e = 0; e < ncig; ++e) {
+      const uint32_t c = __ldg(cig + e), op = c & 15u;
+      const int64_t n = c >> 4;
+      if (op_is_match(op)) {
+        if (n > 0 && (pm + n > (int64_t)ml || pr + n > (int64_t)R || pq + n > (int64_t)L)) skip = true;
+        pm += n; pr += n; pq += n;
+      } else if (op == 3u) {
+        pr += n; pq += n;
+      } else if (op == 1u || op == 2u) {
+        if (n > 0 && pm + n > (int64_t)ml) { raise_fault(P.fault, ordinal, PS_THROW_INDEL_FILL); return plan; }
+        pm += n;
+        if (op == 1u) pq += n; else pr += n;
+        uint32_t* arr = S.s_indel + (op == 1u ? 0u : max_len);
+        for (int64_t q = 1; q <= n; ++q) {
+          if (pm + q >= (int64_t)max_len) { raise_fault(P.fault, ordinal, PS_THROW_INDEL_POS); return plan; }
+          atomicAdd(arr + (pm + q), 1u);
+        }
+        if (n > 1) atomicAdd(&S.s_ctr[PS_PC_LONGER_INDELS], 1ull);
+      }
+    }
+    atomicAdd(&S.s_ctr[PS_PC_INDEL_READ], 1ull);                               // :296
+    if (skip) { atomicAdd(&S.s_ctr[PS_PC_SKIPPED_READS], 1ull); return plan; } // :303-306
+  }
+  plan.g0 = g0; plan.ml = ml; plan.bits = (has_indel ? 1u : 0u) | (L != R ? 2u : 0u);
+  return plan;
+}
+
+// Count loop of one read by the WHOLE warp (ErrorProfiling.java:349-408).
+__device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const GenericSmem& S, uint32_t convT, uint32_t pad,
+                                                  uint64_t r, uint32_t meta, ReadOffsets off, ReadPlan plan, WarpAcc& A) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t max_len = P.lay.max_len;
+  const uint32_t flags = PS_META_FLAGS(meta), L = PS_META_LEN(meta), ncig = PS_META_NCIGAR(meta);
+  const uint64_t ordinal = P.ordinal0 + r;
+  const uint32_t* cig = P.b.cigar + off.cigar;
+  const uint64_t g0 = plan.g0;
+  const uint32_t ml = plan.ml;
+  const bool has_indel = (plan.bits & 1u) != 0, walked = (plan.bits & 2u) != 0;
+  // count loop :349-408
+  const bool rev = flags & PS_RF_REVERSE;
+  const bool has_inv = flags & PS_RF_HAS_INVALID;
+  ExcRange xr{0, 0};
+  if (has_inv) xr = read_exc_range(P.b, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS));
+  const uint32_t qual_len = (flags & PS_RF_QUAL_MISSING) ? 0u : L;
+  const uint8_t* rb = P.b.bases2 + off.base;
+  const uint8_t* rq = P.b.qual + off.qual;
+  const uint32_t flip = rev ? 15u : 0u;           // complementing both bases: pair -> 15 - pair
+  uint32_t f_key = 0xFFFFFFFFu;                   // first uncaught exception: min over (i << 1 | QUAL_RANGE)
+  long long qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;
+  uint32_t qc0 = 0, qc1 = 0, qc2 = 0, qc3 = 0, checked = 0;
+  {
+    uint32_t pr = 0, pq = 0, pm = 0;              // the read was not skipped: every block lies inside ml, R and L
+    const uint32_t n_ops = walked ? ncig : 1u;
+    for (uint32_t e = 0; e < n_ops; ++e) {
+      uint32_t n;
+      if (!walked) n = L;                         // L == R: ungapped compare (Q1)
+      else {
+        const uint32_t c = __ldg(cig + e), op = c & 15u;
+        n = c >> 4;
+        if (op == 3u) { pr += n; pq += n; continue; }
+        if (op == 1u) { pm += n; pq += n; continue; }
+        if (op == 2u) { pm += n; pr += n; continue; }
+        if (!op_is_match(op)) continue;
+      }
+      for (uint32_t z = lane; z < n; z += 32) {
+        const uint64_t g = g0 + pr + z;
+        const uint32_t p = pq + z, col = pm + z;
+        bool ok = !((__ldg(P.ref.inv + (g >> 5)) >> (g & 31u)) & 1u);
+        if (ok && has_inv) ok = !read_pos_invalid(P.b, xr, p);
+        if (!ok) continue;
+        const uint32_t ra = (__ldg(P.ref.seq2 + (g >> 4)) >> (2u * (uint32_t)(g & 15u))) & 3u;
+        const uint32_t rd = ((uint32_t)__ldg(rb + (p >> 2)) >> (2u * (p & 3u))) & 3u;
+        const uint32_t pair = (ra * 4u + rd) ^ flip;
+        const uint32_t i = rev ? ml - 1u - col : col;
+        if (i >= max_len) { f_key = min(f_key, i << 1); continue; }                 // :377
+        red_shared_add(convT + (pair * pad + i) * 4u, 1u);
+        ++checked;
+        if (!has_indel) {
+          if (i >= qual_len) { f_key = min(f_key, (i << 1) | 1u); continue; }       // :388
+          const int qv = (int)(signed char)__ldg(rq + i);   // qualities are NOT reversed (Q10)
+          if (ra == rd) {
+            const uint32_t a = pair >> 2;
+            if (a == 0) { qa0 += qv; qc0++; } else if (a == 1) { qa1 += qv; qc1++; }
+            else if (a == 2) { qa2 += qv; qc2++; } else { qa3 += qv; qc3++; }
+          } else {
+            atomicAdd(&S.s_q[pair], (unsigned long long)(long long)qv);
+            atomicAdd(&S.s_q[16 + pair], 1ull);
+          }
+        }
+      }
+      pm += n; pr += n; pq += n;
+    }
+  }
+  f_key = __reduce_min_sync(0xFFFFFFFFu, f_key);
+  uint32_t f_i = f_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : f_key >> 1;
+  uint32_t f_code = (f_key & 1u) ? PS_THROW_QUAL_RANGE : PS_THROW_POS_MAXLEN;
+  if (P.lay.infer_q) {   // :402-407 touches baseQualitiesPerPos[i] / readQualities[i] for EVERY i < ml
+    const uint32_t iq = max_len < qual_len ? max_len : qual_len;
+    if (ml > iq && iq < f_i) { f_i = iq; f_code = max_len <= qual_len ? PS_THROW_POS_MAXLEN : PS_THROW_QUAL_RANGE; }
+  }
+  if (f_i != 0xFFFFFFFFu) { if (lane == 0) raise_fault(P.fault, ordinal, f_code); return; }
+  A.q_acc[0] += qa0; A.q_acc[1] += qa1; A.q_acc[2] += qa2; A.q_acc[3] += qa3;
+  A.q_cnt[0] += qc0; A.q_cnt[1] += qc1; A.q_cnt[2] += qc2; A.q_cnt[3] += qc3;
+  A.checked += checked;
+  if (P.lay.infer_q)
+    for (uint32_t i = lane; i < ml; i += 32) atomicAdd(P.acc + P.lay.qhist + (size_t)i * 256 + __ldg(rq + i), 1ull);
+}
+
+// Shared memory: s_q[32] u64 | s_ctr[16] u64 | histogram [16][pad] u32 (pad = max_len | 1) | s_indel[2*max_len] u32
+// Work unit = a warp-tile of 32 consecutive reads, handed out by an atomic counter: no block barrier in the loop.  The
+// tile's per-read stream offsets come from one warp scan; the warp then takes the 32 reads one after the other.
+__global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
+  const uint32_t max_len = P.lay.max_len, pad = max_len | 1u;
   S.s_q = reinterpret_cast<unsigned long long*>(smem_raw);
   S.s_ctr = S.s_q + 32;
-  S.s_conv = reinterpret_cast<uint32_t*>(S.s_ctr + 16);
-  S.s_indel = S.s_conv + P.lay.max_len * 16;
-  for (uint32_t k = threadIdx.x; k < P.lay.max_len * 18; k += blockDim.x) S.s_conv[k] = 0;   // s_conv and s_indel
-  if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q, s_ctr, pad are contiguous
+  S.s_conv = reinterpret_cast<uint32_t*>(S.s_ctr + 16);      // transposed here: [pair][pad]
+  S.s_indel = S.s_conv + 16 * pad;
+  for (uint32_t k = threadIdx.x; k < 16 * pad + 2 * max_len; k += blockDim.x) S.s_conv[k] = 0;
+  if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q and s_ctr are contiguous
   __syncthreads();
+  const uint32_t convT = (uint32_t)__cvta_generic_to_shared(S.s_conv);
   const uint32_t lane = threadIdx.x & 31;
+  WarpAcc A;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) { A.q_acc[b] = 0; A.q_cnt[b] = 0; }
+  A.checked = 0;
   unsigned int* counter = reinterpret_cast<unsigned int*>(P.fault + 3);   // zeroed by the launcher
   for (;;) {
     unsigned int wt = 0;
@@ -263,11 +433,50 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_generic_kernel(const
     const bool in_range = r < P.b.n_reads;
     const uint32_t meta = in_range ? __ldg(P.b.meta + r) : 0;
     const ReadOffsets off = warp_read_offsets(P.b, q, r, in_range, meta);
-    if (in_range) profile_read_generic(P, S, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS), r, meta, off);
-    __syncwarp();
+    ReadPlan plan;
+    plan.g0 = 0; plan.ml = 0; plan.bits = 0;
+    if (in_range) plan = profile_read_prologue(P, S, r, meta, off);
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, plan.ml != 0);
+    while (todo) {
+      const int j = __ffs((int)todo) - 1;
+      todo &= todo - 1;
+      ReadOffsets oj;
+      oj.base = __shfl_sync(0xFFFFFFFFu, off.base, j);
+      oj.qual = __shfl_sync(0xFFFFFFFFu, off.qual, j);
+      oj.cigar = __shfl_sync(0xFFFFFFFFu, off.cigar, j);
+      ReadPlan pj;
+      pj.g0 = __shfl_sync(0xFFFFFFFFu, plan.g0, j);
+      pj.ml = __shfl_sync(0xFFFFFFFFu, plan.ml, j);
+      pj.bits = __shfl_sync(0xFFFFFFFFu, plan.bits, j);
+      profile_read_warp(P, S, convT, pad, q + j, __shfl_sync(0xFFFFFFFFu, meta, j), oj, pj, A);
+      __syncwarp();
+    }
+  }
+  // per-lane registers -> shared
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    long long t = A.q_acc[b];
+    unsigned long long c = A.q_cnt[b];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { t += __shfl_xor_sync(0xFFFFFFFFu, t, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d); }
+    if (lane == 0 && c) { atomicAdd(&S.s_q[b * 5], (unsigned long long)t); atomicAdd(&S.s_q[16 + b * 5], c); }
+  }
+  {
+    unsigned long long c = A.checked;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if (lane == 0 && c) atomicAdd(&S.s_ctr[PS_PC_TOTAL_BASES_CHECKED], c);
   }
   __syncthreads();
-  flush_generic(P, S);
+  // flush (the histogram is [pair][position] here)
+  for (uint32_t k = threadIdx.x; k < max_len * 16; k += blockDim.x) {
+    const uint32_t v = S.s_conv[(k & 15u) * pad + (k >> 4)];
+    if (v) atomicAdd(P.acc + P.lay.conv + k, (unsigned long long)v);
+  }
+  for (uint32_t k = threadIdx.x; k < 2 * max_len; k += blockDim.x)
+    if (S.s_indel[k]) atomicAdd(P.acc + P.lay.ins + k, (unsigned long long)S.s_indel[k]);
+  if (threadIdx.x < 32 && S.s_q[threadIdx.x]) atomicAdd(P.acc + P.lay.qsum + threadIdx.x, S.s_q[threadIdx.x]);
+  if (threadIdx.x < PS_PC_COUNT && S.s_ctr[threadIdx.x]) atomicAdd(P.acc + P.lay.ctr + threadIdx.x, S.s_ctr[threadIdx.x]);
 }
 
 // Reads the fast kernel could not take (flags, other cigars, contig edges): a dense list, so every thread of a
@@ -306,7 +515,7 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   const uint64_t n_wt = (P.b.n_reads - first_read + 31) / 32;
   if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
   P.n_tiles = (uint32_t)n_wt;
-  size_t smem = 48 * 8 + (size_t)ctx->layout.max_len * 18 * 4;
+  size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
