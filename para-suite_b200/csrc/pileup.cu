@@ -49,6 +49,9 @@ struct PlState {                  // device-side run state (one per call)
   unsigned int unsorted;
   unsigned int tile_ctr_flag;
   unsigned int tile_ctr_compact;
+  unsigned int first_slot1;       // first read of slot 1 (end of the head partial); n_reads if there is no slot 1
+  unsigned int pad0;
+  ps_cluster head, open;          // final records of slot 0 and of the last slot (written by pl_compact_kernel)
 };
 
 struct PlRead {              // what the pileup needs from one read
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_con
     if ((fl >> j) & 1u) {
       ++slot;
       if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
+      if (slot == 1) P.st->first_slot1 = (unsigned int)(r0 + j);
     }
   if (tile == P.n_tiles - 1 && threadIdx.x == PL_THREADS - 1) {
     if (slot + 1 <= P.cap_cl) P.cl_first[slot + 1] = (uint32_t)n;   // slots 0 .. n_flags, the last one is the open cluster
@@ -937,6 +941,12 @@ __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_con
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.dst + to);
     for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];     // a site is 24 bytes
     *reinterpret_cast<ulonglong2*>(&P.cl[c0 + j].site_begin) = make_ulonglong2(to, to + cnt[j]);
+    if (c0 + j == 0 || c0 + j == n_slots - 1) {      // the two boundary records ride home with the run state
+      ps_cluster rec = P.cl[c0 + j];
+      rec.site_begin = to; rec.site_end = to + cnt[j];
+      if (c0 + j == 0) P.st->head = rec;
+      if (c0 + j == n_slots - 1) P.st->open = rec;
+    }
     to += cnt[j];
   }
 }
@@ -956,7 +966,7 @@ __global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint
 __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
     st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_flags = 0;
-    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0;
+    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu;
   }
 }
 
@@ -971,7 +981,7 @@ struct ps_pileup {
   // device results, owned by the handle (stream-ordered allocations)
   ps_cluster* d_cl = nullptr;        // slot 0 = head partial, 1..n_flags-1 closed, n_flags = open
   ps_site* d_sites = nullptr;
-  uint32_t* d_first = nullptr;       // [n_slots + 1] first read of each slot
+  uint32_t first_slot1 = 0;          // first read of slot 1 = end of the head partial
   uint64_t n_slots = 0, n_reads = 0;
   ps_cluster head{}, open{};
   bool has_head = false;
@@ -1058,16 +1068,15 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
     if (H->d_cl) { cudaFreeAsync(H->d_cl, st); H->d_cl = nullptr; }
     if (H->d_sites) { cudaFreeAsync(H->d_sites, st); H->d_sites = nullptr; }
-    if (H->d_first) { cudaFreeAsync(H->d_first, st); H->d_first = nullptr; }
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_cl, cap_cl * sizeof(ps_cluster), st));
     PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (cap_sites + 1) * sizeof(ps_site), st));
-    ps_site* d_tmp = nullptr;
-    PS_CUDA(ctx, cudaMallocAsync((void**)&d_tmp, (cap_sites + 1) * sizeof(ps_site), st));
-    PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_first, (cap_cl + 2) * sizeof(uint32_t), st));
+    ps_site* d_tmp = scratch<ps_site>(ctx, 10, cap_sites + 1, err);
+    uint32_t* d_first = scratch<uint32_t>(ctx, 4, cap_cl + 2, err);
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
 
     FlagParams P;
     P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
-    P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = H->d_first; P.cap_cl = cap_cl;
+    P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
     pl_init_state<<<1, 32, 0, st>>>(d_state);
     const bool ev = ctx->timers_on;
     if (ev) cudaEventRecord(ctx->pl_ev[0], st);
@@ -1076,7 +1085,7 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     if (ev) cudaEventRecord(ctx->pl_ev[1], st);
     ClusterParams Q;
     Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
-    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = H->d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
+    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
     Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
     launch_cluster(nw, c_tiles, st, Q);
     if (ev) cudaEventRecord(ctx->pl_ev[2], st);
@@ -1085,17 +1094,12 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     R.cap_cl = cap_cl; R.cap_sites = cap_sites;
     pl_compact_kernel<<<(uint32_t)((cap_cl + PL_THREADS * 4 - 1) / (PL_THREADS * 4)), PL_THREADS, 0, st>>>(R);
     if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
-    cudaFreeAsync(d_tmp, st);
     ctx->launches += 4;
     PS_CUDA(ctx, cudaGetLastError());
     PlState* hsp = ctx->h_pinned ? static_cast<PlState*>(ctx->h_pinned) : &hs;
     PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
-    // head partial (slot 0) rides along; the open cluster's slot is only known once the state is here
-    ps_cluster* hhead = ctx->h_pinned ? reinterpret_cast<ps_cluster*>(static_cast<char*>(ctx->h_pinned) + 256) : &H->head;
-    PS_CUDA(ctx, cudaMemcpyAsync(hhead, H->d_cl, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));
     hs = *hsp;
-    H->head = *hhead;
     const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
     if (need_cl <= cap_cl && need_sites <= cap_sites) break;
     if (attempt >= 2) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }
@@ -1116,12 +1120,9 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   const uint64_t n_slots = (uint64_t)hs.n_flags + 1;
   H->n_slots = n_slots;
   // summary: head partial (slot 0), open cluster (last slot)
-  if (hs.n_flags) {
-    ps_cluster* hopen = ctx->h_pinned ? reinterpret_cast<ps_cluster*>(static_cast<char*>(ctx->h_pinned) + 512) : &H->open;
-    PS_CUDA(ctx, cudaMemcpyAsync(hopen, H->d_cl + hs.n_flags, sizeof(ps_cluster), cudaMemcpyDeviceToHost, st));
-    PS_CUDA(ctx, cudaStreamSynchronize(st));
-    H->open = *hopen;
-  }
+  H->head = hs.head;
+  if (hs.n_flags) H->open = hs.open;
+  H->first_slot1 = hs.first_slot1 == 0xFFFFFFFFu ? (uint32_t)n : hs.first_slot1;
   H->has_head = H->head.num_reads != 0;
   H->counters.has_open_cluster = hs.n_flags ? 1 : 0;
   H->counters.double_stranded = hs.dstr;
@@ -1145,7 +1146,6 @@ static void free_handle(ps_pileup* h) {
   if (h->ctx) cudaSetDevice(h->ctx->device);
   if (h->d_cl) cudaFreeAsync(h->d_cl, h->stream);
   if (h->d_sites) cudaFreeAsync(h->d_sites, h->stream);
-  if (h->d_first) cudaFreeAsync(h->d_first, h->stream);
   delete h;
 }
 
@@ -1188,8 +1188,7 @@ static int boundary_coverage(ps_pileup* h) {
   };
   const uint64_t n_flags = h->n_slots - 1;
   if (h->has_head) {
-    uint32_t r1 = (uint32_t)h->n_reads;
-    if (n_flags) PS_CUDA(ctx, cudaMemcpy(&r1, h->d_first + 1, 4, cudaMemcpyDeviceToHost));
+    const uint32_t r1 = n_flags ? h->first_slot1 : (uint32_t)h->n_reads;
     int rc = dense(0, r1, h->head_cov, h->head_cov_pos0);
     if (rc) return rc;
   }
