@@ -401,11 +401,11 @@ __device__ __forceinline__ uint32_t compress_even(uint32_t c) {   // even bits o
 
 template <int NW>
 __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref, uint32_t g0, uint32_t L, bool rev,
-                                                            const uint32_t* __restrict__ brow_w, uint32_t bshift) {
+                                                            const uint32_t (&bw)[NW + 1], uint32_t bshift) {
   const uint32_t wi = g0 >> 4, sh = (g0 & 15u) * 2u;
-  uint32_t w[NW + 1], bw[NW + 1];
+  uint32_t w[NW + 1];
 #pragma unroll
-  for (int k = 0; k <= NW; ++k) { w[k] = __ldg(ref.seq2 + wi + k); bw[k] = __ldg(brow_w + k); }
+  for (int k = 0; k <= NW; ++k) w[k] = __ldg(ref.seq2 + wi + k);
   const uint32_t ii = g0 >> 5, s1 = g0 & 31u;
   const uint32_t i0 = __ldg(ref.inv + ii), i1 = __ldg(ref.inv + ii + 1), i2 = NW > 2 ? __ldg(ref.inv + ii + 2) : 0u;
   unsigned long long m = 0;
@@ -425,15 +425,42 @@ __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref
   return m;
 }
 
+// the words of one record that do not depend on anything else: loaded one read ahead of their use (PAR-CLIP shape)
+template <int NW>
+struct PlRaw {
+  uint32_t meta, g0, cg;
+  uint32_t bw[NW > 0 ? NW + 1 : 1];
+};
+template <int NW>
+__device__ __forceinline__ PlRaw<NW> pl_load_raw(const ClusterParams& P, uint64_t r, bool in) {
+  PlRaw<NW> w;
+  w.meta = in ? __ldg(P.b.meta + r) : 0u;
+  w.g0 = 0; w.cg = 0;
+  if constexpr (NW > 0) {
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) w.bw[k] = 0;
+    if (in) {
+      w.g0 = __ldg(P.b.ref_start + r);
+      w.cg = __ldg(P.b.cigar + r);
+      const uint64_t boff = r * (uint64_t)((P.b.uniform_len + 3) >> 2);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.b.bases2 + (boff & ~3ull));
+#pragma unroll
+      for (int k = 0; k <= NW; ++k) w.bw[k] = __ldg(src + k);
+    }
+  }
+  return w;
+}
+
 // one lane decodes read r (r < n); NW > 0: the batch has the PAR-CLIP shape and most reads take the bit-parallel path
 template <int NW>
-__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, ContigCache& cc, PlRead& x) {
+__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, const PlRaw<NW>& raw,
+                                          ContigCache& cc, PlRead& x) {
   x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
-  const uint32_t meta = in ? __ldg(P.b.meta + r) : 0u;
+  const uint32_t meta = raw.meta;
   if constexpr (NW > 0) {
     if (!in) return;
     const uint32_t L = P.b.uniform_len, bpr = (L + 3) >> 2;
-    const uint32_t flags = PS_META_FLAGS(meta), g0 = __ldg(P.b.ref_start + r), cg = __ldg(P.b.cigar + r);
+    const uint32_t flags = PS_META_FLAGS(meta), g0 = raw.g0, cg = raw.cg;
     // N calls are stored as code 0 (A): never read C (forward T>C) nor read G (reverse), so such reads need no
     // look at the exception list; duplicates are not filtered by this tool and qualities are never read
     constexpr uint32_t kHarmless = PS_RF_REVERSE | PS_RF_HAS_INVALID | PS_RF_DUPLICATE | PS_RF_QUAL_MISSING;
@@ -442,8 +469,7 @@ __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, ui
     if (fast) {
       const bool rev = (flags & PS_RF_REVERSE) != 0;
       const uint64_t boff = r * (uint64_t)bpr;
-      unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, reinterpret_cast<const uint32_t*>(P.b.bases2 + (boff & ~3ull)),
-                                               (uint32_t)(boff & 3u) * 8u);
+      unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, raw.bw, (uint32_t)(boff & 3u) * 8u);
       const int32_t start = (int32_t)((uint64_t)g0 - cc.lo) + 1, end = start + (int32_t)L - 1;
       if (L > 51u && (m >> 51)) { raise_fault(&P.st->fault, r, PS_THROW_MASK51); return; }
       x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = rev; x.contig = cc.idx;
@@ -454,6 +480,10 @@ __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, ui
     const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);    // warp-collective
     if (in) pl_decode_generic(P, r, meta, off.base, off.cigar, x);
   }
+}
+template <int NW>
+__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, ContigCache& cc, PlRead& x) {
+  pl_decode<NW>(P, q, r, in, pl_load_raw<NW>(P, r, in), cc, x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -718,10 +748,13 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
     }
     __syncthreads();
     // ---- A, thread per read: decode; T>C positions into the cluster's key set -------------------------------------
+    PlRaw<NW> nxt = pl_load_raw<NW>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
     for (uint32_t q = rs + warp * 32; q < re; q += PL_THREADS) {
       const uint32_t r = q + lane;
+      const PlRaw<NW> raw = nxt;
+      if (q + PL_THREADS < re) nxt = pl_load_raw<NW>(P, r + PL_THREADS, r + PL_THREADS < re);   // in flight during this decode
       PlRead x;
-      pl_decode<NW>(P, q, r, r < re, cc, x);
+      pl_decode<NW>(P, q, r, r < re, raw, cc, x);
       if (r < re) {
         const uint32_t i = r - rs;
         S.mask[i] = x.mask | ((unsigned long long)x.rev << 62) | ((unsigned long long)x.kept << 63);
