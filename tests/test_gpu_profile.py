@@ -7,7 +7,7 @@ import pytest
 import py_oracle as po
 from helpers import assert_profile_equal, kat_records, random_genome, random_records, to_py
 from kat_vectors import KAT_MAXLEN, KAT_REF, PROFILE_KATS
-from parasuite_b200 import PackedReference, ReadBatch, abi
+from parasuite_b200 import PackedReference, ReadBatch, Record, abi
 
 pytestmark = pytest.mark.gpu
 
@@ -155,3 +155,47 @@ def test_full_size_config2(ctx, oracle):
     assert got["position_conversions"][36:].sum() == 0
     exp = oracle.profile(ref, batch, 51, threads=16)
     assert_profile_equal(got, exp, "config 2 full size")
+
+
+@pytest.mark.parametrize("infer_q", [False, True])
+def test_long_reads_dense_cigar(ctx, oracle, infer_q):
+    """Maximum sizes: reads of up to 2500 bases with soft clips, indels, splices and `=`/`X` blocks at the largest
+    maxReadLength the library accepts (3000): many 32-column passes per block in the general kernel; with -q also the
+    per-position quality histogram."""
+    rng = random.Random(77)
+    contigs = random_genome(rng, n_contigs=2, length=30000, n_frac=0.002, lower_frac=0.05)
+    recs = random_records(rng, contigs, 600, kinds=("M", "clip", "indel", "wild"), Lrange=(800, 2500), flags_special=0.02)
+    ref = PackedReference.from_contigs(contigs)
+    ok = []
+    for r in recs:      # keep what the JVM survives (C++ oracle, one record at a time)
+        try:
+            oracle.profile(ref, ReadBatch.from_records([r], ref), 3000, infer_q)
+            ok.append(r)
+        except oracle.OracleFault:
+            pass
+    assert len(ok) > 200
+    batch = ReadBatch.from_records(ok, ref)
+    ctx.upload_reference(ref)
+    got = ctx.profile(batch, 3000, infer_q)
+    exp = oracle.profile(ref, batch, 3000, infer_q)
+    assert_profile_equal(got, exp, "long reads")
+    if infer_q:
+        assert np.array_equal(got["quality_hist"], exp["quality_hist"])
+
+
+def test_more_than_255_cigar_ops_is_flagged(ctx, oracle):
+    """A record with > 255 cigar ops cannot be represented (PS_RF_CIGAR_OVERFLOW): it reaches the kernels without ops,
+    i.e. as an empty-CIGAR mapped read, on which the JVM dies (refSequenceForRead[0] of an empty array)."""
+    contigs = [("chr1", b"ACGT" * 400)]
+    cig = "".join("1M1I" for _ in range(130)) + "1M"          # 261 ops, 261 read bases... 131 M + 130 I
+    seq = b"A" * 261
+    rec = Record(0, "chr1", 10, cig, seq, bytes([30] * 261))
+    ref = PackedReference.from_contigs(contigs)
+    batch = ReadBatch.from_records([rec], ref)
+    assert (int(batch.meta[0]) >> 24) & abi.PS_RF_CIGAR_OVERFLOW
+    ctx.upload_reference(ref)
+    with pytest.raises(abi.ReferenceWouldThrow) as e:
+        ctx.profile(batch, 600)
+    with pytest.raises(oracle.OracleFault) as eo:
+        oracle.profile(ref, batch, 600)
+    assert e.value.fault == (eo.value.code, eo.value.ordinal)
