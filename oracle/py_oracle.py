@@ -20,6 +20,7 @@ SAMUtils.getAlignmentBlocks, SequenceUtil.reverseComplement, IndexedFastaSequenc
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -675,3 +676,98 @@ def pileup(records: List[Rec], genome: Genome, snps: SnpDb, min_cov: int) -> Pil
     if have_cluster:
         st.open_cluster = snapshot(False)
     return st
+
+
+# ------------------------------------------------------------------------------------------
+# Post-loop of the `error` tool: the six output files (ErrorProfiling.java:410-591), literally
+# ------------------------------------------------------------------------------------------
+def _jdiv(a: float, b: float) -> float:
+    """Java double division (no exceptions: x/0 = +-Infinity, 0/0 = NaN)."""
+    a, b = float(a), float(b)
+    if b == 0.0:
+        if a == 0.0 or a != a:
+            return float("nan")
+        return float("inf") if a > 0 else float("-inf")
+    return a / b
+
+
+def profile_outputs(st: ProfileState, infer_qual: bool, fmt) -> Dict[str, str]:
+    """Text of <bam>.errorprofile, .errorprofile.vcf, .qualityPerMismatch, .indels, .indelprofile, .qualities and the
+    'Averaged T2C' log value.  `fmt` = Double.toString.  Loops and statement order follow the Java."""
+    w = st.wrapped()
+    pc, qmm, qcnt = w["pos_conv"], w["qual_mm"], w["qual_mm_cnt"]
+    n_proc = w["counters"][0]
+    m = st.max_len
+    base = ["A", "C", "G", "T"]
+    out = {k: "" for k in ("errorprofile", "errorprofile.vcf", "qualityPerMismatch", "indels", "indelprofile", "qualities")}
+    nl = "\n"
+    if infer_qual:                                                   # :421-437
+        for i in range(m):
+            vals = []
+            for q, c in sorted(st.qual_hist[i].items()):
+                vals += [q] * c
+            n = len(vals)
+            mean = _jdiv(float(sum(vals)), n)
+            tmp = 0.0
+            for v in vals:
+                tmp += (v - mean) ** 2
+            sd = math.sqrt(_jdiv(tmp, n)) if n else float("nan")
+            out["qualities"] += fmt(mean) + "\t" + fmt(sd) + nl
+    qpct = [[_jdiv(qmm[i][j], qcnt[i][j]) for j in range(4)] for i in range(4)]      # :439-446
+    total_err = [[0.0] * 4 for _ in range(4)]
+    total_base = [0.0] * 4
+    total_pos = [0] * m
+    for i in range(m):                                               # :448-459
+        for j in range(4):
+            for k in range(4):
+                total_err[j][k] += pc[i][j][k]
+                total_base[j] += pc[i][j][k]
+                total_pos[i] = _i32(total_pos[i] + pc[i][j][k])
+    t2c = [0.0] * m
+    for i in range(m):                                               # :464-502
+        t2c[i] = _jdiv(float(pc[i][3][1]), n_proc) * 100
+    for j in range(4):                                               # :504-531
+        for k in range(4):
+            out["errorprofile.vcf"] += base[j] + "\t" + base[k] + "\t" + fmt(total_err[j][k]) + nl
+            total_err[j][k] = _jdiv(total_err[j][k], total_base[j])
+            out["errorprofile"] += fmt(total_err[j][k]) + "\t"
+            out["qualityPerMismatch"] += fmt(qpct[j][k]) + "\t"
+        out["errorprofile"] += nl
+        out["qualityPerMismatch"] += nl
+        out["errorprofile.vcf"] += nl
+    avg = 0.0                                                        # :532-542
+    for j in range(m):
+        if t2c[j] > 0:
+            avg += t2c[j]
+        else:
+            avg = avg / (j + 1)
+            break
+    ins, dele = list(w["ins_per_pos"]), list(w["del_per_pos"])
+    ins_all = del_all = 0.0
+    ins_zero = del_zero = 0
+    for i in range(m):                                               # :553-578
+        if total_pos[i] == 0:
+            ins[i] = 0.0
+            dele[i] = 0.0
+            ins_zero += 1
+            del_zero += 1
+        else:
+            ins[i] = ins[i] / total_pos[i]
+            if ins[i] > 0:
+                ins_all += ins[i]
+            else:
+                ins_zero += 1
+            dele[i] = dele[i] / total_pos[i]
+            if dele[i] > 0:
+                del_all += dele[i]
+            else:
+                del_zero += 1
+        out["indels"] += fmt(ins[i]) + "\t" + fmt(dele[i]) + nl
+    if m == ins_zero and m == del_zero:                              # :579-589
+        ins_all = del_all = 0.0
+    else:
+        ins_all = _jdiv(ins_all, m - ins_zero)
+        del_all = _jdiv(del_all, m - del_zero)
+    out["indelprofile"] = fmt(ins_all) + "\t" + fmt(del_all)
+    out["averaged_t2c_epr"] = fmt(avg)
+    return out
