@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -186,13 +187,38 @@ struct Slab {            // one SoA batch in a single (page-locked when possible
 
 struct Block { uint64_t coff; uint32_t clen, isize; };
 
+struct ByteBuf {         // growable byte buffer without value-initialisation (inflate writes every byte it exposes)
+  uint8_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  ~ByteBuf() { free(p); }
+  uint8_t* data() { return p; }
+  const uint8_t* data() const { return p; }
+  size_t size() const { return n; }
+  bool grow_to(size_t want) {       // keeps the first n bytes
+    if (want > cap) {
+      size_t c = cap ? cap : ((size_t)1 << 20);
+      while (c < want) c += c / 2 + 4096;
+      uint8_t* q = (uint8_t*)realloc(p, c);
+      if (!q) return false;
+      p = q; cap = c;
+    }
+    n = want;
+    return true;
+  }
+  void drop_front(size_t k) {       // discard the first k bytes
+    if (k == 0) return;
+    if (k < n) memmove(p, p + k, n - k);
+    n -= k;
+  }
+};
+
 }  // namespace
 
 struct ps_bam {
   MappedFile mf;
   std::vector<Block> blocks;
   size_t next_block = 0;
-  std::vector<uint8_t> buf;        // inflated bytes not yet consumed
+  ByteBuf buf;                     // inflated bytes not yet consumed
   size_t head = 0;
   bool header_done = false;
   bool sorted = false;
@@ -206,6 +232,7 @@ struct ps_bam {
   uint64_t ordinal = 0;
   std::string err;
   std::vector<uint64_t> rec_off;   // scratch: offsets of the records of the batch being built
+  double t_fill = 0, t_locate = 0, t_pass1 = 0, t_pass2 = 0;   // seconds (PARASUITE_B200_BATCHER_TIMING=1 prints them)
 };
 
 static int bam_fail(ps_bam* B, int st, const std::string& m) { B->err = m; return st; }
@@ -236,15 +263,19 @@ static int bam_scan_blocks(ps_bam* B) {
 }
 
 // inflate blocks until at least `want` unconsumed bytes are buffered (or the file ends)
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int bam_fill(ps_bam* B, size_t want) {
+  const double t0 = now_s();
+  struct Acc { ps_bam* b; double t0; ~Acc() { b->t_fill += now_s() - t0; } } acc{B, t0};
   while (B->buf.size() - B->head < want && B->next_block < B->blocks.size()) {
     // a window of blocks: enough for `want`, at least 64 MB when a big batch is being assembled
     size_t b1 = B->next_block, total = 0;
-    const size_t target = std::max<size_t>(want - (B->buf.size() - B->head), (size_t)16 << 20);
+    const size_t target = std::max<size_t>(want - (B->buf.size() - B->head), (size_t)128 << 20);
     std::vector<size_t> at;
     while (b1 < B->blocks.size() && total < target) { at.push_back(total); total += B->blocks[b1].isize; ++b1; }
     const size_t base = B->buf.size();
-    B->buf.resize(base + total);
+    if (!B->buf.grow_to(base + total)) return bam_fail(B, PS_ERR_OOM, "out of host memory for the inflated records");
     std::atomic<int> bad{0};
     const size_t b0 = B->next_block;
     parallel_for(B->threads, b1 - b0, [&](int, uint64_t lo, uint64_t hi) {
@@ -364,6 +395,9 @@ const char* ps_bam_error(const ps_bam* b) { return b ? b->err.c_str() : "no obje
 
 void ps_bam_close(ps_bam* b) {
   if (!b) return;
+  if (getenv("PARASUITE_B200_BATCHER_TIMING"))
+    fprintf(stderr, "[ps_bam] inflate %.3f s, locate %.3f s, sizes %.3f s, pack %.3f s, %llu records, %d threads\n", b->t_fill, b->t_locate,
+            b->t_pass1, b->t_pass2, (unsigned long long)b->ordinal, b->threads);
   b->slab[0].release();
   b->slab[1].release();
   delete b;
@@ -376,10 +410,11 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   if (!B->header_done) return bam_fail(B, PS_ERR_STATE, "BAM not open");
   // drop consumed bytes (offsets below are relative to the new start)
   if (B->head) {
-    B->buf.erase(B->buf.begin(), B->buf.begin() + (ptrdiff_t)B->head);
+    B->buf.drop_front(B->head);
     B->head = 0;
   }
   // ---- locate records -------------------------------------------------------------------------------------
+  const double t_loc0 = now_s(), fill0 = B->t_fill;
   std::vector<uint64_t>& ro = B->rec_off;
   ro.clear();
   size_t o = 0;
@@ -403,6 +438,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
     o += 4 + (size_t)bs;
   }
   B->head = o;
+  B->t_locate += (now_s() - t_loc0) - (B->t_fill - fill0);
   const uint64_t n = ro.size();
   memset(out, 0, sizeof *out);
   if (n == 0) return 0;
@@ -410,6 +446,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   const uint64_t n_tiles = (n + PS_TILE_READS - 1) / PS_TILE_READS;
 
   // ---- pass 1: sizes, per tile ----------------------------------------------------------------------------
+  const double t_p1 = now_s();
   std::vector<uint64_t> tb(n_tiles + 1, 0), tq(n_tiles + 1, 0), tc(n_tiles + 1, 0);
   std::vector<uint32_t> te(n_tiles + 1, 0);
   std::atomic<int> bad{0};
@@ -444,6 +481,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   for (uint64_t t = 0; t < n_tiles; ++t) { tb[t + 1] += tb[t]; tq[t + 1] += tq[t]; tc[t + 1] += tc[t]; te[t + 1] += te[t]; }
   const uint64_t bases_bytes = tb[n_tiles], qual_bytes = tq[n_tiles], cigar_count = tc[n_tiles], exc_count = te[n_tiles];
 
+  B->t_pass1 += now_s() - t_p1;
   // ---- slab layout ----------------------------------------------------------------------------------------------
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   size_t off_meta = 0, off_start = up(off_meta + n * 4), off_bases = up(off_start + n * 4);
@@ -470,6 +508,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   memset(exc + exc_count, 0, 64);
 
   // ---- pass 2: fill ---------------------------------------------------------------------------------------------
+  const double t_p2 = now_s();
   static const int8_t kNib[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};   // "=ACMGRSVTWYHKDBN"
   const ps_packed_fasta* fa = B->fa;
   parallel_for(B->threads, n_tiles, [&](int, uint64_t lo, uint64_t hi) {
@@ -526,6 +565,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
     }
   });
 
+  B->t_pass2 += now_s() - t_p2;
   out->n_reads = n;
   out->meta = meta;
   out->ref_start = ref_start;
