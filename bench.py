@@ -191,7 +191,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from parasuite_b200.distributed import sharded_pileup_carry
+    from parasuite_b200.distributed import all_gather_keys_async, sharded_pileup_carry
     from parasuite_b200.runtime import Context, DeviceBatch, PinnedBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,6 +203,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     name, ref, batch, max_len = workload(args.gpus, rank, args.small)
@@ -223,14 +224,16 @@ def main():
         # the whole hot path on a batch that is already in HBM: profile kernel (+ the tiny all-reduce), read-back of
         # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
         # their counters come back to the host
+        exchange = None
+        if world > 1:   # region sharding: exclusive prefix-max of one (contig, end) pair per rank = this region's carry-in;
+            # the all-gather is started first and travels while the profile kernel runs
+            exchange = all_gather_keys_async(ctx.pileup_max_key(dbatch, stream.cuda_stream), device=dev)
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
         if world > 1:
             dist.all_reduce(ctx.profile_acc_tensor())
         res = ctx.profile_end()
-        carry = None
-        if world > 1:   # region sharding: exclusive prefix-max of one (contig, end) pair per rank = this region's carry-in
-            carry = sharded_pileup_carry(ctx.pileup_max_key(dbatch, stream.cuda_stream), device=dev)
+        carry = exchange.carry() if exchange is not None else None
         with ctx.pileup_run(dbatch, first_running_id=1, carry=carry, stream=stream.cuda_stream) as h:
             pile["counters"] = h.counters
         return res

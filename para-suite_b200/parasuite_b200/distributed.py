@@ -31,19 +31,36 @@ def exclusive_prefix_max(keys: Sequence[Key]) -> list:
     return out
 
 
+class _KeyGather:
+    """In-flight all-gather of one (valid, contig, end) triple per rank."""
+
+    def __init__(self, local: Key, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        world = dist.get_world_size(group)
+        self.t = torch.tensor([1 if local is not None else 0, local[0] if local else 0, local[1] if local else 0],
+                              dtype=torch.int64, device=device)
+        self.got = torch.empty(world * 3, dtype=torch.int64, device=device)
+        self.work = dist.all_gather_into_tensor(self.got, self.t, group=group, async_op=True)
+
+    def keys(self) -> list:
+        self.work.wait()
+        flat = self.got.tolist()          # device -> host (synchronises the collective's stream)
+        return [(int(flat[k + 1]), int(flat[k + 2])) if flat[k] else None for k in range(0, len(flat), 3)]
+
+    def carry(self) -> Key:
+        import torch.distributed as dist
+        return exclusive_prefix_max(self.keys())[dist.get_rank(self.group)]
+
+
+def all_gather_keys_async(local: Key, group=None, device=None) -> _KeyGather:
+    """Start the exchange; call .carry() when the carry-in is needed (other work can be queued in between)."""
+    return _KeyGather(local, group, device)
+
+
 def all_gather_keys(local: Key, group=None, device=None) -> list:
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    t = torch.tensor([1 if local is not None else 0, local[0] if local else 0, local[1] if local else 0],
-                     dtype=torch.int64, device=device)
-    got = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(got, t, group=group)
-    keys = []
-    for g in got:
-        v = g.tolist()
-        keys.append((int(v[1]), int(v[2])) if v[0] else None)
-    return keys
+    return _KeyGather(local, group, device).keys()
 
 
 def sharded_pileup_carry(local_key: Key, group=None, device=None) -> Key:
