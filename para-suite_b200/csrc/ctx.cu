@@ -55,20 +55,23 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
   const uint64_t n = hb->n_reads;
   const uint64_t nt = (n + PS_TILE_READS - 1) / PS_TILE_READS;
   struct Item { DevBuf* d; const void* h; size_t bytes; };
+  // qualities last: they are more than half of the bytes and only the profile kernel reads them
   Item items[] = {
       {&s.meta, hb->meta, n * 4},
       {&s.ref_start, hb->ref_start, n * 4},
-      {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
-      {&s.qual, hb->qual, with_qual ? (size_t)hb->qual_bytes : 0},   // the pileup never reads qualities
       {&s.cigar, hb->cigar, (size_t)hb->cigar_count * 4},
+      {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
       {&s.tbo, hb->tile_base_off, hb->tile_base_off ? (nt + 1) * 8 : 0},
       {&s.tqo, hb->tile_qual_off, hb->tile_qual_off ? (nt + 1) * 8 : 0},
       {&s.tco, hb->tile_cigar_off, hb->tile_cigar_off ? (nt + 1) * 8 : 0},
       {&s.teo, hb->tile_exc_off, (nt + 1) * 4},
       {&s.exc, hb->exc, (size_t)hb->exc_count * 4},
+      {&s.qual, hb->qual, with_qual ? (size_t)hb->qual_bytes : 0},   // the pileup never reads qualities
   };
+  if (!ctx->staged_core[slot]) cudaEventCreateWithFlags(&ctx->staged_core[slot], cudaEventDisableTiming);
   for (auto& it : items) {
     PS_CUDA(ctx, it.d->reserve(it.bytes + 64));   // +64: kernels may read a few bytes past the last read
+    if (it.d == &s.qual) cudaEventRecord(ctx->staged_core[slot], ctx->stream);
     if (it.bytes) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (!ctx->staged_done[slot]) cudaEventCreateWithFlags(&ctx->staged_done[slot], cudaEventDisableTiming);
@@ -138,6 +141,7 @@ int ps_create(ps_ctx** out, int device) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PS_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->stream2 = nullptr; }
   for (int i = 0; i < PS_TIMER_RING; ++i) {
     cudaEventCreate(&ctx->ev_start[i]);
     cudaEventCreate(&ctx->ev_stop[i]);
@@ -170,6 +174,8 @@ void ps_destroy(ps_ctx* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->fasta) ps_fasta_free(ctx->fasta);
   for (auto& e : ctx->staged_done) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->staged_core) if (e) cudaEventDestroy(e);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release();
   for (auto& s : ctx->staged) {

@@ -110,6 +110,8 @@ struct ps_ctx {
   cudaStream_t stream = nullptr;
   StagedBatch staged[2];
   cudaEvent_t staged_done[2] = {nullptr, nullptr};
+  cudaEvent_t staged_core[2] = {nullptr, nullptr};   // everything but the qualities of the slot's batch has arrived
+  cudaStream_t stream2 = nullptr;                      // auxiliary stream: pileup of a batch whose qualities are still in flight
   int staged_next = 0;
   uint64_t stage_serial = 0;   // uploads so far (a staged batch stays valid until the second-next one)
   // instrumentation

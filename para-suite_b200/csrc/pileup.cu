@@ -1063,6 +1063,16 @@ static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const Cluster
 }
 
 static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out) {
+  // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch) and is run on the context's
+  // own stream: the pileup never reads qualities, so it goes to the auxiliary stream as soon as the other streams of
+  // the records have arrived, while the quality bytes (more than half of the upload) are still on their way.
+  if (st == ctx->stream && ctx->stream2) {
+    for (int slot = 0; slot < 2; ++slot)
+      if (b.n_reads && b.meta == ctx->staged[slot].view.meta && ctx->staged_core[slot]) {
+        cudaStreamWaitEvent(ctx->stream2, ctx->staged_core[slot], 0);
+        st = ctx->stream2;
+      }
+  }
   ps_pileup* H = new ps_pileup();
   *out = H;
   H->ctx = ctx;
@@ -1304,6 +1314,17 @@ int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint6
   cudaSetDevice(ctx->device);
   uint64_t cnt = std::min<uint64_t>(max_clusters, n_closed - first);
   // closed clusters are slots 1 .. n_flags-1; their sites are contiguous and in slot order
+  if (first == 0 && cnt == n_closed && h->counters.n_sites <= max_sites) {
+    // everything at once (the common call): the site range is known from the boundary records, so both copies are
+    // queued back to back and the host waits once
+    const uint64_t sb = h->head.site_end, ns = h->counters.n_sites;
+    PS_CUDA(ctx, cudaMemcpyAsync(clusters, h->d_cl + 1, cnt * sizeof(ps_cluster), cudaMemcpyDeviceToHost, h->stream));
+    if (ns) PS_CUDA(ctx, cudaMemcpyAsync(sites, h->d_sites + sb, ns * sizeof(ps_site), cudaMemcpyDeviceToHost, h->stream));
+    PS_CUDA(ctx, cudaStreamSynchronize(h->stream));
+    if (sb)
+      for (uint64_t k = 0; k < cnt; ++k) { clusters[k].site_begin -= sb; clusters[k].site_end -= sb; }
+    return (int64_t)cnt;
+  }
   PS_CUDA(ctx, cudaMemcpyAsync(clusters, h->d_cl + 1 + first, cnt * sizeof(ps_cluster), cudaMemcpyDeviceToHost, h->stream));
   PS_CUDA(ctx, cudaStreamSynchronize(h->stream));
   const uint64_t sb = clusters[0].site_begin;
@@ -1315,7 +1336,8 @@ int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint6
     PS_CUDA(ctx, cudaMemcpyAsync(sites, h->d_sites + sb, ns * sizeof(ps_site), cudaMemcpyDeviceToHost, h->stream));
     PS_CUDA(ctx, cudaStreamSynchronize(h->stream));
   }
-  for (uint64_t k = 0; k < m; ++k) { clusters[k].site_begin -= sb; clusters[k].site_end -= sb; }
+  if (sb)
+    for (uint64_t k = 0; k < m; ++k) { clusters[k].site_begin -= sb; clusters[k].site_end -= sb; }
   return (int64_t)m;
 }
 
