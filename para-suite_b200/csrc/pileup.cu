@@ -1045,11 +1045,8 @@ static int flavour_of(const DeviceBatch& b) {   // 0 = generic decode, 1..4 = PA
 
 template <int NW>
 static void launch_cluster_nw(uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(pl_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
-    configured = true;
-  }
+  // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
+  cudaFuncSetAttribute(pl_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
   pl_cluster_kernel<NW><<<grid, PL_THREADS, kClusterSmemBytes, st>>>(Q);
 }
 static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const ClusterParams& Q) {

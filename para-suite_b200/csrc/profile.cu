@@ -516,14 +516,11 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
   P.n_tiles = (uint32_t)n_wt;
   size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
+  cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, profile_generic_kernel, PS_BLOCK_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, profile_generic_kernel, PS_BLOCK_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)per_sm;
