@@ -21,6 +21,8 @@
 //
 // The flush-time logic (SNP filter, anchor site, text rows: :178-344) stays on the host side of the boundary.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_common.cuh"
@@ -52,6 +54,7 @@ struct PlState {                  // device-side run state (one per call)
   unsigned int first_slot1;       // first read of slot 1 (end of the head partial); n_reads if there is no slot 1
   unsigned int pad0;
   ps_cluster head, open;          // final records of slot 0 and of the last slot (written by pl_compact_kernel)
+  unsigned long long dbg[4];      // PARASUITE_B200_DEBUG: warp-routine calls, sweep give-ups, window passes, chunk decodes in windows
 };
 
 struct PlRead {              // what the pileup needs from one read
@@ -495,13 +498,21 @@ struct WarpTables {     // one window of PL_WINDOW positions
   unsigned long long first[PL_WINDOW];   // min over events of (read << 6 | i) = first insertion
 };
 
+constexpr int PL_RING = 256;          // positions of the sliding window of the streaming sweep (power of two)
+struct WarpRing {
+  int32_t diff[PL_RING];
+  uint32_t cnt[PL_RING];
+  unsigned long long first[PL_RING];
+};
+
 __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xFFFFFFFFu, v); }
 
 // One cluster = reads [f, fe) (slot `slot`), whole warp.  Fills *rec (shared memory) when `fill`, writes up to `cap`
 // sites to `dest` in position order and returns the number of sites the cluster has.
 template <int NW>
 __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slot, uint32_t f, uint32_t fe, WarpTables& T,
-                                            ps_cluster* rec, bool fill, ps_site* dest, uint32_t cap, unsigned long long& dstr) {
+                                            WarpRing& G, ps_cluster* rec, bool fill, ps_site* dest, uint32_t cap,
+                                            unsigned long long& dstr) {
   const uint32_t lane = threadIdx.x & 31;
   ContigCache cc;
   PlRead x;
@@ -599,10 +610,91 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
     return n_sites;
   }
 
-  // ---- sites: per-warp tables, one window of positions at a time -------------------------------------------------
+  if (lane == 0) atomicAdd(&P.st->dbg[0], 1ull);
+  // ---- sites: streaming sweep (any number of reads, one decode per read) ------------------------------------------
+  // Records are sorted by start and no read touches a position before its own start, so every position before the
+  // start of the read being added is final: a ring of PL_RING positions slides along the cluster, finished positions
+  // are emitted (in position order) and their slots recycled.  Gives up -- and leaves the cluster to the window loop
+  // below -- if starts ever go backwards (input not sorted inside a contig) or a single read is longer than the ring.
+  {
+    for (uint32_t k = lane; k < PL_RING; k += 32) { G.diff[k] = 0; G.cnt[k] = 0; G.first[k] = ~0ull; }
+    __syncwarp();
+    uint32_t written = 0;
+    int32_t wlo = 0, carry = 0;          // first position not yet emitted; coverage just before it
+    bool started = false, ok = true;
+    auto flush_to = [&](int32_t upto) {  // emit positions [wlo, upto)
+      const int64_t stop = min((int64_t)upto, (int64_t)wlo + PL_RING);     // nothing beyond the ring was ever touched
+      for (int64_t p0 = wlo; p0 < stop; p0 += 32) {
+        const int64_t pp = p0 + lane;
+        const bool in = pp < stop;
+        const uint32_t sl = (uint32_t)pp & (PL_RING - 1);
+        int32_t c = in ? G.diff[sl] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int32_t y = __shfl_up_sync(0xFFFFFFFFu, c, d);
+          if (lane >= (uint32_t)d) c += y;
+        }
+        c += carry;
+        carry = __shfl_sync(0xFFFFFFFFu, c, 31);
+        const uint32_t n = in ? G.cnt[sl] : 0u;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, n != 0);
+        const uint32_t at = written + __popc(bal & ((1u << lane) - 1u));
+        if (n && at < cap) {
+          ps_site s;
+          s.pos = (int32_t)pp; s.t2c = n; s.cov = (uint32_t)c; s.reserved = 0; s.order_key = G.first[sl];
+          dest[at] = s;
+        }
+        written += __popc(bal);
+        if (in) { G.diff[sl] = 0; G.cnt[sl] = 0; G.first[sl] = ~0ull; }
+      }
+      wlo = upto;
+      __syncwarp();
+    };
+    for (uint32_t q = f; q < fe && ok; q += 32) {
+      const uint32_t r = q + lane;
+      pl_decode<NW>(P, q, r, r < fe, cc, x);
+      uint32_t pending = __ballot_sync(0xFFFFFFFFu, x.kept);
+      while (pending) {
+        const bool mine = (pending >> lane) & 1u;
+        const int32_t bstart = __reduce_min_sync(0xFFFFFFFFu, mine ? x.start : INT32_MAX);
+        if (!started) { wlo = bstart; started = true; }
+        if (bstart < wlo) { ok = false; break; }
+        flush_to(bstart);
+        const uint32_t fits = __ballot_sync(0xFFFFFFFFu, mine && (int64_t)x.hi + 2 - (int64_t)wlo <= PL_RING && x.lo >= wlo);
+        const uint32_t first_pending = (uint32_t)__ffs((int)pending) - 1u;
+        if (!((fits >> first_pending) & 1u)) { ok = false; break; }        // one read longer than the ring
+        const uint32_t misfit = pending & ~fits;
+        const uint32_t take = misfit ? pending & ((1u << ((uint32_t)__ffs((int)misfit) - 1u)) - 1u) : pending;
+        if ((take >> lane) & 1u) {
+          unsigned long long m = x.mask;
+          while (m) {
+            const int i = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const uint32_t sl = (uint32_t)(x.rev ? x.hi - i : x.lo + i) & (PL_RING - 1);
+            atomicAdd(&G.cnt[sl], 1u);
+            atomicMin(&G.first[sl], ((unsigned long long)r << 6) | (unsigned)i);
+          }
+          atomicAdd(&G.diff[(uint32_t)x.lo & (PL_RING - 1)], 1);
+          atomicAdd(&G.diff[(uint32_t)(x.hi + 1) & (PL_RING - 1)], -1);
+        }
+        __syncwarp();
+        pending &= ~take;
+      }
+    }
+    if (ok) {
+      // tail: every touched position lies inside the ring
+      if (started) flush_to((int32_t)min((int64_t)INT32_MAX, (int64_t)wlo + PL_RING));
+      return written;
+    }
+  }
+
+  // ---- sites: per-warp tables, one window of positions at a time (quadratic in the worst case; only reached by
+  //      clusters the sweep above gave up on) ---------------------------------------------------------------------------
   uint32_t written = 0;
+  if (lane == 0) atomicAdd(&P.st->dbg[1], 1ull);
   for (int64_t w0 = ev_min; w0 <= ev_max; w0 += PL_WINDOW) {
     const int64_t w1 = w0 + PL_WINDOW - 1;
+    if (lane == 0) atomicAdd(&P.st->dbg[2], 1ull);
     for (uint32_t k = lane; k < PL_WINDOW; k += 32) { T.diff[k] = 0; T.cnt[k] = 0; T.first[k] = ~0ull; }
     __syncwarp();
     for (uint32_t q = f; q < fe; q += 32) {
@@ -666,7 +758,7 @@ struct ClusterSmem {
   uint8_t* cid;               // [CB_CHUNK] cluster (index inside the block) of each read
 };
 constexpr size_t kClusterSmemBytes = (size_t)CB_CHUNK * (8 + 5 * 4 + 1) + (size_t)CB_CLUSTERS * (8 + CB_SITES * 12 + 4 * 4) + 64;
-static_assert((size_t)CB_CHUNK * 28 >= PL_WARPS * (sizeof(WarpTables) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
+static_assert((size_t)CB_CHUNK * 28 >= PL_WARPS * (sizeof(WarpTables) + sizeof(WarpRing) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
 static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is one byte / one thread per cluster");
 
 // One block = CB_CLUSTERS consecutive clusters = one contiguous run of reads, taken in chunks of CB_CHUNK reads.
@@ -887,18 +979,19 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
   __syncthreads();
   {
     WarpTables* T = reinterpret_cast<WarpTables*>(smem_raw) + warp;
-    ps_cluster* wrec = reinterpret_cast<ps_cluster*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + warp;
+    WarpRing* G = reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + warp;
+    ps_cluster* wrec = reinterpret_cast<ps_cluster*>(reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + PL_WARPS) + warp;
     const uint32_t nfb = s_nfb;
     for (uint32_t e = warp; e < nfb; e += PL_WARPS) {
       const uint32_t k = S.fb[e], slot = c0 + k;
       const uint32_t f = S.first[k], fe = S.first[k + 1];
-      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, wrec, true, nullptr, 0, dstr);
+      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr);
       unsigned long long sb = 0;
       if (lane == 0 && cnt) sb = atomicAdd(&P.st->n_sites, (unsigned long long)cnt);
       sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
       if (cnt && sb < P.cap_sites) {
         unsigned long long unused = 0;
-        pl_cluster<NW>(P, slot, f, fe, *T, nullptr, false, P.sites + sb, (uint32_t)min((unsigned long long)cnt, P.cap_sites - sb), unused);
+        pl_cluster<NW>(P, slot, f, fe, *T, *G, nullptr, false, P.sites + sb, (uint32_t)min((unsigned long long)cnt, P.cap_sites - sb), unused);
       }
       __syncwarp();
       if (lane == 0) { wrec->site_begin = sb; wrec->site_end = sb + cnt; }
@@ -1000,6 +1093,7 @@ __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
     st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_flags = 0;
     st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu;
+    st->dbg[0] = st->dbg[1] = st->dbg[2] = st->dbg[3] = 0;
   }
 }
 
@@ -1160,6 +1254,8 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   const uint64_t n_slots = (uint64_t)hs.n_flags + 1;
   H->n_slots = n_slots;
   // summary: head partial (slot 0), open cluster (last slot)
+  if (getenv("PARASUITE_B200_DEBUG"))
+    fprintf(stderr, "[ps_pileup] warp-routine site passes %llu, sweep give-ups %llu, window passes %llu\n", hs.dbg[0], hs.dbg[1], hs.dbg[2]);
   H->head = hs.head;
   if (hs.n_flags) H->open = hs.open;
   H->first_slot1 = hs.first_slot1 == 0xFFFFFFFFu ? (uint32_t)n : hs.first_slot1;

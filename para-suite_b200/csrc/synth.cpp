@@ -247,6 +247,25 @@ Synth* ps_synth_reads(const ps_synth_params* P, const ps_reference* ref) {
     for (int t = 0; t < threads; ++t) pool.emplace_back(phase1, nc * t / threads, nc * (t + 1) / threads);
     for (auto& th : pool) th.join();
   }
+  // ---- coordinate order ------------------------------------------------------------------------------
+  // A BAM is sorted by start throughout, not only inside a cluster: neighbouring clusters that overlap interleave.
+  // slot[rd] = place of generator read rd in the batch (stable: ties keep generator order); contents stay keyed by rd.
+  std::vector<uint64_t> slot(n);
+  {
+    std::vector<uint64_t> idx(n);
+    for (uint64_t r = 0; r < n; ++r) idx[r] = r;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return S->ref_start[a] < S->ref_start[b]; });
+    std::vector<uint32_t> m2(n), s2(n);
+    std::vector<uint8_t> c2(n);
+    std::vector<uint32_t> g2(cigtmp.size());
+    for (uint64_t k = 0; k < n; ++k) {
+      const uint64_t r = idx[k];
+      slot[r] = k;
+      m2[k] = S->meta[r]; s2[k] = S->ref_start[r]; c2[k] = ncig[r];
+      if (P->mode) std::memcpy(&g2[k * 7], &cigtmp[r * 7], 7 * 4);
+    }
+    S->meta.swap(m2); S->ref_start.swap(s2); ncig.swap(c2); cigtmp.swap(g2);
+  }
   // ---- offsets ---------------------------------------------------------------------------------------
   const uint32_t bpr = (L + 3) / 4;
   std::vector<uint64_t> coff(n + 1, 0);
@@ -285,14 +304,15 @@ Synth* ps_synth_reads(const ps_synth_params* P, const ps_reference* ref) {
         }
       }
       for (uint32_t j = 0; j < x.n_reads; ++j) {
-        uint64_t rd = first[c] + j;
+        const uint64_t gen = first[c] + j;       // generator ordinal: keys the random streams
+        const uint64_t rd = slot[gen];           // place in the batch
         uint32_t m = S->meta[rd];
         bool minus = PS_META_FLAGS(m) & PS_RF_REVERSE;
         uint32_t k = ncig[rd];
         uint32_t one = (L << 4) | 0;
         const uint32_t* cg = P->mode ? &cigtmp[rd * 7] : &one;
         std::memcpy(&S->cigar[coff[rd]], cg, 4 * k);
-        Rng r(P->seed, 6, rd);
+        Rng r(P->seed, 6, gen);
         // true forward bases through the cigar
         uint64_t g = S->ref_start[rd];
         uint32_t p = 0;
@@ -343,7 +363,7 @@ Synth* ps_synth_reads(const ps_synth_params* P, const ps_reference* ref) {
     for (int t = 0; t < threads; ++t) pool.emplace_back(phase2, t, nc * t / threads, nc * (t + 1) / threads);
     for (auto& th : pool) th.join();
   }
-  // exceptions: threads own increasing read ranges, so concatenation is ordered by read; sort positions per read
+  // exceptions: ordered by (read, position)
   {
     std::vector<std::pair<uint64_t, uint32_t>> all;
     for (int t = 0; t < threads; ++t)

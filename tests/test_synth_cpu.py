@@ -39,3 +39,12 @@ def test_synth_dense_cigar(synth, oracle):
     c = r["counters"]
     assert c[4] > 0 and c[5] > 0 and c[6] > 0                      # indel reads, skipped (Q5), longer indels
     assert r["insertions_per_pos"].sum() > 0 and r["deletions_per_pos"].sum() > 0
+
+
+def test_synth_dense_is_sorted_throughout(synth):
+    """Overlapping neighbouring clusters interleave: the batch is sorted by start like a BAM, not only inside clusters."""
+    ref = synth.synth_reference(3, [30_000], n_run=0)
+    a = synth.synth_reads(ref, 40_000, 36, seed=11, threads=2)
+    assert np.all(np.diff(a.ref_start.astype(np.int64)) >= 0)
+    b = synth.synth_reads(ref, 40_000, 150, seed=11, mode=1, threads=2)
+    assert np.all(np.diff(b.ref_start.astype(np.int64)) >= 0)
