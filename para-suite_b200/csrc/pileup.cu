@@ -46,7 +46,8 @@ struct PlState {                  // device-side run state (one per call)
   unsigned long long fault;       // min over (ordinal << 8 | code); ~0 = none
   unsigned long long skipped;     // skippedDueIndel (:156)
   unsigned long long dstr;        // doubleStranded (:496)
-  unsigned long long n_sites;     // distinct (cluster, position)
+  unsigned long long n_sites;     // site slots handed out by pl_cluster_kernel (>= the number of sites: upper bounds)
+  unsigned long long n_sites_final;   // distinct (cluster, position), written by pl_compact_kernel
   unsigned int n_flags;           // clusters opened
   unsigned int unsorted;
   unsigned int tile_ctr_flag;
@@ -512,7 +513,7 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_syn
 template <int NW>
 __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slot, uint32_t f, uint32_t fe, WarpTables& T,
                                             WarpRing& G, ps_cluster* rec, bool fill, ps_site* dest, uint32_t cap,
-                                            unsigned long long& dstr) {
+                                            unsigned long long& dstr, unsigned long long* site_base = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
   ContigCache cc;
   PlRead x;
@@ -571,6 +572,17 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
     if (slot && !first_rev) dstr += maf;                     // doubleStranded++ (:494-498), incl. the never-flushed last cluster
   }
   if (t2c == 0) return 0;
+  if (site_base) {
+    // the caller wants the sites written in ONE pass: take an upper bound of slots (events, or positions between the
+    // first and the last event) from the block-order site array; pl_compact_kernel drops the unused ones
+    const unsigned long long ub = min((unsigned long long)t2c, (unsigned long long)((int64_t)ev_max - (int64_t)ev_min + 1));
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&P.st->n_sites, ub);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    *site_base = base;
+    dest = P.sites + base;
+    cap = base < P.cap_sites ? (uint32_t)min(ub, P.cap_sites - base) : 0u;
+  }
 
   // ---- sites: one chunk of reads, all events inside one window -> warp ballots, no shared memory ----------------
   if (fe - f <= 32 && (int64_t)ev_max - (int64_t)ev_min < PL_WINDOW) {
@@ -985,14 +997,8 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
     for (uint32_t e = warp; e < nfb; e += PL_WARPS) {
       const uint32_t k = S.fb[e], slot = c0 + k;
       const uint32_t f = S.first[k], fe = S.first[k + 1];
-      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr);
       unsigned long long sb = 0;
-      if (lane == 0 && cnt) sb = atomicAdd(&P.st->n_sites, (unsigned long long)cnt);
-      sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
-      if (cnt && sb < P.cap_sites) {
-        unsigned long long unused = 0;
-        pl_cluster<NW>(P, slot, f, fe, *T, *G, nullptr, false, P.sites + sb, (uint32_t)min((unsigned long long)cnt, P.cap_sites - sb), unused);
-      }
+      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr, &sb);
       __syncwarp();
       if (lane == 0) { wrec->site_begin = sb; wrec->site_end = sb + cnt; }
       __syncwarp();
@@ -1056,7 +1062,10 @@ __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_con
       pre = lb_exclusive_prefix(P.d_cnt, (int)tile, P.epoch, LbSum(), 0ull);
       if (lane == 0) lb_publish(&P.d_cnt[tile], pre + total, 2u, P.epoch);
     }
-    if (lane == 0) s_pre = pre;
+    if (lane == 0) {
+      s_pre = pre;
+      if (tile == n_tiles - 1) P.st->n_sites_final = pre + total;
+    }
   }
   __syncthreads();
   unsigned long long to = s_pre + ex;
@@ -1091,7 +1100,7 @@ __global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint
 
 __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
-    st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_flags = 0;
+    st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_sites_final = 0; st->n_flags = 0;
     st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu;
     st->dbg[0] = st->dbg[1] = st->dbg[2] = st->dbg[3] = 0;
   }
@@ -1263,7 +1272,7 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   H->counters.has_open_cluster = hs.n_flags ? 1 : 0;
   H->counters.double_stranded = hs.dstr;
   H->counters.n_clusters = hs.n_flags ? hs.n_flags - 1 : 0;
-  const uint64_t sites_before_open = hs.n_flags ? H->open.site_begin : hs.n_sites;
+  const uint64_t sites_before_open = hs.n_flags ? H->open.site_begin : hs.n_sites_final;
   H->counters.n_sites = sites_before_open - H->head.site_end;
   return PS_OK;
 }
