@@ -173,3 +173,33 @@ def test_region_sharding_halo_merge(ctx, oracle):
             carry = merge_pileup_shards.carry_after(shard_results, carry)
         merged = merge_pileup_shards(shard_results, [0, cut])
         assert_pileup_equal(merged, whole, f"cut {cut}")
+
+
+def test_deep_pileup_one_cluster(ctx, oracle):
+    """A cluster far larger than the shared-memory chunk (60 000 reads on 3 kb, one chain): the streaming sweep of the
+    warp routine (sliding ring of positions) against the oracle."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(91, [3_000], n_run=0)
+    batch = synth.synth_reads(ref, 60_000, 36, seed=13)
+    assert np.all(np.diff(batch.ref_start.astype(np.int64)) >= 0)
+    ctx.upload_reference(ref)
+    got, exp = ctx.pileup(batch), oracle.pileup(ref, batch)
+    assert_pileup_equal(got, exp, "deep pileup")
+    assert exp["open_cluster"] is not None and int(exp["open_cluster"]["num_reads"]) > 10_000
+
+
+def test_records_out_of_order_inside_a_contig(ctx, oracle):
+    """The tools only check the header's sort order and take records in FILE order.  Records whose starts go backwards
+    inside a contig must give the file-order result too (the sweep gives up, the window loop takes over)."""
+    from parasuite_b200 import synth
+    from parasuite_b200.sharding import take_uniform
+    ref = synth.synth_reference(92, [40_000], n_run=0)
+    batch = synth.synth_reads(ref, 30_000, 36, seed=14, n_ppm=0)
+    rng = np.random.default_rng(5)
+    idx = np.arange(batch.n_reads)
+    for k in range(0, batch.n_reads - 8, 8):                # shuffle inside windows of 8 reads
+        rng.shuffle(idx[k:k + 8])
+    shuffled = take_uniform(batch, idx)
+    assert np.any(np.diff(shuffled.ref_start.astype(np.int64)) < 0)
+    ctx.upload_reference(ref)
+    assert_pileup_equal(ctx.pileup(shuffled), oracle.pileup(ref, shuffled), "out of order inside a contig")
