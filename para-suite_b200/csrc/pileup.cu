@@ -1074,13 +1074,30 @@ __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_con
     if (c0 + j >= n_slots) break;
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.src + from[j]);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.dst + to);
-    for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];     // a site is 24 bytes
+    if (cnt[j] <= 16)
+      for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];   // a site is 24 bytes
     *reinterpret_cast<ulonglong2*>(&P.cl[c0 + j].site_begin) = make_ulonglong2(to, to + cnt[j]);
     if (c0 + j == 0 || c0 + j == n_slots - 1) {      // the two boundary records ride home with the run state
       ps_cluster rec = P.cl[c0 + j];
       rec.site_begin = to; rec.site_end = to + cnt[j];
       if (c0 + j == 0) P.st->head = rec;
       if (c0 + j == n_slots - 1) P.st->open = rec;
+    }
+    to += cnt[j];
+  }
+  // long site runs (deep or long clusters): the whole warp copies them
+  to = s_pre + ex;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    uint32_t big = __ballot_sync(0xFFFFFFFFu, c0 + j < n_slots && cnt[j] > 16);
+    while (big) {
+      const int src_lane = __ffs((int)big) - 1;
+      big &= big - 1;
+      const unsigned long long f0 = __shfl_sync(0xFFFFFFFFu, from[j], src_lane), t0 = __shfl_sync(0xFFFFFFFFu, to, src_lane);
+      const uint32_t n3 = __shfl_sync(0xFFFFFFFFu, cnt[j], src_lane) * 3u;
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.src + f0);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.dst + t0);
+      for (uint32_t e = lane; e < n3; e += 32) dst[e] = src[e];
     }
     to += cnt[j];
   }
