@@ -36,8 +36,10 @@ namespace {
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int CB_CLUSTERS = 128;                      // clusters per block of pl_cluster_kernel (thread per cluster)
-constexpr int CB_CHUNK = 2048;                        // reads decoded into shared memory at a time
+constexpr int CB_THREADS = 128;                       // threads per block of pl_cluster_kernel
+constexpr int CB_WARPS = CB_THREADS / 32;
+constexpr int CB_CLUSTERS = 64;                       // clusters per block of pl_cluster_kernel (thread per cluster)
+constexpr int CB_CHUNK = 1024;                        // reads decoded into shared memory at a time
 constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
 constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
 constexpr int PL_WINDOW = 128;                        // positions per window
@@ -154,9 +156,9 @@ __global__ void __launch_bounds__(PL_THREADS) pl_maxkey_kernel(const __grid_cons
 }
 
 // block-wide exclusive scan over one 64-bit value per thread (PL_THREADS threads); also returns the block total
-template <typename Op>
+template <typename Op, int WARPS = PL_WARPS>
 __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long v, Op op, unsigned long long identity,
-                                                              unsigned long long* warp_tot /* [8] smem */,
+                                                              unsigned long long* warp_tot /* [WARPS] smem */,
                                                               unsigned long long& total) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long x = v;
@@ -169,7 +171,7 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
   __syncthreads();
   unsigned long long prefix = identity, tot = identity;
 #pragma unroll
-  for (uint32_t w = 0; w < PL_WARPS; ++w) {
+  for (uint32_t w = 0; w < (uint32_t)WARPS; ++w) {
     const unsigned long long t = warp_tot[w];
     if (w < warp) prefix = op(prefix, t);
     tot = op(tot, t);
@@ -770,8 +772,8 @@ struct ClusterSmem {
   uint8_t* cid;               // [CB_CHUNK] cluster (index inside the block) of each read
 };
 constexpr size_t kClusterSmemBytes = (size_t)CB_CHUNK * (8 + 5 * 4 + 1) + (size_t)CB_CLUSTERS * (8 + CB_SITES * 12 + 4 * 4) + 64;
-static_assert((size_t)CB_CHUNK * 28 >= PL_WARPS * (sizeof(WarpTables) + sizeof(WarpRing) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
-static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is one byte / one thread per cluster");
+static_assert((size_t)CB_CHUNK * 28 >= CB_WARPS * (sizeof(WarpTables) + sizeof(WarpRing) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
+static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= CB_THREADS, "cluster index is one byte / one thread per cluster");
 
 // One block = CB_CLUSTERS consecutive clusters = one contiguous run of reads, taken in chunks of CB_CHUNK reads.
 //   A   thread per READ:    decode (T>C mask, interval, strand) into shared memory -- full lanes whatever the cluster
@@ -786,9 +788,9 @@ static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= PL_THREADS, "cluster index is
 // Clusters that do not fit (more than CB_CHUNK reads, T>C positions more than 64 apart, more than CB_SITES of them)
 // are left to the warp-per-cluster routine above at the end of the block.
 template <int NW>
-__global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
+__global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned long long s_wtot[PL_WARPS];
+  __shared__ unsigned long long s_wtot[CB_WARPS];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_nfb;
   ClusterSmem S;
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
   if (c0 >= n_slots) return;
   const uint32_t ncl = min((uint32_t)CB_CLUSTERS, n_slots - c0);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (uint32_t k = tid; k <= ncl; k += PL_THREADS) S.first[k] = __ldg(P.cl_first + c0 + k);
+  for (uint32_t k = tid; k <= ncl; k += CB_THREADS) S.first[k] = __ldg(P.cl_first + c0 + k);
   if (tid == 0) s_nfb = 0;
   __syncthreads();
 
@@ -853,10 +855,10 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
     __syncthreads();
     // ---- A, thread per read: decode; T>C positions into the cluster's key set -------------------------------------
     PlRaw<NW> nxt = pl_load_raw<NW>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
-    for (uint32_t q = rs + warp * 32; q < re; q += PL_THREADS) {
+    for (uint32_t q = rs + warp * 32; q < re; q += CB_THREADS) {
       const uint32_t r = q + lane;
       const PlRaw<NW> raw = nxt;
-      if (q + PL_THREADS < re) nxt = pl_load_raw<NW>(P, r + PL_THREADS, r + PL_THREADS < re);   // in flight during this decode
+      if (q + CB_THREADS < re) nxt = pl_load_raw<NW>(P, r + CB_THREADS, r + CB_THREADS < re);   // in flight during this decode
       PlRead x;
       pl_decode<NW>(P, q, r, r < re, raw, cc, x);
       if (r < re) {
@@ -904,7 +906,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
       }
     }
     // ---- B2 -----------------------------------------------------------------------------------------------------
-    for (uint32_t i = tid; i < nrd; i += PL_THREADS) {
+    for (uint32_t i = tid; i < nrd; i += CB_THREADS) {
       unsigned long long m = S.mask[i];
       if (!(m >> 63)) continue;
       const uint32_t k = S.cid[i];
@@ -943,7 +945,7 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
       if (left) { S.fb[atomicAdd(&s_nfb, 1u)] = cur + tid; ns = 0; }
     }
     unsigned long long total;
-    const unsigned long long ex = block_exclusive((unsigned long long)ns, LbSum(), 0ull, s_wtot, total);
+    const unsigned long long ex = block_exclusive<LbSum, CB_WARPS>((unsigned long long)ns, LbSum(), 0ull, s_wtot, total);
     if (tid == 0) s_base = total ? atomicAdd(&P.st->n_sites, total) : 0ull;
     __syncthreads();
     if (mine && !left) {
@@ -991,10 +993,10 @@ __global__ void __launch_bounds__(PL_THREADS, 3) pl_cluster_kernel(const __grid_
   __syncthreads();
   {
     WarpTables* T = reinterpret_cast<WarpTables*>(smem_raw) + warp;
-    WarpRing* G = reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + warp;
-    ps_cluster* wrec = reinterpret_cast<ps_cluster*>(reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + PL_WARPS) + PL_WARPS) + warp;
+    WarpRing* G = reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + CB_WARPS) + warp;
+    ps_cluster* wrec = reinterpret_cast<ps_cluster*>(reinterpret_cast<WarpRing*>(reinterpret_cast<WarpTables*>(smem_raw) + CB_WARPS) + CB_WARPS) + warp;
     const uint32_t nfb = s_nfb;
-    for (uint32_t e = warp; e < nfb; e += PL_WARPS) {
+    for (uint32_t e = warp; e < nfb; e += CB_WARPS) {
       const uint32_t k = S.fb[e], slot = c0 + k;
       const uint32_t f = S.first[k], fe = S.first[k + 1];
       unsigned long long sb = 0;
@@ -1167,7 +1169,7 @@ template <int NW>
 static void launch_cluster_nw(uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
   // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
   cudaFuncSetAttribute(pl_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
-  pl_cluster_kernel<NW><<<grid, PL_THREADS, kClusterSmemBytes, st>>>(Q);
+  pl_cluster_kernel<NW><<<grid, CB_THREADS, kClusterSmemBytes, st>>>(Q);
 }
 static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
   switch (nw) {
