@@ -41,6 +41,8 @@ constexpr int CB_WARPS = CB_THREADS / 32;
 constexpr int CB_CLUSTERS = 64;                       // clusters per block of pl_cluster_kernel (thread per cluster)
 constexpr int CB_CHUNK = 1024;                        // reads decoded into shared memory at a time
 constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
+constexpr int FLAG_THREADS = 128;                     // threads per block of pl_flag_kernel
+constexpr int FLAG_WARPS = FLAG_THREADS / 32;
 constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
 constexpr int PL_WINDOW = 128;                        // positions per window
 
@@ -186,10 +188,9 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
 // ITEMS == PL_FLAG_ITEMS: every read has one cigar op and the streams are 16-byte aligned (vector loads);
 // ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
 template <int ITEMS>
-__global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_constant__ FlagParams P) {
-  constexpr int TILE = PL_THREADS * ITEMS;
-  __shared__ unsigned long long s_wtot[PL_WARPS];
-  __shared__ uint64_t s_scan[8];
+__global__ void __launch_bounds__(FLAG_THREADS, 4) pl_flag_kernel(const __grid_constant__ FlagParams P) {
+  constexpr int TILE = FLAG_THREADS * ITEMS;
+  __shared__ unsigned long long s_wtot[FLAG_WARPS];
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_pre;
 
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_con
   } else {
     const bool in_range = r0 < n;
     const uint32_t meta = in_range ? __ldg(P.b.meta + r0) : PS_MAKE_META(0, 0, PS_RF_UNMAPPED);
-    const ReadOffsets off = read_offsets(P.b, tile, r0, meta, in_range, s_scan);
+    const ReadOffsets off = warp_read_offsets(P.b, (uint64_t)tile * TILE + (threadIdx.x & ~31u), r0, in_range, meta);
     key[0] = in_range ? pl_key(P, r0, meta, P.b.cigar + off.cigar, __ldg(P.b.ref_start + r0), cc, start[0]) : 0ull;
     if (!in_range) start[0] = 0;
   }
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_con
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) tmax = key[j] > tmax ? key[j] : tmax;
   unsigned long long block_max;
-  const unsigned long long ex_max = block_exclusive(tmax, LbMax(), 0ull, s_wtot, block_max);
+  const unsigned long long ex_max = block_exclusive<LbMax, FLAG_WARPS>(tmax, LbMax(), 0ull, s_wtot, block_max);
   if (warp == 0) {
     if (tile == 0) {
       if (lane == 0) { lb_publish(&P.d_max[0], block_max, 2u, P.epoch); s_pre = 0; }
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_con
 
   // ---- look-back #2: cluster slots ---------------------------------------------------------------------------------
   unsigned long long block_cnt;
-  const unsigned long long ex_cnt = block_exclusive((unsigned long long)nfl, LbSum(), 0ull, s_wtot, block_cnt);
+  const unsigned long long ex_cnt = block_exclusive<LbSum, FLAG_WARPS>((unsigned long long)nfl, LbSum(), 0ull, s_wtot, block_cnt);
   if (warp == 0) {
     if (tile == 0) {
       if (lane == 0) { lb_publish(&P.d_cnt[0], block_cnt, 2u, P.epoch); s_pre = 0; }
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(PL_THREADS, 2) pl_flag_kernel(const __grid_con
       if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
       if (slot == 1) P.st->first_slot1 = (unsigned int)(r0 + j);
     }
-  if (tile == P.n_tiles - 1 && threadIdx.x == PL_THREADS - 1) {
+  if (tile == P.n_tiles - 1 && threadIdx.x == FLAG_THREADS - 1) {
     if (slot + 1 <= P.cap_cl) P.cl_first[slot + 1] = (uint32_t)n;   // slots 0 .. n_flags, the last one is the open cluster
     P.st->n_flags = (unsigned int)slot;
   }
@@ -1204,7 +1205,7 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   if (n >= 0xFFFFFFFFull) return set_error(ctx, PS_ERR_UNSUPPORTED, "pileup batch of >= 2^32 reads");
 
   const bool vec = b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start) && aligned16p(b.cigar);
-  const uint32_t tile_reads = PL_THREADS * (vec ? (uint32_t)PL_FLAG_ITEMS : 1u);
+  const uint32_t tile_reads = FLAG_THREADS * (vec ? (uint32_t)PL_FLAG_ITEMS : 1u);
   const uint32_t n_tiles = (uint32_t)((n + tile_reads - 1) / tile_reads);
   const int nw = flavour_of(b);
   H->nw = nw;
@@ -1242,8 +1243,8 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     pl_init_state<<<1, 32, 0, st>>>(d_state);
     const bool ev = ctx->timers_on;
     if (ev) cudaEventRecord(ctx->pl_ev[0], st);
-    if (vec) pl_flag_kernel<PL_FLAG_ITEMS><<<n_tiles, PL_THREADS, 0, st>>>(P);
-    else pl_flag_kernel<1><<<n_tiles, PL_THREADS, 0, st>>>(P);
+    if (vec) pl_flag_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+    else pl_flag_kernel<1><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
     if (ev) cudaEventRecord(ctx->pl_ev[1], st);
     ClusterParams Q;
     Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
