@@ -2,16 +2,18 @@
 // /root/reference/src/src/utils/errorprofile/ErrorProfiling.java) for one SoA batch.
 //
 // profile_fast_kernel   the common PAR-CLIP shape: uniform read length L <= 64, one M/=/X cigar op (L == R).
-//   * persistent CTAs; each iteration stages a 512-read super-tile (meta, ref_start, cigar, 2-bit bases,
-//     qualities: contiguous runs in HBM) into shared memory with cp.async.bulk + mbarrier, 3 stages deep;
+//   * persistent CTAs of 4 warps (5 per SM); every WARP owns a 2-stage ring of cp.async.bulk (TMA) copies with its own
+//     mbarriers (64 reads per warp-tile: meta, ref_start, cigar, 2-bit bases, qualities are contiguous runs in HBM),
+//     so there is no block barrier in the main loop;
 //   * one thread per read, all per-base work bit-parallel on 2-bit packed words:
 //       match counts   -> per-thread bit-sliced ("vertical") counters, one-hot (A|C, G|T) x position lanes,
 //                         merged across the warp with a carry-save butterfly every 2^P-2 reads; no atomics
-//       mismatches     -> rare: one 64-bit shared atomic (count | quality sum) per mismatching base
+//       mismatches     -> rare: two native 32-bit shared atomics (count, quality sum) per mismatching base
 //       quality sums   -> dp4a of the quality bytes against 0/-1 byte masks built with PRMT from the codes
-//   * reads that do not fit the fast shape (flags, N calls, other cigars, contig edges) fall through to the
-//     generic per-read routine inside the same kernel.
-// profile_generic_kernel  every CIGAR / every flag; literal per-read walk (also the tail of a batch).
+//   * reads that do not fit the fast shape (flags, other cigars, contig edges) are appended to a dense list for
+//     profile_deferred_kernel (thread per read, the literal routine).
+// profile_generic_kernel  every CIGAR / flag / length: lane-per-read prologue, warp-per-read count loop
+//     (lanes = alignment columns), warp-tiles from an atomic counter.
 //
 // Counts land in per-block shared-memory histograms and are flushed once per block with 64-bit global atomics
 // into the accumulator vector (internal.h ProfileLayout) -- the unit of the multi-GPU all-reduce.
