@@ -4,8 +4,6 @@
 
 #include "internal.h"
 
-__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { return __ldg(p); }
-
 // 2-bit reference code at global offset g (undefined where the invalid bit is set)
 __device__ __forceinline__ uint32_t ref_code_at(const DeviceRef& ref, uint64_t g) {
   return (__ldg(ref.seq2 + (g >> 4)) >> (2 * (g & 15))) & 3u;
@@ -20,8 +18,6 @@ __device__ __forceinline__ uint32_t read_code_at(const uint8_t* b, uint32_t p) {
 
 // htsjdk Cigar.getReferenceLength: M, D, N, =, X consume the reference
 __device__ __forceinline__ bool op_consumes_ref(uint32_t op) { return (0x18Du >> op) & 1u; }   // bits 0,2,3,7,8
-// M, I, S, =, X consume the read
-__device__ __forceinline__ bool op_consumes_read(uint32_t op) { return (0x193u >> op) & 1u; }  // bits 0,1,4,7,8
 __device__ __forceinline__ bool op_is_match(uint32_t op) { return (0x181u >> op) & 1u; }       // M, =, X
 
 __device__ __forceinline__ void raise_fault(unsigned long long* fault, uint64_t ordinal, uint32_t code) {
@@ -38,51 +34,10 @@ __device__ __forceinline__ uint32_t contig_of(const DeviceRef& ref, uint64_t g) 
   return lo;
 }
 
-// per-read stream offsets inside a tile.  Uniform batches: closed form.  Otherwise a block-wide exclusive
-// scan over (L, ceil(L/4), n_cigar) packed into one 64-bit word (25 | 23 | 16 bits: a tile holds 256 reads
-// of L <= 65535 and <= 255 cigar ops).
+// per-read stream offsets (bytes of packed bases, bytes of qualities, cigar elements)
 struct ReadOffsets {
   uint64_t base, qual, cigar;
 };
-
-__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* warp_sums /* [8] smem */) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint64_t x = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-    if (lane >= (uint32_t)d) x += y;
-  }
-  if (lane == 31) warp_sums[warp] = x;
-  __syncthreads();
-  uint64_t prefix = 0;
-  for (uint32_t w = 0; w < warp; ++w) prefix += warp_sums[w];
-  __syncthreads();
-  return prefix + x - v;
-}
-
-__device__ __forceinline__ ReadOffsets read_offsets(const DeviceBatch& b, uint64_t tile, uint64_t r, uint32_t meta,
-                                                    bool in_range, uint64_t* scan_smem) {
-  ReadOffsets o;
-  const uint32_t L = PS_META_LEN(meta), nc = PS_META_NCIGAR(meta);
-  if (b.uniform_len && b.uniform_ncigar) {
-    o.base = r * (uint64_t)((b.uniform_len + 3) >> 2);
-    o.qual = r * (uint64_t)b.uniform_len;
-    o.cigar = r * (uint64_t)b.uniform_ncigar;
-    return o;
-  }
-  uint64_t packed = in_range ? ((uint64_t)L | ((uint64_t)((L + 3) >> 2) << 25) | ((uint64_t)nc << 48)) : 0;
-  uint64_t ex = block_exclusive_scan_u64(packed, scan_smem);
-  if (b.uniform_len) {
-    o.base = r * (uint64_t)((b.uniform_len + 3) >> 2);
-    o.qual = r * (uint64_t)b.uniform_len;
-  } else {
-    o.base = __ldg(b.tile_base_off + tile) + ((ex >> 25) & 0x7FFFFFu);
-    o.qual = __ldg(b.tile_qual_off + tile) + (ex & 0x1FFFFFFu);
-  }
-  o.cigar = b.uniform_ncigar ? r * (uint64_t)b.uniform_ncigar : __ldg(b.tile_cigar_off + tile) + (ex >> 48);
-  return o;
-}
 
 // Stream offsets of the reads of one warp chunk [q, q+32) (lane l holds read r = q + l; `in` = r exists), without a
 // block barrier: tile tables + the metas between the tile start and the chunk + a warp scan.  A chunk may straddle one
