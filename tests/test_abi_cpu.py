@@ -52,3 +52,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(abi, "LIB_DIR", str(tmp_path))
     with pytest.raises(abi.NativeLibraryMissing):
         abi.load_library()
+
+
+def test_jni_shim_type_checks_against_stub_header():
+    """No JDK in this image: the JNI shim (jni/parasuite_jni.c) is compiled with -fsyntax-only against a stand-in jni.h
+    that declares exactly the JNI calls it makes, together with the real C ABI header."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    repo = os.path.dirname(abi.INCLUDE_DIR)
+    cmd = [gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(repo, "tests", "jni_stub"),
+           "-I", abi.INCLUDE_DIR, os.path.join(repo, "jni", "parasuite_jni.c")]
+    subprocess.run(cmd, check=True, capture_output=True)
+    src = open(os.path.join(repo, "jni", "parasuite_jni.c")).read()
+    for sym in ("ps_create", "ps_destroy", "ps_reference_load_fasta", "ps_profile_bam", "ps_pileup_bam", "ps_pileup_next",
+                "ps_pileup_counters_get", "ps_pileup_close"):
+        assert sym in src and sym in abi.EXPORTS
