@@ -191,7 +191,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from parasuite_b200.distributed import all_gather_keys_async, sharded_pileup_carry
+    from parasuite_b200.distributed import gather_keys_device, sharded_pileup_carry
     from parasuite_b200.runtime import Context, DeviceBatch, PinnedBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,8 +203,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     name, ref, batch, max_len = workload(args.gpus, rank, args.small)
     ctx = Context(local_rank)
@@ -224,17 +234,17 @@ def main():
         # the whole hot path on a batch that is already in HBM: profile kernel (+ the tiny all-reduce), read-back of
         # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
         # their counters come back to the host
-        exchange = None
-        if world > 1:   # region sharding: exclusive prefix-max of one (contig, end) pair per rank = this region's carry-in;
-            # the all-gather is started first and travels while the profile kernel runs
-            exchange = all_gather_keys_async(ctx.pileup_max_key(dbatch, stream.cuda_stream), device=dev)
+        keys = None
+        if world > 1:   # region sharding: the maximum (contig, end) of every region, all-gathered; the exclusive prefix-max
+            # (this region's carry-in) is taken on the device by the flag kernel -- no host round trip
+            keys = gather_keys_device(ctx.pileup_max_key_tensor(dbatch, stream.cuda_stream))
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
         if world > 1:
             dist.all_reduce(ctx.profile_acc_tensor())
         res = ctx.profile_end()
-        carry = exchange.carry() if exchange is not None else None
-        with ctx.pileup_run(dbatch, first_running_id=1, carry=carry, stream=stream.cuda_stream) as h:
+        carry_keys = (keys.data_ptr(), rank) if keys is not None else None
+        with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream) as h:
             pile["counters"] = h.counters
         return res
 

@@ -235,6 +235,11 @@ typedef struct ps_pileup_opts {
   uint32_t carry_valid;
   uint32_t carry_contig;
   int32_t carry_cluster_end;
+  /* the same carry-in left on the DEVICE: carry_keys_n keys as ps_pileup_max_key_device writes them, one per preceding
+   * shard (e.g. the first `rank` entries of an NCCL all-gather); their maximum is the carry-in, no host round trip.
+   * Ignored when carry_keys_n == 0; combined (max) with the host triple above when both are given. */
+  uint32_t carry_keys_n;
+  const uint64_t* carry_keys_device;
 } ps_pileup_opts;
 
 int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* host_batch, const ps_pileup_opts* opts, ps_pileup** out);
@@ -244,6 +249,9 @@ int ps_pileup_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, const ps
  * over the shards (one pair per shard: an all-gather of 8 scalars) is shard s's carry-in, so all shards run at once. */
 int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,
                       int32_t* end);
+/* The same maximum left on the device, asynchronously on `stream`: *dev_key points to one uint64 owned by the context,
+ * (contig + 1) << 32 | end, 0 if the batch holds no kept record; valid until the next call of this function. */
+int ps_pileup_max_key_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint64_t** dev_key);
 int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out);
 /* copy up to `max_clusters` closed clusters starting at `first` (and their sites) into caller arrays;
  * returns the number copied (>= 0) or a negative status */

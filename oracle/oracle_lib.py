@@ -124,7 +124,7 @@ def pileup_count(ref, batch) -> int:
     lib = load()
     rs = ref.as_struct()
     bs = batch.as_struct()
-    opts = abi.ps_pileup_opts(1, 0, 0, 0)
+    opts = abi.ps_pileup_opts(1, 0, 0, 0, 0, None)
     h = lib.or_pileup_run(C.byref(rs), C.byref(bs), C.byref(opts))
     try:
         ctr = abi.ps_pileup_counters()
@@ -140,7 +140,7 @@ def pileup(ref, batch, first_running_id: int = 1, carry=None) -> dict:
     lib = load()
     rs = ref.as_struct()
     bs = batch.as_struct()
-    opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+    opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None)
     if carry is not None:
         opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
     h = lib.or_pileup_run(C.byref(rs), C.byref(bs), C.byref(opts))

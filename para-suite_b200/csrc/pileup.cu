@@ -96,6 +96,8 @@ struct FlagParams {
   unsigned int epoch;
   uint32_t n_tiles;
   unsigned long long carry_key;
+  const unsigned long long* carry_keys;   // device: keys of the preceding shards (may be null)
+  uint32_t carry_keys_n;
   uint32_t* cl_first;       // [cap_cl + 2] first read of each slot; slot 0 = reads continuing the carry-in cluster
   uint64_t cap_cl;
 };
@@ -259,6 +261,10 @@ __global__ void __launch_bounds__(FLAG_THREADS, 4) pl_flag_kernel(const __grid_c
   __syncthreads();
   unsigned long long E = s_pre > ex_max ? s_pre : ex_max;
   E = E > P.carry_key ? E : P.carry_key;
+  for (uint32_t k = 0; k < P.carry_keys_n; ++k) {        // a handful of shards: every thread reads them (L1 broadcast)
+    const unsigned long long ck = __ldg(P.carry_keys + k);
+    E = E > ck ? E : ck;
+  }
 
   // ---- boundary flags (:175-176) ---------------------------------------------------------------------------------
   uint32_t fl = 0, nfl = 0;
@@ -1241,6 +1247,8 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     FlagParams P;
     P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
     P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
+    P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
+    P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
     pl_init_state<<<1, 32, 0, st>>>(d_state);
     const bool ev = ctx->timers_on;
     if (ev) cudaEventRecord(ctx->pl_ev[0], st);
@@ -1395,24 +1403,34 @@ int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* hb, const ps_pileup_opts* 
   return rc;
 }
 
-int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,
-                      int32_t* end) {
-  if (!ctx || !dev_batch || !valid || !contig || !end) return PS_ERR_INVALID_ARG;
+int ps_pileup_max_key_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint64_t** dev_key) {
+  if (!ctx || !dev_batch || !dev_key) return PS_ERR_INVALID_ARG;
   if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
   cudaSetDevice(ctx->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  *valid = 0; *contig = 0; *end = 0;
-  if (dev_batch->n_reads == 0) return PS_OK;
   cudaError_t err = cudaSuccess;
   unsigned long long* d_key = scratch<unsigned long long>(ctx, 9, 1, err);
   if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+  *dev_key = reinterpret_cast<uint64_t*>(d_key);
+  PS_CUDA(ctx, cudaMemsetAsync(d_key, 0, 8, st));
+  if (dev_batch->n_reads == 0) return PS_OK;
   FlagParams P{};
   P.b = pl_view_of(dev_batch); P.ref = ctx->ref;
-  PS_CUDA(ctx, cudaMemsetAsync(d_key, 0, 8, st));
   const uint32_t grid = (uint32_t)std::min<uint64_t>((dev_batch->n_reads + PL_THREADS - 1) / PL_THREADS, (uint64_t)ctx->sm_count * 8);
   pl_maxkey_kernel<<<grid, PL_THREADS, 0, st>>>(P, d_key);
   ctx->launches++;
   PS_CUDA(ctx, cudaGetLastError());
+  return PS_OK;
+}
+
+int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,
+                      int32_t* end) {
+  if (!ctx || !dev_batch || !valid || !contig || !end) return PS_ERR_INVALID_ARG;
+  *valid = 0; *contig = 0; *end = 0;
+  uint64_t* d_key = nullptr;
+  const int rc = ps_pileup_max_key_device(ctx, dev_batch, stream, &d_key);
+  if (rc != PS_OK) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   unsigned long long* hk = ctx->h_pinned ? reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->h_pinned) + 1024) : nullptr;
   unsigned long long tmp = 0;
   PS_CUDA(ctx, cudaMemcpyAsync(hk ? hk : &tmp, d_key, 8, cudaMemcpyDeviceToHost, st));

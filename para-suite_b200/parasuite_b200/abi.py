@@ -110,7 +110,7 @@ class ps_pileup_counters(C.Structure):
 
 class ps_pileup_opts(C.Structure):
     _fields_ = [("first_running_id", C.c_uint32), ("carry_valid", C.c_uint32), ("carry_contig", C.c_uint32),
-                ("carry_cluster_end", C.c_int32)]
+                ("carry_cluster_end", C.c_int32), ("carry_keys_n", C.c_uint32), ("carry_keys_device", C.c_void_p)]
 
 
 class ps_flush_totals(C.Structure):
@@ -153,6 +153,7 @@ EXPORTS = {
                                          C.POINTER(VP)]),
     "ps_pileup_max_key": (C.c_int, [VP, C.POINTER(ps_read_batch), VP, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                 C.POINTER(C.c_int32)]),
+    "ps_pileup_max_key_device": (C.c_int, [VP, C.POINTER(ps_read_batch), VP, C.POINTER(VP)]),
     "ps_pileup_counters_get": (C.c_int, [VP, C.POINTER(ps_pileup_counters)]),
     "ps_pileup_next": (C.c_int64, [VP, C.c_uint64, VP, C.c_uint64, VP, C.c_uint64]),
     "ps_pileup_open_cluster": (C.c_int, [VP, VP, VP, C.c_uint64]),

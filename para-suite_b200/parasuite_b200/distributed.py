@@ -63,6 +63,17 @@ def all_gather_keys(local: Key, group=None, device=None) -> list:
     return _KeyGather(local, group, device).keys()
 
 
+def gather_keys_device(key_tensor, group=None):
+    """All-gather of the 1-element device key tensors of Context.pileup_max_key_tensor.  Nothing comes back to the host:
+    the call is enqueued (the current stream waits for the collective) and the gathered keys stay in HBM, where
+    pileup_run(carry_keys=(ptr, rank)) takes the maximum of the first `rank` of them as this shard's carry-in."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty(dist.get_world_size(group), dtype=torch.int64, device=key_tensor.device)
+    dist.all_gather_into_tensor(out, key_tensor, group=group)
+    return out
+
+
 def sharded_pileup_carry(local_key: Key, group=None, device=None) -> Key:
     """The carry-in of this rank's region: one all-gather of 3 scalars per rank + a prefix-max on the host."""
     import torch.distributed as dist

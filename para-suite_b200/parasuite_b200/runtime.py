@@ -124,7 +124,7 @@ class Context:
 
     def pileup_bam(self, bam_path: str, first_running_id: int = 1) -> "PileupResult":
         """The record loop of the `clust` tool (PileupClusters.java:62-500) on a coordinate-sorted BAM."""
-        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None)
         h = C.c_void_p()
         st = self.lib.ps_pileup_bam(self.h, bam_path.encode(), C.byref(opts), C.byref(h))
         res = PileupResult(self, h, None)
@@ -213,13 +213,17 @@ class Context:
         return self.profile_end()
 
     # ---- T>C pileup (PileupClusters.java:137-500, 585-673) ----------------------------------------
-    def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> "PileupResult":
+    def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0, carry_keys=None) -> "PileupResult":
         """Run the pileup kernels; the cluster and site records stay in HBM behind the returned handle.
         batch: ReadBatch / PinnedBatch (host buffers, H2D inside) or DeviceBatch / UploadedBatch (resident).
-        carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None."""
-        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0)
+        carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None;
+        carry_keys = (device pointer, n): the keys of the n preceding shards left on the device (pileup_max_key_tensor +
+        all-gather), an alternative to `carry` without a host round trip."""
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None)
         if carry is not None:
             opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
+        if carry_keys is not None and carry_keys[1] > 0:
+            opts.carry_keys_device, opts.carry_keys_n = int(carry_keys[0]), int(carry_keys[1])
         h = C.c_void_p()
         if isinstance(batch, (DeviceBatch, UploadedBatch)):
             st = self.lib.ps_pileup_batch_device(self.h, C.byref(batch.struct), C.byref(opts), stream or None,
@@ -245,6 +249,18 @@ class Context:
         _check(self.lib, self.h, self.lib.ps_pileup_max_key(self.h, C.byref(dbatch.struct), stream or None, C.byref(v),
                                                              C.byref(c), C.byref(e)))
         return (int(c.value), int(e.value)) if v.value else None
+
+    def pileup_max_key_tensor(self, dbatch, stream: int = 0):
+        """The same maximum as a 1-element int64 CUDA tensor aliasing library memory ((contig + 1) << 32 | end, 0 = none),
+        computed asynchronously on `stream`: feed it to an all-gather and hand the gathered keys to pileup_run(carry_keys=)."""
+        import torch
+        p = C.c_void_p()
+        _check(self.lib, self.h, self.lib.ps_pileup_max_key_device(self.h, C.byref(dbatch.struct), stream or None, C.byref(p)))
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (1,), "typestr": "<i8", "data": (p.value, False), "version": 3}
+
+        return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
 
     def pileup(self, batch, first_running_id: int = 1, carry=None, stream: int = 0) -> dict:
         """pileup_run + fetch of every record into host arrays."""

@@ -203,3 +203,28 @@ def test_records_out_of_order_inside_a_contig(ctx, oracle):
     assert np.any(np.diff(shuffled.ref_start.astype(np.int64)) < 0)
     ctx.upload_reference(ref)
     assert_pileup_equal(ctx.pileup(shuffled), oracle.pileup(ref, shuffled), "out of order inside a contig")
+
+
+def test_device_resident_carry_keys(ctx, oracle):
+    """Region sharding without a host round trip: the shards' maximum (contig, end) keys stay on the device (as after an
+    all-gather) and the flag kernel takes the prefix-max itself; same result as the host carry and as the whole stream."""
+    import torch
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import DeviceBatch
+    from parasuite_b200.sharding import merge_pileup_shards, slice_batch
+    ref = synth.synth_reference(33, [2_000_000, 1_500_000], n_run=1000)
+    batch = synth.synth_reads(ref, 150_000, 36, seed=16)
+    ctx.upload_reference(ref)
+    whole = oracle.pileup(ref, batch)
+    cuts = [0, 40_003, 90_000, 90_001, batch.n_reads]
+    shards = [DeviceBatch(slice_batch(batch, lo, hi), "cuda:0") for lo, hi in zip(cuts[:-1], cuts[1:])]
+    keys = torch.cat([ctx.pileup_max_key_tensor(s).clone() for s in shards])       # what the all-gather leaves on every rank
+    torch.cuda.synchronize()
+    host_keys = [ctx.pileup_max_key(s) for s in shards]
+    for k, hk in zip(keys.tolist(), host_keys):
+        assert (None if k == 0 else ((k >> 32) - 1, k & 0xFFFFFFFF)) == hk
+    results = []
+    for r, s in enumerate(shards):
+        with ctx.pileup_run(s, carry_keys=(keys.data_ptr(), r)) as h:
+            results.append(h.fetch())
+    assert_pileup_equal(merge_pileup_shards(results, cuts[:-1]), whole, "device carry keys")
