@@ -42,6 +42,9 @@ constexpr int CB_WARPS = CB_THREADS / 32;
 constexpr int CB_CLUSTERS = 64;                       // clusters per block of pl_cluster_kernel (thread per cluster)
 constexpr int CB_CHUNK = 1024;                        // reads decoded into shared memory at a time
 constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
+#ifndef CB_BLOCKS_PER_SM
+#define CB_BLOCKS_PER_SM 6
+#endif
 constexpr int FLAG_THREADS = 128;                     // threads per block of pl_flag_kernel
 constexpr int FLAG_WARPS = FLAG_THREADS / 32;
 constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
@@ -489,7 +492,9 @@ __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, ui
       x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = rev; x.contig = cc.idx;
       return;
     }
-    pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, x);
+    PlRead t;               // the literal routine takes its result by address: keep x itself in registers
+    pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, t);
+    x = t;
   } else {
     const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);    // warp-collective
     if (in) pl_decode_generic(P, r, meta, off.base, off.cigar, x);
@@ -769,34 +774,64 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
 // Shared-memory plan of pl_cluster_kernel (dynamic): decoded reads of one chunk, per-cluster site tables
 struct ClusterSmem {
   unsigned long long* mask;   // [CB_CHUNK] T>C mask | rev << 62 | kept << 63
-  int32_t *lo, *hi, *start, *end;   // [CB_CHUNK]
-  uint32_t* contig;           // [CB_CHUNK]
+  int32_t *lo, *hi, *end;     // [CB_CHUNK]
   unsigned long long* umask;  // [CB_CLUSTERS] mutationMap key set: bit p = position base + p holds a T>C
   uint32_t *scnt, *scov, *skey;   // [CB_SITES * CB_CLUSTERS] site s of cluster k at [s * CB_CLUSTERS + k]
-  int32_t* base;              // [CB_CLUSTERS] position of bit 0 of umask
+  int32_t* base;              // [CB_CLUSTERS] position of bit 0 of umask = start of the read that opened the cluster
   uint32_t* ovf;              // [CB_CLUSTERS] != 0: the cluster does not fit the tables
+  uint8_t* cid;               // [CB_CHUNK] cluster (index inside the chunk) of each read
   uint32_t* first;            // [CB_CLUSTERS + 1] cl_first of the block's clusters
   uint32_t* fb;               // [CB_CLUSTERS] clusters left to the warp routine
-  uint8_t* cid;               // [CB_CHUNK] cluster (index inside the block) of each read
 };
-constexpr size_t kClusterSmemBytes = (size_t)CB_CHUNK * (8 + 5 * 4 + 1) + (size_t)CB_CLUSTERS * (8 + CB_SITES * 12 + 4 * 4) + 64;
-static_assert((size_t)CB_CHUNK * 28 >= CB_WARPS * (sizeof(WarpTables) + sizeof(WarpRing) + sizeof(ps_cluster)), "fallback tables alias the read arrays");
-static_assert(CB_CLUSTERS <= 256 && CB_CLUSTERS <= CB_THREADS, "cluster index is one byte / one thread per cluster");
+constexpr size_t kClusterAliasBytes = (size_t)CB_CHUNK * (8 + 3 * 4 + 1) + (size_t)CB_CLUSTERS * (8 + CB_SITES * 12 + 2 * 4);
+constexpr size_t kClusterSmemBytes = kClusterAliasBytes + (size_t)CB_CLUSTERS * 2 * 4 + 64;
+static_assert(kClusterAliasBytes >= CB_WARPS * (sizeof(WarpTables) + sizeof(WarpRing) + sizeof(ps_cluster)),
+              "fallback tables alias the read arrays and the site tables (not first / fb)");
+static_assert(CB_CLUSTERS <= 256 && CB_THREADS % CB_CLUSTERS == 0 && CB_CHUNK % 4 == 0,
+              "cluster index is one byte; CB_SPLIT threads per cluster");
+constexpr int CB_SPLIT = CB_THREADS / CB_CLUSTERS;    // threads that share one cluster in the per-cluster phases
+static_assert(CB_SPLIT >= 1 && CB_SPLIT <= 32 && (CB_SPLIT & (CB_SPLIT - 1)) == 0, "the CB_SPLIT threads of a cluster are neighbouring lanes");
+
+__device__ __forceinline__ unsigned long long bits_below(int n) { return n >= 64 ? ~0ull : (1ull << n) - 1ull; }
+
+// checkPosition (:638-643) for all T>C indices of a read at once: index ib lies at position lo + ib (plus strand) or
+// hi - ib (minus strand).  Returns false when a position falls outside [base, base + 64).
+__device__ __forceinline__ bool t2c_positions(unsigned long long mask, bool rev, int32_t lo, int32_t hi, int32_t base,
+                                              unsigned long long& bits) {
+  bits = 0;
+  if (!rev) {
+    const int32_t s = lo - base;
+    if ((uint32_t)s > 63u) return false;
+    bits = mask << s;
+    return (bits >> s) == mask;
+  }
+  const unsigned long long rv = __brevll(mask);          // index ib -> bit 63 - ib; wanted: bit (hi - base) - ib
+  const int32_t d = hi - base - 63;
+  if (d >= 0) {
+    if (d > 63) return false;
+    bits = rv << d;
+    return (bits >> d) == rv;
+  }
+  if (d < -63) return false;
+  bits = rv >> -d;
+  return (bits << -d) == rv;
+}
 
 // One block = CB_CLUSTERS consecutive clusters = one contiguous run of reads, taken in chunks of CB_CHUNK reads.
+//   pre CB_SPLIT threads per CLUSTER: cluster of every read; origin of the key set = start of the opening read
 //   A   thread per READ:    decode (T>C mask, interval, strand) into shared memory -- full lanes whatever the cluster
-//                           sizes are
-//       (and ORs the read's T>C positions into its cluster's 64-position key set: shared atomics)
-//   B0  thread per CLUSTER: counters over the cluster's decoded reads (P3 counters, P4, P6)
-//   B2  thread per READ:    per key: mutationMap count, first-insertion key (min), and baseCoveredMap -- every read adds
-//                           itself to the keys its interval covers.  A key's slot is its rank in the key set, so the
-//                           sites come out in position order.
+//                           sizes are -- and OR of the read's T>C positions (two shifts) into its cluster's
+//                           64-position key set: shared atomics
+//   B0  CB_SPLIT threads per CLUSTER: counters over the cluster's decoded reads (P3 counters, P4, P6)
+//   B2  thread per READ:    per T>C: mutationMap count and first-insertion key (min); baseCoveredMap: the keys a read's
+//                           interval covers are one run of slots (a key's slot is its rank in the key set, so the
+//                           sites come out in position order): +1 / -1 at the ends of the run, summed up in B3
 //   B3  thread per CLUSTER: record (64 contiguous bytes per thread) and sites; the block's sites go to one run of
 //                           slots taken with a single atomic, pl_compact_kernel orders the runs afterwards
 // Clusters that do not fit (more than CB_CHUNK reads, T>C positions more than 64 apart, more than CB_SITES of them)
 // are left to the warp-per-cluster routine above at the end of the block.
 template <int NW>
-__global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
+__global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_wtot[CB_WARPS];
   __shared__ unsigned long long s_base;
@@ -804,17 +839,16 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
   ClusterSmem S;
   S.mask = reinterpret_cast<unsigned long long*>(smem_raw);
   S.lo = reinterpret_cast<int32_t*>(S.mask + CB_CHUNK);
-  S.hi = S.lo + CB_CHUNK; S.start = S.hi + CB_CHUNK; S.end = S.start + CB_CHUNK;
-  S.contig = reinterpret_cast<uint32_t*>(S.end + CB_CHUNK);
-  S.umask = reinterpret_cast<unsigned long long*>(S.contig + CB_CHUNK);
+  S.hi = S.lo + CB_CHUNK; S.end = S.hi + CB_CHUNK;
+  S.umask = reinterpret_cast<unsigned long long*>(S.end + CB_CHUNK);
   S.scnt = reinterpret_cast<uint32_t*>(S.umask + CB_CLUSTERS);
   S.scov = S.scnt + CB_SITES * CB_CLUSTERS;
   S.skey = S.scov + CB_SITES * CB_CLUSTERS;
   S.base = reinterpret_cast<int32_t*>(S.skey + CB_SITES * CB_CLUSTERS);
   S.ovf = reinterpret_cast<uint32_t*>(S.base + CB_CLUSTERS);
-  S.first = S.ovf + CB_CLUSTERS;
+  S.cid = reinterpret_cast<uint8_t*>(S.ovf + CB_CLUSTERS);
+  S.first = reinterpret_cast<uint32_t*>(S.cid + CB_CHUNK);
   S.fb = S.first + CB_CLUSTERS + 1;
-  S.cid = reinterpret_cast<uint8_t*>(S.fb + CB_CLUSTERS);
 
   const uint32_t n_slots = P.st->n_flags + 1;          // written by pl_flag_kernel
   if (n_slots > P.cap_cl) return;                       // the host re-runs the kernels with larger arrays
@@ -822,6 +856,7 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
   if (c0 >= n_slots) return;
   const uint32_t ncl = min((uint32_t)CB_CLUSTERS, n_slots - c0);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t kk = tid / CB_SPLIT, part = tid % CB_SPLIT;    // per-cluster phases: cluster inside the chunk, share
   for (uint32_t k = tid; k <= ncl; k += CB_THREADS) S.first[k] = __ldg(P.cl_first + c0 + k);
   if (tid == 0) s_nfb = 0;
   __syncthreads();
@@ -841,23 +876,29 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
       continue;
     }
     const uint32_t re = S.first[cur + ncomp], nrd = re - rs;
-    const bool mine = tid < ncomp;
-    // ---- pre-pass, thread per cluster: cluster of every read, origin of the key set ----------------------------------
+    const bool mine = kk < ncomp, owner = mine && part == 0;
+    // ---- pre-pass, per cluster: cluster of every read, origin of the key set -----------------------------------------
+    uint32_t ra = 0, rb = 0, op_contig = 0;
+    int32_t base = 0;
     if (mine) {
-      const uint32_t k = cur + tid;
-      const uint32_t a = S.first[k] - rs, b = S.first[k + 1] - rs;
-      for (uint32_t i = a; i < b; ++i) S.cid[i] = (uint8_t)tid;
-      // sorted input: no position of a cluster lies before the start of the read that opened it (slot 0, the reads
-      // continuing the preceding shard's cluster, has no opener: it is left to the warp routine)
-      int32_t base = 0;
-      const uint32_t g0 = __ldg(P.b.ref_start + S.first[k]);
-      if (c0 + k != 0 && contig_lookup(P.ref, g0, cc)) base = (int32_t)((uint64_t)g0 - cc.lo) + 1;
-      S.base[tid] = base;
-      S.umask[tid] = 0;
-      S.ovf[tid] = (c0 + k == 0 && b > a) ? 1u : 0u;
+      const uint32_t k = cur + kk;
+      ra = S.first[k] - rs; rb = S.first[k + 1] - rs;
+      for (uint32_t i = ra + part; i < rb; i += CB_SPLIT) S.cid[i] = (uint8_t)kk;
+      if (part == 0) {
+        // sorted input: no position of a cluster lies before the start of the read that opened it, and that read is
+        // the cluster's first kept one (pl_flag_kernel flags kept reads only).  Slot 0, the reads continuing the
+        // preceding shard's cluster, has no opener: it is left to the warp routine
+        if (c0 + k != 0) {
+          const uint32_t g0 = __ldg(P.b.ref_start + S.first[k]);
+          if (contig_lookup(P.ref, g0, cc)) { base = (int32_t)((uint64_t)g0 - cc.lo) + 1; op_contig = cc.idx; }
+        }
+        S.base[kk] = base;
+        S.umask[kk] = 0;
+        S.ovf[kk] = (c0 + k == 0 && rb > ra) ? 1u : 0u;
 #pragma unroll
-      for (int u = 0; u < CB_SITES; ++u) {
-        S.scnt[u * CB_CLUSTERS + tid] = 0; S.scov[u * CB_CLUSTERS + tid] = 0; S.skey[u * CB_CLUSTERS + tid] = 0xFFFFFFFFu;
+        for (int u = 0; u < CB_SITES; ++u) {
+          S.scnt[u * CB_CLUSTERS + kk] = 0; S.scov[u * CB_CLUSTERS + kk] = 0; S.skey[u * CB_CLUSTERS + kk] = 0xFFFFFFFFu;
+        }
       }
     }
     __syncthreads();
@@ -872,46 +913,44 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
       if (r < re) {
         const uint32_t i = r - rs;
         S.mask[i] = x.mask | ((unsigned long long)x.rev << 62) | ((unsigned long long)x.kept << 63);
-        S.lo[i] = x.lo; S.hi[i] = x.hi; S.start[i] = x.start; S.end[i] = x.end; S.contig[i] = x.contig;
+        S.lo[i] = x.lo; S.hi[i] = x.hi; S.end[i] = x.end;
         if (x.mask) {
           const uint32_t k = S.cid[i];
-          const int32_t base = S.base[k];
-          unsigned long long m = x.mask, bits = 0;
-          bool bad = false;
-          while (m) {
-            const int ib = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const int32_t rel = (x.rev ? x.hi - ib : x.lo + ib) - base;           // checkPosition (:638-643)
-            if ((uint32_t)rel >= 64u) bad = true; else bits |= 1ull << rel;
+          unsigned long long bits;
+          if (!t2c_positions(x.mask, x.rev, x.lo, x.hi, S.base[k], bits)) S.ovf[k] = 1u;
+          else {
+            // two native 32-bit atomics (a 64-bit OR on shared memory is a compare-and-swap loop)
+            uint32_t* um32 = reinterpret_cast<uint32_t*>(&S.umask[k]);
+            if ((uint32_t)bits) atomicOr(um32, (uint32_t)bits);
+            if ((uint32_t)(bits >> 32)) atomicOr(um32 + 1, (uint32_t)(bits >> 32));
           }
-          if (bad) S.ovf[k] = 1u;
-          // two native 32-bit atomics (a 64-bit OR on shared memory is a compare-and-swap loop)
-          uint32_t* um32 = reinterpret_cast<uint32_t*>(&S.umask[k]);
-          if ((uint32_t)bits) atomicOr(um32, (uint32_t)bits);
-          if ((uint32_t)(bits >> 32)) atomicOr(um32 + 1, (uint32_t)(bits >> 32));
         }
       }
     }
     __syncthreads();
-    // ---- B0, thread per cluster: counters ---------------------------------------------------------------------------
-    uint32_t reads = 0, t2c = 0, minus = 0, first_rev = 0, contig = 0;
-    int32_t end = INT32_MIN, cstart = 0;
-    unsigned long long mask = 0, first_read = 0;
+    // ---- B0, per cluster: counters -----------------------------------------------------------------------------------
+    uint32_t reads = 0, t2c = 0, minus = 0, first_rev = 0;
+    int32_t end = INT32_MIN;
+    unsigned long long mask = 0;
     if (mine) {
-      const uint32_t k = cur + tid;
-      const uint32_t a = S.first[k] - rs, b = S.first[k + 1] - rs;
-      first_read = S.first[k];
-      for (uint32_t i = a; i < b; ++i) {
+      for (uint32_t i = ra + part; i < rb; i += CB_SPLIT) {
         unsigned long long m = S.mask[i];
         if (!(m >> 63)) continue;
-        const uint32_t rev = (uint32_t)(m >> 62) & 1u;
-        m &= (1ull << 51) - 1ull;
-        if (reads == 0) { first_read = rs + i; cstart = S.start[i]; contig = S.contig[i]; first_rev = rev; }
-        ++reads; minus += rev;
+        ++reads; minus += (uint32_t)(m >> 62) & 1u;
         end = max(end, S.end[i]);
+        m &= (1ull << 51) - 1ull;
         t2c += __popcll(m);
         mask |= m;
       }
+      if (part == 0 && rb > ra) first_rev = (uint32_t)(S.mask[ra] >> 62) & 1u;     // the opening read
+    }
+#pragma unroll
+    for (int d = 1; d < CB_SPLIT; d <<= 1) {
+      reads += __shfl_xor_sync(0xFFFFFFFFu, reads, d);
+      minus += __shfl_xor_sync(0xFFFFFFFFu, minus, d);
+      t2c += __shfl_xor_sync(0xFFFFFFFFu, t2c, d);
+      end = max(end, __shfl_xor_sync(0xFFFFFFFFu, end, d));
+      mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, d);
     }
     // ---- B2 -----------------------------------------------------------------------------------------------------
     for (uint32_t i = tid; i < nrd; i += CB_THREADS) {
@@ -919,25 +958,25 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
       if (!(m >> 63)) continue;
       const uint32_t k = S.cid[i];
       const unsigned long long um = S.umask[k];
-      if (um == 0 || S.ovf[k] || __popcll(um) > CB_SITES) continue;
+      if (um == 0) continue;
+      if (S.ovf[k] || __popcll(um) > CB_SITES) continue;
       const bool rev = (m >> 62) & 1ull;
       m &= (1ull << 51) - 1ull;
-      const int32_t lo = S.lo[i], hi = S.hi[i], base = S.base[k];
+      const int32_t lo = S.lo[i] - S.base[k], hi = S.hi[i] - S.base[k];       // relative to bit 0 of the key set
       while (m) {
         const int ib = __ffsll((long long)m) - 1;
         m &= m - 1;
-        const int32_t rel = (rev ? hi - ib : lo + ib) - base;
+        const int32_t rel = rev ? hi - ib : lo + ib;
         const uint32_t slot = __popcll(um & ((1ull << rel) - 1ull));
         atomicAdd(&S.scnt[slot * CB_CLUSTERS + k], 1u);                   // mutationMap.put(pos, old + 1)
         atomicMin(&S.skey[slot * CB_CLUSTERS + k], (i << 6) | (uint32_t)ib);   // first insertion = earliest read
       }
-      const int32_t l = max(lo - base, 0), h = min(hi - base, 63);       // baseCoveredMap (:662-667) at the keys
+      const int32_t l = max(lo, 0), h = min(hi, 63);                     // baseCoveredMap (:662-667) at the keys
       if (l <= h) {
-        unsigned long long cov = um & (~0ull << l) & (~0ull >> (63 - h));
-        while (cov) {
-          const int bit = __ffsll((long long)cov) - 1;
-          cov &= cov - 1;
-          atomicAdd(&S.scov[__popcll(um & ((1ull << bit) - 1ull)) * CB_CLUSTERS + k], 1u);
+        const uint32_t sa = __popcll(um & bits_below(l)), sb = __popcll(um & bits_below(h + 1));
+        if (sa < sb) {
+          atomicAdd(&S.scov[sa * CB_CLUSTERS + k], 1u);
+          if (sb < (uint32_t)CB_SITES) atomicSub(&S.scov[sb * CB_CLUSTERS + k], 1u);
         }
       }
     }
@@ -946,25 +985,25 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
     uint32_t ns = 0;
     bool left = false;
     unsigned long long um = 0;
-    if (mine) {
-      um = S.umask[tid];
+    if (owner) {
+      um = S.umask[kk];
       ns = __popcll(um);
-      left = S.ovf[tid] != 0 || ns > (uint32_t)CB_SITES;
-      if (left) { S.fb[atomicAdd(&s_nfb, 1u)] = cur + tid; ns = 0; }
+      left = S.ovf[kk] != 0 || ns > (uint32_t)CB_SITES;
+      if (left) { S.fb[atomicAdd(&s_nfb, 1u)] = cur + kk; ns = 0; }
     }
     unsigned long long total;
     const unsigned long long ex = block_exclusive<LbSum, CB_WARPS>((unsigned long long)ns, LbSum(), 0ull, s_wtot, total);
     if (tid == 0) s_base = total ? atomicAdd(&P.st->n_sites, total) : 0ull;
     __syncthreads();
-    if (mine && !left) {
-      const uint32_t slot = c0 + cur + tid;
+    if (owner && !left) {
+      const uint32_t slot = c0 + cur + kk;
       const unsigned long long sb = s_base + ex;
       const uint32_t maf = slot ? minus - first_rev : minus;   // slot 0 continues a cluster opened by the preceding shard
       ps_cluster rec;
-      rec.first_read = first_read;
+      rec.first_read = rs + ra;
       rec.running_id = slot ? P.first_id + slot : 0;           // runningID++ then "cl_<id>_<chr>" (:355): first cluster is cl_2
-      rec.contig = contig;
-      rec.start = cstart;
+      rec.contig = reads ? op_contig : 0u;
+      rec.start = reads ? base : 0;
       rec.end = reads ? end : 0;
       rec.num_reads = reads;
       rec.num_t2c = t2c;
@@ -980,15 +1019,16 @@ __global__ void __launch_bounds__(CB_THREADS, 6) pl_cluster_kernel(const __grid_
       uint4* dst = reinterpret_cast<uint4*>(P.cl + slot);
 #pragma unroll
       for (int w = 0; w < 4; ++w) dst[w] = src[w];
-      const int32_t base = S.base[tid];
+      uint32_t cov = 0;
       for (uint32_t u = 0; u < ns; ++u) {
         const int bit = __ffsll((long long)um) - 1;
         um &= um - 1;
+        cov += S.scov[u * CB_CLUSTERS + kk];
         if (sb + u >= P.cap_sites) break;
         ps_site o;
-        o.pos = base + bit; o.t2c = S.scnt[u * CB_CLUSTERS + tid]; o.cov = S.scov[u * CB_CLUSTERS + tid];
+        o.pos = base + bit; o.t2c = S.scnt[u * CB_CLUSTERS + kk]; o.cov = cov;
         o.reserved = 0;
-        const uint32_t key = S.skey[u * CB_CLUSTERS + tid];
+        const uint32_t key = S.skey[u * CB_CLUSTERS + kk];
         o.order_key = ((unsigned long long)(rs + (key >> 6)) << 6) | (key & 63u);
         P.sites[sb + u] = o;
       }

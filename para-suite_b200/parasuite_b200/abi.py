@@ -194,7 +194,8 @@ class NativeLibraryMissing(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(LIB_DIR, LIB_NAME)
+    # PARASUITE_B200_LIB: development override (kernel variants built side by side under lib/)
+    return os.environ.get("PARASUITE_B200_LIB") or os.path.join(LIB_DIR, LIB_NAME)
 
 
 def load_library() -> C.CDLL:
