@@ -37,14 +37,24 @@ namespace {
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int CB_THREADS = 128;                       // threads per block of pl_cluster_kernel
-constexpr int CB_WARPS = CB_THREADS / 32;
-constexpr int CB_CLUSTERS = 64;                       // clusters per block of pl_cluster_kernel (thread per cluster)
-constexpr int CB_CHUNK = 1024;                        // reads decoded into shared memory at a time
-constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
-#ifndef CB_BLOCKS_PER_SM
-#define CB_BLOCKS_PER_SM 6
+// pl_cluster_kernel tuning (overridable with -D for side-by-side variants: tools/build_variants.sh)
+#ifndef CB_THREADS_
+#define CB_THREADS_ 128
 #endif
+#ifndef CB_CLUSTERS_
+#define CB_CLUSTERS_ 64
+#endif
+#ifndef CB_CHUNK_
+#define CB_CHUNK_ 1024
+#endif
+#ifndef CB_BLOCKS_PER_SM
+#define CB_BLOCKS_PER_SM 8
+#endif
+constexpr int CB_THREADS = CB_THREADS_;               // threads per block of pl_cluster_kernel
+constexpr int CB_WARPS = CB_THREADS / 32;
+constexpr int CB_CLUSTERS = CB_CLUSTERS_;             // clusters per block of pl_cluster_kernel
+constexpr int CB_CHUNK = CB_CHUNK_;                   // reads decoded into shared memory at a time
+constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
 constexpr int FLAG_THREADS = 128;                     // threads per block of pl_flag_kernel
 constexpr int FLAG_WARPS = FLAG_THREADS / 32;
 constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
@@ -78,6 +88,18 @@ struct ContigCache {         // contig bounds of the last read looked up by this
   uint64_t lo = 1, hi = 0;
   uint32_t idx = 0;
 };
+struct ContigCache32 {       // same in 32 bits (the global coordinate space is < 2^32 bases: set_contigs in ctx.cu)
+  uint32_t lo = 1, hi = 0;
+  uint32_t idx = 0;
+};
+__device__ __forceinline__ bool contig_lookup(const DeviceRef& ref, uint64_t g0, ContigCache32& c) {
+  if (g0 >= c.lo && g0 < c.hi) return true;
+  if (g0 >= ref.n_bases) return false;
+  c.idx = contig_of(ref, g0);
+  c.lo = (uint32_t)__ldg(ref.contig_off + c.idx);
+  c.hi = (uint32_t)__ldg(ref.contig_off + c.idx + 1);
+  return true;
+}
 __device__ __forceinline__ bool contig_lookup(const DeviceRef& ref, uint64_t g0, ContigCache& c) {
   if (g0 >= c.lo && g0 < c.hi) return true;
   if (g0 >= ref.n_bases) return false;
@@ -469,9 +491,9 @@ __device__ __forceinline__ PlRaw<NW> pl_load_raw(const ClusterParams& P, uint64_
 }
 
 // one lane decodes read r (r < n); NW > 0: the batch has the PAR-CLIP shape and most reads take the bit-parallel path
-template <int NW>
+template <int NW, typename CC>
 __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, const PlRaw<NW>& raw,
-                                          ContigCache& cc, PlRead& x) {
+                                          CC& cc, PlRead& x) {
   x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
   const uint32_t meta = raw.meta;
   if constexpr (NW > 0) {
@@ -862,7 +884,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
   __syncthreads();
 
   unsigned long long dstr = 0;
-  ContigCache cc;
+  ContigCache32 cc;
   uint32_t cur = 0;
   while (cur < ncl) {
     const uint32_t rs = S.first[cur];
