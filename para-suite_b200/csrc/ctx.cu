@@ -172,6 +172,7 @@ void ps_destroy(ps_ctx* ctx) {
   for (auto& e : ctx->pl_ev) cudaEventDestroy(e);
   cudaEventDestroy(ctx->reset_ev);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
   if (ctx->fasta) ps_fasta_free(ctx->fasta);
   for (auto& e : ctx->staged_done) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->staged_core) if (e) cudaEventDestroy(e);
@@ -317,13 +318,23 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
   cudaSetDevice(ctx->device);
   const ProfileLayout& l = ctx->layout;
-  std::vector<int64_t> acc(l.total);
-  unsigned long long fw = 0;
+  // page-locked landing buffer: accumulator followed by the fault word (a pageable target would go through a staged,
+  // synchronous copy)
+  const size_t acc_bytes = (size_t)l.total * 8;
+  if (ctx->h_acc_bytes < acc_bytes + 8) {
+    if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
+    ctx->h_acc = nullptr; ctx->h_acc_bytes = 0;
+    PS_CUDA(ctx, cudaHostAlloc(&ctx->h_acc, acc_bytes + 8, cudaHostAllocDefault));
+    ctx->h_acc_bytes = acc_bytes + 8;
+  }
+  const int64_t* acc = static_cast<const int64_t*>(ctx->h_acc);
   // the last batch's stream (the context's or the caller's); earlier batches on other streams are the caller's to order
   cudaStream_t ps = ctx->profile_stream ? ctx->profile_stream : ctx->stream;
-  PS_CUDA(ctx, cudaMemcpyAsync(acc.data(), ctx->acc.p, (size_t)l.total * 8, cudaMemcpyDeviceToHost, ps));
-  PS_CUDA(ctx, cudaMemcpyAsync(&fw, ctx->fault.p, 8, cudaMemcpyDeviceToHost, ps));
+  PS_CUDA(ctx, cudaMemcpyAsync(ctx->h_acc, ctx->acc.p, acc_bytes, cudaMemcpyDeviceToHost, ps));
+  PS_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(ctx->h_acc) + acc_bytes, ctx->fault.p, 8, cudaMemcpyDeviceToHost, ps));
   PS_CUDA(ctx, cudaStreamSynchronize(ps));
+  unsigned long long fw;
+  memcpy(&fw, static_cast<const char*>(ctx->h_acc) + acc_bytes, 8);
   ctx->profile_open = false;
   out->fault.code = 0;
   out->fault.read_ordinal = 0;
@@ -344,7 +355,7 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (out->deletions_per_pos) for (uint32_t k = 0; k < m; ++k) out->deletions_per_pos[k] = (double)acc[l.del + k];
   if (out->counters) for (int k = 0; k < PS_PC_COUNT; ++k) out->counters[k] = wrap(acc[l.ctr + k]);
   if (out->quality_hist && l.infer_q) memcpy(out->quality_hist, &acc[l.qhist], (size_t)256 * m * 8);
-  if (out->wide) memcpy(out->wide, acc.data(), (size_t)l.total * 8);
+  if (out->wide) memcpy(out->wide, acc, (size_t)l.total * 8);
   return PS_OK;
 }
 

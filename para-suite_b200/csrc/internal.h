@@ -124,6 +124,8 @@ struct ps_ctx {
   cudaEvent_t reset_ev = nullptr;   // accumulators of the current profile run have been cleared
   bool pl_ev_valid = false;
   void* h_pinned = nullptr;   // 4 KB of page-locked host memory for small read-backs
+  void* h_acc = nullptr;      // page-locked landing buffer of the profile accumulator (ps_profile_end), grown on demand
+  size_t h_acc_bytes = 0;
   // pileup scratch (pileup.cu): run state, look-back descriptors
   DevBuf pl_scratch[12];
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)
