@@ -229,24 +229,32 @@ def main():
         torch.cuda.synchronize()
 
     pile = {}
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step_resident():
         # the whole hot path on a batch that is already in HBM: profile kernel (+ the tiny all-reduce), read-back of
         # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
         # their counters come back to the host
         keys = None
-        if world > 1:   # region sharding: the maximum (contig, end) of every region, all-gathered; the exclusive prefix-max
-            # (this region's carry-in) is taken on the device by the flag kernel -- no host round trip
-            keys = gather_keys_device(ctx.pileup_max_key_tensor(dbatch, stream.cuda_stream))
+        work = None
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
         if world > 1:
-            dist.all_reduce(ctx.profile_acc_tensor())
+            # region sharding: the maximum (contig, end) of every region, all-gathered; the exclusive prefix-max (this
+            # region's carry-in) is taken on the device by the flag kernel -- no host round trip.  The key kernel and its
+            # all-gather run on a side stream underneath the profile kernel (launched first, so the host-side cost of
+            # the collectives is hidden too); the all-reduce of the count vector travels while the pileup kernels run
+            with torch.cuda.stream(side):
+                keys = gather_keys_device(ctx.pileup_max_key_tensor(dbatch, side.cuda_stream))
+            work = dist.all_reduce(ctx.profile_acc_tensor(), async_op=True)
+            stream.wait_stream(side)
         # the pileup kernels are queued right behind the profile kernel; the counts of both come back afterwards, so the
         # device does not sit idle between the two tools
         carry_keys = (keys.data_ptr(), rank) if keys is not None else None
         with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream) as h:
             pile["counters"] = h.counters
+        if work is not None:
+            work.wait()
         res = ctx.profile_end()
         return res
 
