@@ -899,6 +899,8 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
     }
     const uint32_t re = S.first[cur + ncomp], nrd = re - rs;
     const bool mine = kk < ncomp, owner = mine && part == 0;
+    // the first round's record words are requested before the pre-pass, whose own loads they overlap
+    PlRaw<NW> nxt = pl_load_raw<NW>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
     // ---- pre-pass, per cluster: cluster of every read, origin of the key set -----------------------------------------
     uint32_t ra = 0, rb = 0, op_contig = 0;
     int32_t base = 0;
@@ -925,10 +927,11 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
     }
     __syncthreads();
     // ---- A, thread per read: decode; T>C positions into the cluster's key set -------------------------------------
-    PlRaw<NW> nxt = pl_load_raw<NW>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
     for (uint32_t q = rs + warp * 32; q < re; q += CB_THREADS) {
       const uint32_t r = q + lane;
       const PlRaw<NW> raw = nxt;
+      // one round in flight: a second one costs registers, and the kernel gains more from 8 resident blocks per SM
+      // (measured: 2 rounds at 8 / 7 / 6 blocks 0.52 / 0.31 / 0.32 ms against 0.28 ms)
       if (q + CB_THREADS < re) nxt = pl_load_raw<NW>(P, r + CB_THREADS, r + CB_THREADS < re);   // in flight during this decode
       PlRead x;
       pl_decode<NW>(P, q, r, r < re, raw, cc, x);
