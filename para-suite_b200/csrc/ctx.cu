@@ -148,6 +148,7 @@ int ps_create(ps_ctx** out, int device) {
   }
   for (auto& e : ctx->pl_ev) cudaEventCreate(&e);
   cudaEventCreateWithFlags(&ctx->reset_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->early_ev, cudaEventDisableTiming);
   if (cudaHostAlloc(&ctx->h_pinned, 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->h_pinned = nullptr; }
   {   // result buffers are stream-ordered allocations: keep freed blocks in the pool instead of returning them to the OS
     cudaMemPool_t pool;
@@ -171,6 +172,7 @@ void ps_destroy(ps_ctx* ctx) {
   }
   for (auto& e : ctx->pl_ev) cudaEventDestroy(e);
   cudaEventDestroy(ctx->reset_ev);
+  if (ctx->early_ev) cudaEventDestroy(ctx->early_ev);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
   if (ctx->fasta) ps_fasta_free(ctx->fasta);
@@ -236,6 +238,35 @@ size_t ps_profile_acc_len(uint32_t max_read_length, uint32_t infer_qualities) {
   return make_layout(max_read_length, infer_qualities).total;
 }
 
+// zero the accumulator vector, arm the fault word; kernels of the run may be queued on another stream: reset_ev orders
+// them after the clearing
+static cudaError_t clear_accumulators(ps_ctx* ctx, size_t acc_bytes, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(ctx->acc.p, 0, acc_bytes, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->fault.p, 0xFF, 8, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync((char*)ctx->fault.p + 8, 0, 56, s);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->reset_ev, s);
+  ctx->reset_stream = s;
+  return e;
+}
+
+// accumulator + fault word -> page-locked host memory, queued on s
+static cudaError_t queue_readback(ps_ctx* ctx, cudaStream_t s) {
+  const size_t acc_bytes = (size_t)ctx->layout.total * 8;
+  cudaError_t e = cudaMemcpyAsync(ctx->h_acc, ctx->acc.p, acc_bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(static_cast<char*>(ctx->h_acc) + acc_bytes, ctx->fault.p, 8, cudaMemcpyDeviceToHost, s);
+  return e;
+}
+constexpr size_t kEarlyReadbackMax = 64 << 10;   // with -q the vector holds a 256 x maxLen histogram: read back once, at the end
+
+static void early_readback(ps_ctx* ctx, cudaStream_t s) {
+  ctx->early_valid = false;
+  if ((size_t)ctx->layout.total * 8 > kEarlyReadbackMax) return;
+  if (queue_readback(ctx, s) != cudaSuccess || cudaEventRecord(ctx->early_ev, s) != cudaSuccess) { cudaGetLastError(); return; }
+  ctx->early_valid = true;
+  ctx->early_reads = ctx->reads_seen;
+  ctx->early_stream = s;
+}
+
 int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
   if (!ctx || !opts) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
   if (opts->max_read_length == 0 || opts->max_read_length > 3000)
@@ -243,13 +274,22 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
   if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
   cudaSetDevice(ctx->device);
   ctx->layout = make_layout(opts->max_read_length, opts->infer_qualities ? 1 : 0);
-  PS_CUDA(ctx, ctx->acc.reserve((size_t)ctx->layout.total * 8));
+  const size_t acc_bytes = (size_t)ctx->layout.total * 8;
+  PS_CUDA(ctx, ctx->acc.reserve(acc_bytes));
   PS_CUDA(ctx, ctx->fault.reserve(64));
-  PS_CUDA(ctx, cudaMemsetAsync(ctx->acc.p, 0, (size_t)ctx->layout.total * 8, ctx->stream));
-  PS_CUDA(ctx, cudaMemsetAsync(ctx->fault.p, 0xFF, 8, ctx->stream));
-  PS_CUDA(ctx, cudaMemsetAsync((char*)ctx->fault.p + 8, 0, 56, ctx->stream));
-  // kernels of this run may be queued on a caller's stream: order them after the resets
-  PS_CUDA(ctx, cudaEventRecord(ctx->reset_ev, ctx->stream));
+  if (!(ctx->clean_ptr == ctx->acc.p && ctx->clean_bytes >= acc_bytes)) {   // else: cleared behind the last read-back
+    PS_CUDA(ctx, clear_accumulators(ctx, acc_bytes, ctx->stream));
+  }
+  ctx->clean_ptr = nullptr;
+  ctx->clean_bytes = 0;
+  if (ctx->h_acc_bytes < acc_bytes + 8) {     // page-locked landing buffer: accumulator followed by the fault word
+    if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
+    ctx->h_acc = nullptr; ctx->h_acc_bytes = 0;
+    PS_CUDA(ctx, cudaHostAlloc(&ctx->h_acc, acc_bytes + 8, cudaHostAllocDefault));
+    ctx->h_acc_bytes = acc_bytes + 8;
+  }
+  ctx->early_valid = false;
+  ctx->profile_stream = nullptr;
   ctx->reads_seen = 0;
   ctx->profile_open = true;
   return PS_OK;
@@ -262,12 +302,13 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
   if (st) return st;
   cudaSetDevice(ctx->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-  if (s != ctx->stream) PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));
+  if (s != ctx->reset_stream) PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));
   ctx->profile_stream = s;
   timer_begin(ctx, s);
   PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s));
   timer_end(ctx, s);
   ctx->reads_seen += b->n_reads;
+  early_readback(ctx, s);
   return PS_OK;
 }
 
@@ -281,11 +322,13 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
   StagedBatch* sb = nullptr;
   st = stage_batch(ctx, hb, true, &sb);
   if (st) return st;
+  if (ctx->stream != ctx->reset_stream) PS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->reset_ev, 0));
   ctx->profile_stream = ctx->stream;
   timer_begin(ctx, ctx->stream);
   PS_CUDA(ctx, launch_profile(ctx, sb->view, ctx->reads_seen, ctx->stream));
   timer_end(ctx, ctx->stream);
   ctx->reads_seen += hb->n_reads;
+  early_readback(ctx, ctx->stream);
   return PS_OK;
 }
 
@@ -310,6 +353,7 @@ int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64) {
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
   *dev_ptr = ctx->acc.p;
   *n_int64 = ctx->layout.total;
+  ctx->early_valid = false;      // the caller may change the vector (all-reduce): ps_profile_end reads it again
   return PS_OK;
 }
 
@@ -318,21 +362,20 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
   cudaSetDevice(ctx->device);
   const ProfileLayout& l = ctx->layout;
-  // page-locked landing buffer: accumulator followed by the fault word (a pageable target would go through a staged,
-  // synchronous copy)
   const size_t acc_bytes = (size_t)l.total * 8;
-  if (ctx->h_acc_bytes < acc_bytes + 8) {
-    if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
-    ctx->h_acc = nullptr; ctx->h_acc_bytes = 0;
-    PS_CUDA(ctx, cudaHostAlloc(&ctx->h_acc, acc_bytes + 8, cudaHostAllocDefault));
-    ctx->h_acc_bytes = acc_bytes + 8;
-  }
   const int64_t* acc = static_cast<const int64_t*>(ctx->h_acc);
   // the last batch's stream (the context's or the caller's); earlier batches on other streams are the caller's to order
   cudaStream_t ps = ctx->profile_stream ? ctx->profile_stream : ctx->stream;
-  PS_CUDA(ctx, cudaMemcpyAsync(ctx->h_acc, ctx->acc.p, acc_bytes, cudaMemcpyDeviceToHost, ps));
-  PS_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(ctx->h_acc) + acc_bytes, ctx->fault.p, 8, cudaMemcpyDeviceToHost, ps));
-  PS_CUDA(ctx, cudaStreamSynchronize(ps));
+  if (ctx->early_valid && ctx->early_reads == ctx->reads_seen && ctx->early_stream == ps) {
+    PS_CUDA(ctx, cudaEventSynchronize(ctx->early_ev));     // queued right behind the last batch's kernel
+  } else {
+    PS_CUDA(ctx, queue_readback(ctx, ps));
+    PS_CUDA(ctx, cudaStreamSynchronize(ps));
+  }
+  ctx->early_valid = false;
+  // clear for the next run now, behind everything queued on that stream, instead of in front of its first kernel
+  if (clear_accumulators(ctx, acc_bytes, ps) == cudaSuccess) { ctx->clean_ptr = ctx->acc.p; ctx->clean_bytes = acc_bytes; }
+  else cudaGetLastError();
   unsigned long long fw;
   memcpy(&fw, static_cast<const char*>(ctx->h_acc) + acc_bytes, 8);
   ctx->profile_open = false;

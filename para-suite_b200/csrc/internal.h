@@ -126,6 +126,16 @@ struct ps_ctx {
   void* h_pinned = nullptr;   // 4 KB of page-locked host memory for small read-backs
   void* h_acc = nullptr;      // page-locked landing buffer of the profile accumulator (ps_profile_end), grown on demand
   size_t h_acc_bytes = 0;
+  // early read-back: every profile batch queues the copy of the (small) accumulator behind its kernel, so that
+  // ps_profile_end usually finds it done; void once the caller took the device pointer (ps_profile_acc_device)
+  cudaEvent_t early_ev = nullptr;
+  uint64_t early_reads = 0;
+  cudaStream_t early_stream = nullptr;
+  bool early_valid = false;
+  // ps_profile_end clears the accumulators for the next run behind its read-back: ps_profile_begin finds them clean
+  const void* clean_ptr = nullptr;
+  size_t clean_bytes = 0;
+  cudaStream_t reset_stream = nullptr;   // stream reset_ev was recorded on
   // pileup scratch (pileup.cu): run state, look-back descriptors
   DevBuf pl_scratch[12];
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)

@@ -55,9 +55,18 @@ constexpr int CB_WARPS = CB_THREADS / 32;
 constexpr int CB_CLUSTERS = CB_CLUSTERS_;             // clusters per block of pl_cluster_kernel
 constexpr int CB_CHUNK = CB_CHUNK_;                   // reads decoded into shared memory at a time
 constexpr int CB_SITES = 6;                           // distinct T>C positions per cluster kept in shared memory
-constexpr int FLAG_THREADS = 128;                     // threads per block of pl_flag_kernel
+#ifndef FLAG_THREADS_
+#define FLAG_THREADS_ 128
+#endif
+#ifndef FLAG_ITEMS_
+#define FLAG_ITEMS_ 16
+#endif
+#ifndef FLAG_BLOCKS_PER_SM
+#define FLAG_BLOCKS_PER_SM 4
+#endif
+constexpr int FLAG_THREADS = FLAG_THREADS_;           // threads per block of pl_flag_kernel
 constexpr int FLAG_WARPS = FLAG_THREADS / 32;
-constexpr int PL_FLAG_ITEMS = 16;                     // reads per thread of pl_flag_kernel on the vector path
+constexpr int PL_FLAG_ITEMS = FLAG_ITEMS_;            // reads per thread of pl_flag_kernel on the vector path
 constexpr int PL_WINDOW = 128;                        // positions per window
 
 struct PlState {                  // device-side run state (one per call)
@@ -216,7 +225,7 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
 // ITEMS == PL_FLAG_ITEMS: every read has one cigar op and the streams are 16-byte aligned (vector loads);
 // ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
 template <int ITEMS>
-__global__ void __launch_bounds__(FLAG_THREADS, 4) pl_flag_kernel(const __grid_constant__ FlagParams P) {
+__global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kernel(const __grid_constant__ FlagParams P) {
   constexpr int TILE = FLAG_THREADS * ITEMS;
   __shared__ unsigned long long s_wtot[FLAG_WARPS];
   __shared__ unsigned int s_tile;

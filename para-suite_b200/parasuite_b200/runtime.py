@@ -177,27 +177,30 @@ class Context:
         return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
 
     def _profile_result_arrays(self):
+        """Fresh result arrays for one run, carved out of ONE allocation (a numpy .ctypes lookup per array costs more
+        than the copy itself on the small PAR-CLIP profile)."""
         m = self._max_len
-        out = {
-            "position_conversions": np.zeros((m, 4, 4), dtype=np.int32),
-            "quality_per_mismatch": np.zeros((4, 4), dtype=np.int32),
-            "quality_per_mismatch_counts": np.zeros((4, 4), dtype=np.int32),
-            "insertions_per_pos": np.zeros(m, dtype=np.float64),
-            "deletions_per_pos": np.zeros(m, dtype=np.float64),
-            "counters": np.zeros(abi.PS_PC_COUNT, dtype=np.int32),
-            "wide": np.zeros(self.lib.ps_profile_acc_len(m, int(self._infer_q)), dtype=np.int64),
-        }
+        wide_n = self.lib.ps_profile_acc_len(m, int(self._infer_q))
+        parts = [("position_conversions", np.int32, (m, 4, 4)), ("quality_per_mismatch", np.int32, (4, 4)),
+                 ("quality_per_mismatch_counts", np.int32, (4, 4)), ("counters", np.int32, (abi.PS_PC_COUNT,)),
+                 ("insertions_per_pos", np.float64, (m,)), ("deletions_per_pos", np.float64, (m,)),
+                 ("wide", np.int64, (wide_n,))]
         if self._infer_q:
-            out["quality_hist"] = np.zeros((m, 256), dtype=np.int64)
-        r = abi.ps_profile_result()
-        r.position_conversions = out["position_conversions"].ctypes.data
-        r.quality_per_mismatch = out["quality_per_mismatch"].ctypes.data
-        r.quality_per_mismatch_counts = out["quality_per_mismatch_counts"].ctypes.data
-        r.insertions_per_pos = out["insertions_per_pos"].ctypes.data
-        r.deletions_per_pos = out["deletions_per_pos"].ctypes.data
-        r.counters = out["counters"].ctypes.data
-        r.quality_hist = out["quality_hist"].ctypes.data if self._infer_q else None
-        r.wide = out["wide"].ctypes.data
+            parts.append(("quality_hist", np.int64, (m, 256)))
+        offs, total = [], 0
+        for _, dt, shape in parts:
+            total = (total + 7) & ~7
+            offs.append(total)
+            total += int(np.prod(shape)) * np.dtype(dt).itemsize
+        buf = np.zeros(total, dtype=np.uint8)
+        base = buf.__array_interface__["data"][0]
+        out, r = {}, abi.ps_profile_result()
+        for (name, dt, shape), off in zip(parts, offs):
+            n = int(np.prod(shape))
+            out[name] = buf[off:off + n * np.dtype(dt).itemsize].view(dt).reshape(shape)
+            setattr(r, name, base + off)
+        if not self._infer_q:
+            r.quality_hist = None
         return out, r
 
     def profile_end(self) -> dict:
