@@ -332,6 +332,10 @@ int ps_kernel_times(ps_ctx* ctx, float* ms, int max);
 void ps_kernel_times_reset(ps_ctx* ctx, int enabled);
 /* device times (ms) of the three kernels of the last pileup call: flag scan, cluster kernel, site compaction */
 int ps_pileup_stage_times(ps_ctx* ctx, float* ms3);
+/* 0: pileup calls on this context use the speculative boundary-flag pass (carry-in of a tile = maximum over its 32
+ * predecessors, checked afterwards); 1: a check failed once (a record spanning more than 32 tiles of reads) and the
+ * context keeps to the exact look-back pass.  Results are identical either way. */
+int ps_pileup_flag_mode(const ps_ctx* ctx);
 
 #ifdef __cplusplus
 }

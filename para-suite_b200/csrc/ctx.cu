@@ -440,6 +440,8 @@ int ps_pileup_stage_times(ps_ctx* ctx, float* ms3) {
   return PS_OK;
 }
 
+int ps_pileup_flag_mode(const ps_ctx* ctx) { return ctx && ctx->pl_exact_flags ? 1 : 0; }
+
 void ps_kernel_times_reset(ps_ctx* ctx, int enabled) {
   if (!ctx) return;
   ctx->ev_count = 0;

@@ -80,7 +80,7 @@ struct PlState {                  // device-side run state (one per call)
   unsigned int tile_ctr_flag;
   unsigned int tile_ctr_compact;
   unsigned int first_slot1;       // first read of slot 1 (end of the head partial); n_reads if there is no slot 1
-  unsigned int pad0;
+  unsigned int spec_failed;       // the speculative flag pass used a carry-in that pl_flag_scan_kernel found too small
   ps_cluster head, open;          // final records of slot 0 and of the last slot (written by pl_compact_kernel)
   unsigned long long dbg[4];      // PARASUITE_B200_DEBUG: warp-routine calls, sweep give-ups, window passes, chunk decodes in windows
 };
@@ -134,6 +134,11 @@ struct FlagParams {
   uint32_t carry_keys_n;
   uint32_t* cl_first;       // [cap_cl + 2] first read of each slot; slot 0 = reads continuing the carry-in cluster
   uint64_t cap_cl;
+  // speculative three-kernel path (pl_flag_kernel<.., true>, pl_flag_scan_kernel, pl_flag_expand_kernel)
+  unsigned long long* tile_ein;   // [n_tiles] carry-in every tile assumed: maximum over the FLAG_HALO reads in front of it
+  unsigned long long* tile_agg;   // [n_tiles] maximum over the tile's own reads
+  uint32_t* tile_cnt;             // [n_tiles] boundary flags per tile, then (scan kernel) their exclusive prefix
+  uint32_t* flag_words;           // one word per thread (bit j = read j of the thread)
 };
 
 // (contig+1) << 32 | end of a kept record, 0 otherwise (PileupClusters.java:146-158)
@@ -224,16 +229,28 @@ __device__ __forceinline__ unsigned long long block_exclusive(unsigned long long
 
 // ITEMS == PL_FLAG_ITEMS: every read has one cigar op and the streams are 16-byte aligned (vector loads);
 // ITEMS == 1: any batch (per-read cigar offsets from the tile tables)
-template <int ITEMS>
+// SPEC (vector path only): the two chained look-backs are what the exact kernel waits for (every tile needs the running
+// maximum of ALL earlier tiles, then the flag count of all earlier tiles).  In a coordinate-sorted batch the running
+// maximum in front of a tile is, bar a record reaching over more than FLAG_HALO of its successors, the maximum over the
+// FLAG_HALO reads in front of it: the speculative variant loads those next to its own reads (no dependency between
+// tiles at all), records the carry-in it assumed, its own aggregate, flag bits and a per-tile count;
+// pl_flag_scan_kernel (one block) takes the exact prefixes over the tile table and checks every assumption (a failed
+// one makes the host repeat the call with the exact variant); pl_flag_expand_kernel writes cl_first.
+constexpr int FLAG_HALO = FLAG_THREADS;     // one read in front of the tile per thread
+template <int ITEMS, bool SPEC>
 __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kernel(const __grid_constant__ FlagParams P) {
   constexpr int TILE = FLAG_THREADS * ITEMS;
+  static_assert(!SPEC || ITEMS > 1, "the speculative pass is built for the vector path");
   __shared__ unsigned long long s_wtot[FLAG_WARPS];
+  __shared__ unsigned long long s_halo[FLAG_WARPS];
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_pre;
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_flag, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  if constexpr (!SPEC) {      // the look-backs need forward progress: tile numbers in the order the blocks start
+    if (threadIdx.x == 0) s_tile = atomicAdd(&P.st->tile_ctr_flag, 1u);
+    __syncthreads();
+  }
+  const uint32_t tile = SPEC ? blockIdx.x : s_tile;
   const uint64_t n = P.b.n_reads;
   const uint64_t r0 = (uint64_t)tile * TILE + (uint64_t)threadIdx.x * ITEMS;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,6 +258,14 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
   unsigned long long key[ITEMS];
   int32_t start[ITEMS];
   ContigCache cc;
+  [[maybe_unused]] uint32_t h_meta = PS_MAKE_META(0, 0, PS_RF_UNMAPPED), h_start = 0, h_cig = 0;
+  if constexpr (SPEC) {       // one read of the halo per thread, requested together with the tile's own reads
+    const uint64_t t0 = (uint64_t)tile * TILE;
+    if (t0 + threadIdx.x >= (uint64_t)FLAG_HALO) {
+      const uint64_t hr = t0 + threadIdx.x - FLAG_HALO;          // < t0 <= n
+      h_meta = __ldg(P.b.meta + hr); h_start = __ldg(P.b.ref_start + hr); h_cig = __ldg(P.b.cigar + hr);
+    }
+  }
   if constexpr (ITEMS > 1) {
     static_assert(ITEMS % 4 == 0, "vector loads take 4 reads at a time");
 #pragma unroll
@@ -278,10 +303,22 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
   unsigned long long tmax = 0;
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) tmax = key[j] > tmax ? key[j] : tmax;
+  if constexpr (SPEC) {
+    int32_t hs;
+    unsigned long long hk = pl_key1(P, h_meta, h_cig, h_start, cc, hs);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, hk, d); hk = o > hk ? o : hk; }
+    if (lane == 0) s_halo[warp] = hk;           // read after the barriers of the scan below
+  }
   unsigned long long block_max;
   const unsigned long long ex_max = block_exclusive<LbMax, FLAG_WARPS>(tmax, LbMax(), 0ull, s_wtot, block_max);
   if (warp == 0) {
-    if (tile == 0) {
+    if constexpr (SPEC) {
+      unsigned long long pre = lane < FLAG_WARPS ? s_halo[lane] : 0ull;
+#pragma unroll
+      for (int d = FLAG_WARPS / 2; d >= 1; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, pre, d); pre = o > pre ? o : pre; }
+      if (lane == 0) { s_pre = pre; P.tile_ein[tile] = pre; P.tile_agg[tile] = block_max; }
+    } else if (tile == 0) {
       if (lane == 0) { lb_publish(&P.d_max[0], block_max, 2u, P.epoch); s_pre = 0; }
     } else {
       if (lane == 0) lb_publish(&P.d_max[tile], block_max, 1u, P.epoch);
@@ -318,6 +355,19 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
     }
   }
   if (unsorted) P.st->unsorted = 1u;
+  if constexpr (SPEC) {
+    P.flag_words[(size_t)tile * FLAG_THREADS + threadIdx.x] = fl;
+    const uint32_t wsum = __reduce_add_sync(0xFFFFFFFFu, nfl);
+    if (lane == 0) s_wtot[warp] = wsum;          // the scan is done with s_wtot (its second barrier is behind us)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int w = 0; w < FLAG_WARPS; ++w) c += (uint32_t)s_wtot[w];
+      P.tile_cnt[tile] = c;
+    }
+    return;
+  }
   __syncthreads();   // s_pre is reused below
 
   // ---- look-back #2: cluster slots ---------------------------------------------------------------------------------
@@ -349,6 +399,78 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
     if (slot + 1 <= P.cap_cl) P.cl_first[slot + 1] = (uint32_t)n;   // slots 0 .. n_flags, the last one is the open cluster
     P.st->n_flags = (unsigned int)slot;
   }
+}
+
+// One block over the tile table of the speculative flag pass: exact running maximum in front of every tile (checked
+// against the carry-in the tile assumed) and exclusive prefix of the per-tile flag counts.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 8;        // consecutive tiles per thread and round
+__global__ void __launch_bounds__(SCAN_THREADS) pl_flag_scan_kernel(const __grid_constant__ FlagParams P) {
+  __shared__ unsigned long long s_wtot[SCAN_THREADS / 32];
+  unsigned long long carry = P.carry_key;
+  for (uint32_t k = 0; k < P.carry_keys_n; ++k) {
+    const unsigned long long ck = __ldg(P.carry_keys + k);
+    carry = carry > ck ? carry : ck;
+  }
+  unsigned long long run_max = 0, run_cnt = 0;
+  bool bad = false;
+  for (uint64_t c0 = 0; c0 < P.n_tiles; c0 += (uint64_t)SCAN_THREADS * SCAN_ITEMS) {
+    const uint64_t t0 = c0 + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long agg[SCAN_ITEMS], ein[SCAN_ITEMS];
+    uint32_t cnt[SCAN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      const bool in = t0 + j < P.n_tiles;
+      agg[j] = in ? P.tile_agg[t0 + j] : 0ull;
+      ein[j] = in ? P.tile_ein[t0 + j] : 0ull;
+      cnt[j] = in ? P.tile_cnt[t0 + j] : 0u;
+    }
+    unsigned long long tmax = 0, tcnt = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) { tmax = agg[j] > tmax ? agg[j] : tmax; tcnt += cnt[j]; }
+    unsigned long long tot_max, tot_cnt;
+    unsigned long long m = block_exclusive<LbMax, SCAN_THREADS / 32>(tmax, LbMax(), 0ull, s_wtot, tot_max);
+    unsigned long long c = block_exclusive<LbSum, SCAN_THREADS / 32>(tcnt, LbSum(), 0ull, s_wtot, tot_cnt) + run_cnt;
+    m = m > run_max ? m : run_max;
+    m = m > carry ? m : carry;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j)
+      if (t0 + j < P.n_tiles) {
+        const unsigned long long used = ein[j] > carry ? ein[j] : carry;
+        bad |= m != used;                         // m = exact running maximum in front of tile t0 + j
+        P.tile_cnt[t0 + j] = (uint32_t)c;
+        m = agg[j] > m ? agg[j] : m;
+        c += cnt[j];
+      }
+    run_max = run_max > tot_max ? run_max : tot_max;
+    run_cnt += tot_cnt;
+  }
+  if (bad) P.st->spec_failed = 1u;
+  if (threadIdx.x == 0) {
+    P.cl_first[0] = 0;
+    if (run_cnt + 1 <= P.cap_cl) P.cl_first[run_cnt + 1] = (uint32_t)P.b.n_reads;   // slots 0 .. n_flags, the last one is the open cluster
+    P.st->n_flags = (unsigned int)run_cnt;
+  }
+}
+
+// cl_first from the flag bits and the per-tile prefix (same tiling as the flag kernel)
+template <int ITEMS>
+__global__ void __launch_bounds__(FLAG_THREADS) pl_flag_expand_kernel(const __grid_constant__ FlagParams P) {
+  __shared__ unsigned long long s_wtot[FLAG_WARPS];
+  const uint32_t tile = blockIdx.x;
+  const uint32_t fl = P.flag_words[(size_t)tile * FLAG_THREADS + threadIdx.x];
+  unsigned long long total;
+  const unsigned long long ex = block_exclusive<LbSum, FLAG_WARPS>((unsigned long long)__popc(fl), LbSum(), 0ull, s_wtot, total);
+  if (total == 0) return;
+  uint64_t slot = (uint64_t)P.tile_cnt[tile] + ex;
+  const uint64_t r0 = (uint64_t)tile * (FLAG_THREADS * ITEMS) + (uint64_t)threadIdx.x * ITEMS;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    if ((fl >> j) & 1u) {
+      ++slot;
+      if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
+      if (slot == 1) P.st->first_slot1 = (unsigned int)(r0 + j);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1202,7 +1324,7 @@ __global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint
 __global__ void pl_init_state(PlState* st) {
   if (threadIdx.x == 0) {
     st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_sites_final = 0; st->n_flags = 0;
-    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu;
+    st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu; st->spec_failed = 0;
     st->dbg[0] = st->dbg[1] = st->dbg[2] = st->dbg[3] = 0;
   }
 }
@@ -1326,8 +1448,20 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     pl_init_state<<<1, 32, 0, st>>>(d_state);
     const bool ev = ctx->timers_on;
     if (ev) cudaEventRecord(ctx->pl_ev[0], st);
-    if (vec) pl_flag_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-    else pl_flag_kernel<1><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+    const bool spec = vec && !ctx->pl_exact_flags;
+    P.tile_ein = nullptr; P.tile_agg = nullptr; P.tile_cnt = nullptr; P.flag_words = nullptr;
+    if (spec) {
+      P.tile_ein = scratch<unsigned long long>(ctx, 1, n_tiles, err);
+      P.tile_agg = scratch<unsigned long long>(ctx, 7, n_tiles, err);
+      P.tile_cnt = scratch<uint32_t>(ctx, 5, n_tiles, err);
+      P.flag_words = scratch<uint32_t>(ctx, 6, (size_t)n_tiles * FLAG_THREADS, err);
+      if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+      pl_flag_kernel<PL_FLAG_ITEMS, true><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+      pl_flag_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(P);
+      pl_flag_expand_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+      ctx->launches += 2;
+    } else if (vec) pl_flag_kernel<PL_FLAG_ITEMS, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+    else pl_flag_kernel<1, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
     if (ev) cudaEventRecord(ctx->pl_ev[1], st);
     ClusterParams Q;
     Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
@@ -1346,6 +1480,11 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
     PS_CUDA(ctx, cudaStreamSynchronize(st));
     hs = *hsp;
+    if (spec && hs.spec_failed) {     // a read spans more than 32 tiles: this context keeps to the exact kernel from now on
+      ctx->pl_exact_flags = true;
+      --attempt;
+      continue;
+    }
     const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
     if (need_cl <= cap_cl && need_sites <= cap_sites) break;
     if (attempt >= 2) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }

@@ -183,6 +183,7 @@ EXPORTS = {
     "ps_kernel_times": (C.c_int, [VP, VP, C.c_int]),
     "ps_kernel_times_reset": (None, [VP, C.c_int]),
     "ps_pileup_stage_times": (C.c_int, [VP, VP]),
+    "ps_pileup_flag_mode": (C.c_int, [VP]),
 }
 
 LIB_NAME = "libparasuite_b200.so"

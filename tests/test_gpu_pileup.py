@@ -228,3 +228,32 @@ def test_device_resident_carry_keys(ctx, oracle):
         with ctx.pileup_run(s, carry_keys=(keys.data_ptr(), r)) as h:
             results.append(h.fetch())
     assert_pileup_equal(merge_pileup_shards(results, cuts[:-1]), whole, "device carry keys")
+
+
+def test_record_reaching_over_the_halo_falls_back_to_exact_flags(oracle):
+    """The boundary-flag pass of the vector path assumes that the running maximum of (contig, end) in front of a tile of
+    2048 reads is the maximum over the 128 reads in front of it, and checks that afterwards.  One record with a 6 kb
+    reference span in front of some 600 successors breaks the assumption: the call must notice, repeat with the exact
+    look-back pass and give the file-order result; the context then stays in exact mode."""
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context
+    ref = synth.synth_reference(93, [2_000_000], n_run=0)
+    batch = synth.synth_reads(ref, 200_000, 36, seed=15)
+    k = 2048 * 3 - 200                                  # its reach crosses a tile boundary by more than the halo
+    span = 6_000
+    assert int(batch.ref_start[k]) + span < 2_000_000
+    reached = int(np.searchsorted(batch.ref_start, batch.ref_start[k] + span)) - k
+    assert reached > 400
+    batch.cigar[k] = (span << 4) | 3                    # a lone N op: no aligned block, alignment end 6 kb downstream
+    c = Context(0)
+    try:
+        c.upload_reference(ref)
+        assert c.lib.ps_pileup_flag_mode(c.h) == 0
+        exp = oracle.pileup(ref, batch)
+        got = c.pileup(batch)
+        assert c.lib.ps_pileup_flag_mode(c.h) == 1
+        assert_pileup_equal(got, exp, "record reaching over the halo")
+        assert int(exp["clusters"]["num_reads"].max()) >= reached
+        assert_pileup_equal(c.pileup(batch), exp, "exact mode, second call")
+    finally:
+        c.close()
