@@ -1003,14 +1003,18 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
   S.first = reinterpret_cast<uint32_t*>(S.cid + CB_CHUNK);
   S.fb = S.first + CB_CLUSTERS + 1;
 
-  const uint32_t n_slots = P.st->n_flags + 1;          // written by pl_flag_kernel
-  if (n_slots > P.cap_cl) return;                       // the host re-runs the kernels with larger arrays
   const uint32_t c0 = blockIdx.x * CB_CLUSTERS;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the block's slice of cl_first is requested before the slot count it is checked against arrives (entries past the
+  // last slot are never looked at)
+  static_assert(CB_CLUSTERS < CB_THREADS, "one cl_first entry per thread");
+  const uint32_t f_pre = (tid <= (uint32_t)CB_CLUSTERS && (uint64_t)c0 + tid < P.cap_cl + 2) ? __ldg(P.cl_first + c0 + tid) : 0u;
+  const uint32_t n_slots = P.st->n_flags + 1;          // written by the flag stage
+  if (n_slots > P.cap_cl) return;                       // the host re-runs the kernels with larger arrays
   if (c0 >= n_slots) return;
   const uint32_t ncl = min((uint32_t)CB_CLUSTERS, n_slots - c0);
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t kk = tid / CB_SPLIT, part = tid % CB_SPLIT;    // per-cluster phases: cluster inside the chunk, share
-  for (uint32_t k = tid; k <= ncl; k += CB_THREADS) S.first[k] = __ldg(P.cl_first + c0 + k);
+  if (tid <= ncl) S.first[tid] = f_pre;
   if (tid == 0) s_nfb = 0;
   __syncthreads();
 
