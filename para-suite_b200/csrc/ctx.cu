@@ -1,6 +1,7 @@
 // C ABI of libparasuite_b200.so: context, reference residency, error-profile entry points.
 // (include/parasuite_b200.h documents which reference lines each call replaces.)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -140,6 +141,7 @@ int ps_create(ps_ctx** out, int device) {
   ps_ctx* ctx = new ps_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("PARASUITE_B200_COMPACT_LOOKBACK")) ctx->pl_compact_lookback = e[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PS_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->stream2 = nullptr; }
   for (int i = 0; i < PS_TIMER_RING; ++i) {

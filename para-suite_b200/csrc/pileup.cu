@@ -485,7 +485,14 @@ struct ClusterParams {
   ps_cluster* cl;
   ps_site* sites;           // pl_cluster_kernel: sites grouped by block in completion order; pl_compact_kernel orders them
   uint64_t cap_cl, cap_sites;
+  unsigned int* tile_sites;   // [slots / COMPACT_TILE] sites per tile of pl_compact_kernel (zeroed by the host), or nullptr
 };
+#ifndef COMPACT_ITEMS_
+#define COMPACT_ITEMS_ 2
+#endif
+constexpr int COMPACT_ITEMS = COMPACT_ITEMS_;
+constexpr int COMPACT_TILE = PL_THREADS * COMPACT_ITEMS;     // cluster slots per block of pl_compact_kernel
+static_assert(COMPACT_TILE % CB_CLUSTERS == 0, "a block of pl_cluster_kernel lies inside one tile of pl_compact_kernel");
 
 // Literal per-read routine (any CIGAR, any flag): PileupClusters.java:146-158, :585-673
 __device__ __noinline__ void pl_decode_generic(const ClusterParams& P, uint64_t r, uint32_t meta, uint64_t off_base,
@@ -1019,6 +1026,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
   __syncthreads();
 
   unsigned long long dstr = 0;
+  unsigned long long blk_sites = 0;     // sites of this block's clusters (identical in every thread until the warp routine)
   ContigCache32 cc;
   uint32_t cur = 0;
   while (cur < ncl) {
@@ -1153,6 +1161,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
     }
     unsigned long long total;
     const unsigned long long ex = block_exclusive<LbSum, CB_WARPS>((unsigned long long)ns, LbSum(), 0ull, s_wtot, total);
+    blk_sites += total;
     if (tid == 0) s_base = total ? atomicAdd(&P.st->n_sites, total) : 0ull;
     __syncthreads();
     if (owner && !left) {
@@ -1209,6 +1218,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
       const uint32_t f = S.first[k], fe = S.first[k + 1];
       unsigned long long sb = 0;
       const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr, &sb);
+      if (lane == 0 && cnt && P.tile_sites) atomicAdd(P.tile_sites + slot / COMPACT_TILE, cnt);
       __syncwarp();
       if (lane == 0) { wrec->site_begin = sb; wrec->site_end = sb + cnt; }
       __syncwarp();
@@ -1216,6 +1226,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
       __syncwarp();
     }
   }
+  if (tid == 0 && blk_sites && P.tile_sites) atomicAdd(P.tile_sites + c0 / COMPACT_TILE, (unsigned int)blk_sites);
   // doubleStranded of the block
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) dstr += __shfl_xor_sync(0xFFFFFFFFu, dstr, d);
@@ -1233,10 +1244,12 @@ struct CompactParams {
   const ps_site* src;
   ps_site* dst;
   uint64_t cap_cl, cap_sites;
+  const unsigned int* tile_sites;   // sites per tile, summed up by pl_cluster_kernel: every tile adds up the entries in
+                                    // front of it (no chain between the tiles); nullptr = decoupled look-back
 };
 
 __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_constant__ CompactParams P) {
-  constexpr int ITEMS = 4;
+  constexpr int ITEMS = COMPACT_ITEMS;
   __shared__ unsigned long long s_wtot[PL_WARPS];
   __shared__ unsigned long long s_pre;
   __shared__ unsigned int s_tile;
@@ -1263,7 +1276,21 @@ __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_con
   }
   unsigned long long total;
   const unsigned long long ex = block_exclusive((unsigned long long)mine, LbSum(), 0ull, s_wtot, total);
-  if (warp == 0) {
+  if (P.tile_sites != nullptr) {
+    unsigned long long part = 0;
+    for (uint32_t t = threadIdx.x; t < tile; t += PL_THREADS) part += __ldg(P.tile_sites + t);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+    if (lane == 0) s_wtot[warp] = part;      // block_exclusive is done with s_wtot
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long pre = 0;
+#pragma unroll
+      for (int w = 0; w < PL_WARPS; ++w) pre += s_wtot[w];
+      s_pre = pre;
+      if (tile == n_tiles - 1) P.st->n_sites_final = pre + total;
+    }
+  } else if (warp == 0) {
     unsigned long long pre = 0;
     if (tile == 0) {
       if (lane == 0) lb_publish(&P.d_cnt[0], total, 2u, P.epoch);
@@ -1284,8 +1311,15 @@ __global__ void __launch_bounds__(PL_THREADS) pl_compact_kernel(const __grid_con
     if (c0 + j >= n_slots) break;
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.src + from[j]);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.dst + to);
-    if (cnt[j] <= 16)
-      for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];   // a site is 24 bytes
+    if (cnt[j] <= 4) {            // the common case: every word requested before the first one is stored
+      unsigned long long w[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) w[e] = (uint32_t)e < cnt[j] * 3 ? src[e] : 0ull;   // a site is 24 bytes
+#pragma unroll
+      for (int e = 0; e < 12; ++e)
+        if ((uint32_t)e < cnt[j] * 3) dst[e] = w[e];
+    } else if (cnt[j] <= 16)
+      for (uint32_t e = 0; e < cnt[j] * 3; ++e) dst[e] = src[e];
     *reinterpret_cast<ulonglong2*>(&P.cl[c0 + j].site_begin) = make_ulonglong2(to, to + cnt[j]);
     if (c0 + j == 0 || c0 + j == n_slots - 1) {      // the two boundary records ride home with the run state
       ps_cluster rec = P.cl[c0 + j];
@@ -1389,6 +1423,8 @@ static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const Cluster
   }
 }
 
+constexpr uint64_t kCompactSumTiles = 4096;     // 2 M cluster slots
+
 static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out) {
   // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch) and is run on the context's
   // own stream: the pileup never reads qualities, so it goes to the auxiliary stream as soon as the other streams of
@@ -1471,12 +1507,21 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
     Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
     Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
     Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
+    // site totals per compaction tile, added up by the cluster kernel: up to kCompactSumTiles tiles every compaction
+    // block sums the entries in front of it itself; beyond that (quadratic work) the decoupled look-back takes over
+    const uint64_t n_ctiles = (cap_cl + COMPACT_TILE - 1) / COMPACT_TILE;
+    Q.tile_sites = nullptr;
+    if (n_ctiles <= kCompactSumTiles && !ctx->pl_compact_lookback) {
+      Q.tile_sites = scratch<unsigned int>(ctx, 11, n_ctiles, err);
+      if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+      PS_CUDA(ctx, cudaMemsetAsync(Q.tile_sites, 0, n_ctiles * sizeof(unsigned int), st));
+    }
     launch_cluster(nw, c_tiles, st, Q);
     if (ev) cudaEventRecord(ctx->pl_ev[2], st);
     CompactParams R;
     R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
-    R.cap_cl = cap_cl; R.cap_sites = cap_sites;
-    pl_compact_kernel<<<(uint32_t)((cap_cl + PL_THREADS * 4 - 1) / (PL_THREADS * 4)), PL_THREADS, 0, st>>>(R);
+    R.cap_cl = cap_cl; R.cap_sites = cap_sites; R.tile_sites = Q.tile_sites;
+    pl_compact_kernel<<<(uint32_t)n_ctiles, PL_THREADS, 0, st>>>(R);
     if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
     ctx->launches += 4;
     PS_CUDA(ctx, cudaGetLastError());

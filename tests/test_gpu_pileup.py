@@ -257,3 +257,19 @@ def test_record_reaching_over_the_halo_falls_back_to_exact_flags(oracle):
         assert_pileup_equal(c.pileup(batch), exp, "exact mode, second call")
     finally:
         c.close()
+
+
+def test_site_compaction_by_look_back(oracle, monkeypatch):
+    """Past 2 M cluster slots per batch the site runs are ordered with a decoupled look-back over the compaction tiles
+    instead of per-tile sums; PARASUITE_B200_COMPACT_LOOKBACK=1 (read by ps_create) forces that path."""
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context
+    monkeypatch.setenv("PARASUITE_B200_COMPACT_LOOKBACK", "1")
+    ref = synth.synth_reference(94, [3_000_000], n_run=500)
+    batch = synth.synth_reads(ref, 250_000, 36, seed=17)
+    c = Context(0)
+    try:
+        c.upload_reference(ref)
+        assert_pileup_equal(c.pileup(batch), oracle.pileup(ref, batch), "compaction by look-back")
+    finally:
+        c.close()
