@@ -11,7 +11,7 @@ ctx = Context(0); ctx.upload_reference(ref)
 d = DeviceBatch(b, "cuda:0")
 ctx.lib.ps_debug_word.restype = C.c_uint64
 ctx.lib.ps_debug_word.argtypes = [C.c_void_p, C.c_int]
-for it in range(3):
+for it in range(8):
     ctx.profile_begin(51)
     ctx.kernel_times_reset(True)
     ctx.profile_batch_device(d, torch.cuda.current_stream().cuda_stream)
