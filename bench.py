@@ -251,11 +251,13 @@ def main():
         # the pileup kernels are queued right behind the profile kernel; the counts of both come back afterwards, so the
         # device does not sit idle between the two tools
         carry_keys = (keys.data_ptr(), rank) if keys is not None else None
-        with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream) as h:
+        # ps_pileup_submit_device: the call returns behind its launches, so the host takes back the profile (and does its
+        # own bookkeeping) while the pileup kernels run; the wait for the pileup is the only one left at the end
+        with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream, defer=True) as h:
+            if work is not None:
+                work.wait()
+            res = ctx.profile_end()
             pile["counters"] = h.counters
-        if work is not None:
-            work.wait()
-        res = ctx.profile_end()
         return res
 
     # ---- warm-up ------------------------------------------------------------------------------------

@@ -245,6 +245,14 @@ typedef struct ps_pileup_opts {
 int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* host_batch, const ps_pileup_opts* opts, ps_pileup** out);
 int ps_pileup_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, const ps_pileup_opts* opts, void* stream,
                            ps_pileup** out);
+/* The same call in two halves: ps_pileup_submit_device queues the kernels on `stream` and returns without waiting for
+ * the device; ps_pileup_wait completes the call (it may have to repeat a pass with larger arrays) and returns what
+ * ps_pileup_batch_device would have returned.  In between the host is free (e.g. to take back the profile of the same
+ * batch); every other ps_pileup_* call on the handle except ps_pileup_close answers PS_ERR_STATE until the wait, and a
+ * context takes one submitted call at a time.  ps_pileup_close on a submitted handle waits first. */
+int ps_pileup_submit_device(ps_ctx* ctx, const ps_read_batch* dev_batch, const ps_pileup_opts* opts, void* stream,
+                            ps_pileup** out);
+int ps_pileup_wait(ps_pileup* h);
 /* Region sharding: max over the batch's kept records of (contig, alignment end).  The exclusive prefix-max of these
  * over the shards (one pair per shard: an all-gather of 8 scalars) is shard s's carry-in, so all shards run at once. */
 int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream, uint32_t* valid, uint32_t* contig,

@@ -1387,6 +1387,14 @@ struct ps_pileup {
   bool cov_done = false;
   ps_pileup_counters counters{};
   ps_fault fault{};
+  // call in flight (ps_pileup_submit_device ... ps_pileup_wait)
+  bool pending = false;              // kernels queued, run state not looked at yet
+  int rc = PS_OK;                    // what the completed call returned
+  bool has_opts = false;
+  ps_pileup_opts opts{};
+  bool spec = false;                 // the attempt in flight used the speculative flag pass
+  uint64_t cap_cl = 0, cap_sites = 0;   // capacities of the attempt in flight
+  PlState hs_fallback{};             // landing place of the run state when the context has no page-locked scratch
 };
 
 template <typename T>
@@ -1425,131 +1433,135 @@ static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const Cluster
 
 constexpr uint64_t kCompactSumTiles = 4096;     // 2 M cluster slots
 
-static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out) {
-  // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch) and is run on the context's
-  // own stream: the pileup never reads qualities, so it goes to the auxiliary stream as soon as the other streams of
-  // the records have arrived, while the quality bytes (more than half of the upload) are still on their way.
-  if (st == ctx->stream && ctx->stream2) {
-    for (int slot = 0; slot < 2; ++slot)
-      if (b.n_reads && b.meta == ctx->staged[slot].view.meta && ctx->staged_core[slot]) {
-        cudaStreamWaitEvent(ctx->stream2, ctx->staged_core[slot], 0);
-        st = ctx->stream2;
-      }
-  }
-  ps_pileup* H = new ps_pileup();
-  *out = H;
-  H->ctx = ctx;
-  H->stream = st;
-  H->batch = b;
+// One attempt of the three stages on H->stream: allocations, kernels and the copy of the run state into page-locked
+// memory -- nothing here waits for the device.
+static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
+  const DeviceBatch& b = H->batch;
+  const ps_pileup_opts* opts = H->has_opts ? &H->opts : nullptr;
+  cudaStream_t st = H->stream;
   const uint64_t n = b.n_reads;
-  H->n_reads = n;
-  H->counters.num_reads_processed = n;
-  if (n == 0) return PS_OK;
-  if (n >= 0xFFFFFFFFull) return set_error(ctx, PS_ERR_UNSUPPORTED, "pileup batch of >= 2^32 reads");
-
   const bool vec = b.uniform_ncigar == 1 && aligned16p(b.meta) && aligned16p(b.ref_start) && aligned16p(b.cigar);
   const uint32_t tile_reads = FLAG_THREADS * (vec ? (uint32_t)PL_FLAG_ITEMS : 1u);
   const uint32_t n_tiles = (uint32_t)((n + tile_reads - 1) / tile_reads);
-  const int nw = flavour_of(b);
-  H->nw = nw;
+  const int nw = H->nw;
 
   cudaError_t err = cudaSuccess;
   PlState* d_state = scratch<PlState>(ctx, 0, 1, err);
   LbDesc* d_max = scratch<LbDesc>(ctx, 2, n_tiles, err, true);
   LbDesc* d_cnt = scratch<LbDesc>(ctx, 3, n_tiles, err, true);
   if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-  if (ctx->pl_cap_cl < 1024) ctx->pl_cap_cl = std::max<uint64_t>(1024, n / 8);
-  if (ctx->pl_cap_ev < 1024) ctx->pl_cap_ev = std::max<uint64_t>(1024, n / 4);   // site capacity
 
   unsigned long long carry_key = 0;
   if (opts && opts->carry_valid)
     carry_key = ((unsigned long long)(opts->carry_contig + 1) << 32) | (uint32_t)opts->carry_cluster_end;
 
-  PlState hs{};
-  timer_begin(ctx, st);
-  for (int attempt = 0;; ++attempt) {
-    const uint64_t cap_cl = std::min<uint64_t>(ctx->pl_cap_cl, n + 2), cap_sites = ctx->pl_cap_ev;
-    const uint32_t c_tiles = (uint32_t)((cap_cl + CB_CLUSTERS - 1) / CB_CLUSTERS);
-    LbDesc* d_sc = scratch<LbDesc>(ctx, 8, c_tiles, err, true);
-    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-    if (H->d_cl) { cudaFreeAsync(H->d_cl, st); H->d_cl = nullptr; }
-    if (H->d_sites) { cudaFreeAsync(H->d_sites, st); H->d_sites = nullptr; }
-    PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_cl, cap_cl * sizeof(ps_cluster), st));
-    PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (cap_sites + 1) * sizeof(ps_site), st));
-    ps_site* d_tmp = scratch<ps_site>(ctx, 10, cap_sites + 1, err);
-    uint32_t* d_first = scratch<uint32_t>(ctx, 4, cap_cl + 2, err);
-    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+  const uint64_t cap_cl = std::min<uint64_t>(ctx->pl_cap_cl, n + 2), cap_sites = ctx->pl_cap_ev;
+  H->cap_cl = cap_cl; H->cap_sites = cap_sites;
+  const uint32_t c_tiles = (uint32_t)((cap_cl + CB_CLUSTERS - 1) / CB_CLUSTERS);
+  LbDesc* d_sc = scratch<LbDesc>(ctx, 8, c_tiles, err, true);
+  if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+  if (H->d_cl) { cudaFreeAsync(H->d_cl, st); H->d_cl = nullptr; }
+  if (H->d_sites) { cudaFreeAsync(H->d_sites, st); H->d_sites = nullptr; }
+  PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_cl, cap_cl * sizeof(ps_cluster), st));
+  PS_CUDA(ctx, cudaMallocAsync((void**)&H->d_sites, (cap_sites + 1) * sizeof(ps_site), st));
+  ps_site* d_tmp = scratch<ps_site>(ctx, 10, cap_sites + 1, err);
+  uint32_t* d_first = scratch<uint32_t>(ctx, 4, cap_cl + 2, err);
+  if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
 
-    FlagParams P;
-    P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
-    P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
-    P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
-    P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
-    pl_init_state<<<1, 32, 0, st>>>(d_state);
-    const bool ev = ctx->timers_on;
-    if (ev) cudaEventRecord(ctx->pl_ev[0], st);
-    const bool spec = vec && !ctx->pl_exact_flags;
-    P.tile_ein = nullptr; P.tile_agg = nullptr; P.tile_cnt = nullptr; P.flag_words = nullptr;
-    if (spec) {
-      P.tile_ein = scratch<unsigned long long>(ctx, 1, n_tiles, err);
-      P.tile_agg = scratch<unsigned long long>(ctx, 7, n_tiles, err);
-      P.tile_cnt = scratch<uint32_t>(ctx, 5, n_tiles, err);
-      P.flag_words = scratch<uint32_t>(ctx, 6, (size_t)n_tiles * FLAG_THREADS, err);
-      if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-      pl_flag_kernel<PL_FLAG_ITEMS, true><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-      pl_flag_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(P);
-      pl_flag_expand_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-      ctx->launches += 2;
-    } else if (vec) pl_flag_kernel<PL_FLAG_ITEMS, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-    else pl_flag_kernel<1, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-    if (ev) cudaEventRecord(ctx->pl_ev[1], st);
-    ClusterParams Q;
-    Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
-    Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
-    Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
-    // site totals per compaction tile, added up by the cluster kernel: up to kCompactSumTiles tiles every compaction
-    // block sums the entries in front of it itself; beyond that (quadratic work) the decoupled look-back takes over
-    const uint64_t n_ctiles = (cap_cl + COMPACT_TILE - 1) / COMPACT_TILE;
-    Q.tile_sites = nullptr;
-    if (n_ctiles <= kCompactSumTiles && !ctx->pl_compact_lookback) {
-      Q.tile_sites = scratch<unsigned int>(ctx, 11, n_ctiles, err);
-      if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-      PS_CUDA(ctx, cudaMemsetAsync(Q.tile_sites, 0, n_ctiles * sizeof(unsigned int), st));
-    }
-    launch_cluster(nw, c_tiles, st, Q);
-    if (ev) cudaEventRecord(ctx->pl_ev[2], st);
-    CompactParams R;
-    R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
-    R.cap_cl = cap_cl; R.cap_sites = cap_sites; R.tile_sites = Q.tile_sites;
-    pl_compact_kernel<<<(uint32_t)n_ctiles, PL_THREADS, 0, st>>>(R);
-    if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
-    ctx->launches += 4;
-    PS_CUDA(ctx, cudaGetLastError());
-    PlState* hsp = ctx->h_pinned ? static_cast<PlState*>(ctx->h_pinned) : &hs;
-    PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
-    PS_CUDA(ctx, cudaStreamSynchronize(st));
+  FlagParams P;
+  P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
+  P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
+  P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
+  P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
+  pl_init_state<<<1, 32, 0, st>>>(d_state);
+  const bool ev = ctx->timers_on;
+  if (ev) cudaEventRecord(ctx->pl_ev[0], st);
+  const bool spec = vec && !ctx->pl_exact_flags;
+  H->spec = spec;
+  P.tile_ein = nullptr; P.tile_agg = nullptr; P.tile_cnt = nullptr; P.flag_words = nullptr;
+  if (spec) {
+    P.tile_ein = scratch<unsigned long long>(ctx, 1, n_tiles, err);
+    P.tile_agg = scratch<unsigned long long>(ctx, 7, n_tiles, err);
+    P.tile_cnt = scratch<uint32_t>(ctx, 5, n_tiles, err);
+    P.flag_words = scratch<uint32_t>(ctx, 6, (size_t)n_tiles * FLAG_THREADS, err);
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+    pl_flag_kernel<PL_FLAG_ITEMS, true><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+    pl_flag_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(P);
+    pl_flag_expand_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+    ctx->launches += 2;
+  } else if (vec) pl_flag_kernel<PL_FLAG_ITEMS, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+  else pl_flag_kernel<1, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
+  if (ev) cudaEventRecord(ctx->pl_ev[1], st);
+  ClusterParams Q;
+  Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
+  Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
+  Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
+  // site totals per compaction tile, added up by the cluster kernel: up to kCompactSumTiles tiles every compaction
+  // block sums the entries in front of it itself; beyond that (quadratic work) the decoupled look-back takes over
+  const uint64_t n_ctiles = (cap_cl + COMPACT_TILE - 1) / COMPACT_TILE;
+  Q.tile_sites = nullptr;
+  if (n_ctiles <= kCompactSumTiles && !ctx->pl_compact_lookback) {
+    Q.tile_sites = scratch<unsigned int>(ctx, 11, n_ctiles, err);
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+    PS_CUDA(ctx, cudaMemsetAsync(Q.tile_sites, 0, n_ctiles * sizeof(unsigned int), st));
+  }
+  launch_cluster(nw, c_tiles, st, Q);
+  if (ev) cudaEventRecord(ctx->pl_ev[2], st);
+  CompactParams R;
+  R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
+  R.cap_cl = cap_cl; R.cap_sites = cap_sites; R.tile_sites = Q.tile_sites;
+  pl_compact_kernel<<<(uint32_t)n_ctiles, PL_THREADS, 0, st>>>(R);
+  if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
+  ctx->launches += 4;
+  PS_CUDA(ctx, cudaGetLastError());
+  PlState* hsp = ctx->h_pinned ? static_cast<PlState*>(ctx->h_pinned) : &H->hs_fallback;
+  PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
+  return PS_OK;
+}
+
+// Waits for the attempt in flight; repeats it with the exact flag kernel or larger arrays where the run state asks for
+// that; fills the handle's counters.  Returns what the synchronous call returns.
+static int pileup_finish(ps_ctx* ctx, ps_pileup* H) {
+  if (!H->pending) return H->rc;
+  H->pending = false;
+  if (ctx->pl_pending == H) ctx->pl_pending = nullptr;
+  auto done = [&](int rc) { H->rc = rc; return rc; };
+  cudaStream_t st = H->stream;
+  const uint64_t n = H->n_reads;
+  PlState hs{};
+  for (int attempt = 0;; ++attempt) {
+    const PlState* hsp = ctx->h_pinned ? static_cast<const PlState*>(ctx->h_pinned) : &H->hs_fallback;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(cuda_fail(ctx, e, "pileup"));
     hs = *hsp;
-    if (spec && hs.spec_failed) {     // a read spans more than 32 tiles: this context keeps to the exact kernel from now on
+    bool again = false;
+    if (H->spec && hs.spec_failed) {     // a record reaches over the halo: this context keeps to the exact kernel from now on
       ctx->pl_exact_flags = true;
       --attempt;
-      continue;
+      again = true;
+    } else {
+      const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
+      if (need_cl > H->cap_cl || need_sites > H->cap_sites) {
+        if (attempt >= 2) { timer_end(ctx, st); return done(set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed")); }
+        // the totals do not depend on the capacities (dropped writes only); the site total is only known once the
+        // cluster slots fit, so a batch may need two more passes the first time a context sees its shape
+        ctx->pl_cap_cl = std::max(ctx->pl_cap_cl, need_cl + need_cl / 16 + 2);
+        ctx->pl_cap_ev = std::max(ctx->pl_cap_ev, need_sites + need_sites / 16);
+        again = true;
+      }
     }
-    const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
-    if (need_cl <= cap_cl && need_sites <= cap_sites) break;
-    if (attempt >= 2) { timer_end(ctx, st); return set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"); }
-    // the totals do not depend on the capacities (dropped writes only); the site total is only known once the
-    // cluster slots fit, so a batch may need two more passes the first time a context sees its shape
-    ctx->pl_cap_cl = std::max(ctx->pl_cap_cl, need_cl + need_cl / 16 + 2);
-    ctx->pl_cap_ev = std::max(ctx->pl_cap_ev, need_sites + need_sites / 16);
+    if (!again) break;
+    const int rc = pileup_launch(ctx, H);
+    if (rc != PS_OK) return done(rc);
   }
   timer_end(ctx, st);
   H->counters.skipped_due_indel = hs.skipped;
   if (hs.fault != PS_FAULT_NONE) {
     H->fault.code = (int32_t)(hs.fault & 0xFF);
     H->fault.read_ordinal = hs.fault >> 8;
-    return set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, "pileup: the JVM would die on a record of this batch");
+    return done(set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, "pileup: the JVM would die on a record of this batch"));
   }
-  if (hs.unsorted) return set_error(ctx, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED));
+  if (hs.unsorted) return done(set_error(ctx, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED)));
 
   const uint64_t n_slots = (uint64_t)hs.n_flags + 1;
   H->n_slots = n_slots;
@@ -1565,7 +1577,45 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   H->counters.n_clusters = hs.n_flags ? hs.n_flags - 1 : 0;
   const uint64_t sites_before_open = hs.n_flags ? H->open.site_begin : hs.n_sites_final;
   H->counters.n_sites = sites_before_open - H->head.site_end;
-  return PS_OK;
+  return done(PS_OK);
+}
+
+// Creates the handle and queues the first attempt.  wait == false: returns right behind the launches (ps_pileup_wait
+// completes the call); one submitted call per context at a time (run state and scratch belong to the context).
+static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out,
+                      bool wait = true) {
+  if (ctx->pl_pending) return set_error(ctx, PS_ERR_STATE, "a submitted pileup call of this context has not been waited for");
+  // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch) and is run on the context's
+  // own stream: the pileup never reads qualities, so it goes to the auxiliary stream as soon as the other streams of
+  // the records have arrived, while the quality bytes (more than half of the upload) are still on their way.
+  if (st == ctx->stream && ctx->stream2) {
+    for (int slot = 0; slot < 2; ++slot)
+      if (b.n_reads && b.meta == ctx->staged[slot].view.meta && ctx->staged_core[slot]) {
+        cudaStreamWaitEvent(ctx->stream2, ctx->staged_core[slot], 0);
+        st = ctx->stream2;
+      }
+  }
+  ps_pileup* H = new ps_pileup();
+  *out = H;
+  H->ctx = ctx;
+  H->stream = st;
+  H->batch = b;
+  H->has_opts = opts != nullptr;
+  if (opts) H->opts = *opts;
+  const uint64_t n = b.n_reads;
+  H->n_reads = n;
+  H->counters.num_reads_processed = n;
+  if (n == 0) return PS_OK;
+  if (n >= 0xFFFFFFFFull) return set_error(ctx, PS_ERR_UNSUPPORTED, "pileup batch of >= 2^32 reads");
+  H->nw = flavour_of(b);
+  if (ctx->pl_cap_cl < 1024) ctx->pl_cap_cl = std::max<uint64_t>(1024, n / 8);
+  if (ctx->pl_cap_ev < 1024) ctx->pl_cap_ev = std::max<uint64_t>(1024, n / 4);   // site capacity
+  timer_begin(ctx, st);
+  const int rc = pileup_launch(ctx, H);
+  if (rc != PS_OK) { H->rc = rc; return rc; }
+  H->pending = true;
+  ctx->pl_pending = H;
+  return wait ? pileup_finish(ctx, H) : PS_OK;
 }
 
 static DeviceBatch pl_view_of(const ps_read_batch* b) {
@@ -1580,6 +1630,8 @@ static DeviceBatch pl_view_of(const ps_read_batch* b) {
 static void free_handle(ps_pileup* h) {
   if (!h) return;
   if (h->ctx) cudaSetDevice(h->ctx->device);
+  if (h->pending && h->ctx) pileup_finish(h->ctx, h);     // the kernels in flight use the handle's arrays
+  if (h->ctx && h->ctx->pl_pending == h) h->ctx->pl_pending = nullptr;
   if (h->d_cl) cudaFreeAsync(h->d_cl, h->stream);
   if (h->d_sites) cudaFreeAsync(h->d_sites, h->stream);
   delete h;
@@ -1650,6 +1702,23 @@ int ps_pileup_batch_device(ps_ctx* ctx, const ps_read_batch* b, const ps_pileup_
   return rc;
 }
 
+int ps_pileup_submit_device(ps_ctx* ctx, const ps_read_batch* b, const ps_pileup_opts* opts, void* stream,
+                            ps_pileup** out) {
+  if (!ctx || !b || !out) return PS_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc = run_pileup(ctx, pl_view_of(b), opts, st, out, /*wait=*/false);
+  if (rc != PS_OK) { free_handle(*out); *out = nullptr; }
+  return rc;
+}
+int ps_pileup_wait(ps_pileup* h) {
+  if (!h) return PS_ERR_INVALID_ARG;
+  if (!h->ctx) return PS_OK;
+  cudaSetDevice(h->ctx->device);
+  return pileup_finish(h->ctx, h);
+}
 int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* hb, const ps_pileup_opts* opts, ps_pileup** out) {
   if (!ctx || !hb || !out) return PS_ERR_INVALID_ARG;
   *out = nullptr;
@@ -1704,6 +1773,7 @@ int ps_pileup_max_key(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream,
 
 int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out) {
   if (!h || !out) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   *out = h->counters;
   return PS_OK;
 }
@@ -1711,6 +1781,7 @@ int ps_pileup_counters_get(const ps_pileup* h, ps_pileup_counters* out) {
 int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint64_t max_clusters, ps_site* sites,
                        uint64_t max_sites) {
   if (!h || !clusters || (!sites && max_sites)) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   const uint64_t n_closed = h->counters.n_clusters;
   if (first >= n_closed || max_clusters == 0) return 0;
   ps_ctx* ctx = h->ctx;
@@ -1762,18 +1833,21 @@ static int copy_boundary(ps_pileup* h, const ps_cluster& src, ps_cluster* cluste
 
 int ps_pileup_open_cluster(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites) {
   if (!h || !cluster) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   if (!h->counters.has_open_cluster) return 0;
   return copy_boundary(h, h->open, cluster, sites, max_sites);
 }
 
 int ps_pileup_head_partial(ps_pileup* h, ps_cluster* cluster, ps_site* sites, uint64_t max_sites) {
   if (!h || !cluster) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   if (!h->has_head) return 0;
   return copy_boundary(h, h->head, cluster, sites, max_sites);
 }
 
 int64_t ps_pileup_boundary_coverage(ps_pileup* h, int which, int32_t* first_pos, uint32_t* cov, uint64_t max) {
   if (!h || !first_pos) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   int rc = boundary_coverage(h);
   if (rc) return rc;
   const std::vector<uint32_t>& v = which ? h->open_cov : h->head_cov;
@@ -1786,6 +1860,7 @@ int64_t ps_pileup_boundary_coverage(ps_pileup* h, int which, int32_t* first_pos,
 
 int ps_pileup_fault(const ps_pileup* h, ps_fault* out) {
   if (!h || !out) return PS_ERR_INVALID_ARG;
+  if (h->pending) return PS_ERR_STATE;
   *out = h->fault;
   return PS_OK;
 }

@@ -89,6 +89,7 @@ class Context:
         self._infer_q = False
         self._keep = []
         self._pinned_bufs = {}
+        self._result_plans = {}
 
     def close(self):
         if self.h:
@@ -176,28 +177,40 @@ class Context:
 
         return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
 
+    def _profile_result_plan(self):
+        """(name, dtype, shape, count, byte offset) of every result array inside one allocation, cached per run shape."""
+        key = (self._max_len, bool(self._infer_q))
+        plan = self._result_plans.get(key)
+        if plan is None:
+            m = self._max_len
+            wide_n = self.lib.ps_profile_acc_len(m, int(self._infer_q))
+            parts = [("position_conversions", np.int32, (m, 4, 4)), ("quality_per_mismatch", np.int32, (4, 4)),
+                     ("quality_per_mismatch_counts", np.int32, (4, 4)), ("counters", np.int32, (abi.PS_PC_COUNT,)),
+                     ("insertions_per_pos", np.float64, (m,)), ("deletions_per_pos", np.float64, (m,)),
+                     ("wide", np.int64, (wide_n,))]
+            if self._infer_q:
+                parts.append(("quality_hist", np.int64, (m, 256)))
+            items, total = [], 0
+            for name, dt, shape in parts:
+                n = 1
+                for d in shape:
+                    n *= int(d)
+                total = (total + 7) & ~7
+                items.append((name, np.dtype(dt), shape, n, total))
+                total += n * np.dtype(dt).itemsize
+            plan = (items, total)
+            self._result_plans[key] = plan
+        return plan
+
     def _profile_result_arrays(self):
-        """Fresh result arrays for one run, carved out of ONE allocation (a numpy .ctypes lookup per array costs more
-        than the copy itself on the small PAR-CLIP profile)."""
-        m = self._max_len
-        wide_n = self.lib.ps_profile_acc_len(m, int(self._infer_q))
-        parts = [("position_conversions", np.int32, (m, 4, 4)), ("quality_per_mismatch", np.int32, (4, 4)),
-                 ("quality_per_mismatch_counts", np.int32, (4, 4)), ("counters", np.int32, (abi.PS_PC_COUNT,)),
-                 ("insertions_per_pos", np.float64, (m,)), ("deletions_per_pos", np.float64, (m,)),
-                 ("wide", np.int64, (wide_n,))]
-        if self._infer_q:
-            parts.append(("quality_hist", np.int64, (m, 256)))
-        offs, total = [], 0
-        for _, dt, shape in parts:
-            total = (total + 7) & ~7
-            offs.append(total)
-            total += int(np.prod(shape)) * np.dtype(dt).itemsize
+        """Fresh result arrays for one run, carved out of ONE allocation (per-array numpy / ctypes bookkeeping costs more
+        than the copy itself on the small PAR-CLIP profile, and the device sits idle while the host does it)."""
+        items, total = self._profile_result_plan()
         buf = np.zeros(total, dtype=np.uint8)
-        base = buf.__array_interface__["data"][0]
+        base = buf.ctypes.data
         out, r = {}, abi.ps_profile_result()
-        for (name, dt, shape), off in zip(parts, offs):
-            n = int(np.prod(shape))
-            out[name] = buf[off:off + n * np.dtype(dt).itemsize].view(dt).reshape(shape)
+        for name, dt, shape, n, off in items:
+            out[name] = np.frombuffer(buf, dtype=dt, count=n, offset=off).reshape(shape)
             setattr(r, name, base + off)
         if not self._infer_q:
             r.quality_hist = None
@@ -216,8 +229,11 @@ class Context:
         return self.profile_end()
 
     # ---- T>C pileup (PileupClusters.java:137-500, 585-673) ----------------------------------------
-    def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0, carry_keys=None) -> "PileupResult":
+    def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0, carry_keys=None,
+                   defer: bool = False) -> "PileupResult":
         """Run the pileup kernels; the cluster and site records stay in HBM behind the returned handle.
+        defer=True (device-resident batches): return right behind the kernel launches (ps_pileup_submit_device); the
+        call is completed by PileupResult.wait(), which the first look at the counters / records does by itself.
         batch: ReadBatch / PinnedBatch (host buffers, H2D inside) or DeviceBatch / UploadedBatch (resident).
         carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None;
         carry_keys = (device pointer, n): the keys of the n preceding shards left on the device (pileup_max_key_tensor +
@@ -228,6 +244,14 @@ class Context:
         if carry_keys is not None and carry_keys[1] > 0:
             opts.carry_keys_device, opts.carry_keys_n = int(carry_keys[0]), int(carry_keys[1])
         h = C.c_void_p()
+        if defer:
+            if not isinstance(batch, (DeviceBatch, UploadedBatch)):
+                raise TypeError("defer=True needs a device-resident batch")
+            self._keep_opts = opts                     # the library copies it; kept for symmetry with the batch
+            st = self.lib.ps_pileup_submit_device(self.h, C.byref(batch.struct), C.byref(opts), stream or None,
+                                                  C.byref(h))
+            _check(self.lib, self.h, st)
+            return PileupResult(self, h, batch, pending=True)
         if isinstance(batch, (DeviceBatch, UploadedBatch)):
             st = self.lib.ps_pileup_batch_device(self.h, C.byref(batch.struct), C.byref(opts), stream or None,
                                                  C.byref(h))
@@ -301,11 +325,25 @@ class Context:
 class PileupResult:
     """Handle of one pileup call: counters on the host, cluster / site records resident in HBM until fetched."""
 
-    def __init__(self, ctx: Context, h, batch):
+    def __init__(self, ctx: Context, h, batch, pending: bool = False):
         self.ctx = ctx
         self.h = h
         self._batch = batch            # the records must outlive the halo-merge coverage query
         self._counters = None
+        self._pending = pending        # submitted, not waited for (Context.pileup_run(defer=True))
+
+    def wait(self):
+        """Complete a deferred call (no-op otherwise); raises what the synchronous call would have raised."""
+        if not self._pending:
+            return self
+        self._pending = False
+        st = self.ctx.lib.ps_pileup_wait(self.h)
+        if st == abi.PS_ERR_REFERENCE_WOULD_THROW:
+            f = abi.ps_fault()
+            self.ctx.lib.ps_pileup_fault(self.h, C.byref(f))
+            _check(self.ctx.lib, self.ctx.h, st, fault=(f.code, f.read_ordinal))
+        _check(self.ctx.lib, self.ctx.h, st)
+        return self
 
     def __enter__(self):
         return self
@@ -321,6 +359,7 @@ class PileupResult:
     @property
     def counters(self) -> dict:
         if self._counters is None:
+            self.wait()
             ctr = abi.ps_pileup_counters()
             self.ctx.lib.ps_pileup_counters_get(self.h, C.byref(ctr))
             self._counters = {f: getattr(ctr, f) for f, _ in abi.ps_pileup_counters._fields_}

@@ -273,3 +273,30 @@ def test_site_compaction_by_look_back(oracle, monkeypatch):
         assert_pileup_equal(c.pileup(batch), oracle.pileup(ref, batch), "compaction by look-back")
     finally:
         c.close()
+
+
+def test_submit_and_wait(ctx, oracle):
+    """ps_pileup_submit_device / ps_pileup_wait: the call in two halves gives the result of the synchronous call; until
+    the wait the handle answers PS_ERR_STATE, the context refuses a second pileup call, and closing a submitted handle
+    without waiting is safe."""
+    import ctypes as C
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import DeviceBatch
+    ref = synth.synth_reference(95, [1_500_000], n_run=300)
+    batch = synth.synth_reads(ref, 120_000, 36, seed=18)
+    ctx.upload_reference(ref)
+    exp = oracle.pileup(ref, batch)
+    d = DeviceBatch(batch, "cuda:0")
+    h = ctx.pileup_run(d, defer=True)
+    ctr = abi.ps_pileup_counters()
+    assert ctx.lib.ps_pileup_counters_get(h.h, C.byref(ctr)) == abi.PS_ERR_STATE
+    with pytest.raises(abi.PsError):
+        ctx.pileup_run(d)                                  # one submitted call per context
+    prof = ctx.profile(batch, 51)                          # other work of the context goes on in between
+    got = h.wait().fetch()
+    h.close()
+    assert_pileup_equal(got, exp, "submit + wait")
+    assert np.array_equal(prof["wide"], oracle.profile_acc(ref, batch, 51))
+    h2 = ctx.pileup_run(d, defer=True)
+    h2.close()                                             # waits, then frees
+    assert_pileup_equal(ctx.pileup(d), exp, "after closing a submitted handle")

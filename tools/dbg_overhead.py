@@ -39,3 +39,19 @@ for _ in range(5): both_small()
 t0 = time.perf_counter()
 for _ in range(200): both_small()
 print("tiny batch, both tools:", (time.perf_counter() - t0) * 1e3 / 200, "ms/step host")
+# host time of every call of the step (big batch: includes waiting for the device inside the two syncs)
+import collections
+acc = collections.defaultdict(float)
+def timed(name, fn, *a, **k):
+    t = time.perf_counter(); r = fn(*a, **k); acc[name] += time.perf_counter() - t; return r
+K = 100
+for which, batch in (("tiny", ds), ("10M", d)):
+    acc.clear()
+    for _ in range(K):
+        timed("profile_begin", ctx.profile_begin, 51)
+        timed("profile_batch_device", ctx.profile_batch_device, batch, st.cuda_stream)
+        h = timed("pileup_run", ctx.pileup_run, batch, first_running_id=1, stream=st.cuda_stream)
+        timed("counters", lambda: h.counters)
+        timed("close", h.close)
+        timed("profile_end", ctx.profile_end)
+    print(which, {k: round(v * 1e6 / K, 1) for k, v in acc.items()}, "us per call")
