@@ -1,24 +1,30 @@
 // K2/K3: T>C conversion pileup.  Replaces the loop PileupClusters.java:137-500 and
 // calculateClusterInformation :585-673 (reference: /root/reference/src/src/utils/pileupclusters/).
 //
-// Three kernels over one coordinate-sorted SoA batch; every output record is assembled on the device:
+// Three stages over one coordinate-sorted SoA batch; every output record is assembled on the device:
 //
-//   pl_flag_kernel     the only ORDERED step, kept as light as possible (12 B/read: meta, ref_start, cigar):
+//   flag stage         the only ORDERED step, kept as light as possible (12 B/read: meta, ref_start, cigar):
 //       per read       filter (P1), (contig, start, end)
-//       look-back #1   running max of (contig, end) over all earlier reads = the cluster end the Java loop holds
-//                      (tempClusterEnd) -> boundary flag (clusterEnd - start) < 5 or contig changed (P2)
-//       look-back #2   prefix sum of the flags = cluster slot; the opening read writes cl_first[slot]
+//       running max    of (contig, end) over all earlier reads = the cluster end the Java loop holds (tempClusterEnd)
+//                      -> boundary flag (clusterEnd - start) < 5 or contig changed (P2)
+//       prefix sum     of the flags = cluster slot; the opening read's index goes to cl_first[slot]
+//     one-op-per-read batches: pl_flag_kernel<16, true> (no dependency between tiles: the running max in front of a
+//     tile is taken over a halo of 128 reads and recorded), pl_flag_scan_kernel (one block: exact prefixes over the
+//     tile table, every assumption checked -- a failed one makes the host repeat the call with the exact kernel),
+//     pl_flag_expand_kernel (flag words + tile prefix -> cl_first).  Other batches and the fallback:
+//     pl_flag_kernel<.., false>, two decoupled look-backs over 16-byte single-word descriptors.
 //   pl_cluster_kernel  one block = 64 consecutive clusters = one contiguous run of reads, no inter-block dependency:
 //       thread per read      T>C bit mask over the concatenated alignment blocks (P3) -- bit-parallel on 2-bit packed
 //                            words for the PAR-CLIP shape (uniform length, one M op), a literal CIGAR walk otherwise --
 //                            decoded into shared memory; T>C positions ORed into the cluster's 64-position key set
-//       thread per cluster   reads, T>C count, end, 51-bit position mask, strand state (P4, P6)
+//       per cluster          reads, T>C count, end, 51-bit position mask, strand state (P4, P6)
 //       thread per read      mutationMap values, first-insertion key and baseCoveredMap at the keys (P3, P7): native
 //                            shared-memory atomics, slot = rank of the key in the key set (position order)
 //       thread per cluster   64-byte record and the sites; the block takes ONE run of site slots with one atomic
 //       warp per cluster     what does not fit (> 1024 reads, > 6 keys, keys > 64 apart): warp ballots for <= 32 reads,
 //                            else a streaming sweep over a sliding ring of positions, else window tables
-//   pl_compact_kernel  look-back #3 over the per-cluster site counts: site runs into (cluster, position) order
+//   pl_compact_kernel  site runs into (cluster, position) order; the prefix over the per-cluster site counts comes from
+//                      per-tile totals the cluster kernel adds up (a look-back past 2 M cluster slots)
 //
 // The flush-time logic (SNP filter, anchor site, text rows: :178-344) stays on the host side of the boundary.
 #include <algorithm>
