@@ -300,3 +300,48 @@ def test_submit_and_wait(ctx, oracle):
     h2 = ctx.pileup_run(d, defer=True)
     h2.close()                                             # waits, then frees
     assert_pileup_equal(ctx.pileup(d), exp, "after closing a submitted handle")
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 2047, 2048, 2049, 4096, 6145])
+def test_flag_tiles_and_halo_edges(ctx, oracle, n):
+    """Batch sizes around the tile (2048 reads) and halo (128 reads) of the speculative boundary-flag pass, two contigs so
+    that a contig change falls next to a tile edge for some of them."""
+    from parasuite_b200 import synth
+    from parasuite_b200.sharding import slice_batch
+    ref = synth.synth_reference(96, [30_000, 30_000], n_run=0)
+    whole = synth.synth_reads(ref, 8_192, 36, seed=19, n_ppm=0)
+    cut = int(np.searchsorted(whole.ref_start, 30_000))          # first read of the second contig
+    lo = max(0, min(cut - n // 2, whole.n_reads - n))            # the contig change lies inside the slice where it can
+    batch = slice_batch(whole, lo, lo + n)
+    ctx.upload_reference(ref)
+    assert_pileup_equal(ctx.pileup(batch), oracle.pileup(ref, batch), f"n={n}")
+    assert ctx.lib.ps_pileup_flag_mode(ctx.h) == 0
+
+
+def test_contig_order_backwards_is_refused(ctx, oracle):
+    """Records of an earlier contig behind records of a later one: PS_ERR_UNSORTED from the speculative pass too."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(97, [40_000, 40_000], n_run=0)
+    whole = synth.synth_reads(ref, 9_000, 36, seed=20, n_ppm=0)
+    cut = int(np.searchsorted(whole.ref_start, 40_000))
+    assert 0 < cut < whole.n_reads
+    idx = np.concatenate([np.arange(cut, whole.n_reads), np.arange(0, cut)])     # second contig first
+    ctx.upload_reference(ref)
+    with pytest.raises(abi.PsError) as e:
+        ctx.pileup(_reorder(whole, idx))
+    assert e.value.status == abi.PS_ERR_UNSORTED
+
+
+def _reorder(batch, idx):
+    """Reads of a uniform batch in the order `idx` (any order)."""
+    import copy
+    assert batch.uniform_len and batch.uniform_ncigar == 1 and not batch.exc_count
+    b = copy.copy(batch)
+    n, L = batch.n_reads, batch.uniform_len
+    bpr = (L + 3) // 4
+    b.meta = batch.meta[idx].copy(); b.ref_start = batch.ref_start[idx].copy(); b.cigar = batch.cigar[idx].copy()
+    bases, qual = batch.bases2.copy(), batch.qual.copy()
+    bases[:n * bpr] = batch.bases2[:n * bpr].reshape(n, bpr)[idx].reshape(-1)
+    qual[:n * L] = batch.qual[:n * L].reshape(n, L)[idx].reshape(-1)
+    b.bases2, b.qual = bases, qual
+    return b
