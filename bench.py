@@ -366,7 +366,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": name, "stages": ["profile", "pileup"], "reads_per_gpu": batch.n_reads,
-                       "stage_ms": {"profile_kernel": k_prof, "pileup_device_incl_sync": k_pile, "pl_flag_kernel": k_flag,
+                       "stage_ms": {"profile_kernel": k_prof, "pileup_device": k_pile, "pl_flag_kernel": k_flag,
                                     "pl_cluster_kernel": k_cluster, "pl_compact_kernel": k_compact},
                        "stage_note": "pl_flag_kernel = flag pass + one-block scan + cl_first expansion (3 launches)",
                        "pileup": {"clusters": n_cl, "sites": n_sites, "covered_loci": covered},

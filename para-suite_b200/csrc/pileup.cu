@@ -1479,6 +1479,8 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
   P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
   P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
+  timer_begin(ctx, st);        // the timer pair is complete when the launch returns (a submitted call may be waited for
+                               // after other timed calls of the context)
   pl_init_state<<<1, 32, 0, st>>>(d_state);
   const bool ev = ctx->timers_on;
   if (ev) cudaEventRecord(ctx->pl_ev[0], st);
@@ -1522,6 +1524,7 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   PS_CUDA(ctx, cudaGetLastError());
   PlState* hsp = ctx->h_pinned ? static_cast<PlState*>(ctx->h_pinned) : &H->hs_fallback;
   PS_CUDA(ctx, cudaMemcpyAsync(hsp, d_state, sizeof(PlState), cudaMemcpyDeviceToHost, st));
+  timer_end(ctx, st);
   return PS_OK;
 }
 
@@ -1548,7 +1551,7 @@ static int pileup_finish(ps_ctx* ctx, ps_pileup* H) {
     } else {
       const uint64_t need_cl = (uint64_t)hs.n_flags + 1, need_sites = hs.n_sites;
       if (need_cl > H->cap_cl || need_sites > H->cap_sites) {
-        if (attempt >= 2) { timer_end(ctx, st); return done(set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed")); }
+        if (attempt >= 2) return done(set_error(ctx, PS_ERR_CUDA, "pileup: capacity retry failed"));
         // the totals do not depend on the capacities (dropped writes only); the site total is only known once the
         // cluster slots fit, so a batch may need two more passes the first time a context sees its shape
         ctx->pl_cap_cl = std::max(ctx->pl_cap_cl, need_cl + need_cl / 16 + 2);
@@ -1560,7 +1563,6 @@ static int pileup_finish(ps_ctx* ctx, ps_pileup* H) {
     const int rc = pileup_launch(ctx, H);
     if (rc != PS_OK) return done(rc);
   }
-  timer_end(ctx, st);
   H->counters.skipped_due_indel = hs.skipped;
   if (hs.fault != PS_FAULT_NONE) {
     H->fault.code = (int32_t)(hs.fault & 0xFF);
@@ -1616,7 +1618,6 @@ static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* o
   H->nw = flavour_of(b);
   if (ctx->pl_cap_cl < 1024) ctx->pl_cap_cl = std::max<uint64_t>(1024, n / 8);
   if (ctx->pl_cap_ev < 1024) ctx->pl_cap_ev = std::max<uint64_t>(1024, n / 4);   // site capacity
-  timer_begin(ctx, st);
   const int rc = pileup_launch(ctx, H);
   if (rc != PS_OK) { H->rc = rc; return rc; }
   H->pending = true;
