@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "device_common.cuh"
 #include "lookback.cuh"
@@ -104,11 +105,11 @@ struct ContigCache {         // contig bounds of the last read looked up by this
   uint32_t idx = 0;
 };
 struct ContigCache32 {       // same in 32 bits (the global coordinate space is < 2^32 bases: set_contigs in ctx.cu)
-  uint32_t lo = 1, hi = 0;
+  uint32_t lo = 0, hi = 0;     // empty: hi - lo == 0, no offset passes the one-compare range test
   uint32_t idx = 0;
 };
-__device__ __forceinline__ bool contig_lookup(const DeviceRef& ref, uint64_t g0, ContigCache32& c) {
-  if (g0 >= c.lo && g0 < c.hi) return true;
+__device__ __forceinline__ bool contig_lookup(const DeviceRef& ref, uint32_t g0, ContigCache32& c) {
+  if (g0 - c.lo < c.hi - c.lo) return true;       // lo <= g0 < hi in one unsigned compare
   if (g0 >= ref.n_bases) return false;
   c.idx = contig_of(ref, g0);
   c.lo = (uint32_t)__ldg(ref.contig_off + c.idx);
@@ -173,14 +174,15 @@ __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64
 }
 
 // same for a record with exactly one cigar op `cg` (a lone I or D next to no N is kept: :152-157 needs both)
+template <typename CC>
 __device__ __forceinline__ unsigned long long pl_key1(const FlagParams& P, uint32_t meta, uint32_t cg, uint32_t g0,
-                                                      ContigCache& cc, int32_t& start) {
+                                                      CC& cc, int32_t& start) {
   const uint32_t flags = PS_META_FLAGS(meta);
   start = 0;
   if (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) return 0;
   if (!contig_lookup(P.ref, g0, cc)) return 0;
   const uint32_t R = op_consumes_ref(cg & 15u) ? cg >> 4 : 0u;
-  start = (int32_t)((uint64_t)g0 - cc.lo) + 1;
+  start = (int32_t)(g0 - (uint32_t)cc.lo) + 1;      // offsets inside a contig fit 32 bits (the whole reference does)
   return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(start + (int32_t)R - 1);
 }
 
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
 
   unsigned long long key[ITEMS];
   int32_t start[ITEMS];
-  ContigCache cc;
+  typename std::conditional<(ITEMS > 1), ContigCache32, ContigCache>::type cc;
   [[maybe_unused]] uint32_t h_meta = PS_MAKE_META(0, 0, PS_RF_UNMAPPED), h_start = 0, h_cig = 0;
   if constexpr (SPEC) {       // one read of the halo per thread, requested together with the tile's own reads
     const uint64_t t0 = (uint64_t)tile * TILE;
