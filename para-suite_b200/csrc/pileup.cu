@@ -177,13 +177,16 @@ __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64
 template <typename CC>
 __device__ __forceinline__ unsigned long long pl_key1(const FlagParams& P, uint32_t meta, uint32_t cg, uint32_t g0,
                                                       CC& cc, int32_t& start) {
+  // straight-line on purpose (16 reads per thread are unrolled around this: early returns cost a convergence
+  // barrier each); only the contig table walk of a cache miss is a branch
   const uint32_t flags = PS_META_FLAGS(meta);
-  start = 0;
-  if (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) return 0;
-  if (!contig_lookup(P.ref, g0, cc)) return 0;
+  bool ok = (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0;
+  if (ok) ok = contig_lookup(P.ref, g0, cc);
   const uint32_t R = op_consumes_ref(cg & 15u) ? cg >> 4 : 0u;
-  start = (int32_t)(g0 - (uint32_t)cc.lo) + 1;      // offsets inside a contig fit 32 bits (the whole reference does)
-  return ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(start + (int32_t)R - 1);
+  const int32_t s = (int32_t)(g0 - (uint32_t)cc.lo) + 1;      // offsets inside a contig fit 32 bits (the whole reference does)
+  start = ok ? s : 0;
+  const unsigned long long key = ((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(s + (int32_t)R - 1);
+  return ok ? key : 0ull;
 }
 
 // max over the records of a batch of (contig, end): what a following shard needs as carry-in (region sharding: the
@@ -351,16 +354,14 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned long long my = key[j];
-    if (my) {
-      const uint32_t pc = (uint32_t)(E >> 32), mc = (uint32_t)(my >> 32);
-      bool f;
-      if (E == 0) f = true;                             // tempClusterEnd = 0, tempClusterChr = "" (:118-120)
-      else if (pc != mc) f = true;
-      else f = ((int64_t)(int32_t)(uint32_t)E - (int64_t)start[j]) < 5;
-      unsorted |= pc > mc;                              // contig order went backwards: not coordinate sorted
-      E = my > E ? my : E;
-      if (f) { fl |= 1u << j; ++nfl; }
-    }
+    const bool kept = my != 0;
+    const uint32_t pc = (uint32_t)(E >> 32), mc = (uint32_t)(my >> 32);
+    // tempClusterEnd = 0, tempClusterChr = "" (:118-120) | contig changed | (clusterEnd - start) < 5; predicated, no branches
+    const bool f = kept && (E == 0 || pc != mc || ((int64_t)(int32_t)(uint32_t)E - (int64_t)start[j]) < 5);
+    unsorted |= kept && pc > mc;                        // contig order went backwards: not coordinate sorted
+    E = my > E ? my : E;                                // my == 0 leaves E alone
+    fl |= (uint32_t)f << j;
+    nfl += (uint32_t)f;
   }
   if (unsorted) P.st->unsorted = 1u;
   if constexpr (SPEC) {
