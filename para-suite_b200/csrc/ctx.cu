@@ -247,7 +247,6 @@ static cudaError_t clear_accumulators(ps_ctx* ctx, size_t acc_bytes, cudaStream_
   if (e == cudaSuccess) e = cudaMemsetAsync(ctx->fault.p, 0xFF, 8, s);
   if (e == cudaSuccess) e = cudaMemsetAsync((char*)ctx->fault.p + 8, 0, 56, s);
   if (e == cudaSuccess) e = cudaEventRecord(ctx->reset_ev, s);
-  ctx->reset_stream = s;
   return e;
 }
 
@@ -304,7 +303,7 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
   if (st) return st;
   cudaSetDevice(ctx->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-  if (s != ctx->reset_stream) PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));
+  PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));     // the clearing may have been queued on another stream
   ctx->profile_stream = s;
   timer_begin(ctx, s);
   PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s));
@@ -324,7 +323,7 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
   StagedBatch* sb = nullptr;
   st = stage_batch(ctx, hb, true, &sb);
   if (st) return st;
-  if (ctx->stream != ctx->reset_stream) PS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->reset_ev, 0));
+  PS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->reset_ev, 0));
   ctx->profile_stream = ctx->stream;
   timer_begin(ctx, ctx->stream);
   PS_CUDA(ctx, launch_profile(ctx, sb->view, ctx->reads_seen, ctx->stream));

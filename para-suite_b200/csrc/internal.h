@@ -135,7 +135,6 @@ struct ps_ctx {
   // ps_profile_end clears the accumulators for the next run behind its read-back: ps_profile_begin finds them clean
   const void* clean_ptr = nullptr;
   size_t clean_bytes = 0;
-  cudaStream_t reset_stream = nullptr;   // stream reset_ev was recorded on
   // pileup scratch (pileup.cu): run state, look-back descriptors
   DevBuf pl_scratch[12];
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)
