@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
     const bool kept = my != 0;
     const uint32_t pc = (uint32_t)(E >> 32), mc = (uint32_t)(my >> 32);
     // tempClusterEnd = 0, tempClusterChr = "" (:118-120) | contig changed | (clusterEnd - start) < 5; predicated, no branches
-    const bool f = kept && (E == 0 || pc != mc || ((int64_t)(int32_t)(uint32_t)E - (int64_t)start[j]) < 5);
-    unsorted |= kept && pc > mc;                        // contig order went backwards: not coordinate sorted
+    const bool f = kept & ((E == 0) | (pc != mc) | (((int64_t)(int32_t)(uint32_t)E - (int64_t)start[j]) < 5));
+    unsorted |= kept & (pc > mc);                       // contig order went backwards: not coordinate sorted
     E = my > E ? my : E;                                // my == 0 leaves E alone
     fl |= (uint32_t)f << j;
     nfl += (uint32_t)f;
@@ -473,13 +473,12 @@ __global__ void __launch_bounds__(FLAG_THREADS) pl_flag_expand_kernel(const __gr
   if (total == 0) return;
   uint64_t slot = (uint64_t)P.tile_cnt[tile] + ex;
   const uint64_t r0 = (uint64_t)tile * (FLAG_THREADS * ITEMS) + (uint64_t)threadIdx.x * ITEMS;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j)
-    if ((fl >> j) & 1u) {
-      ++slot;
-      if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
-      if (slot == 1) P.st->first_slot1 = (unsigned int)(r0 + j);
-    }
+  for (uint32_t w = fl; w; w &= w - 1) {          // about one flag per thread: walk the set bits, not the 16 reads
+    const uint32_t j = (uint32_t)__ffs((int)w) - 1u;
+    ++slot;
+    if (slot < P.cap_cl) P.cl_first[slot] = (uint32_t)(r0 + j);
+    if (slot == 1) P.st->first_slot1 = (unsigned int)(r0 + j);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
