@@ -355,7 +355,7 @@ def main():
             traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["traffic_bytes_per_launch"]
         except Exception:
             pass
-        if "pl_flag_kernel" in traffic:   # the flag stage is three kernels (flag pass, one-block scan, cl_first expansion)
+        if "pl_flag_kernel" in traffic:   # the flag stage is two kernels (flag pass, cl_first expansion; + a scan kernel for huge batches)
             traffic["pl_flag_kernel"] = sum(traffic.get(k, 0.0) for k in
                                             ("pl_flag_kernel", "pl_flag_scan_kernel", "pl_flag_expand_kernel"))
         kname = max(kernels, key=lambda k: kernels[k][0] if kernels[k][0] == kernels[k][0] else -1.0)
@@ -368,7 +368,7 @@ def main():
             "config": {"workload": name, "stages": ["profile", "pileup"], "reads_per_gpu": batch.n_reads,
                        "stage_ms": {"profile_kernel": k_prof, "pileup_device": k_pile, "pl_flag_kernel": k_flag,
                                     "pl_cluster_kernel": k_cluster, "pl_compact_kernel": k_compact},
-                       "stage_note": "pl_flag_kernel = flag pass + one-block scan + cl_first expansion (3 launches)",
+                       "stage_note": "pl_flag_kernel = flag pass + cl_first expansion (the tile-table prefix is taken inside the expansion kernel; a one-block scan kernel past 16.7 M reads)",
                        "pileup": {"clusters": n_cl, "sites": n_sites, "covered_loci": covered},
                        "max_read_length": max_len, "l2": "inputs larger than L2 (%.0f MB per pass)" % (alg_bytes / 1e6),
                        "parallelism": f"profile: read-batch sharded x{world} + all-reduce of the count vector; "

@@ -140,6 +140,7 @@ struct ps_ctx {
   unsigned int pl_epoch = 0;    // look-back epoch (descriptors are never reset)
   uint64_t pl_cap_cl = 0, pl_cap_ev = 0;   // cluster-slot / site capacities learnt from earlier batches
   struct ps_pileup* pl_pending = nullptr;   // handle of a submitted pileup call that has not been waited for
+  bool pl_flag_scan_kernel = false;   // PARASUITE_B200_FLAG_SCAN_KERNEL=1 at ps_create: always prefix the tile table with the one-block scan (tests)
   bool pl_compact_lookback = false;   // PARASUITE_B200_COMPACT_LOOKBACK=1 at ps_create: always order the site runs with the look-back (tests)
   bool pl_exact_flags = false;   // a speculative flag pass failed on this context: keep to the exact look-back kernel
 };

@@ -146,6 +146,7 @@ struct FlagParams {
   unsigned long long* tile_agg;   // [n_tiles] maximum over the tile's own reads
   uint32_t* tile_cnt;             // [n_tiles] boundary flags per tile, then (scan kernel) their exclusive prefix
   uint32_t* flag_words;           // one word per thread (bit j = read j of the thread)
+  uint32_t scan_in_expand;        // no pl_flag_scan_kernel: the expand kernel sums the tile counts itself
 };
 
 // (contig+1) << 32 | end of a kept record, 0 otherwise (PileupClusters.java:146-158)
@@ -462,16 +463,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) pl_flag_scan_kernel(const __grid
   }
 }
 
-// cl_first from the flag bits and the per-tile prefix (same tiling as the flag kernel)
+// cl_first from the flag bits and the per-tile prefix (same tiling as the flag kernel).
+// P.scan_in_expand (tile tables of up to kFlagSumTiles entries): there is no scan kernel in front of this one; every
+// block adds up the counts of the tiles in front of it itself and checks its own tile's assumption LOCALLY --
+// assumed(t) == max(assumed(t-1), aggregate(t-1)) for every t is, by induction from assumed(0) = carry, the same as
+// assumed(t) == exact running maximum -- and the last tile's block writes the totals.
 template <int ITEMS>
 __global__ void __launch_bounds__(FLAG_THREADS) pl_flag_expand_kernel(const __grid_constant__ FlagParams P) {
   __shared__ unsigned long long s_wtot[FLAG_WARPS];
-  const uint32_t tile = blockIdx.x;
+  __shared__ unsigned long long s_base;
+  const uint32_t tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t fl = P.flag_words[(size_t)tile * FLAG_THREADS + threadIdx.x];
+  unsigned long long part = 0;
+  if (P.scan_in_expand)
+    for (uint32_t t = threadIdx.x; t < tile; t += FLAG_THREADS) part += P.tile_cnt[t];
   unsigned long long total;
   const unsigned long long ex = block_exclusive<LbSum, FLAG_WARPS>((unsigned long long)__popc(fl), LbSum(), 0ull, s_wtot, total);
+  unsigned long long base;
+  if (P.scan_in_expand) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+    if (lane == 0) s_wtot[warp] = part;          // block_exclusive is done with s_wtot
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = 0;
+#pragma unroll
+      for (int w = 0; w < FLAG_WARPS; ++w) b += s_wtot[w];
+      s_base = b;
+      unsigned long long carry = P.carry_key;
+      for (uint32_t k = 0; k < P.carry_keys_n; ++k) {
+        const unsigned long long ck = __ldg(P.carry_keys + k);
+        carry = carry > ck ? carry : ck;
+      }
+      if (tile > 0) {
+        unsigned long long used = P.tile_ein[tile], prev = P.tile_ein[tile - 1];
+        const unsigned long long agg = P.tile_agg[tile - 1];
+        used = used > carry ? used : carry;
+        prev = prev > carry ? prev : carry;
+        prev = prev > agg ? prev : agg;
+        if (used != prev) P.st->spec_failed = 1u;
+      }
+      if (tile == P.n_tiles - 1) {
+        const unsigned long long n_flags = b + total;
+        P.cl_first[0] = 0;
+        if (n_flags + 1 <= P.cap_cl) P.cl_first[n_flags + 1] = (uint32_t)P.b.n_reads;   // slots 0 .. n_flags, the last one is the open cluster
+        P.st->n_flags = (unsigned int)n_flags;
+      }
+    }
+    __syncthreads();
+    base = s_base;
+  } else {
+    base = P.tile_cnt[tile];                     // exclusive prefix, left by pl_flag_scan_kernel
+  }
   if (total == 0) return;
-  uint64_t slot = (uint64_t)P.tile_cnt[tile] + ex;
+  uint64_t slot = base + ex;
   const uint64_t r0 = (uint64_t)tile * (FLAG_THREADS * ITEMS) + (uint64_t)threadIdx.x * ITEMS;
   for (uint32_t w = fl; w; w &= w - 1) {          // about one flag per thread: walk the set bits, not the 16 reads
     const uint32_t j = (uint32_t)__ffs((int)w) - 1u;
@@ -1367,8 +1412,10 @@ __global__ void pl_interval_kernel(const __grid_constant__ ClusterParams P, uint
   }
 }
 
-__global__ void pl_init_state(PlState* st) {
-  if (threadIdx.x == 0) {
+// run state of a call, and the per-tile site totals of the compaction (one launch instead of a kernel and a memset)
+__global__ void pl_init_state(PlState* st, unsigned int* tile_sites, uint32_t n_tile_sites) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_tile_sites; k += gridDim.x * blockDim.x) tile_sites[k] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->fault = PS_FAULT_NONE; st->skipped = 0; st->dstr = 0; st->n_sites = 0; st->n_sites_final = 0; st->n_flags = 0;
     st->unsorted = 0; st->tile_ctr_flag = 0; st->tile_ctr_compact = 0; st->first_slot1 = 0xFFFFFFFFu; st->spec_failed = 0;
     st->dbg[0] = st->dbg[1] = st->dbg[2] = st->dbg[3] = 0;
@@ -1440,6 +1487,7 @@ static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const Cluster
 }
 
 constexpr uint64_t kCompactSumTiles = 4096;     // 2 M cluster slots
+constexpr uint32_t kFlagSumTiles = 8192;        // 16.7 M reads on the vector path
 
 // One attempt of the three stages on H->stream: allocations, kernels and the copy of the run state into page-locked
 // memory -- nothing here waits for the device.
@@ -1481,24 +1529,35 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
   P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
   P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
+  // site totals per compaction tile, added up by the cluster kernel: up to kCompactSumTiles tiles every compaction
+  // block sums the entries in front of it itself; beyond that (quadratic work) the decoupled look-back takes over
+  const uint64_t n_ctiles = (cap_cl + COMPACT_TILE - 1) / COMPACT_TILE;
+  unsigned int* tile_sites = nullptr;
+  if (n_ctiles <= kCompactSumTiles && !ctx->pl_compact_lookback) {
+    tile_sites = scratch<unsigned int>(ctx, 11, n_ctiles, err);
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+  }
   timer_begin(ctx, st);        // the timer pair is complete when the launch returns (a submitted call may be waited for
                                // after other timed calls of the context)
-  pl_init_state<<<1, 32, 0, st>>>(d_state);
+  pl_init_state<<<tile_sites ? (uint32_t)((n_ctiles + 255) / 256) : 1u, 256, 0, st>>>(d_state, tile_sites, tile_sites ? (uint32_t)n_ctiles : 0u);
   const bool ev = ctx->timers_on;
   if (ev) cudaEventRecord(ctx->pl_ev[0], st);
   const bool spec = vec && !ctx->pl_exact_flags;
   H->spec = spec;
-  P.tile_ein = nullptr; P.tile_agg = nullptr; P.tile_cnt = nullptr; P.flag_words = nullptr;
+  P.tile_ein = nullptr; P.tile_agg = nullptr; P.tile_cnt = nullptr; P.flag_words = nullptr; P.scan_in_expand = 0;
   if (spec) {
     P.tile_ein = scratch<unsigned long long>(ctx, 1, n_tiles, err);
     P.tile_agg = scratch<unsigned long long>(ctx, 7, n_tiles, err);
     P.tile_cnt = scratch<uint32_t>(ctx, 5, n_tiles, err);
     P.flag_words = scratch<uint32_t>(ctx, 6, (size_t)n_tiles * FLAG_THREADS, err);
     if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
+    // up to kFlagSumTiles tiles (16.7 M reads) the expand kernel takes the prefix over the tile table itself (every
+    // block sums the counts in front of it: quadratic, but a few thousand entries); beyond that the one-block scan
+    P.scan_in_expand = (n_tiles <= kFlagSumTiles && !ctx->pl_flag_scan_kernel) ? 1u : 0u;
     pl_flag_kernel<PL_FLAG_ITEMS, true><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-    pl_flag_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(P);
+    if (!P.scan_in_expand) { pl_flag_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(P); ctx->launches += 1; }
     pl_flag_expand_kernel<PL_FLAG_ITEMS><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
-    ctx->launches += 2;
+    ctx->launches += 1;
   } else if (vec) pl_flag_kernel<PL_FLAG_ITEMS, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
   else pl_flag_kernel<1, false><<<n_tiles, FLAG_THREADS, 0, st>>>(P);
   if (ev) cudaEventRecord(ctx->pl_ev[1], st);
@@ -1506,15 +1565,7 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   Q.b = b; Q.ref = ctx->ref; Q.st = d_state;
   Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
   Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
-  // site totals per compaction tile, added up by the cluster kernel: up to kCompactSumTiles tiles every compaction
-  // block sums the entries in front of it itself; beyond that (quadratic work) the decoupled look-back takes over
-  const uint64_t n_ctiles = (cap_cl + COMPACT_TILE - 1) / COMPACT_TILE;
-  Q.tile_sites = nullptr;
-  if (n_ctiles <= kCompactSumTiles && !ctx->pl_compact_lookback) {
-    Q.tile_sites = scratch<unsigned int>(ctx, 11, n_ctiles, err);
-    if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
-    PS_CUDA(ctx, cudaMemsetAsync(Q.tile_sites, 0, n_ctiles * sizeof(unsigned int), st));
-  }
+  Q.tile_sites = tile_sites;
   launch_cluster(nw, c_tiles, st, Q);
   if (ev) cudaEventRecord(ctx->pl_ev[2], st);
   CompactParams R;

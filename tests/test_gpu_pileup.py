@@ -345,3 +345,25 @@ def _reorder(batch, idx):
     qual[:n * L] = batch.qual[:n * L].reshape(n, L)[idx].reshape(-1)
     b.bases2, b.qual = bases, qual
     return b
+
+
+def test_flag_prefix_by_scan_kernel(oracle, monkeypatch):
+    """Past 8192 tiles (16.7 M reads) the tile table of the speculative flag pass is prefixed and checked by the
+    one-block scan kernel instead of inside the expansion kernel; PARASUITE_B200_FLAG_SCAN_KERNEL=1 (read by ps_create)
+    forces that path: same results, and a record reaching over the halo is still noticed."""
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context
+    monkeypatch.setenv("PARASUITE_B200_FLAG_SCAN_KERNEL", "1")
+    ref = synth.synth_reference(98, [2_000_000, 500_000], n_run=200)
+    batch = synth.synth_reads(ref, 150_000, 36, seed=21)
+    c = Context(0)
+    try:
+        c.upload_reference(ref)
+        assert_pileup_equal(c.pileup(batch), oracle.pileup(ref, batch), "scan kernel")
+        assert c.lib.ps_pileup_flag_mode(c.h) == 0
+        k, span = 2048 * 5 - 300, 7_000
+        batch.cigar[k] = (span << 4) | 3
+        assert_pileup_equal(c.pileup(batch), oracle.pileup(ref, batch), "scan kernel, record over the halo")
+        assert c.lib.ps_pileup_flag_mode(c.h) == 1
+    finally:
+        c.close()
