@@ -293,6 +293,7 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
   ctx->early_valid = false;
   ctx->profile_stream = nullptr;
   ctx->reads_seen = 0;
+  ctx->profile_batches = 0;
   ctx->profile_open = true;
   return PS_OK;
 }

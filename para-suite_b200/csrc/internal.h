@@ -105,6 +105,7 @@ struct ps_ctx {
   DevBuf fault;      // uint64 fault word + debug / deferred-count words (64 bytes)
   DevBuf deferred;   // uint32 read indices the fast profile kernel hands to the generic routine
   uint64_t reads_seen = 0;
+  uint32_t profile_batches = 0;   // fast-path batches of the open run (selects the deferred-read counter)
   cudaStream_t profile_stream = nullptr;   // stream of the last profile batch
   // streams / staging
   cudaStream_t stream = nullptr;

@@ -34,6 +34,8 @@ struct ProfileParams {
   uint32_t n_tiles;           // generic kernel: tiles from first_read on;  fast kernel: number of super-tiles
   uint32_t* deferred;         // fast kernel: reads that need the generic routine (processed by profile_deferred_kernel)
   unsigned int* deferred_count;
+  unsigned int* deferred_count_next;   // the counter of the run's next batch: cleared by this batch's deferred kernel
+                                       // (two counters take turns, so no memset sits in front of the fast kernel)
 };
 
 // shared-memory histograms of the generic path
@@ -494,6 +496,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(cons
   if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;
   __syncthreads();
   const unsigned int n = *P.deferred_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *P.deferred_count_next = 0;
   const uint32_t bpr = (P.b.uniform_len + 3) >> 2;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint64_t r = P.deferred[k];
@@ -558,7 +561,9 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   P.first_read = 0;
   P.n_tiles = 0;
   P.deferred = nullptr;
-  P.deferred_count = reinterpret_cast<unsigned int*>(P.fault + 2);
+  // both counters are zero at the start of a run (ps_profile_begin clears the words behind the fault word)
+  P.deferred_count = reinterpret_cast<unsigned int*>(P.fault + 2) + (ctx->profile_batches & 1u);
+  P.deferred_count_next = reinterpret_cast<unsigned int*>(P.fault + 2) + ((ctx->profile_batches + 1u) & 1u);
   uint64_t done = 0;
   const uint32_t L = b.uniform_len;
   const bool fast_ok = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && !ctx->layout.infer_q && ctx->layout.max_len <= 256 &&
@@ -568,8 +573,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     cudaError_t ee = ctx->deferred.reserve((size_t)b.n_reads * 4);
     if (ee != cudaSuccess) return ee;
     P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
-    ee = cudaMemsetAsync(P.deferred_count, 0, 4, stream);
-    if (ee != cudaSuccess) return ee;
+    ctx->profile_batches++;
     const uint32_t n_wt = (uint32_t)((b.n_reads + WT_READS - 1) / WT_READS);   // the fast kernel takes every read
     const uint32_t nw = (L + 15) / 16;
     cudaError_t e;

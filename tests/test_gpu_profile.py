@@ -130,6 +130,29 @@ def test_device_resident_and_multibatch(ctx, oracle):
     assert acc_t.numel() == acc.size
 
 
+def test_deferred_reads_in_every_batch_of_a_run(ctx, oracle):
+    """Reads the fast kernel hands over (special flags, contig edges) in each of four batches of one run: the two
+    deferred-read counters take turns, each batch's deferred kernel clearing the next batch's."""
+    import torch
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import DeviceBatch
+    ref = synth.synth_reference(6, [1_000_000, 400_000], n_run=1000)
+    batches = [synth.synth_reads(ref, 40_000 + 7_001 * k, 36, seed=30 + k, special_ppm=30_000) for k in range(4)]
+    ctx.upload_reference(ref)
+    ctx.profile_begin(51)
+    acc = None
+    for k, b in enumerate(batches):
+        if k % 2:
+            ctx.profile_batch(b)
+        else:
+            ctx.profile_batch_device(DeviceBatch(b, "cuda:0"), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        acc = oracle.profile_acc(ref, b, 51, threads=4, acc=acc) if acc is not None else oracle.profile_acc(ref, b, 51, threads=4)
+    got = ctx.profile_end()
+    assert np.array_equal(got["wide"], acc)
+    assert int(got["counters"][1]) + int(got["counters"][2]) > 1000      # unmapped + duplicates went through the deferred list
+
+
 def test_int32_wrap(ctx, oracle):
     """Java int wrap-around: quality sums exceed 2^31 within a few million reads."""
     from parasuite_b200 import synth
