@@ -230,23 +230,28 @@ def main():
 
     pile = {}
     side = torch.cuda.Stream(device=dev) if world > 1 else None
+    red = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step_resident():
         # the whole hot path on a batch that is already in HBM: profile kernel (+ the tiny all-reduce), read-back of
         # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
         # their counters come back to the host
         keys = None
-        work = None
         ctx.profile_begin(max_len)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
         if world > 1:
             # region sharding: the maximum (contig, end) of every region, all-gathered; the exclusive prefix-max (this
             # region's carry-in) is taken on the device by the flag kernel -- no host round trip.  The key kernel and its
             # all-gather run on a side stream underneath the profile kernel (launched first, so the host-side cost of
-            # the collectives is hidden too); the all-reduce of the count vector travels while the pileup kernels run
+            # the collectives is hidden too)
             with torch.cuda.stream(side):
                 keys = gather_keys_device(ctx.pileup_max_key_tensor(dbatch, side.cuda_stream))
-            work = dist.all_reduce(ctx.profile_acc_tensor(), async_op=True)
+            # the all-reduce gets its own stream behind the profile kernel and the counts are read back there
+            # (ps_profile_set_stream), so taking the profile back does not wait for the pileup kernels either
+            red.wait_stream(stream)
+            with torch.cuda.stream(red):
+                dist.all_reduce(ctx.profile_acc_tensor())
+            ctx.profile_set_stream(red.cuda_stream)
             stream.wait_stream(side)
         # the pileup kernels are queued right behind the profile kernel; the counts of both come back afterwards, so the
         # device does not sit idle between the two tools
@@ -254,8 +259,6 @@ def main():
         # ps_pileup_submit_device: the call returns behind its launches, so the host takes back the profile (and does its
         # own bookkeeping) while the pileup kernels run; the wait for the pileup is the only one left at the end
         with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream, defer=True) as h:
-            if work is not None:
-                work.wait()
             res = ctx.profile_end()
             pile["counters"] = h.counters
         return res

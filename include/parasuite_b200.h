@@ -223,6 +223,10 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* host_batch);
 int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream);
 /* device address of the int64 accumulator vector (for an NCCL all-reduce by the caller) */
 int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64);
+/* The accumulator vector of the open run is next touched on `stream` (e.g. an all-reduce queued there, ordered behind
+ * the batch kernels by the caller): ps_profile_end reads it back on that stream and waits for that stream only -- not
+ * for other work queued behind the batch kernels on their own stream (a submitted pileup call, say). */
+int ps_profile_set_stream(ps_ctx* ctx, void* stream);
 /* synchronise, wrap to Java int semantics, fill the caller's arrays */
 int ps_profile_end(ps_ctx* ctx, ps_profile_result* out);
 /* whole tool loop from files (BAM must be coordinate sorted) */

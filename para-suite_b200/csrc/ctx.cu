@@ -360,6 +360,14 @@ int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64) {
   return PS_OK;
 }
 
+int ps_profile_set_stream(ps_ctx* ctx, void* stream) {
+  if (!ctx) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  ctx->profile_stream = stream ? (cudaStream_t)stream : ctx->stream;
+  ctx->early_valid = false;
+  return PS_OK;
+}
+
 int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (!ctx || !out) return PS_ERR_INVALID_ARG;
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");

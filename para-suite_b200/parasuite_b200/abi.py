@@ -146,6 +146,7 @@ EXPORTS = {
     "ps_profile_batch": (C.c_int, [VP, C.POINTER(ps_read_batch)]),
     "ps_profile_batch_device": (C.c_int, [VP, C.POINTER(ps_read_batch), VP]),
     "ps_profile_acc_device": (C.c_int, [VP, C.POINTER(VP), C.POINTER(C.c_size_t)]),
+    "ps_profile_set_stream": (C.c_int, [VP, VP]),
     "ps_profile_end": (C.c_int, [VP, C.POINTER(ps_profile_result)]),
     "ps_profile_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_profile_opts), C.POINTER(ps_profile_result)]),
     "ps_pileup_batch": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_pileup_opts), C.POINTER(VP)]),

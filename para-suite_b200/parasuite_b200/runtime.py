@@ -177,6 +177,11 @@ class Context:
 
         return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
 
+    def profile_set_stream(self, stream: int):
+        """The accumulator vector is next touched on `stream` (an all-reduce queued there): profile_end reads it back
+        there and waits for that stream only."""
+        _check(self.lib, self.h, self.lib.ps_profile_set_stream(self.h, stream or None))
+
     def _profile_result_plan(self):
         """(name, dtype, shape, count, byte offset) of every result array inside one allocation, cached per run shape."""
         key = (self._max_len, bool(self._infer_q))
