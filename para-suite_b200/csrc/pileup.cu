@@ -300,8 +300,25 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
           cigs[j] = in ? __ldg(P.b.cigar + rg + j) : 0u;
         }
       }
+      // four reads at a time: when none of them needs the contig table (all kept ones lie in the cached contig -- every
+      // group but a thread's first, bar contig changes) keys and starts are straight-line code
+      bool need = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) key[g + j] = pl_key1(P, metas[j], cigs[j], starts[j], cc, start[g + j]);
+      for (int j = 0; j < 4; ++j)
+        need |= ((PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0) & !(starts[j] - cc.lo < cc.hi - cc.lo);
+      if (!need) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = (PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0;
+          const uint32_t R = op_consumes_ref(cigs[j] & 15u) ? cigs[j] >> 4 : 0u;
+          const int32_t st = (int32_t)(starts[j] - cc.lo) + 1;
+          start[g + j] = ok ? st : 0;
+          key[g + j] = ok ? (((unsigned long long)(cc.idx + 1) << 32) | (uint32_t)(st + (int32_t)R - 1)) : 0ull;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) key[g + j] = pl_key1(P, metas[j], cigs[j], starts[j], cc, start[g + j]);
+      }
     }
   } else {
     const bool in_range = r0 < n;
