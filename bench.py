@@ -237,8 +237,9 @@ def main():
         # the < 10 KB of counts, then the three pileup kernels; cluster / site records stay in HBM behind the handle,
         # their counters come back to the host
         keys = None
-        ctx.profile_begin(max_len)
+        ctx.profile_begin(max_len, emit_t2c_masks=True)
         ctx.profile_batch_device(dbatch, stream.cuda_stream)
+        masks = ctx.profile_masks()     # one T>C mask word per read, left in HBM by the profile kernel for the pileup
         if world > 1:
             # region sharding: the maximum (contig, end) of every region, all-gathered; the exclusive prefix-max (this
             # region's carry-in) is taken on the device by the flag kernel -- no host round trip.  The key kernel and its
@@ -258,7 +259,8 @@ def main():
         carry_keys = (keys.data_ptr(), rank) if keys is not None else None
         # ps_pileup_submit_device: the call returns behind its launches, so the host takes back the profile (and does its
         # own bookkeeping) while the pileup kernels run; the wait for the pileup is the only one left at the end
-        with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream, defer=True) as h:
+        with ctx.pileup_run(dbatch, first_running_id=1, carry_keys=carry_keys, stream=stream.cuda_stream, defer=True,
+                            masks=masks) as h:
             res = ctx.profile_end()
             pile["counters"] = h.counters
         return res

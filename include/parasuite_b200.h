@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 1
+#define PS_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 #define PS_OK 0
@@ -48,6 +48,9 @@ extern "C" {
 #define PS_THROW_QUAL_RANGE 6      /* readQualities[i] out of range (:388, :405) */
 #define PS_THROW_MASK51 7          /* mutationMapInRead[i], i >= 51 (PileupClusters.java:654) */
 #define PS_THROW_BLOCK_RANGE 8     /* alignment block beyond the read bases (PileupClusters.java:594) */
+/* not a reference exception: ps_fault.code of a record this SoA cannot hold (more than 255 CIGAR operations; htsjdk
+ * takes any number, ErrorProfiling.java:206-207).  Reported with PS_ERR_UNSUPPORTED, never as a "would throw". */
+#define PS_FAULT_CIGAR_OPS 9
 
 /* ---- packed reference ---------------------------------------------------------------------
  * All contigs concatenated into one coordinate space ("global offset", 0-based, < 2^32).
@@ -85,7 +88,8 @@ typedef struct ps_reference {
 #define PS_RF_QUAL_MISSING 0x10u /* first quality byte 0xFF -> getBaseQualities() is empty */
 #define PS_RF_HAS_INVALID 0x20u  /* read holds non-ACGT bases, listed in `exc` */
 #define PS_RF_REF_RANGE 0x40u    /* FASTA fetch [start,end] would raise SAMException */
-#define PS_RF_CIGAR_OVERFLOW 0x80u /* record had > 255 cigar ops; cigar stream holds none (unsupported) */
+#define PS_RF_CIGAR_OVERFLOW 0x80u /* record had > 255 cigar ops; cigar stream holds none: every tool answers
+                                      PS_ERR_UNSUPPORTED (fault code PS_FAULT_CIGAR_OPS) for a batch that holds one */
 
 typedef struct ps_read_batch {
   uint64_t n_reads;
@@ -111,6 +115,9 @@ typedef struct ps_read_batch {
 typedef struct ps_profile_opts {
   uint32_t max_read_length;  /* ErrorProfiling ctor arg (ErrorProfiling.java:58-64) */
   uint32_t infer_qualities;  /* `-q` (ErrorProfiling.java:402-407): also fill the quality histogram */
+  uint32_t emit_t2c_masks;   /* device-resident batches of the PAR-CLIP shape: leave one T>C mask word per read in HBM
+                                (ps_profile_masks_device) for a pileup call on the SAME batch (ps_pileup_opts) */
+  uint32_t reserved;
 } ps_profile_opts;
 
 /* counters[] order (ErrorProfiling.java:134-141, :54) */
@@ -221,6 +228,10 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts);
 int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* host_batch);
 /* device-resident batch (all pointers are device pointers) on `stream` (a cudaStream_t, may be NULL) */
 int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* stream);
+/* With ps_profile_opts.emit_t2c_masks: device address of the mask words of the LAST ps_profile_batch_device call of the
+ * open run (*n_words = its n_reads), written on that call's stream; *dev_masks = NULL when that batch did not have the
+ * PAR-CLIP shape (uniform length <= 62, one cigar op).  Valid until the next profile batch on this context. */
+int ps_profile_masks_device(ps_ctx* ctx, const uint64_t** dev_masks, uint64_t* n_words);
 /* device address of the int64 accumulator vector (for an NCCL all-reduce by the caller) */
 int ps_profile_acc_device(ps_ctx* ctx, void** dev_ptr, size_t* n_int64);
 /* The accumulator vector of the open run is next touched on `stream` (e.g. an all-reduce queued there, ordered behind
@@ -244,6 +255,12 @@ typedef struct ps_pileup_opts {
    * Ignored when carry_keys_n == 0; combined (max) with the host triple above when both are given. */
   uint32_t carry_keys_n;
   const uint64_t* carry_keys_device;
+  /* Optional: the T>C mask words ps_profile_batch_device left for THIS batch (ps_profile_masks_device), one per read:
+   * bit 63 = word valid, bit 62 = minus strand, bits 0..61 = T>C by index of the strand-oriented read
+   * (mutationMapInRead, PileupClusters.java:651-661).  The pileup then reads 12 bytes per record instead of decoding
+   * bases and reference again; records without a valid word are decoded as usual.  The caller vouches that the words
+   * belong to the same records and reference.  NULL: decode every record. */
+  const uint64_t* t2c_masks_device;
 } ps_pileup_opts;
 
 int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* host_batch, const ps_pileup_opts* opts, ps_pileup** out);

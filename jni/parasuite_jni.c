@@ -72,6 +72,7 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
   const char* path = (*env)->GetStringUTFChars(env, bam, NULL);
   if (!path) return;
   ps_profile_opts opts;
+  memset(&opts, 0, sizeof opts);
   opts.max_read_length = (uint32_t)maxReadLength;
   opts.infer_qualities = inferQualities ? 1u : 0u;
   ps_profile_result r;

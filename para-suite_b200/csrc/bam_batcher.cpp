@@ -251,6 +251,7 @@ static int bam_scan_blocks(ps_bam* B) {
     if (xend > n) return bam_fail(B, PS_ERR_FORMAT, "truncated BGZF block");
     while (x + 4 <= xend) {
       const uint32_t slen = rd16(p + x + 2);
+      if (x + 4 + (size_t)slen > xend) return bam_fail(B, PS_ERR_FORMAT, "BGZF extra subfield runs past the extra field");
       if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2) bsize = (uint32_t)rd16(p + x + 4) + 1;
       x += 4 + slen;
     }
@@ -450,6 +451,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   std::vector<uint64_t> tb(n_tiles + 1, 0), tq(n_tiles + 1, 0), tc(n_tiles + 1, 0);
   std::vector<uint32_t> te(n_tiles + 1, 0);
   std::atomic<int> bad{0};
+  std::atomic<uint64_t> many_ops{~0ull};      // first record (index in this batch) with more than 255 CIGAR operations
   std::atomic<uint32_t> lens_min{0xFFFFFFFFu}, lens_max{0}, nc_min{0xFFFFFFFFu}, nc_max{0};
   auto amin = [](std::atomic<uint32_t>& a, uint32_t v) { uint32_t c = a.load(); while (v < c && !a.compare_exchange_weak(c, v)) {} };
   auto amax = [](std::atomic<uint32_t>& a, uint32_t v) { uint32_t c = a.load(); while (v > c && !a.compare_exchange_weak(c, v)) {} };
@@ -465,6 +467,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
         const uint32_t l_name = p[8], n_cig = rd16(p + 12), l_seq = rd32(p + 16);
         if (32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq > bs || l_seq > 0xFFFFu) { bad = 1; return; }
         const uint32_t nc = n_cig > 255 ? 0 : n_cig;
+        if (n_cig > 255) { uint64_t c = many_ops.load(); while (r < c && !many_ops.compare_exchange_weak(c, r)) {} }
         sb += (l_seq + 3) / 4; sq += l_seq; sc += nc;
         const uint8_t* sq4 = p + 32 + l_name + 4ull * n_cig;
         for (uint32_t k = 0; k < l_seq; ++k) {
@@ -478,6 +481,14 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
     amin(lens_min, lmin); amax(lens_max, lmax); amin(nc_min, cmin); amax(nc_max, cmax);
   });
   if (bad) return bam_fail(B, PS_ERR_FORMAT, "malformed BAM record (lengths exceed block_size, or read longer than 65535)");
+  if (many_ops.load() != ~0ull) {
+    // htsjdk takes any number of CIGAR elements (ErrorProfiling.java:206-207); the SoA holds 255 per record.  Fail
+    // here, by name, instead of handing the kernels a record they can only refuse (PS_FAULT_CIGAR_OPS).
+    char msg[160];
+    snprintf(msg, sizeof msg, "record %llu has more than 255 CIGAR operations (not supported)",
+             (unsigned long long)(B->ordinal + many_ops.load()));
+    return bam_fail(B, PS_ERR_UNSUPPORTED, msg);
+  }
   for (uint64_t t = 0; t < n_tiles; ++t) { tb[t + 1] += tb[t]; tq[t + 1] += tq[t]; tc[t + 1] += tc[t]; te[t + 1] += te[t]; }
   const uint64_t bases_bytes = tb[n_tiles], qual_bytes = tq[n_tiles], cigar_count = tc[n_tiles], exc_count = te[n_tiles];
 

@@ -183,7 +183,7 @@ void ps_destroy(ps_ctx* ctx) {
   for (auto& e : ctx->staged_core) if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
-  ctx->acc.release(); ctx->fault.release(); ctx->deferred.release();
+  ctx->acc.release(); ctx->fault.release(); ctx->deferred.release(); ctx->t2c_mask.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
     s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();
@@ -291,6 +291,8 @@ int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts) {
     ctx->h_acc_bytes = acc_bytes + 8;
   }
   ctx->early_valid = false;
+  ctx->emit_masks = opts->emit_t2c_masks != 0;
+  ctx->t2c_mask_n = 0;
   ctx->profile_stream = nullptr;
   ctx->reads_seen = 0;
   ctx->profile_batches = 0;
@@ -307,9 +309,17 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));     // the clearing may have been queued on another stream
   ctx->profile_stream = s;
+  unsigned long long* masks = nullptr;
+  ctx->t2c_mask_n = 0;
+  if (ctx->emit_masks && b->n_reads) {
+    PS_CUDA(ctx, ctx->t2c_mask.reserve((size_t)b->n_reads * 8));
+    masks = static_cast<unsigned long long*>(ctx->t2c_mask.p);
+  }
+  bool written = false;
   timer_begin(ctx, s);
-  PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s));
+  PS_CUDA(ctx, launch_profile(ctx, view_of(b), ctx->reads_seen, s, masks, &written));
   timer_end(ctx, s);
+  if (written) ctx->t2c_mask_n = b->n_reads;
   ctx->reads_seen += b->n_reads;
   early_readback(ctx, s);
   return PS_OK;
@@ -348,6 +358,14 @@ int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* hb, ps_read_batch* dev_vie
   dev_view->meta = v.meta; dev_view->ref_start = v.ref_start; dev_view->bases2 = v.bases2; dev_view->qual = v.qual;
   dev_view->cigar = v.cigar; dev_view->tile_base_off = v.tile_base_off; dev_view->tile_qual_off = v.tile_qual_off;
   dev_view->tile_cigar_off = v.tile_cigar_off; dev_view->tile_exc_off = v.tile_exc_off; dev_view->exc = v.exc;
+  return PS_OK;
+}
+
+int ps_profile_masks_device(ps_ctx* ctx, const uint64_t** dev_masks, uint64_t* n_words) {
+  if (!ctx || !dev_masks || !n_words) return PS_ERR_INVALID_ARG;
+  if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
+  *dev_masks = ctx->t2c_mask_n ? static_cast<const uint64_t*>(ctx->t2c_mask.p) : nullptr;
+  *n_words = ctx->t2c_mask_n;
   return PS_OK;
 }
 
@@ -396,6 +414,10 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
     out->fault.code = (int32_t)(fw & 0xFF);
     out->fault.read_ordinal = fw >> 8;
     char msg[160];
+    if ((fw & 0xFF) == PS_FAULT_CIGAR_OPS) {
+      snprintf(msg, sizeof msg, "record %llu has more than 255 CIGAR operations", (unsigned long long)(fw >> 8));
+      return set_error(ctx, PS_ERR_UNSUPPORTED, msg);
+    }
     snprintf(msg, sizeof msg, "record %llu: the JVM would die here (PS_THROW code %d)", (unsigned long long)(fw >> 8),
              (int)(fw & 0xFF));
     return set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, msg);

@@ -165,11 +165,11 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
     ps_flush_row& row = rows[c];
     memset(&row, 0, sizeof row);
     row.best_pos = -1;
-    if (cl.num_reads < f->min_cov) continue;                           // :180
-    row.emitted = 1;
     if (cl.site_end > cl.site_begin && !sites) return PS_ERR_INVALID_ARG;
     // mutationMap as the record loop left it: cleared at the cluster's first read (:353), keys put in the order
-    // their first T>C was seen (ps_site.order_key)
+    // their first T>C was seen (ps_site.order_key).  The loop fills the ONE map of the run for every cluster, also for
+    // those below minReadCoverage: their puts can grow the table, and clear() keeps the grown capacity, which decides
+    // the iteration order -- and with it the anchor tie-break -- of every later cluster.
     order.clear();
     for (uint64_t s = cl.site_begin; s < cl.site_end; ++s) order.push_back(sites + s);
     std::sort(order.begin(), order.end(), [](const ps_site* a, const ps_site* b) { return a->order_key < b->order_key; });
@@ -177,6 +177,12 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
     mm.clear();
     std::unordered_map<int32_t, uint32_t> cov;                         // baseCoveredMap is only ever read at these keys
     for (const ps_site* s : order) { mm.put(s->pos, (int32_t)s->t2c); cov[s->pos] = s->cov; }
+    if (mm.unsupported) {
+      f->err = "a HashMap bucket would be treeified (9 T>C positions of one cluster in one bucket): iteration order not modelled";
+      return PS_ERR_UNSUPPORTED;
+    }
+    if (cl.num_reads < f->min_cov) continue;                           // :180
+    row.emitted = 1;
     row.num_t2c_sites = (uint32_t)mm.size;                             // :181 (before the SNP filter)
     // SNP filter :187-201
     JMap tmp;

@@ -107,6 +107,9 @@ struct ps_ctx {
   uint64_t reads_seen = 0;
   uint32_t profile_batches = 0;   // fast-path batches of the open run (selects the deferred-read counter)
   cudaStream_t profile_stream = nullptr;   // stream of the last profile batch
+  bool emit_masks = false;        // ps_profile_opts.emit_t2c_masks of the open run
+  DevBuf t2c_mask;                // uint64 per read of the last device-resident fast-path batch
+  uint64_t t2c_mask_n = 0;        // != 0: the words of that many reads are valid (or in flight on profile_stream)
   // streams / staging
   cudaStream_t stream = nullptr;
   StagedBatch staged[2];
@@ -147,7 +150,9 @@ struct ps_ctx {
 };
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------------
-cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream);
+// t2c_mask (optional): n_reads words; *mask_written tells whether the batch took the fast kernel, which fills them
+cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream,
+                           unsigned long long* t2c_mask = nullptr, bool* mask_written = nullptr);
 
 int set_error(ps_ctx* ctx, int status, const std::string& msg);
 int cuda_fail(ps_ctx* ctx, cudaError_t e, const char* what);

@@ -13,7 +13,7 @@
 
 struct alignas(16) LbDesc {
   unsigned long long val;
-  unsigned int status;   // (epoch << 2) | kind;  kind 0 = nothing yet
+  unsigned int status;   // (epoch << 2) | kind;  kind 0 = nothing yet; the epoch is 30 bits wide (next_epoch, pileup.cu)
   unsigned int pad;
 };
 
@@ -26,6 +26,7 @@ __device__ __forceinline__ void lb_publish(LbDesc* d, unsigned long long v, unsi
 __device__ __forceinline__ void lb_load(const LbDesc* d, unsigned long long& v, unsigned int& st) {
   unsigned int a, b, c, e;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(e) : "l"(d) : "memory");
+  (void)e;
   v = ((unsigned long long)b << 32) | a;
   st = c;
 }

@@ -167,7 +167,8 @@ __device__ __forceinline__ unsigned long long pl_key(const FlagParams& P, uint64
     if (COUNT) atomicAdd(&P.st->skipped, 1ull);
     return 0;
   }
-  if (flags & PS_RF_POS_ZERO) return 0;           // the JVM dies on this record: pl_cluster_kernel raises the fault
+  if (flags & (PS_RF_POS_ZERO | PS_RF_CIGAR_OVERFLOW)) return 0;   // the JVM dies on the first, the second cannot be held:
+                                                                   // pl_cluster_kernel raises the fault
   if (!contig_lookup(P.ref, g0, cc)) return 0;    // likewise
   start = (int32_t)((uint64_t)g0 - cc.lo) + 1;
   const int32_t end = start + (int32_t)R - 1;
@@ -181,7 +182,7 @@ __device__ __forceinline__ unsigned long long pl_key1(const FlagParams& P, uint3
   // straight-line on purpose (16 reads per thread are unrolled around this: early returns cost a convergence
   // barrier each); only the contig table walk of a cache miss is a branch
   const uint32_t flags = PS_META_FLAGS(meta);
-  bool ok = (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0;
+  bool ok = (flags & (PS_RF_UNMAPPED | PS_RF_POS_ZERO | PS_RF_CIGAR_OVERFLOW)) == 0;
   if (ok) ok = contig_lookup(P.ref, g0, cc);
   const uint32_t R = op_consumes_ref(cg & 15u) ? cg >> 4 : 0u;
   const int32_t s = (int32_t)(g0 - (uint32_t)cc.lo) + 1;      // offsets inside a contig fit 32 bits (the whole reference does)
@@ -305,11 +306,11 @@ __global__ void __launch_bounds__(FLAG_THREADS, FLAG_BLOCKS_PER_SM) pl_flag_kern
       bool need = false;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        need |= ((PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0) & !(starts[j] - cc.lo < cc.hi - cc.lo);
+        need |= ((PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO | PS_RF_CIGAR_OVERFLOW)) == 0) & !(starts[j] - cc.lo < cc.hi - cc.lo);
       if (!need) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool ok = (PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO)) == 0;
+          const bool ok = (PS_META_FLAGS(metas[j]) & (PS_RF_UNMAPPED | PS_RF_POS_ZERO | PS_RF_CIGAR_OVERFLOW)) == 0;
           const uint32_t R = op_consumes_ref(cigs[j] & 15u) ? cigs[j] >> 4 : 0u;
           const int32_t st = (int32_t)(starts[j] - cc.lo) + 1;
           start[g + j] = ok ? st : 0;
@@ -556,6 +557,8 @@ struct ClusterParams {
   ps_site* sites;           // pl_cluster_kernel: sites grouped by block in completion order; pl_compact_kernel orders them
   uint64_t cap_cl, cap_sites;
   unsigned int* tile_sites;   // [slots / COMPACT_TILE] sites per tile of pl_compact_kernel (zeroed by the host), or nullptr
+  const unsigned long long* t2c_mask;   // optional: one T>C mask word per read, left by profile_fast_kernel for THIS batch
+                                        // (bit 63 valid, bit 62 minus strand, bits 0..61 mask by strand-oriented index)
 };
 #ifndef COMPACT_ITEMS_
 #define COMPACT_ITEMS_ 2
@@ -571,6 +574,7 @@ __device__ __noinline__ void pl_decode_generic(const ClusterParams& P, uint64_t 
   const uint32_t* cig = P.b.cigar + off_cigar;
   x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
   if (flags & PS_RF_UNMAPPED) return;                                        // :146
+  if (flags & PS_RF_CIGAR_OVERFLOW) { raise_fault(&P.st->fault, r, PS_FAULT_CIGAR_OPS); return; }   // not representable
   uint32_t R = 0, alen = 0;
   bool hasI = false, hasD = false, hasN = false;
   for (uint32_t e = 0; e < ncig; ++e) {
@@ -672,67 +676,98 @@ __device__ __forceinline__ unsigned long long t2c_mask_fast(const DeviceRef& ref
   return m;
 }
 
-// the words of one record that do not depend on anything else: loaded one read ahead of their use (PAR-CLIP shape)
-template <int NW>
+// the words of one record that do not depend on anything else: loaded one read ahead of their use (PAR-CLIP shape).
+// MK: the profile kernel left a T>C mask word per read (ClusterParams::t2c_mask): the record is its offset and that word
+template <int NW, bool MK>
 struct PlRaw {
   uint32_t meta, g0, cg;
   uint32_t bw[NW > 0 ? NW + 1 : 1];
 };
 template <int NW>
-__device__ __forceinline__ PlRaw<NW> pl_load_raw(const ClusterParams& P, uint64_t r, bool in) {
-  PlRaw<NW> w;
-  w.meta = in ? __ldg(P.b.meta + r) : 0u;
-  w.g0 = 0; w.cg = 0;
-  if constexpr (NW > 0) {
+struct PlRaw<NW, true> {
+  uint32_t g0;
+  unsigned long long mk;
+};
+template <int NW, bool MK>
+__device__ __forceinline__ PlRaw<NW, MK> pl_load_raw(const ClusterParams& P, uint64_t r, bool in) {
+  PlRaw<NW, MK> w;
+  if constexpr (MK) {
+    w.g0 = in ? __ldg(P.b.ref_start + r) : 0u;
+    w.mk = in ? __ldg(P.t2c_mask + r) : 0ull;
+  } else {
+    w.meta = in ? __ldg(P.b.meta + r) : 0u;
+    w.g0 = 0; w.cg = 0;
+    if constexpr (NW > 0) {
 #pragma unroll
-    for (int k = 0; k <= NW; ++k) w.bw[k] = 0;
-    if (in) {
-      w.g0 = __ldg(P.b.ref_start + r);
-      w.cg = __ldg(P.b.cigar + r);
-      const uint64_t boff = r * (uint64_t)((P.b.uniform_len + 3) >> 2);
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.b.bases2 + (boff & ~3ull));
+      for (int k = 0; k <= NW; ++k) w.bw[k] = 0;
+      if (in) {
+        w.g0 = __ldg(P.b.ref_start + r);
+        w.cg = __ldg(P.b.cigar + r);
+        const uint64_t boff = r * (uint64_t)((P.b.uniform_len + 3) >> 2);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.b.bases2 + (boff & ~3ull));
 #pragma unroll
-      for (int k = 0; k <= NW; ++k) w.bw[k] = __ldg(src + k);
+        for (int k = 0; k <= NW; ++k) w.bw[k] = __ldg(src + k);
+      }
     }
   }
   return w;
 }
 
 // one lane decodes read r (r < n); NW > 0: the batch has the PAR-CLIP shape and most reads take the bit-parallel path
-template <int NW, typename CC>
-__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, const PlRaw<NW>& raw,
+template <int NW, bool MK, typename CC>
+__device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, const PlRaw<NW, MK>& raw,
                                           CC& cc, PlRead& x) {
   x.kept = false; x.mask = 0; x.start = 0; x.end = 0; x.lo = 1; x.hi = 0; x.rev = false; x.contig = 0;
-  const uint32_t meta = raw.meta;
-  if constexpr (NW > 0) {
+  if constexpr (MK) {
+    static_assert(NW > 0, "mask words exist for the PAR-CLIP shape only");
     if (!in) return;
     const uint32_t L = P.b.uniform_len, bpr = (L + 3) >> 2;
-    const uint32_t flags = PS_META_FLAGS(meta), g0 = raw.g0, cg = raw.cg;
-    // N calls are stored as code 0 (A): never read C (forward T>C) nor read G (reverse), so such reads need no
-    // look at the exception list; duplicates are not filtered by this tool and qualities are never read
-    constexpr uint32_t kHarmless = PS_RF_REVERSE | PS_RF_HAS_INVALID | PS_RF_DUPLICATE | PS_RF_QUAL_MISSING;
-    bool fast = (flags & ~kHarmless) == 0 && op_is_match(cg & 15u) && (cg >> 4) == L && PS_META_LEN(meta) == L;
-    fast = fast && contig_lookup(P.ref, g0, cc) && (uint64_t)g0 + L <= cc.hi;
-    if (fast) {
-      const bool rev = (flags & PS_RF_REVERSE) != 0;
-      const uint64_t boff = r * (uint64_t)bpr;
-      unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, raw.bw, (uint32_t)(boff & 3u) * 8u);
-      const int32_t start = (int32_t)((uint64_t)g0 - cc.lo) + 1, end = start + (int32_t)L - 1;
+    const unsigned long long mk = raw.mk;
+    // a valid word: the profile kernel saw flags in {REVERSE, HAS_INVALID}, one M op of length L and the whole read
+    // inside one contig -- everything the bit-parallel path below asks for
+    if ((mk >> 63) && contig_lookup(P.ref, raw.g0, cc)) {
+      const unsigned long long m = mk & ((1ull << 62) - 1ull);
+      const int32_t start = (int32_t)((uint64_t)raw.g0 - cc.lo) + 1, end = start + (int32_t)L - 1;
       if (L > 51u && (m >> 51)) { raise_fault(&P.st->fault, r, PS_THROW_MASK51); return; }
-      x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = rev; x.contig = cc.idx;
+      x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = (mk >> 62) & 1ull;
+      x.contig = cc.idx;
       return;
     }
-    PlRead t;               // the literal routine takes its result by address: keep x itself in registers
-    pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, t);
+    PlRead t;
+    pl_decode_generic(P, r, __ldg(P.b.meta + r), r * (uint64_t)bpr, r, t);
     x = t;
   } else {
-    const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);    // warp-collective
-    if (in) pl_decode_generic(P, r, meta, off.base, off.cigar, x);
+    const uint32_t meta = raw.meta;
+    if constexpr (NW > 0) {
+      if (!in) return;
+      const uint32_t L = P.b.uniform_len, bpr = (L + 3) >> 2;
+      const uint32_t flags = PS_META_FLAGS(meta), g0 = raw.g0, cg = raw.cg;
+      // N calls are stored as code 0 (A): never read C (forward T>C) nor read G (reverse), so such reads need no
+      // look at the exception list; duplicates are not filtered by this tool and qualities are never read
+      constexpr uint32_t kHarmless = PS_RF_REVERSE | PS_RF_HAS_INVALID | PS_RF_DUPLICATE | PS_RF_QUAL_MISSING;
+      bool fast = (flags & ~kHarmless) == 0 && op_is_match(cg & 15u) && (cg >> 4) == L && PS_META_LEN(meta) == L;
+      fast = fast && contig_lookup(P.ref, g0, cc) && (uint64_t)g0 + L <= cc.hi;
+      if (fast) {
+        const bool rev = (flags & PS_RF_REVERSE) != 0;
+        const uint64_t boff = r * (uint64_t)bpr;
+        unsigned long long m = t2c_mask_fast<NW>(P.ref, g0, L, rev, raw.bw, (uint32_t)(boff & 3u) * 8u);
+        const int32_t start = (int32_t)((uint64_t)g0 - cc.lo) + 1, end = start + (int32_t)L - 1;
+        if (L > 51u && (m >> 51)) { raise_fault(&P.st->fault, r, PS_THROW_MASK51); return; }
+        x.kept = true; x.mask = m; x.start = start; x.end = end; x.lo = start; x.hi = end; x.rev = rev; x.contig = cc.idx;
+        return;
+      }
+      PlRead t;               // the literal routine takes its result by address: keep x itself in registers
+      pl_decode_generic(P, r, meta, r * (uint64_t)bpr, r, t);
+      x = t;
+    } else {
+      const ReadOffsets off = warp_read_offsets(P.b, q, r, in, meta);    // warp-collective
+      if (in) pl_decode_generic(P, r, meta, off.base, off.cigar, x);
+    }
   }
 }
-template <int NW>
+template <int NW, bool MK = false>
 __device__ __forceinline__ void pl_decode(const ClusterParams& P, uint64_t q, uint64_t r, bool in, ContigCache& cc, PlRead& x) {
-  pl_decode<NW>(P, q, r, in, pl_load_raw<NW>(P, r, in), cc, x);
+  pl_decode<NW, MK>(P, q, r, in, pl_load_raw<NW, MK>(P, r, in), cc, x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -755,7 +790,7 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_syn
 
 // One cluster = reads [f, fe) (slot `slot`), whole warp.  Fills *rec (shared memory) when `fill`, writes up to `cap`
 // sites to `dest` in position order and returns the number of sites the cluster has.
-template <int NW>
+template <int NW, bool MK>
 __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slot, uint32_t f, uint32_t fe, WarpTables& T,
                                             WarpRing& G, ps_cluster* rec, bool fill, ps_site* dest, uint32_t cap,
                                             unsigned long long& dstr, unsigned long long* site_base = nullptr) {
@@ -769,7 +804,7 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
   bool have_first = false;
   for (uint32_t q = f; q < fe; q += 32) {
     const uint32_t r = q + lane;
-    pl_decode<NW>(P, q, r, r < fe, cc, x);
+    pl_decode<NW, MK>(P, q, r, r < fe, cc, x);
     const uint32_t kb = __ballot_sync(0xFFFFFFFFu, x.kept);
     if (kb == 0) continue;
     if (!have_first) {
@@ -909,7 +944,7 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
     };
     for (uint32_t q = f; q < fe && ok; q += 32) {
       const uint32_t r = q + lane;
-      pl_decode<NW>(P, q, r, r < fe, cc, x);
+      pl_decode<NW, MK>(P, q, r, r < fe, cc, x);
       uint32_t pending = __ballot_sync(0xFFFFFFFFu, x.kept);
       while (pending) {
         const bool mine = (pending >> lane) & 1u;
@@ -956,7 +991,7 @@ __device__ __noinline__ uint32_t pl_cluster(const ClusterParams& P, uint32_t slo
     __syncwarp();
     for (uint32_t q = f; q < fe; q += 32) {
       const uint32_t r = q + lane;
-      pl_decode<NW>(P, q, r, r < fe, cc, x);
+      pl_decode<NW, MK>(P, q, r, r < fe, cc, x);
       if (!x.kept || (int64_t)x.hi < w0 || (int64_t)x.lo > w1) continue;
       unsigned long long m = x.mask;
       while (m) {
@@ -1060,7 +1095,7 @@ __device__ __forceinline__ bool t2c_positions(unsigned long long mask, bool rev,
 //                           slots taken with a single atomic, pl_compact_kernel orders the runs afterwards
 // Clusters that do not fit (more than CB_CHUNK reads, T>C positions more than 64 apart, more than CB_SITES of them)
 // are left to the warp-per-cluster routine above at the end of the block.
-template <int NW>
+template <int NW, bool MK>
 __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_wtot[CB_WARPS];
@@ -1113,7 +1148,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
     const uint32_t re = S.first[cur + ncomp], nrd = re - rs;
     const bool mine = kk < ncomp, owner = mine && part == 0;
     // the first round's record words are requested before the pre-pass, whose own loads they overlap
-    PlRaw<NW> nxt = pl_load_raw<NW>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
+    PlRaw<NW, MK> nxt = pl_load_raw<NW, MK>(P, rs + warp * 32 + lane, rs + warp * 32 + lane < re);
     // ---- pre-pass, per cluster: cluster of every read, origin of the key set -----------------------------------------
     uint32_t ra = 0, rb = 0, op_contig = 0;
     int32_t base = 0;
@@ -1142,12 +1177,12 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
     // ---- A, thread per read: decode; T>C positions into the cluster's key set -------------------------------------
     for (uint32_t q = rs + warp * 32; q < re; q += CB_THREADS) {
       const uint32_t r = q + lane;
-      const PlRaw<NW> raw = nxt;
+      const PlRaw<NW, MK> raw = nxt;
       // one round in flight: a second one costs registers, and the kernel gains more from 8 resident blocks per SM
       // (measured: 2 rounds at 8 / 7 / 6 blocks 0.52 / 0.31 / 0.32 ms against 0.28 ms)
-      if (q + CB_THREADS < re) nxt = pl_load_raw<NW>(P, r + CB_THREADS, r + CB_THREADS < re);   // in flight during this decode
+      if (q + CB_THREADS < re) nxt = pl_load_raw<NW, MK>(P, r + CB_THREADS, r + CB_THREADS < re);   // in flight during this decode
       PlRead x;
-      pl_decode<NW>(P, q, r, r < re, raw, cc, x);
+      pl_decode<NW, MK>(P, q, r, r < re, raw, cc, x);
       if (r < re) {
         const uint32_t i = r - rs;
         S.mask[i] = x.mask | ((unsigned long long)x.rev << 62) | ((unsigned long long)x.kept << 63);
@@ -1287,7 +1322,7 @@ __global__ void __launch_bounds__(CB_THREADS, CB_BLOCKS_PER_SM) pl_cluster_kerne
       const uint32_t k = S.fb[e], slot = c0 + k;
       const uint32_t f = S.first[k], fe = S.first[k + 1];
       unsigned long long sb = 0;
-      const uint32_t cnt = pl_cluster<NW>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr, &sb);
+      const uint32_t cnt = pl_cluster<NW, MK>(P, slot, f, fe, *T, *G, wrec, true, nullptr, 0, dstr, &sb);
       if (lane == 0 && cnt && P.tile_sites) atomicAdd(P.tile_sites + slot / COMPACT_TILE, cnt);
       __syncwarp();
       if (lane == 0) { wrec->site_begin = sb; wrec->site_end = sb + cnt; }
@@ -1481,25 +1516,47 @@ static T* scratch(ps_ctx* ctx, int slot, size_t count, cudaError_t& err, bool ze
 
 static bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Look-back epoch of the next kernel: 30 bits ride in a descriptor's status word (lookback.cuh).  When the counter
+// wraps, descriptors written 2^30 epochs ago would read as current ones: clear the three descriptor arrays (slots 2, 3,
+// 8 of the scratch table) behind everything queued on the stream and start over at 1.
+static unsigned int next_epoch(ps_ctx* ctx, cudaStream_t st) {
+  unsigned int e = (++ctx->pl_epoch) & 0x3FFFFFFFu;
+  if (e == 0) {
+    for (int slot : {2, 3, 8})
+      if (ctx->pl_scratch[slot].p) cudaMemsetAsync(ctx->pl_scratch[slot].p, 0, ctx->pl_scratch[slot].cap, st);
+    e = (++ctx->pl_epoch) & 0x3FFFFFFFu;
+  }
+  return e;
+}
+
 static int flavour_of(const DeviceBatch& b) {   // 0 = generic decode, 1..4 = PAR-CLIP shape with that many 2-bit words
   const uint32_t L = b.uniform_len;
   const bool fast = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && (reinterpret_cast<uintptr_t>(b.bases2) & 3u) == 0;
   return fast ? (int)((L + 15) / 16) : 0;
 }
 
-template <int NW>
+template <int NW, bool MK>
 static void launch_cluster_nw(uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
   // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
-  cudaFuncSetAttribute(pl_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
-  pl_cluster_kernel<NW><<<grid, CB_THREADS, kClusterSmemBytes, st>>>(Q);
+  cudaFuncSetAttribute(pl_cluster_kernel<NW, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kClusterSmemBytes);
+  pl_cluster_kernel<NW, MK><<<grid, CB_THREADS, kClusterSmemBytes, st>>>(Q);
 }
 static void launch_cluster(int nw, uint32_t grid, cudaStream_t st, const ClusterParams& Q) {
+  if (Q.t2c_mask != nullptr) {
+    switch (nw) {
+      case 1: launch_cluster_nw<1, true>(grid, st, Q); return;
+      case 2: launch_cluster_nw<2, true>(grid, st, Q); return;
+      case 3: launch_cluster_nw<3, true>(grid, st, Q); return;
+      case 4: launch_cluster_nw<4, true>(grid, st, Q); return;
+      default: break;      // no mask words exist for other shapes
+    }
+  }
   switch (nw) {
-    case 1: launch_cluster_nw<1>(grid, st, Q); break;
-    case 2: launch_cluster_nw<2>(grid, st, Q); break;
-    case 3: launch_cluster_nw<3>(grid, st, Q); break;
-    case 4: launch_cluster_nw<4>(grid, st, Q); break;
-    default: launch_cluster_nw<0>(grid, st, Q); break;
+    case 1: launch_cluster_nw<1, false>(grid, st, Q); break;
+    case 2: launch_cluster_nw<2, false>(grid, st, Q); break;
+    case 3: launch_cluster_nw<3, false>(grid, st, Q); break;
+    case 4: launch_cluster_nw<4, false>(grid, st, Q); break;
+    default: launch_cluster_nw<0, false>(grid, st, Q); break;
   }
 }
 
@@ -1542,7 +1599,7 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");
 
   FlagParams P;
-  P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = ++ctx->pl_epoch;
+  P.b = b; P.ref = ctx->ref; P.st = d_state; P.d_max = d_max; P.d_cnt = d_cnt; P.epoch = next_epoch(ctx, st);
   P.n_tiles = n_tiles; P.carry_key = carry_key; P.cl_first = d_first; P.cap_cl = cap_cl;
   P.carry_keys = (opts && opts->carry_keys_n) ? (const unsigned long long*)opts->carry_keys_device : nullptr;
   P.carry_keys_n = P.carry_keys ? opts->carry_keys_n : 0;
@@ -1583,10 +1640,11 @@ static int pileup_launch(ps_ctx* ctx, ps_pileup* H) {
   Q.first_id = opts ? opts->first_running_id : 1; Q.cl_first = d_first; Q.cl = H->d_cl; Q.sites = d_tmp;
   Q.cap_cl = cap_cl; Q.cap_sites = cap_sites;
   Q.tile_sites = tile_sites;
+  Q.t2c_mask = (nw > 0 && opts) ? reinterpret_cast<const unsigned long long*>(opts->t2c_masks_device) : nullptr;
   launch_cluster(nw, c_tiles, st, Q);
   if (ev) cudaEventRecord(ctx->pl_ev[2], st);
   CompactParams R;
-  R.st = d_state; R.d_cnt = d_sc; R.epoch = ++ctx->pl_epoch; R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
+  R.st = d_state; R.d_cnt = d_sc; R.epoch = next_epoch(ctx, st); R.cl = H->d_cl; R.src = d_tmp; R.dst = H->d_sites;
   R.cap_cl = cap_cl; R.cap_sites = cap_sites; R.tile_sites = Q.tile_sites;
   pl_compact_kernel<<<(uint32_t)n_ctiles, PL_THREADS, 0, st>>>(R);
   if (ev) { cudaEventRecord(ctx->pl_ev[3], st); ctx->pl_ev_valid = true; }
@@ -1637,6 +1695,8 @@ static int pileup_finish(ps_ctx* ctx, ps_pileup* H) {
   if (hs.fault != PS_FAULT_NONE) {
     H->fault.code = (int32_t)(hs.fault & 0xFF);
     H->fault.read_ordinal = hs.fault >> 8;
+    if (H->fault.code == PS_FAULT_CIGAR_OPS)
+      return done(set_error(ctx, PS_ERR_UNSUPPORTED, "pileup: a record of this batch has more than 255 CIGAR operations"));
     return done(set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, "pileup: the JVM would die on a record of this batch"));
   }
   if (hs.unsorted) return done(set_error(ctx, PS_ERR_UNSORTED, ps_strerror(PS_ERR_UNSORTED)));
@@ -1805,7 +1865,10 @@ int ps_pileup_batch(ps_ctx* ctx, const ps_read_batch* hb, const ps_pileup_opts* 
   StagedBatch* sb = nullptr;
   int rc = stage_batch(ctx, hb, /*with_qual=*/false, &sb);
   if (rc) return rc;
-  rc = run_pileup(ctx, sb->view, opts, ctx->stream, out);
+  ps_pileup_opts o{};
+  if (opts) o = *opts;
+  o.t2c_masks_device = nullptr;      // mask words belong to a device-resident batch the caller ran the profile on
+  rc = run_pileup(ctx, sb->view, opts ? &o : nullptr, ctx->stream, out);
   if (*out) (*out)->stage_serial = ctx->stage_serial;
   if (rc != PS_OK && rc != PS_ERR_REFERENCE_WOULD_THROW) { free_handle(*out); *out = nullptr; }
   return rc;

@@ -36,6 +36,7 @@ struct ProfileParams {
   unsigned int* deferred_count;
   unsigned int* deferred_count_next;   // the counter of the run's next batch: cleared by this batch's deferred kernel
                                        // (two counters take turns, so no memset sits in front of the fast kernel)
+  unsigned long long* t2c_mask;        // fast kernel, optional: one T>C mask word per read (profile_fast.cuh), for the pileup
 };
 
 // shared-memory histograms of the generic path
@@ -62,6 +63,7 @@ __device__ __noinline__ void profile_read_generic(const ProfileParams& P, const 
   if (flags & PS_RF_UNMAPPED) { atomicAdd(&S.s_ctr[PS_PC_UNMAPPED], 1ull); return; }
   if (flags & PS_RF_DUPLICATE) { atomicAdd(&S.s_ctr[PS_PC_DUPLICATES], 1ull); return; }
   if (flags & PS_RF_POS_ZERO) { atomicAdd(&S.s_ctr[PS_PC_START_ZERO], 1ull); return; }
+  if (flags & PS_RF_CIGAR_OVERFLOW) { raise_fault(P.fault, ordinal, PS_FAULT_CIGAR_OPS); return; }   // not representable
 
   const uint32_t* cig = P.b.cigar + off.cigar;
   uint32_t R = 0;
@@ -276,6 +278,7 @@ __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P
   if (flags & PS_RF_UNMAPPED) { atomicAdd(&S.s_ctr[PS_PC_UNMAPPED], 1ull); return plan; }
   if (flags & PS_RF_DUPLICATE) { atomicAdd(&S.s_ctr[PS_PC_DUPLICATES], 1ull); return plan; }
   if (flags & PS_RF_POS_ZERO) { atomicAdd(&S.s_ctr[PS_PC_START_ZERO], 1ull); return plan; }
+  if (flags & PS_RF_CIGAR_OVERFLOW) { raise_fault(P.fault, ordinal, PS_FAULT_CIGAR_OPS); return plan; }   // not representable
   const uint32_t* cig = P.b.cigar + off.cigar;
   uint32_t R = 0;
   bool has_indel = false;
@@ -549,7 +552,9 @@ static cudaError_t launch_deferred(ps_ctx* ctx, const ProfileParams& P, cudaStre
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream) {
+cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream,
+                           unsigned long long* t2c_mask, bool* mask_written) {
+  if (mask_written) *mask_written = false;
   if (b.n_reads == 0) return cudaSuccess;
   ProfileParams P;
   P.b = b;
@@ -561,6 +566,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   P.first_read = 0;
   P.n_tiles = 0;
   P.deferred = nullptr;
+  P.t2c_mask = nullptr;
   // both counters are zero at the start of a run (ps_profile_begin clears the words behind the fault word)
   P.deferred_count = reinterpret_cast<unsigned int*>(P.fault + 2) + (ctx->profile_batches & 1u);
   P.deferred_count_next = reinterpret_cast<unsigned int*>(P.fault + 2) + ((ctx->profile_batches + 1u) & 1u);
@@ -573,6 +579,8 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     cudaError_t ee = ctx->deferred.reserve((size_t)b.n_reads * 4);
     if (ee != cudaSuccess) return ee;
     P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
+    // bits 62 and 63 of a mask word are flags: the mask is offered for L <= 62 only
+    if (t2c_mask && L <= 62) { P.t2c_mask = t2c_mask; if (mask_written) *mask_written = true; }
     ctx->profile_batches++;
     const uint32_t n_wt = (uint32_t)((b.n_reads + WT_READS - 1) / WT_READS);   // the fast kernel takes every read
     const uint32_t nw = (L + 15) / 16;

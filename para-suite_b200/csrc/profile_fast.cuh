@@ -1,16 +1,26 @@
 // Fast path of the error-profile kernel (included by profile.cu inside its anonymous namespace).
 //
-// Shape: uniform read length L <= 64, one M/=/X cigar op per read (L == R) -- the PAR-CLIP case.
+// Shape: uniform read length L <= 64, one M cigar op per read (L == R) -- the PAR-CLIP case.
 //
-// Work unit = a WARP-tile of 64 consecutive reads (2 per lane).  Every warp runs its own 3-stage ring of
-// cp.async.bulk (TMA) copies with its own mbarriers, so there is no block-wide barrier in the main loop:
-// a warp that meets a read with many mismatches delays nobody else.  All per-base work is bit-parallel on
-// 2-bit packed words:
+// Work unit = a WARP-tile of 64 consecutive reads (2 per lane).  Every warp runs its own 2-stage ring of
+// cp.async.bulk (TMA) copies with its own mbarriers, so there is no block-wide barrier in the main loop.  The two reads
+// of a lane are taken through ONE straight-line body (arrays of two, every phase unrolled over both), so the two
+// dependency chains interleave; everything rare (N / IUPAC in the window or in the read, reads outside the shape) sits
+// behind warp-uniform branches.  All per-base work is bit-parallel on 2-bit packed words:
 //   match counts   per-thread bit-sliced ("vertical") counters over one-hot (A|C, G|T) x position lanes, merged
 //                  across the warp with a carry-save butterfly every 2^P-2 reads (no atomics on the hot path)
-//   mismatches     rare path: two native 32-bit shared atomics (count, quality) per mismatching base
-//   quality sums   dp4a of the quality bytes against 0/-1 byte masks built with PRMT from the read codes,
-//                  summed over ALL positions by read base and corrected by the mismatch / invalid sums at the end
+//   quality sums   dp4a of the quality bytes against 0/-1 byte masks.  The masks come straight from the packed read
+//                  codes: a PRMT whose two source operands are the same table word only looks at the low two bits of
+//                  a selector nibble, so the raw code word selects the masks of positions 0,2,4,6 of an 8-position
+//                  chunk and the word shifted by 2 those of positions 1,3,5,7; the quality bytes are put in the same
+//                  even / odd order with one PRMT each.  Sums are by read base over ALL positions and corrected by the
+//                  mismatch / invalid sums at the block flush.
+//   mismatches     rare path, one at a time: the strand-oriented code words of a read are parked in shared memory, the
+//                  loop body looks the event's pair up there and issues two native 32-bit shared reductions (count by
+//                  position and pair, quality by pair); ref T / read C events also set a bit of the read's T>C mask
+//   T>C mask       (optional output) one 64-bit word per read: bit i = conversion at index i of the strand-oriented
+//                  read, bit 62 = minus strand, bit 63 = the word is valid (the read had the fast shape).  The pileup
+//                  consumes it instead of decoding the read again (ps_profile_pileup_batch_device).
 // Reads outside the shape (flags, other cigars, contig edges) are appended to a dense list for
 // profile_deferred_kernel instead of being walked inline (one slow lane would stall the other 31).
 
@@ -18,15 +28,19 @@
 #define WT_READS 64            // reads per warp-tile
 #define FAST_THREADS 128
 #define FAST_WARPS (FAST_THREADS / 32)
+#ifndef FAST_BLOCKS_PER_SM
+#define FAST_BLOCKS_PER_SM 5
+#endif
+#define FAST_QCOPIES 8         // copies of the per-pair mismatch quality cells (spreads same-address reductions)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -35,19 +49,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE;\n"
       "bra WAIT_LOOP;\n"
       "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 // 1-D bulk copy global -> shared (TMA engine), completion signalled on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) {
   int d;
   asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
+}
+// shared-memory accesses by 32-bit shared address (no generic-to-shared conversion in the loops)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s8(uint32_t a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_s32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// prmt.b32, default mode: bits 2..0 of selector nibble n pick the source byte, bit 3 replicates its sign
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+  uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s)); return r;
+}
+// one lane of the (converged) warp: code under this predicate runs with exactly one active thread, so the bulk-copy
+// operands go to the uniform datapath without a uniformisation loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(p));
+  return p != 0;
+}
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // PTX shl: amounts >= 32 give 0
+  uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r;
 }
 
 struct FastStage {      // byte offsets inside one warp-stage buffer
@@ -66,18 +98,21 @@ __host__ __device__ inline FastStage fast_stage_layout(uint32_t L) {
 }
 
 struct FastLayout {     // byte offsets of the block's shared memory
-  uint32_t misc, mm_cnt, mm_q, fast, warp0, warp_stride, inv, bars, stage0, total;
+  uint32_t misc, zero, tbl, mm_cnt, mm_q, fast, warp0, warp_stride, inv, park, bars, stage0, total;
 };
 __host__ __device__ inline FastLayout fast_layout(uint32_t max_len, uint32_t L, uint32_t nw) {
   FastLayout f;
   f.misc = 0;                                   // u64[16]
-  f.mm_cnt = 128;                               // u32[max_len*16]
-  f.mm_q = f.mm_cnt + max_len * 64;             // u32[max_len*16]
-  f.fast = f.mm_q + max_len * 64;               // u32[max_len*4]
+  f.zero = 128;                                 // 96 zero bytes: the quality row of a read outside the shape
+  f.tbl = 224;                                  // u32[4] PRMT tables: byte b of word b is 0xFF
+  f.mm_cnt = 256;                               // u32[max_len*16] mismatch counts by position and pair
+  f.mm_q = f.mm_cnt + max_len * 64;             // u32[16*FAST_QCOPIES] mismatch quality sums by pair
+  f.fast = f.mm_q + 16 * FAST_QCOPIES * 4;      // u32[max_len*4] match counts by (position, base)
   f.warp0 = (f.fast + max_len * 16 + 127) & ~127u;
   f.bars = 0;                                   // per warp: u64[FAST_STAGES] (+pad to 32)
-  f.inv = 32;                                   // per warp: u32[WT_READS*nw]
-  f.stage0 = (32 + WT_READS * nw * 4 + 127) & ~127u;
+  f.inv = 32;                                   // per warp: u32[WT_READS*nw] N calls of the tile's reads
+  f.park = f.inv + WT_READS * nw * 4;           // per warp: u32[2 reads][rf|rd][nw][32 lanes]
+  f.stage0 = (f.park + 2 * 2 * nw * 32 * 4 + 127) & ~127u;
   f.warp_stride = f.stage0 + FAST_STAGES * fast_stage_layout(L).total;
   f.total = f.warp0 + FAST_WARPS * f.warp_stride;
   return f;
@@ -130,14 +165,7 @@ __device__ __noinline__ uint32_t vc_warp_total(Planes<NPL> pl) {
   return tot;
 }
 
-struct FastSmem {
-  unsigned long long* s_misc;   // [0..3] sum of quality by read base over all positions, [4..7] same at invalid positions, [8] fast reads
-  uint32_t* s_mm_cnt;           // [max_len*16] mismatch counts
-  uint32_t* s_mm_q;             // [max_len*16] mismatch quality sums (two's complement)
-  uint32_t* s_fast;             // [max_len*4] match counts by (position, base)
-};
-
-// match count of base a at one position from the four counted lanes E0..E3 (see fast_read)
+// match count of base a at one position from the four counted lanes E0..E3 (see the one-hot words below)
 __device__ __forceinline__ uint32_t fast_base_count(const uint32_t* e, uint32_t a) {
   const uint32_t e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
   return a == 0 ? e0 - e1 - e2 + e3 : (a == 1 ? e1 - e3 : (a == 2 ? e2 - e3 : e3));
@@ -149,195 +177,72 @@ __host__ __device__ constexpr int fast_nc(int NW, int LT) {
   return (LT > 0 && LT - 16 * (NW - 1) <= 8) ? 2 * NW - 1 : 2 * NW;
 }
 
-// One read of the fast shape.  Produces the one-hot match words cw[] for the caller's bit-sliced counters.
-// LT > 0: the (uniform) read length is a compile-time constant.
-template <int NW, int LT>
-__device__ __forceinline__ void fast_read(const DeviceRef& ref, const FastSmem& F, uint32_t Lrt, uint32_t g0, bool rev,
-                                          const uint32_t* __restrict__ brow_w, uint32_t bshift,
-                                          const uint32_t* __restrict__ qrow_w, uint32_t qshift,
-                                          const unsigned char* __restrict__ qrow_b, const uint32_t (&lenmask)[NW],
-                                          uint32_t* __restrict__ inv_row, bool has_n, const uint32_t (&tbl)[4],
-                                          uint32_t (&cw)[fast_nc(NW, LT)], int (&qacc)[4], int (&qinv)[4]) {
-  const uint32_t L = LT > 0 ? (uint32_t)LT : Lrt;
-  constexpr int NC = fast_nc(NW, LT);
-  // ---- reference window: 2-bit codes and invalid bits -------------------------------------------------
-  uint32_t rf[NW], rd[NW], ve[NW];   // ref codes, read codes, valid (even bit of each position)
-  bool ve_dirty;                     // some position < L is invalid (else ve is the plain length mask)
-  {
-    const uint32_t wi = g0 >> 4, sh = (g0 & 15u) * 2u;
-    uint32_t w[NW + 1];
+// even bits of a 16-bit invalid map -> even bits of 32
+__device__ __forceinline__ uint32_t fast_spread16(uint32_t h) {
+  h &= 0xFFFFu;
+  h = (h | (h << 8)) & 0x00FF00FFu;
+  h = (h | (h << 4)) & 0x0F0F0F0Fu;
+  h = (h | (h << 2)) & 0x33333333u;
+  h = (h | (h << 1)) & 0x55555555u;
+  return h;
+}
+
+// reverse the order of the L 2-bit groups held in NW words (groups keep their two bits in place) and complement them
+// when CODES (A<->T, C<->G is a bitwise NOT); the result is masked to the read length
+template <int NW, bool CODES>
+__device__ __forceinline__ void fast_reverse(uint32_t (&v)[NW], uint32_t L, const uint32_t (&lenmask)[NW]) {
+  const uint32_t s = 2u * (16u * NW - L);   // < 32
+  uint32_t a[NW];
 #pragma unroll
-    for (int k = 0; k <= NW; ++k) w[k] = __ldg(ref.seq2 + wi + k);
-    const uint32_t ii = g0 >> 5, s1 = g0 & 31u;
-    const uint32_t i0 = __ldg(ref.inv + ii), i1 = __ldg(ref.inv + ii + 1), i2 = __ldg(ref.inv + ii + 2);
-#pragma unroll
-    for (int k = 0; k < NW; ++k) rf[k] = __funnelshift_r(w[k], w[k + 1], sh);
-    uint32_t iv[2] = {__funnelshift_r(i0, i1, s1), __funnelshift_r(i1, i2, s1)};
-    const uint32_t mask0 = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
-    const uint32_t mask1 = L > 32 ? (L >= 64 ? 0xFFFFFFFFu : ((1u << (L - 32)) - 1u)) : 0u;
-    const uint32_t any = (iv[0] & mask0) | (iv[1] & mask1);
-#pragma unroll
-    for (int k = 0; k < NW; ++k) ve[k] = lenmask[k] & 0x55555555u;
-    ve_dirty = any != 0;
-    if (any) {   // rare: N / IUPAC in the window -> clear those positions
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        uint32_t h = (iv[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;   // 16 invalid bits -> even bits of 32
-        h = (h | (h << 8)) & 0x00FF00FFu;
-        h = (h | (h << 4)) & 0x0F0F0F0Fu;
-        h = (h | (h << 2)) & 0x33333333u;
-        h = (h | (h << 1)) & 0x55555555u;
-        ve[k] &= ~h;
-      }
-    }
-  }
-  // ---- N / IUPAC calls of this read: the warp has OR-ed them into this read's row of the invalid map --------
-  if (has_n) {
-    ve_dirty = true;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) { ve[k] &= ~inv_row[k]; inv_row[k] = 0; }
-  }
-  // ---- read codes (unaligned row in shared memory) ----------------------------------------------------
-  {
-    uint32_t w[NW + 1];
-#pragma unroll
-    for (int k = 0; k <= NW; ++k) w[k] = brow_w[k];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) rd[k] = __funnelshift_r(w[k], w[k + 1], bshift) & lenmask[k];
-  }
-  // ---- minus strand: reverse-complement both arrays (qualities stay forward, Q10) ------------------------
-  if (rev) {
-    const uint32_t s = 2u * (16u * NW - L);   // < 32
-    uint32_t a[NW], b[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) { a[k] = __brev(rf[NW - 1 - k]); b[k] = __brev(rd[NW - 1 - k]); }
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const uint32_t an = k + 1 < NW ? a[k + 1] : 0u, bn = k + 1 < NW ? b[k + 1] : 0u;
-      uint32_t x = __funnelshift_r(a[k], an, s), y = __funnelshift_r(b[k], bn, s);
-      // brev swapped the two bits of every code: swap back, then complement (A<->T, C<->G is bitwise NOT)
-      x = ~(((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u));
-      y = ~(((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u));
-      rf[k] = x & lenmask[k];
-      rd[k] = y & lenmask[k];
-    }
-    if (ve_dirty) {   // the plain length mask is its own mirror image; only a punctured one needs reversing
-      uint32_t v[NW];
-#pragma unroll
-      for (int k = 0; k < NW; ++k) v[k] = __brev(ve[NW - 1 - k]);
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        const uint32_t vn = k + 1 < NW ? v[k + 1] : 0u;
-        ve[k] = (__funnelshift_r(v[k], vn, s) >> 1) & 0x55555555u;   // brev moved the even (valid) bit to the odd one
-      }
-    }
-  }
-  // ---- match / mismatch masks and one-hot match words ---------------------------------------------------
-  uint32_t mm[NW];   // positions to visit one by one: mismatches and invalid positions (even bits)
+  for (int k = 0; k < NW; ++k) a[k] = __brev(v[NW - 1 - k]);
 #pragma unroll
   for (int k = 0; k < NW; ++k) {
-    const uint32_t x = rf[k] ^ rd[k];
-    const uint32_t ne = (x | (x >> 1)) & 0x55555555u;
-    const uint32_t m = ~ne & ve[k];
-    // counted lanes per position (c1 c0 = read code of a matching base):
-    //   U: even bit E0 = match,        odd bit E2 = match & c1      (G or T)
-    //   V: even bit E1 = match & c0,   odd bit E3 = match & c1 & c0 (T)      (C or T)
-    // A = E0-E1-E2+E3, C = E1-E3, G = E2-E3, T = E3 are formed once, at the block flush.
-    const uint32_t ms = m << 1, rds = rd[k] << 1;
-    const uint32_t ac = m | (ms & rd[k]);
-    const uint32_t gt = rd[k] & (m | (ms & rds));
-    if (k == NW - 1 && NC == 2 * NW - 1) cw[2 * k] = ac | (gt << 16);
-    else { cw[2 * k] = ac; cw[2 * k + 1 < NC ? 2 * k + 1 : 0] = gt; }
-    mm[k] = (lenmask[k] & 0x55555555u) & ~m;
-  }
-  // ---- quality sums by read base over ALL positions < L (corrected for mismatches / invalid at the end) ---
-  {
-    constexpr int NQ = 4 * NW;           // quality words (4 positions each)
-    const int nq = (int)((L + 3) >> 2);
-#pragma unroll
-    for (int h = 0; h < 2 * NW; ++h) {   // 8 positions per selector word
-      if (8 * h >= (int)L) break;        // L is uniform over the launch: no divergence
-      uint32_t s = (rd[h >> 1] >> (16 * (h & 1))) & 0xFFFFu;
-      s = (s | (s << 8)) & 0x00FF00FFu;
-      s = (s | (s << 4)) & 0x0F0F0F0Fu;
-      s = (s | (s << 2)) & 0x33333333u;
-      const int first = 8 * h;
-      if ((int)L < first + 8) s |= 0x44444444u << (4 * (L - first));   // positions >= L select a zero byte
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = 2 * h + j;
-        if (k < NQ && 4 * k < (int)L) {
-          uint32_t q = qrow_w[k];
-          if (LT == 0 || (LT & 3)) {     // rows start at any byte unless L is a multiple of 4
-            const uint32_t q1 = (k + 1 <= nq) ? qrow_w[k + 1] : 0u;
-            q = __funnelshift_r(q, q1, qshift);
-          }
-          const uint32_t sel = j ? (s >> 16) : s;
-          // qacc[0] collects the sum over all bases (A = total - C - G - T at the flush)
-          qacc[0] = dp4a_ss(q, (4 * k + 4 <= (int)L) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 * k + 4 - (int)L))), qacc[0]);
-          qacc[1] = dp4a_ss(q, __byte_perm(tbl[1], 0u, sel), qacc[1]);
-          qacc[2] = dp4a_ss(q, __byte_perm(tbl[2], 0u, sel), qacc[2]);
-          qacc[3] = dp4a_ss(q, __byte_perm(tbl[3], 0u, sel), qacc[3]);
-        }
-      }
-    }
-  }
-  // ---- mismatching / invalid positions, one at a time.  Words 0,1 share the even/odd bits of w0, words 2,3 of w1;
-  //      one loop drains both so a warp pays max-over-lanes iterations once ------------------------------------
-  {
-    uint32_t w0 = mm[0] | (NW > 1 ? (mm[NW > 1 ? 1 : 0] << 1) : 0u);
-    uint32_t w1 = NW > 2 ? (mm[NW > 2 ? 2 : 0] | (NW > 3 ? (mm[NW > 3 ? 3 : 0] << 1) : 0u)) : 0u;
-    while (w0 | w1) {
-      const bool first = w0 != 0;
-      const uint32_t word = first ? w0 : w1;
-      const int b = __ffs((int)word) - 1;
-      if (first) w0 &= w0 - 1; else w1 &= w1 - 1;
-      const int k = (first ? 0 : 2) + (b & 1);
-      const int sh = b & ~1;
-      uint32_t rfw = rf[0], rdw = rd[0], vew = ve[0];
-#pragma unroll
-      for (int j = 1; j < NW; ++j)
-        if (k == j) { rfw = rf[j]; rdw = rd[j]; vew = ve[j]; }
-      const uint32_t i = 16u * k + (sh >> 1);
-      const uint32_t a = (rfw >> sh) & 3u, bb = (rdw >> sh) & 3u;
-      const int q = (int)(signed char)qrow_b[i];
-      if ((vew >> sh) & 1u) {
-        atomicAdd(&F.s_mm_cnt[i * 16 + a * 4 + bb], 1u);
-        atomicAdd(&F.s_mm_q[i * 16 + a * 4 + bb], (uint32_t)q);
-      } else {   // invalid position: its quality went into the all-position sums, take it out again
-        qinv[0] += bb == 0u ? q : 0; qinv[1] += bb == 1u ? q : 0; qinv[2] += bb == 2u ? q : 0; qinv[3] += bb == 3u ? q : 0;
-      }
-    }
+    const uint32_t an = k + 1 < NW ? a[k + 1] : 0u;
+    const uint32_t x = __funnelshift_r(a[k], an, s);
+    // brev swapped the two bits of every group: swap back
+    const uint32_t y = ((x << 1) & 0xAAAAAAAAu) | ((x >> 1) & 0x55555555u);
+    v[k] = (CODES ? ~y : y) & lenmask[k];
   }
 }
 
 template <int NW, int NPL, int LT>
-__global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const ProfileParams P) {
+__global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast_kernel(const ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NC = fast_nc(NW, LT);
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t max_len = P.lay.max_len;
   const uint32_t L = LT > 0 ? (uint32_t)LT : P.b.uniform_len;
   const uint32_t bpr = (L + 3) >> 2;
   const FastStage lay = fast_stage_layout(L);
   const FastLayout fl = fast_layout(max_len, L, NW);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  FastSmem F;
-  F.s_misc = reinterpret_cast<unsigned long long*>(smem_raw + fl.misc);
-  F.s_mm_cnt = reinterpret_cast<uint32_t*>(smem_raw + fl.mm_cnt);
-  F.s_mm_q = reinterpret_cast<uint32_t*>(smem_raw + fl.mm_q);
-  F.s_fast = reinterpret_cast<uint32_t*>(smem_raw + fl.fast);
+  unsigned long long* s_misc = reinterpret_cast<unsigned long long*>(smem_raw + fl.misc);
+  // [0..3] sum of quality by read base over all positions, [4..7] same at invalid positions, [8] fast reads,
+  // [12..15] mismatch quality by read base
+  uint32_t* s_mm_cnt = reinterpret_cast<uint32_t*>(smem_raw + fl.mm_cnt);
+  uint32_t* s_mm_q = reinterpret_cast<uint32_t*>(smem_raw + fl.mm_q);
+  uint32_t* s_fast = reinterpret_cast<uint32_t*>(smem_raw + fl.fast);
   unsigned char* wbase = smem_raw + fl.warp0 + (size_t)warp * fl.warp_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + fl.bars);
   uint32_t* s_inv = reinterpret_cast<uint32_t*>(wbase + fl.inv);        // [WT_READS][NW], zero between uses
-  unsigned char* stage0 = wbase + fl.stage0;
+  // 32-bit shared addresses of everything the loops touch
+  const uint32_t a_smem = smem_u32(smem_raw);
+  const uint32_t a_zero = a_smem + fl.zero;
+  const uint32_t a_mm_cnt = a_smem + fl.mm_cnt;
+  const uint32_t a_mm_q = a_smem + fl.mm_q + (lane & (FAST_QCOPIES - 1)) * 4;
+  const uint32_t a_wbase = a_smem + fl.warp0 + warp * fl.warp_stride;
+  const uint32_t a_bars = a_wbase + fl.bars;
+  const uint32_t a_park = a_wbase + fl.park + lane * 4;                 // + ((h*2 + arr)*NW + k) * 128
+  const uint32_t a_stage0 = a_wbase + fl.stage0;
 
   for (uint32_t k = threadIdx.x; k < fl.warp0 / 4; k += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[k] = 0;
   for (uint32_t k = lane; k < WT_READS * NW; k += 32) s_inv[k] = 0;
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < FAST_STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < FAST_STAGES; ++s) mbar_init(reinterpret_cast<uint64_t*>(wbase + fl.bars) + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  if (threadIdx.x < 4) sts32(a_smem + fl.tbl + threadIdx.x * 4, 0xFFu << (8 * threadIdx.x));
   __syncthreads();
 
   const uint64_t n_reads = P.b.n_reads;
@@ -345,19 +250,19 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
   const uint32_t n_full = (uint32_t)(n_reads / WT_READS);
   const uint32_t gw = blockIdx.x * FAST_WARPS + warp;    // global warp id
   const uint32_t GW = gridDim.x * FAST_WARPS;
-  auto issue = [&](uint32_t wt, uint32_t slot) {         // lane 0 only; partial tiles are staged by the warp itself
+  auto issue = [&](uint32_t wt, uint32_t slot) {         // one lane only; partial tiles are staged by the warp itself
     if (wt >= n_full) return;
-    unsigned char* dst = stage0 + (size_t)slot * lay.total;
+    const uint32_t dst = a_stage0 + slot * lay.total, bar = a_bars + slot * 8;
     const uint64_t r0 = (uint64_t)wt * WT_READS;
     const uint32_t bb = WT_READS * bpr, qb = WT_READS * L;
-    mbar_expect_tx(&bars[slot], 3 * WT_READS * 4 + bb + qb);
-    bulk_g2s(dst + lay.meta, P.b.meta + r0, WT_READS * 4, &bars[slot]);
-    bulk_g2s(dst + lay.start, P.b.ref_start + r0, WT_READS * 4, &bars[slot]);
-    bulk_g2s(dst + lay.cigar, P.b.cigar + r0, WT_READS * 4, &bars[slot]);
-    bulk_g2s(dst + lay.bases, P.b.bases2 + r0 * bpr, bb, &bars[slot]);
-    bulk_g2s(dst + lay.qual, P.b.qual + r0 * L, qb, &bars[slot]);
+    mbar_expect_tx(bar, 3 * WT_READS * 4 + bb + qb);
+    bulk_g2s(dst + lay.meta, P.b.meta + r0, WT_READS * 4, bar);
+    bulk_g2s(dst + lay.start, P.b.ref_start + r0, WT_READS * 4, bar);
+    bulk_g2s(dst + lay.cigar, P.b.cigar + r0, WT_READS * 4, bar);
+    bulk_g2s(dst + lay.bases, P.b.bases2 + r0 * bpr, bb, bar);
+    bulk_g2s(dst + lay.qual, P.b.qual + r0 * L, qb, bar);
   };
-  if (lane == 0) {
+  if (elect_one()) {
 #pragma unroll
     for (int s = 0; s < FAST_STAGES; ++s) {
       const uint32_t wt = gw + (uint32_t)s * GW;
@@ -371,12 +276,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
     const int rem = (int)L - 16 * k;
     lenmask[k] = rem >= 16 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << (2 * rem)) - 1u));
   }
-  // PRMT source tables (byte b = 0xFF): kept opaque so they live in registers instead of being re-materialised
-  uint32_t tbl[4];
-  asm volatile("mov.u32 %0, 0x000000FF;" : "=r"(tbl[0]));
-  asm volatile("mov.u32 %0, 0x0000FF00;" : "=r"(tbl[1]));
-  asm volatile("mov.u32 %0, 0x00FF0000;" : "=r"(tbl[2]));
-  asm volatile("mov.u32 %0, 0xFF000000;" : "=r"(tbl[3]));
+  // PRMT tables (byte b = 0xFF) in vector registers: read back from shared memory so that they are no compile-time
+  // constants, which would live in the uniform register file and cost a move at every use
+  const uint32_t tbl1 = lds32(a_smem + fl.tbl + 4), tbl2 = lds32(a_smem + fl.tbl + 8), tbl3 = lds32(a_smem + fl.tbl + 12);
+  const uint32_t ivmask0 = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+  const uint32_t ivmask1 = L > 32 ? (L >= 64 ? 0xFFFFFFFFu : ((1u << (L - 32)) - 1u)) : 0u;
+  const uint32_t metaE = PS_MAKE_META(L, 1, 0), cgE = L << 4;      // the shape: length L, one op, L x M
+  constexpr uint32_t kMetaMask = ~((uint32_t)(PS_RF_REVERSE | PS_RF_HAS_INVALID) << 24);
 
   Planes<NPL> pl[NC];
   uint32_t tot[NC];
@@ -402,10 +308,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
     qacc[0] -= qacc[1] + qacc[2] + qacc[3];   // qacc[0] held the all-base total
 #pragma unroll
     for (int b = 0; b < 4; ++b) {        // dp4a accumulated -q; keep the int32 far from overflow
-      const int t = __reduce_add_sync(0xFFFFFFFFu, qacc[b]);
-      const int u = __reduce_add_sync(0xFFFFFFFFu, qinv[b]);
-      if (lane == 0 && t) atomicAdd(&F.s_misc[b], (unsigned long long)(long long)(-t));
-      if (lane == 0 && u) atomicAdd(&F.s_misc[4 + b], (unsigned long long)(long long)u);
+      const int t = __reduce_add_sync(FULL, qacc[b]);
+      const int u = __reduce_add_sync(FULL, qinv[b]);
+      if (lane == 0 && t) atomicAdd(&s_misc[b], (unsigned long long)(long long)(-t));
+      if (lane == 0 && u) atomicAdd(&s_misc[4 + b], (unsigned long long)(long long)u);
       qacc[b] = 0;
       qinv[b] = 0;
     }
@@ -426,10 +332,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
       e_lo = __ldg(P.b.tile_exc_off + ((wt + GW) >> 2));
       e_hi = __ldg(P.b.tile_exc_off + ((wt + GW) >> 2) + 1);
     }
-    unsigned char* sbw = stage0 + (size_t)slot * lay.total;
+    const uint32_t a_sb = a_stage0 + slot * lay.total;
+    unsigned char* sbw = wbase + fl.stage0 + (size_t)slot * lay.total;
     uint32_t n_here = WT_READS;
     if (wt < n_full) {
-      mbar_wait(&bars[slot], parity);
+      mbar_wait(a_bars + slot * 8, parity);
     } else {   // the batch's last, partial warp-tile: bounds-checked cooperative copy instead of TMA
       const uint64_t r0 = (uint64_t)wt * WT_READS;
       n_here = (uint32_t)(n_reads - r0);
@@ -446,13 +353,36 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
       for (uint32_t k = lane; k < (n_here * L + 3) / 4; k += 32) d32[lay.qual / 4 + k] = __ldg(gq + k);
       __syncwarp();
     }
-    const unsigned char* sb = sbw;
-    const uint32_t* s_meta = reinterpret_cast<const uint32_t*>(sb + lay.meta);
-    const uint32_t* s_start = reinterpret_cast<const uint32_t*>(sb + lay.start);
-    const uint32_t* s_cig = reinterpret_cast<const uint32_t*>(sb + lay.cigar);
+    // ---- record words and the reference window of this lane's two reads: requested first, so the loads are in flight
+    //      while the warp looks at the contig bounds and the N calls.  The window offset is clamped to the reference, so
+    //      the loads need no knowledge of the read's fate (a read outside the shape may carry any offset)
+    uint32_t meta[2], g0[2], cg[2];
+    uint32_t rf[2][NW], iv[2][2];
+    {
+      const uint32_t g_last = (uint32_t)(P.ref.n_bases - 1);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t rit = lane + h * 32;
+        meta[h] = lds32(a_sb + lay.meta + rit * 4);
+        g0[h] = lds32(a_sb + lay.start + rit * 4);
+        cg[h] = lds32(a_sb + lay.cigar + rit * 4);
+        const uint32_t g = min(g0[h], g_last);
+        const uint32_t wi = g >> 4, sh = (g & 15u) * 2u;
+        uint32_t w[NW + 1];
+#pragma unroll
+        for (int k = 0; k <= NW; ++k) w[k] = __ldg(P.ref.seq2 + wi + k);
+        const uint32_t ii = g >> 5, s1 = g & 31u;
+        const uint32_t i0 = __ldg(P.ref.inv + ii), i1 = __ldg(P.ref.inv + ii + 1);
+        const uint32_t i2 = (LT == 0 || LT > 32) ? __ldg(P.ref.inv + ii + 2) : 0u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) rf[h][k] = __funnelshift_r(w[k], w[k + 1], sh);
+        iv[h][0] = __funnelshift_r(i0, i1, s1) & ivmask0;
+        iv[h][1] = (LT == 0 || LT > 32) ? (__funnelshift_r(i1, i2, s1) & ivmask1) : 0u;
+      }
+    }
     // contig bounds: reads starting and ending inside the contig of the tile's first read pass the range test
     {
-      const uint64_t g = s_start[0];
+      const uint64_t g = lds32(a_sb + lay.start);
       if (!(g >= c_lo && g < c_hi)) {
         if (g < P.ref.n_bases) {
           const uint32_t c = contig_of(P.ref, g);
@@ -461,8 +391,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
         } else { c_lo = 1; c_hi = 0; }
       }
     }
+    // one unsigned compare per read: lo <= g0 and g0 + L <= hi  <=>  g0 - lo <= hi - lo - L  (offsets fit 32 bits)
+    const bool span_ok = c_hi >= c_lo + L && L <= max_len;
+    const uint32_t lo32 = (uint32_t)c_lo, span32 = span_ok ? (uint32_t)(c_hi - c_lo - L) : 0u;
     // scatter this warp-tile's N calls into the per-read invalid map
-    {
+    if (cur_hi > cur_lo) {
       const uint32_t quarter = wt & 3u;
       uint32_t x = ex;
       for (uint32_t e = cur_lo; e < cur_hi; e += 32) {
@@ -475,33 +408,214 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
       __syncwarp();
     }
 
-    uint32_t xw[2][NC];
+    // ================= the two reads of this lane, one straight-line body =======================================
+    bool ok[2], rev[2], hasn[2], anyinv[2], punct[2];
+    uint32_t rd[2][NW], ve[2][NW];
+    uint32_t a_qrow[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t rit = lane + h * 32;
-      const uint32_t meta = s_meta[rit];
-      const uint32_t g0 = s_start[rit];
-      const uint32_t cg = s_cig[rit];
-      const uint32_t flags = PS_META_FLAGS(meta);
-      const bool has_n = (flags & PS_RF_HAS_INVALID) != 0;
-      const bool fast = (flags & ~(PS_RF_REVERSE | PS_RF_HAS_INVALID)) == 0 && op_is_match(cg & 15u) &&
-                        (cg >> 4) == L && L <= max_len && (uint64_t)g0 >= c_lo && (uint64_t)g0 + L <= c_hi &&
-                        rit < n_here;
+      const bool shaped = ((meta[h] ^ metaE) & kMetaMask) == 0 && cg[h] == cgE;
+      ok[h] = shaped && (g0[h] - lo32) <= span32 && span_ok && rit < n_here;
+      rev[h] = ok[h] && (meta[h] & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
+      hasn[h] = (meta[h] & ((uint32_t)PS_RF_HAS_INVALID << 24)) != 0 && rit < n_here;
+      anyinv[h] = ok[h] && (iv[h][0] | iv[h][1]) != 0;
+      punct[h] = anyinv[h];
+      // ---- read codes (unaligned row in shared memory) ----------------------------------------------------
+      const uint32_t boff = rit * bpr, bshift = (boff & 3u) * 8u;
+      const uint32_t a_brow = a_sb + lay.bases + (boff & ~3u);
+      uint32_t bw[NW + 1];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) xw[h][c] = 0;
-      if (fast) {
-        const uint32_t boff = rit * bpr, qoff = rit * L;
-        fast_read<NW, LT>(P.ref, F, L, g0, (flags & PS_RF_REVERSE) != 0,
-                          reinterpret_cast<const uint32_t*>(sb + lay.bases + (boff & ~3u)), (boff & 3u) * 8u,
-                          reinterpret_cast<const uint32_t*>(sb + lay.qual + (qoff & ~3u)), (qoff & 3u) * 8u,
-                          sb + lay.qual + qoff, lenmask, s_inv + rit * NW, has_n, tbl, xw[h], qacc, qinv);
-        ++n_fast;
-      } else if (rit < n_here) {
-        if (has_n) {
+      for (int k = 0; k <= NW; ++k) bw[k] = lds32(a_brow + 4 * k);
+      const uint32_t vmask = ok[h] ? 0x55555555u : 0u;
 #pragma unroll
-          for (int k = 0; k < NW; ++k) s_inv[rit * NW + k] = 0;
+      for (int k = 0; k < NW; ++k) {
+        rd[h][k] = __funnelshift_r(bw[k], bw[k + 1], bshift) & lenmask[k];
+        ve[h][k] = lenmask[k] & vmask;
+      }
+      a_qrow[h] = ok[h] ? a_sb + lay.qual + rit * L : a_zero;    // a read outside the shape adds zeros
+      n_fast += ok[h] ? 1u : 0u;
+    }
+    // ---- N / IUPAC in the reference window (rare) or in the read -> clear those positions --------------------------
+    if (__any_sync(FULL, anyinv[0] | anyinv[1] | hasn[0] | hasn[1])) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (anyinv[h]) {
+#pragma unroll
+          for (int k = 0; k < NW; ++k) ve[h][k] &= ~fast_spread16(iv[h][k >> 1] >> (16 * (k & 1)));
         }
-        P.deferred[atomicAdd(P.deferred_count, 1u)] = (uint32_t)(P.first_read + (uint64_t)wt * WT_READS + rit);
+        if (hasn[h]) {     // the warp has OR-ed the read's N calls into its row of the invalid map
+          uint32_t* row = s_inv + (lane + h * 32) * NW;
+          punct[h] = ok[h];
+#pragma unroll
+          for (int k = 0; k < NW; ++k) {
+            uint32_t r = row[k];
+            row[k] = 0;
+            ve[h][k] &= ~r;
+            // the quality of an N call went into the all-position sums (code 0 = A; T once the minus strand is
+            // complemented): take it out here, where the calls are at hand -- unless the window holds invalid
+            // reference positions too, in which case the loop over all invalid positions below does it
+            if (ok[h] && !anyinv[h])
+              while (r) {
+                const uint32_t b = (uint32_t)__ffs((int)r) - 1u;
+                r &= r - 1u;
+                const uint32_t p = 16u * k + (b >> 1);
+                const int q = lds_s8(a_qrow[h] + (rev[h] ? L - 1u - p : p));
+                qinv[0] += rev[h] ? 0 : q;
+                qinv[3] += rev[h] ? q : 0;
+              }
+          }
+        }
+      }
+    }
+    // ---- minus strand: reverse-complement both arrays (qualities stay forward, Q10) ------------------------------
+    if (__any_sync(FULL, rev[0] | rev[1])) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a[NW], b[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { a[k] = rf[h][k]; b[k] = rd[h][k]; }
+        fast_reverse<NW, true>(a, L, lenmask);
+        fast_reverse<NW, true>(b, L, lenmask);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { rf[h][k] = rev[h] ? a[k] : rf[h][k]; rd[h][k] = rev[h] ? b[k] : rd[h][k]; }
+        if (punct[h] && rev[h]) {   // the plain length mask is its own mirror image; only a punctured one needs reversing
+          uint32_t v[NW];
+#pragma unroll
+          for (int k = 0; k < NW; ++k) v[k] = ve[h][k];
+          fast_reverse<NW, false>(v, L, lenmask);
+#pragma unroll
+          for (int k = 0; k < NW; ++k) ve[h][k] = v[k] & 0x55555555u;
+        }
+      }
+    }
+    // ---- match / mismatch masks, one-hot match words, codes parked for the mismatch loop --------------------------
+    uint32_t xw[2][NC], mmv[2][NW];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const uint32_t x = rf[h][k] ^ rd[h][k];
+        const uint32_t ne = (x | (x >> 1)) & 0x55555555u;
+        const uint32_t m = ~ne & ve[h][k];
+        mmv[h][k] = ne & ve[h][k];
+        // counted lanes per position (c1 c0 = read code of a matching base):
+        //   U: even bit E0 = match,        odd bit E2 = match & c1      (G or T)
+        //   V: even bit E1 = match & c0,   odd bit E3 = match & c1 & c0 (T)      (C or T)
+        // A = E0-E1-E2+E3, C = E1-E3, G = E2-E3, T = E3 are formed once, at the block flush.
+        const uint32_t ms = m << 1, rds = rd[h][k] << 1;
+        const uint32_t ac = m | (ms & rd[h][k]);
+        const uint32_t gt = rd[h][k] & (m | (ms & rds));
+        if (k == NW - 1 && NC == 2 * NW - 1) xw[h][2 * k] = ac | (gt << 16);
+        else { xw[h][2 * k] = ac; xw[h][2 * k + 1 < NC ? 2 * k + 1 : 0] = gt; }
+        sts32(a_park + ((h * 2 + 0) * NW + k) * 128, rf[h][k]);
+        sts32(a_park + ((h * 2 + 1) * NW + k) * 128, rd[h][k]);
+      }
+    }
+    // ---- quality sums by read base over ALL positions < L (corrected for mismatches / invalid at the end) ---------
+    {
+      constexpr int NCH = 2 * NW;                 // chunks of 8 positions
+      const bool unaligned = LT == 0 || (LT & 3);   // rows start at any byte unless L is a multiple of 4
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (8 * c >= (int)L) break;               // L is uniform over the launch: no divergence
+        const bool half = 8 * c + 4 >= (int)L;    // at most four positions left: one quality word, natural order
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t qsh = (a_qrow[h] & 3u) * 8u, a_q = (a_qrow[h] & ~3u) + 8 * c;
+          uint32_t q0 = lds32(a_q), q1 = half ? 0u : lds32(a_q + 4);
+          if (unaligned) {
+            const uint32_t q2 = lds32(a_q + (half ? 4 : 8));
+            if (half) q0 = __funnelshift_r(q0, q2, qsh);
+            else { q0 = __funnelshift_r(q0, q1, qsh); q1 = __funnelshift_r(q1, q2, qsh); }
+          }
+          const int left = (int)L - 8 * c;        // positions of this chunk that exist
+          // qacc[0] collects the sum over all bases (A = total - C - G - T at the flush)
+          qacc[0] = dp4a_ss(q0, left >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - left))), qacc[0]);
+          const uint32_t codes = rd[h][c >> 1] >> (16 * (c & 1));     // PRMT reads the low 16 bits only
+          if (half) {
+            uint32_t s = codes & 0xFFu;             // four codes -> four selector nibbles
+            s = (s | (s << 4)) & 0x0F0Fu;
+            s = (s | (s << 2)) & 0x3333u;
+            qacc[1] = dp4a_ss(q0, prmt(tbl1, tbl1, s), qacc[1]);
+            qacc[2] = dp4a_ss(q0, prmt(tbl2, tbl2, s), qacc[2]);
+            qacc[3] = dp4a_ss(q0, prmt(tbl3, tbl3, s), qacc[3]);
+          } else {
+            if (left < 8) qacc[0] = dp4a_ss(q1, 0xFFFFFFFFu >> (8 * (8 - left)), qacc[0]);
+            else qacc[0] = dp4a_ss(q1, 0xFFFFFFFFu, qacc[0]);
+            // nibble j of `codes` = codes of positions 2j+1 | 2j: with the same table in both PRMT operands only the low
+            // two bits of a nibble pick the byte (bit 2 picks the copy, bit 3 replicates the sign of a 0x00 / 0xFF byte)
+            const uint32_t qe = prmt(q0, q1, 0x6420), qo = prmt(q0, q1, 0x7531);
+            const uint32_t so = codes >> 2;
+            qacc[1] = dp4a_ss(qe, prmt(tbl1, tbl1, codes), qacc[1]);
+            qacc[2] = dp4a_ss(qe, prmt(tbl2, tbl2, codes), qacc[2]);
+            qacc[3] = dp4a_ss(qe, prmt(tbl3, tbl3, codes), qacc[3]);
+            qacc[1] = dp4a_ss(qo, prmt(tbl1, tbl1, so), qacc[1]);
+            qacc[2] = dp4a_ss(qo, prmt(tbl2, tbl2, so), qacc[2]);
+            qacc[3] = dp4a_ss(qo, prmt(tbl3, tbl3, so), qacc[3]);
+          }
+        }
+      }
+    }
+    // ---- mismatching positions, one at a time.  Words 0,1 share the even/odd bits of w0, words 2,3 of w1 -----------
+    uint32_t tc_lo[2] = {0, 0}, tc_hi[2] = {0, 0};
+    __syncwarp();      // parked words are read back by their own lane only; the fence orders the shared accesses
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t w0 = mmv[h][0] | (NW > 1 ? (mmv[h][NW > 1 ? 1 : 0] << 1) : 0u);
+      uint32_t w1 = NW > 2 ? (mmv[h][NW > 2 ? 2 : 0] | (NW > 3 ? (mmv[h][NW > 3 ? 3 : 0] << 1) : 0u)) : 0u;
+      const uint32_t a_pk = a_park + (h * 2 * NW) * 128;
+      while (w0 | w1) {
+        const bool first = NW <= 2 || w0 != 0;
+        const uint32_t word = first ? w0 : w1;
+        const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
+        const uint32_t rest = word & (word - 1u);
+        if (first) w0 = rest; else w1 = rest;
+        const uint32_t k = (first ? 0u : 2u) + (b & 1u), sh = b & ~1u;
+        const uint32_t rfw = lds32(a_pk + k * 128), rdw = lds32(a_pk + (NW + k) * 128);
+        const uint32_t i = 16u * k + (b >> 1);
+        const uint32_t pair = ((rfw >> sh) & 3u) * 4u + ((rdw >> sh) & 3u);
+        const int q = lds_s8(a_qrow[h] + i);
+        red_s32(a_mm_cnt + (i * 16u + pair) * 4u, 1u);
+        red_s32(a_mm_q + pair * (FAST_QCOPIES * 4u), (uint32_t)q);
+        const uint32_t one = pair == 13u ? 1u : 0u;         // ref T, read C on the oriented strand
+        tc_lo[h] |= shl_clamp(one, i);
+        tc_hi[h] |= shl_clamp(one, i - 32u);               // i < 32 wraps to a huge amount: 0
+      }
+    }
+    // ---- rare: invalid reference positions in the window -- the quality of every invalid position went into the
+    //      all-position sums, take it out again -----------------------------------------------------------------------
+    if (__any_sync(FULL, anyinv[0] | anyinv[1])) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!anyinv[h]) continue;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          uint32_t mi = (lenmask[k] & 0x55555555u) & ~ve[h][k];
+          while (mi) {
+            const uint32_t b = (uint32_t)__ffs((int)mi) - 1u;
+            mi &= mi - 1u;
+            const uint32_t bb = (rd[h][k] >> b) & 3u;
+            const int q = lds_s8(a_qrow[h] + 16u * k + (b >> 1));
+            qinv[0] += bb == 0u ? q : 0; qinv[1] += bb == 1u ? q : 0; qinv[2] += bb == 2u ? q : 0; qinv[3] += bb == 3u ? q : 0;
+          }
+        }
+      }
+    }
+    // ---- outputs of the tile: T>C masks, deferred reads, counters -----------------------------------------------------
+    if (P.t2c_mask != nullptr) {
+      unsigned long long* mp = P.t2c_mask + ((uint64_t)wt * WT_READS + lane);
+      const uint32_t hi0 = ok[0] ? (tc_hi[0] | 0x80000000u | ((uint32_t)rev[0] << 30)) : 0u;
+      const uint32_t hi1 = ok[1] ? (tc_hi[1] | 0x80000000u | ((uint32_t)rev[1] << 30)) : 0u;
+      if (lane < n_here) mp[0] = ((unsigned long long)hi0 << 32) | tc_lo[0];        // !ok: tc_lo is 0 (no events)
+      if (lane + 32 < n_here) mp[32] = ((unsigned long long)hi1 << 32) | tc_lo[1];
+    }
+    if (__any_sync(FULL, (!ok[0] && lane < n_here) | (!ok[1] && lane + 32 < n_here))) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t rit = lane + h * 32;
+        if (!ok[h] && rit < n_here)
+          P.deferred[atomicAdd(P.deferred_count, 1u)] = (uint32_t)(P.first_read + (uint64_t)wt * WT_READS + rit);
       }
     }
 #pragma unroll
@@ -510,9 +624,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
     if (since_flush >= kFlushEvery) flush_vc();
 
     __syncwarp();   // every lane is done with this stage buffer
-    if (lane == 0) {
-      const uint32_t nxt = wt + FAST_STAGES * GW;
-      if (nxt < n_wt) issue(nxt, slot);
+    if (wt + FAST_STAGES * GW < n_wt) {
+      if (elect_one()) issue(wt + FAST_STAGES * GW, slot);
     }
   }
   flush_vc();
@@ -529,50 +642,51 @@ __global__ void __launch_bounds__(FAST_THREADS, 5) profile_fast_kernel(const Pro
       i = 16u * (c >> 1) + (lane >> 1);
       base = 2u * (lane & 1u) + (c & 1u);
     }
-    if (i < max_len) atomicAdd(&F.s_fast[i * 4 + base], tot[c]);
+    if (i < max_len) atomicAdd(&s_fast[i * 4 + base], tot[c]);
   }
   {
-    const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, n_fast);
-    if (lane == 0 && t) atomicAdd(&F.s_misc[8], (unsigned long long)t);
+    const uint32_t t = __reduce_add_sync(FULL, n_fast);
+    if (lane == 0 && t) atomicAdd(&s_misc[8], (unsigned long long)t);
   }
   __syncthreads();
   // ---- block flush ---------------------------------------------------------------------------------------------
   for (uint32_t k = threadIdx.x; k < max_len * 16; k += blockDim.x) {
     const uint32_t a = (k >> 2) & 3u, b = k & 3u, i = k >> 4;
-    const unsigned long long cnt = a == b ? fast_base_count(F.s_fast + i * 4, a) : F.s_mm_cnt[k];
+    const unsigned long long cnt = a == b ? fast_base_count(s_fast + i * 4, a) : s_mm_cnt[k];
     if (cnt) atomicAdd(P.acc + P.lay.conv + k, cnt);
   }
   if (threadIdx.x < 16) {   // per (ref, read) pair: counts and mismatch quality over all positions
     const uint32_t a = threadIdx.x >> 2, b = threadIdx.x & 3u;
     unsigned long long cnt = 0;
     long long qs = 0;
-    for (uint32_t i = 0; i < max_len; ++i) {
-      cnt += a == b ? fast_base_count(F.s_fast + i * 4, a) : F.s_mm_cnt[i * 16 + threadIdx.x];
-      if (a != b) qs += (long long)(int)F.s_mm_q[i * 16 + threadIdx.x];
-    }
+    for (uint32_t i = 0; i < max_len; ++i)
+      cnt += a == b ? fast_base_count(s_fast + i * 4, a) : s_mm_cnt[i * 16 + threadIdx.x];
+    if (a != b)
+      for (uint32_t c = 0; c < FAST_QCOPIES; ++c) qs += (long long)(int)s_mm_q[threadIdx.x * FAST_QCOPIES + c];
     if (cnt) {
       atomicAdd(P.acc + P.lay.qcnt + threadIdx.x, cnt);   // fast reads never hold I/D: every counted base has a quality
       atomicAdd(P.acc + P.lay.ctr + PS_PC_TOTAL_BASES_CHECKED, cnt);
     }
     if (a != b && qs) {
       atomicAdd(P.acc + P.lay.qsum + threadIdx.x, (unsigned long long)qs);
-      atomicAdd(&F.s_misc[12 + b], (unsigned long long)qs);             // mismatch quality by read base
+      atomicAdd(&s_misc[12 + b], (unsigned long long)qs);             // mismatch quality by read base
     }
   }
   __syncthreads();
   if (threadIdx.x < 4) {
     const uint32_t b = threadIdx.x;
-    const long long v = (long long)F.s_misc[b] - (long long)F.s_misc[4 + b] - (long long)F.s_misc[12 + b];
+    const long long v = (long long)s_misc[b] - (long long)s_misc[4 + b] - (long long)s_misc[12 + b];
     if (v) atomicAdd(P.acc + P.lay.qsum + b * 5, (unsigned long long)v);
   }
-  if (threadIdx.x == 8 && F.s_misc[8]) {
-    atomicAdd(P.acc + P.lay.ctr + PS_PC_NUM_READS_PROCESSED, F.s_misc[8]);
-    atomicAdd(P.fault + 1, F.s_misc[8]);   // debug word: reads that took the fast path
+  if (threadIdx.x == 8 && s_misc[8]) {
+    atomicAdd(P.acc + P.lay.ctr + PS_PC_NUM_READS_PROCESSED, s_misc[8]);
+    atomicAdd(P.fault + 1, s_misc[8]);   // debug word: reads that took the fast path
   }
 }
 
 // a block may add this many reads before the 32-bit shared mismatch-quality cells could overflow
-#define FAST_MAX_READS_PER_BLOCK (1u << 18)
+// (64 positions x |q| <= 128 x 2^17 reads = 2^30)
+#define FAST_MAX_READS_PER_BLOCK (1u << 17)
 
 template <int NW, int NPL, int LT>
 cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cudaStream_t stream) {
@@ -600,6 +714,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
     Q.b.tile_exc_off += r0 / PS_TILE_READS;
     Q.b.n_reads = std::min<uint64_t>(P.b.n_reads - r0, cnt * WT_READS);
     Q.first_read = r0;    // offset added to deferred read indices
+    if (Q.t2c_mask) Q.t2c_mask += r0;
     kern<<<grid, FAST_THREADS, smem, stream>>>(Q);
     ctx->launches++;
     e = cudaGetLastError();

@@ -15,7 +15,7 @@ CSRC_DIR = os.path.join(ROOT_DIR, "csrc")
 REPO_DIR = os.path.dirname(ROOT_DIR)
 INCLUDE_DIR = os.path.join(REPO_DIR, "include")
 
-PS_ABI_VERSION = 1
+PS_ABI_VERSION = 2
 PS_OK = 0
 PS_ERR_INVALID_ARG = -1
 PS_ERR_NO_DEVICE = -2
@@ -37,6 +37,7 @@ PS_THROW_POS_MAXLEN = 5
 PS_THROW_QUAL_RANGE = 6
 PS_THROW_MASK51 = 7
 PS_THROW_BLOCK_RANGE = 8
+PS_FAULT_CIGAR_OPS = 9
 
 PS_TILE_READS = 256
 PS_RF_UNMAPPED = 0x01
@@ -75,7 +76,8 @@ class ps_read_batch(C.Structure):
 
 
 class ps_profile_opts(C.Structure):
-    _fields_ = [("max_read_length", C.c_uint32), ("infer_qualities", C.c_uint32)]
+    _fields_ = [("max_read_length", C.c_uint32), ("infer_qualities", C.c_uint32), ("emit_t2c_masks", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class ps_fault(C.Structure):
@@ -110,7 +112,8 @@ class ps_pileup_counters(C.Structure):
 
 class ps_pileup_opts(C.Structure):
     _fields_ = [("first_running_id", C.c_uint32), ("carry_valid", C.c_uint32), ("carry_contig", C.c_uint32),
-                ("carry_cluster_end", C.c_int32), ("carry_keys_n", C.c_uint32), ("carry_keys_device", C.c_void_p)]
+                ("carry_cluster_end", C.c_int32), ("carry_keys_n", C.c_uint32), ("carry_keys_device", C.c_void_p),
+                ("t2c_masks_device", C.c_void_p)]
 
 
 class ps_flush_totals(C.Structure):
@@ -143,6 +146,7 @@ EXPORTS = {
     "ps_batch_upload": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_read_batch)]),
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "ps_profile_begin": (C.c_int, [VP, C.POINTER(ps_profile_opts)]),
+    "ps_profile_masks_device": (C.c_int, [VP, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ps_profile_batch": (C.c_int, [VP, C.POINTER(ps_read_batch)]),
     "ps_profile_batch_device": (C.c_int, [VP, C.POINTER(ps_read_batch), VP]),
     "ps_profile_acc_device": (C.c_int, [VP, C.POINTER(VP), C.POINTER(C.c_size_t)]),

@@ -118,14 +118,14 @@ class Context:
         """The record loop of the `error` tool (ErrorProfiling.java:104-409) on a coordinate-sorted BAM."""
         self._max_len, self._infer_q = max_read_length, infer_qualities
         out, r = self._profile_result_arrays()
-        o = abi.ps_profile_opts(max_read_length, int(infer_qualities))
+        o = abi.ps_profile_opts(max_read_length, int(infer_qualities), 0, 0)
         st = self.lib.ps_profile_bam(self.h, bam_path.encode(), C.byref(o), C.byref(r))
         _check(self.lib, self.h, st, fault=(r.fault.code, r.fault.read_ordinal))
         return out
 
     def pileup_bam(self, bam_path: str, first_running_id: int = 1) -> "PileupResult":
         """The record loop of the `clust` tool (PileupClusters.java:62-500) on a coordinate-sorted BAM."""
-        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None)
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None, None)
         h = C.c_void_p()
         st = self.lib.ps_pileup_bam(self.h, bam_path.encode(), C.byref(opts), C.byref(h))
         res = PileupResult(self, h, None)
@@ -150,8 +150,10 @@ class Context:
         return UploadedBatch(v, batch.n_reads, batch)
 
     # ---- error profile (ErrorProfiling.java:146-409) ---------------------------------------------
-    def profile_begin(self, max_read_length: int, infer_qualities: bool = False):
-        o = abi.ps_profile_opts(max_read_length, int(infer_qualities))
+    def profile_begin(self, max_read_length: int, infer_qualities: bool = False, emit_t2c_masks: bool = False):
+        """emit_t2c_masks: device-resident batches of the PAR-CLIP shape leave one T>C mask word per read in HBM
+        (profile_masks()), which a pileup call on the same batch takes instead of decoding the reads again."""
+        o = abi.ps_profile_opts(max_read_length, int(infer_qualities), int(emit_t2c_masks), 0)
         _check(self.lib, self.h, self.lib.ps_profile_begin(self.h, C.byref(o)))
         self._max_len = max_read_length
         self._infer_q = infer_qualities
@@ -164,6 +166,12 @@ class Context:
 
     def profile_batch_device(self, dbatch, stream: int = 0):
         _check(self.lib, self.h, self.lib.ps_profile_batch_device(self.h, C.byref(dbatch.struct), stream or None))
+
+    def profile_masks(self):
+        """(device pointer, n) of the T>C mask words of the last profile_batch_device call, or None."""
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(self.lib, self.h, self.lib.ps_profile_masks_device(self.h, C.byref(p), C.byref(n)))
+        return (p.value, n.value) if p.value else None
 
     def profile_acc_tensor(self):
         """The int64 accumulator vector as a torch tensor aliasing library memory (for dist.all_reduce)."""
@@ -235,7 +243,7 @@ class Context:
 
     # ---- T>C pileup (PileupClusters.java:137-500, 585-673) ----------------------------------------
     def pileup_run(self, batch, first_running_id: int = 1, carry=None, stream: int = 0, carry_keys=None,
-                   defer: bool = False) -> "PileupResult":
+                   defer: bool = False, masks=None) -> "PileupResult":
         """Run the pileup kernels; the cluster and site records stay in HBM behind the returned handle.
         defer=True (device-resident batches): return right behind the kernel launches (ps_pileup_submit_device); the
         call is completed by PileupResult.wait(), which the first look at the counters / records does by itself.
@@ -243,7 +251,11 @@ class Context:
         carry = (contig_index, cluster_end) of the cluster left open by the preceding shard, or None;
         carry_keys = (device pointer, n): the keys of the n preceding shards left on the device (pileup_max_key_tensor +
         all-gather), an alternative to `carry` without a host round trip."""
-        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None)
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None, None)
+        if masks is not None:          # profile_masks() of the SAME batch (same stream, or ordered behind it)
+            if int(masks[1]) != batch.n_reads:
+                raise ValueError("mask words belong to another batch")
+            opts.t2c_masks_device = int(masks[0])
         if carry is not None:
             opts.carry_valid, opts.carry_contig, opts.carry_cluster_end = 1, int(carry[0]), int(carry[1])
         if carry_keys is not None and carry_keys[1] > 0:

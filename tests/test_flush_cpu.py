@@ -132,3 +132,29 @@ def test_java_double_formatting():
     for x, e in [(0.5, "0.5"), (1.0, "1.0"), (1e-4, "1.0E-4"), (1e7, "1.0E7"), (1 / 3, "0.3333333333333333"),
                  (0.0, "0.0"), (float("nan"), "NaN"), (123456.789, "123456.789"), (2.5e-5, "2.5E-5")]:
         assert java_double(x) == e
+
+
+def test_thin_cluster_still_grows_the_map(oracle):
+    """A cluster below minReadCoverage is not flushed, but the record loop has put its T>C keys into the run's one
+    mutationMap (PileupClusters.java:126, :353, :651-661): 13 keys grow the table from 16 to 32 buckets and clear() keeps
+    that capacity, so the tied sites 80 and 97 of the next cluster iterate as 97, 80 (buckets 1, 16) instead of 80, 97
+    (buckets 0, 1) and the anchor -- the LAST maximum -- is 80."""
+    ref = bytearray(b"A" * 140)
+    t_pos = list(range(12, 12 + 26, 2))            # 13 T positions (1-based) inside the first read
+    for p in t_pos + [80, 97]:
+        ref[p - 1] = ord("T")
+    contigs = [("chr1", bytes(ref))]
+    r1 = bytearray(ref[10:50])                      # start 11, 40M
+    for p in t_pos:
+        r1[p - 11] = ord("C")
+    r2 = bytearray(ref[69:109])                     # start 70, 40M: covers 80 and 97
+    r2[80 - 70] = ord("C"); r2[97 - 70] = ord("C")
+    r3 = bytearray(ref[70:110])                     # start 71, 40M: the same two conversions -> both sites at 2/2
+    r3[80 - 71] = ord("C"); r3[97 - 71] = ord("C")
+    recs = [Record(0, "chr1", 11, "40M", bytes(r1), bytes([30] * 40)),
+            Record(0, "chr1", 70, "40M", bytes(r2), bytes([30] * 40)),
+            Record(0, "chr1", 71, "40M", bytes(r3), bytes([30] * 40)),
+            Record(0, "chr1", 130, "5M", b"AAAAA", bytes([30] * 5))]      # closes the second cluster
+    rows, st, _ = check(oracle, contigs, recs, [], 2)
+    assert not rows[0]["emitted"] and rows[1]["emitted"]
+    assert st.clusters[1].best_pos == 80 and int(rows[1]["best_pos"]) == 80

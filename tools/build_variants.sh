@@ -4,8 +4,8 @@
 set -e
 R=$(cd "$(dirname "$0")/.." && pwd); C=$R/para-suite_b200/csrc; O=${TMPDIR:-/tmp}/vb; mkdir -p $O
 NV="nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3,-pthread -I $R/include -I $C"
-for f in ctx; do [ $O/$f.o -nt $C/$f.cu ] || $NV -c $C/$f.cu -o $O/$f.o; done
-for f in bam_batcher flush; do [ $O/$f.o -nt $C/$f.cpp ] || g++ -O3 -std=c++17 -fPIC -pthread -I $R/include -I $C -I /usr/local/cuda/include -c $C/$f.cpp -o $O/$f.o; done
+for f in ctx; do [ $O/$f.o -nt $C/$f.cu -a $O/$f.o -nt $C/internal.h -a $O/$f.o -nt $R/include/parasuite_b200.h ] || $NV -c $C/$f.cu -o $O/$f.o; done
+for f in bam_batcher flush; do [ $O/$f.o -nt $C/$f.cpp -a $O/$f.o -nt $R/include/parasuite_b200.h ] || g++ -O3 -std=c++17 -fPIC -pthread -I $R/include -I $C -I /usr/local/cuda/include -c $C/$f.cpp -o $O/$f.o; done
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   $NV $flags -c $C/pileup.cu -o $O/pileup_$name.o &
