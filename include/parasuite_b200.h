@@ -221,6 +221,9 @@ int ps_reference_adopt_device(ps_ctx* ctx, const ps_reference* dev_ref, const ui
  * the same stream, after the copy).  The view stays valid until the second-next ps_batch_upload / ps_*_batch call on
  * this context (two staging slots).  Lets the two tools share one upload of the same records. */
 int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* host_batch, ps_read_batch* dev_view);
+/* (A *_batch_device / ps_pileup_max_key_device call that is handed such a view together with a stream of the caller's
+ * waits, on that stream, for the part of the upload it reads: everything for the profile, everything but the quality
+ * bytes -- which travel last -- for the pileup and the key kernel.) */
 
 /* ---- error profile: replaces the loop ErrorProfiling.java:146-409 ---------------------------- */
 int ps_profile_begin(ps_ctx* ctx, const ps_profile_opts* opts);
@@ -361,9 +364,10 @@ int ps_kernel_times(ps_ctx* ctx, float* ms, int max);
 void ps_kernel_times_reset(ps_ctx* ctx, int enabled);
 /* device times (ms) of the three kernels of the last pileup call: flag scan, cluster kernel, site compaction */
 int ps_pileup_stage_times(ps_ctx* ctx, float* ms3);
-/* 0: pileup calls on this context use the speculative boundary-flag pass (carry-in of a tile = maximum over its 32
- * predecessors, checked afterwards); 1: a check failed once (a record spanning more than 32 tiles of reads) and the
- * context keeps to the exact look-back pass.  Results are identical either way. */
+/* 0: pileup calls on this context use the speculative boundary-flag pass (carry-in of a 2048-read tile = maximum over
+ * the 128 reads in front of it, every assumption checked afterwards); 1: a check failed once (a record reaching over
+ * more than 128 of its successors) and the context keeps to the exact look-back pass.  Results are identical either
+ * way. */
 int ps_pileup_flag_mode(const ps_ctx* ctx);
 
 #ifdef __cplusplus

@@ -27,6 +27,11 @@ static void throw_status(JNIEnv* env, ps_ctx* ctx, int status) {
   if (cls) (*env)->ThrowNew(env, cls, msg);
 }
 
+static void throw_illegal(JNIEnv* env, const char* msg) {
+  jclass cls = (*env)->FindClass(env, "java/lang/IllegalArgumentException");
+  if (cls) (*env)->ThrowNew(env, cls, msg);
+}
+
 /* ---- context ------------------------------------------------------------------------------------------- */
 
 /* static native long create(int device); */
@@ -75,6 +80,19 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
   memset(&opts, 0, sizeof opts);
   opts.max_read_length = (uint32_t)maxReadLength;
   opts.infer_qualities = inferQualities ? 1u : 0u;
+  /* the library writes 16*maxLen, 16, 16, maxLen, maxLen, 8 and 256*maxLen elements: a shorter Java array would mean a
+   * write past its end, i.e. a corrupted JVM heap */
+  const jsize m = (jsize)maxReadLength;
+  if (maxReadLength <= 0 || !positionConversions || !qualityPerMismatch || !qualityPerMismatchCounts || !insertionsPerPos ||
+      !deletionsPerPos || !counters || (*env)->GetArrayLength(env, positionConversions) < 16 * m ||
+      (*env)->GetArrayLength(env, qualityPerMismatch) < 16 || (*env)->GetArrayLength(env, qualityPerMismatchCounts) < 16 ||
+      (*env)->GetArrayLength(env, insertionsPerPos) < m || (*env)->GetArrayLength(env, deletionsPerPos) < m ||
+      (*env)->GetArrayLength(env, counters) < PS_PC_COUNT ||
+      (inferQualities && (!qualityHist || (*env)->GetArrayLength(env, qualityHist) < 256 * m))) {
+    (*env)->ReleaseStringUTFChars(env, bam, path);
+    throw_illegal(env, "profileBam: a result array is missing or shorter than maxReadLength implies");
+    return;
+  }
   ps_profile_result r;
   memset(&r, 0, sizeof r);
   /* plain Get/Release (not Critical): the call runs for a while and must not block the collector */
@@ -84,17 +102,20 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
   r.insertions_per_pos = (double*)(*env)->GetDoubleArrayElements(env, insertionsPerPos, NULL);
   r.deletions_per_pos = (double*)(*env)->GetDoubleArrayElements(env, deletionsPerPos, NULL);
   r.counters = (int32_t*)(*env)->GetIntArrayElements(env, counters, NULL);
-  r.quality_hist = qualityHist ? (int64_t*)(*env)->GetLongArrayElements(env, qualityHist, NULL) : NULL;
-  int st = ps_profile_bam(ctx, path, &opts, &r);
-  (*env)->ReleaseIntArrayElements(env, positionConversions, (jint*)r.position_conversions, 0);
-  (*env)->ReleaseIntArrayElements(env, qualityPerMismatch, (jint*)r.quality_per_mismatch, 0);
-  (*env)->ReleaseIntArrayElements(env, qualityPerMismatchCounts, (jint*)r.quality_per_mismatch_counts, 0);
-  (*env)->ReleaseDoubleArrayElements(env, insertionsPerPos, (jdouble*)r.insertions_per_pos, 0);
-  (*env)->ReleaseDoubleArrayElements(env, deletionsPerPos, (jdouble*)r.deletions_per_pos, 0);
-  (*env)->ReleaseIntArrayElements(env, counters, (jint*)r.counters, 0);
-  if (qualityHist) (*env)->ReleaseLongArrayElements(env, qualityHist, (jlong*)r.quality_hist, 0);
+  r.quality_hist = (inferQualities && qualityHist) ? (int64_t*)(*env)->GetLongArrayElements(env, qualityHist, NULL) : NULL;
+  /* Get*ArrayElements returns NULL (with an OutOfMemoryError pending) when the VM cannot pin or copy */
+  const int got_all = r.position_conversions && r.quality_per_mismatch && r.quality_per_mismatch_counts && r.insertions_per_pos &&
+                      r.deletions_per_pos && r.counters && (!(inferQualities && qualityHist) || r.quality_hist);
+  int st = got_all ? ps_profile_bam(ctx, path, &opts, &r) : PS_OK;
+  if (r.position_conversions) (*env)->ReleaseIntArrayElements(env, positionConversions, (jint*)r.position_conversions, 0);
+  if (r.quality_per_mismatch) (*env)->ReleaseIntArrayElements(env, qualityPerMismatch, (jint*)r.quality_per_mismatch, 0);
+  if (r.quality_per_mismatch_counts) (*env)->ReleaseIntArrayElements(env, qualityPerMismatchCounts, (jint*)r.quality_per_mismatch_counts, 0);
+  if (r.insertions_per_pos) (*env)->ReleaseDoubleArrayElements(env, insertionsPerPos, (jdouble*)r.insertions_per_pos, 0);
+  if (r.deletions_per_pos) (*env)->ReleaseDoubleArrayElements(env, deletionsPerPos, (jdouble*)r.deletions_per_pos, 0);
+  if (r.counters) (*env)->ReleaseIntArrayElements(env, counters, (jint*)r.counters, 0);
+  if (r.quality_hist) (*env)->ReleaseLongArrayElements(env, qualityHist, (jlong*)r.quality_hist, 0);
   (*env)->ReleaseStringUTFChars(env, bam, path);
-  if (st != PS_OK) throw_status(env, ctx, st);
+  if (got_all && st != PS_OK) throw_status(env, ctx, st);     /* !got_all: the VM's own exception is pending */
 }
 
 /* ---- T>C pileup ------------------------------------------------------------------------------------------
@@ -141,12 +162,23 @@ JNIEXPORT jint JNICALL Java_utils_pileupclusters_NativePileup_nextClusters(JNIEn
                                                                              jlongArray cluster64, jint maxClusters,
                                                                              jlongArray site64, jint maxSites) {
   (void)c;
+  /* ps_cluster = 8 and ps_site = 3 64-bit words: the arrays must hold maxClusters / maxSites records */
+  if (!cluster64 || maxClusters < 0 || maxSites < 0 || (maxSites > 0 && !site64) ||
+      (jlong)(*env)->GetArrayLength(env, cluster64) < 8 * (jlong)maxClusters ||
+      (site64 && (jlong)(*env)->GetArrayLength(env, site64) < 3 * (jlong)maxSites)) {
+    throw_illegal(env, "nextClusters: cluster64 / site64 are shorter than maxClusters * 8 / maxSites * 3");
+    return 0;
+  }
   jlong* cl = (*env)->GetLongArrayElements(env, cluster64, NULL);
-  jlong* si = (*env)->GetLongArrayElements(env, site64, NULL);
-  int64_t n = ps_pileup_next((ps_pileup*)(intptr_t)handle, (uint64_t)first, (ps_cluster*)cl, (uint64_t)maxClusters,
-                             (ps_site*)si, (uint64_t)maxSites);
-  (*env)->ReleaseLongArrayElements(env, cluster64, cl, 0);
-  (*env)->ReleaseLongArrayElements(env, site64, si, 0);
+  jlong* si = site64 ? (*env)->GetLongArrayElements(env, site64, NULL) : NULL;
+  int64_t n = 0;
+  const int got_all = cl && (si || !site64);
+  if (got_all)
+    n = ps_pileup_next((ps_pileup*)(intptr_t)handle, (uint64_t)first, (ps_cluster*)cl, (uint64_t)maxClusters, (ps_site*)si,
+                       si ? (uint64_t)maxSites : 0);
+  if (cl) (*env)->ReleaseLongArrayElements(env, cluster64, cl, 0);
+  if (si) (*env)->ReleaseLongArrayElements(env, site64, si, 0);
+  if (!got_all) return 0;                                       /* the VM's OutOfMemoryError is pending */
   if (n < 0) { throw_status(env, NULL, (int)n); return 0; }
   return (jint)n;
 }

@@ -308,6 +308,10 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
   cudaSetDevice(ctx->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->reset_ev, 0));     // the clearing may have been queued on another stream
+  // a batch in a staging slot of this context (ps_batch_upload) run on a caller's stream: wait for its upload
+  for (int slot = 0; slot < 2; ++slot)
+    if (s != ctx->stream && b->n_reads && b->meta == ctx->staged[slot].view.meta && ctx->staged_done[slot])
+      PS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->staged_done[slot], 0));
   ctx->profile_stream = s;
   unsigned long long* masks = nullptr;
   ctx->t2c_mask_n = 0;

@@ -1723,16 +1723,15 @@ static int pileup_finish(ps_ctx* ctx, ps_pileup* H) {
 static int run_pileup(ps_ctx* ctx, const DeviceBatch& b, const ps_pileup_opts* opts, cudaStream_t st, ps_pileup** out,
                       bool wait = true) {
   if (ctx->pl_pending) return set_error(ctx, PS_ERR_STATE, "a submitted pileup call of this context has not been waited for");
-  // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch) and is run on the context's
-  // own stream: the pileup never reads qualities, so it goes to the auxiliary stream as soon as the other streams of
-  // the records have arrived, while the quality bytes (more than half of the upload) are still on their way.
-  if (st == ctx->stream && ctx->stream2) {
-    for (int slot = 0; slot < 2; ++slot)
-      if (b.n_reads && b.meta == ctx->staged[slot].view.meta && ctx->staged_core[slot]) {
-        cudaStreamWaitEvent(ctx->stream2, ctx->staged_core[slot], 0);
-        st = ctx->stream2;
-      }
-  }
+  // A batch that sits in a staging slot of this context (ps_batch_upload / ps_pileup_batch): the pileup never reads
+  // qualities, so it may start as soon as the other streams of the records have arrived (event staged_core), while the
+  // quality bytes (more than half of the upload) are still on their way.  Asked to run on the context's own stream --
+  // behind the whole upload -- it goes to the auxiliary stream instead; on a caller's stream it waits for the event.
+  for (int slot = 0; slot < 2; ++slot)
+    if (b.n_reads && b.meta == ctx->staged[slot].view.meta && ctx->staged_core[slot]) {
+      if (st == ctx->stream && ctx->stream2) st = ctx->stream2;
+      if (st != ctx->stream) cudaStreamWaitEvent(st, ctx->staged_core[slot], 0);
+    }
   ps_pileup* H = new ps_pileup();
   *out = H;
   H->ctx = ctx;
@@ -1879,6 +1878,11 @@ int ps_pileup_max_key_device(ps_ctx* ctx, const ps_read_batch* dev_batch, void* 
   if (!ctx->ref_loaded) return set_error(ctx, PS_ERR_STATE, "no reference loaded");
   cudaSetDevice(ctx->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // a batch in a staging slot of this context, keyed on a caller's stream: meta / ref_start / cigar have arrived once
+  // the slot's core event has fired (the key kernel reads nothing else)
+  for (int slot = 0; slot < 2; ++slot)
+    if (st != ctx->stream && dev_batch->n_reads && dev_batch->meta == ctx->staged[slot].view.meta && ctx->staged_core[slot])
+      cudaStreamWaitEvent(st, ctx->staged_core[slot], 0);
   cudaError_t err = cudaSuccess;
   unsigned long long* d_key = scratch<unsigned long long>(ctx, 9, 1, err);
   if (err != cudaSuccess) return cuda_fail(ctx, err, "pileup scratch");

@@ -29,7 +29,7 @@
 #define FAST_THREADS 128
 #define FAST_WARPS (FAST_THREADS / 32)
 #ifndef FAST_BLOCKS_PER_SM
-#define FAST_BLOCKS_PER_SM 5
+#define FAST_BLOCKS_PER_SM 4
 #endif
 #define FAST_QCOPIES 8         // copies of the per-pair mismatch quality cells (spreads same-address reductions)
 
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
     //      while the warp looks at the contig bounds and the N calls.  The window offset is clamped to the reference, so
     //      the loads need no knowledge of the read's fate (a read outside the shape may carry any offset)
     uint32_t meta[2], g0[2], cg[2];
-    uint32_t rf[2][NW], iv[2][2];
+    uint32_t rw[2][NW + 1], ri[2][3], rsh[2];      // raw window words; funnel-shifted into place further down
     {
       const uint32_t g_last = (uint32_t)(P.ref.n_bases - 1);
 #pragma unroll
@@ -367,17 +367,12 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
         g0[h] = lds32(a_sb + lay.start + rit * 4);
         cg[h] = lds32(a_sb + lay.cigar + rit * 4);
         const uint32_t g = min(g0[h], g_last);
-        const uint32_t wi = g >> 4, sh = (g & 15u) * 2u;
-        uint32_t w[NW + 1];
+        rsh[h] = g & 31u;
 #pragma unroll
-        for (int k = 0; k <= NW; ++k) w[k] = __ldg(P.ref.seq2 + wi + k);
-        const uint32_t ii = g >> 5, s1 = g & 31u;
-        const uint32_t i0 = __ldg(P.ref.inv + ii), i1 = __ldg(P.ref.inv + ii + 1);
-        const uint32_t i2 = (LT == 0 || LT > 32) ? __ldg(P.ref.inv + ii + 2) : 0u;
-#pragma unroll
-        for (int k = 0; k < NW; ++k) rf[h][k] = __funnelshift_r(w[k], w[k + 1], sh);
-        iv[h][0] = __funnelshift_r(i0, i1, s1) & ivmask0;
-        iv[h][1] = (LT == 0 || LT > 32) ? (__funnelshift_r(i1, i2, s1) & ivmask1) : 0u;
+        for (int k = 0; k <= NW; ++k) rw[h][k] = __ldg(P.ref.seq2 + (g >> 4) + k);
+        ri[h][0] = __ldg(P.ref.inv + (g >> 5));
+        ri[h][1] = __ldg(P.ref.inv + (g >> 5) + 1);
+        ri[h][2] = (LT == 0 || LT > 32) ? __ldg(P.ref.inv + (g >> 5) + 2) : 0u;
       }
     }
     // contig bounds: reads starting and ending inside the contig of the tile's first read pass the range test
@@ -402,7 +397,14 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
         if (e != cur_lo) x = (e + lane < cur_hi) ? __ldg(P.b.exc + e + lane) : 0xFFFFFFFFu;
         if (x != 0xFFFFFFFFu && ((x >> 22) & 3u) == quarter) {
           const uint32_t rit = (x >> 16) & 63u, p = x & 0xFFFFu;
-          if (p < 16u * NW) atomicOr(&s_inv[rit * NW + (p >> 4)], 1u << (2u * (p & 15u)));
+          if (p < L) {
+            atomicOr(&s_inv[rit * NW + (p >> 4)], 1u << (2u * (p & 15u)));
+            // An N call is never counted, but the quality sums below run over ALL positions: clear the byte that pairs
+            // with this base in the warp's copy of the qualities (index = distance from the 5' end: qualities are not
+            // reversed with the bases, Q10), so that nothing has to be taken out again afterwards.
+            const bool minus = (lds32(a_sb + lay.meta + rit * 4) & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_sb + lay.qual + rit * L + (minus ? L - 1u - p : p)), "r"(0u) : "memory");
+          }
         }
       }
       __syncwarp();
@@ -410,11 +412,15 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
 
     // ================= the two reads of this lane, one straight-line body =======================================
     bool ok[2], rev[2], hasn[2], anyinv[2], punct[2];
-    uint32_t rd[2][NW], ve[2][NW];
+    uint32_t rf[2][NW], iv[2][2], rd[2][NW], ve[2][NW];
     uint32_t a_qrow[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t rit = lane + h * 32;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) rf[h][k] = __funnelshift_r(rw[h][k], rw[h][k + 1], (rsh[h] & 15u) * 2u);
+      iv[h][0] = __funnelshift_r(ri[h][0], ri[h][1], rsh[h]) & ivmask0;
+      iv[h][1] = (LT == 0 || LT > 32) ? (__funnelshift_r(ri[h][1], ri[h][2], rsh[h]) & ivmask1) : 0u;
       const bool shaped = ((meta[h] ^ metaE) & kMetaMask) == 0 && cg[h] == cgE;
       ok[h] = shaped && (g0[h] - lo32) <= span32 && span_ok && rit < n_here;
       rev[h] = ok[h] && (meta[h] & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
@@ -448,23 +454,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
           uint32_t* row = s_inv + (lane + h * 32) * NW;
           punct[h] = ok[h];
 #pragma unroll
-          for (int k = 0; k < NW; ++k) {
-            uint32_t r = row[k];
-            row[k] = 0;
-            ve[h][k] &= ~r;
-            // the quality of an N call went into the all-position sums (code 0 = A; T once the minus strand is
-            // complemented): take it out here, where the calls are at hand -- unless the window holds invalid
-            // reference positions too, in which case the loop over all invalid positions below does it
-            if (ok[h] && !anyinv[h])
-              while (r) {
-                const uint32_t b = (uint32_t)__ffs((int)r) - 1u;
-                r &= r - 1u;
-                const uint32_t p = 16u * k + (b >> 1);
-                const int q = lds_s8(a_qrow[h] + (rev[h] ? L - 1u - p : p));
-                qinv[0] += rev[h] ? 0 : q;
-                qinv[3] += rev[h] ? q : 0;
-              }
-          }
+          for (int k = 0; k < NW; ++k) { ve[h][k] &= ~row[k]; row[k] = 0; }
         }
       }
     }

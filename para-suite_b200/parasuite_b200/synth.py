@@ -105,3 +105,58 @@ def synth_reads(ref: PackedReference, n_reads: int, read_len: int, seed: int = 0
     batch._owner = _SynthHandle(h)
     batch.n_clusters_generated = int(lib.ps_synth_n_clusters(h))
     return batch
+
+
+def bridge_cluster(ref: PackedReference, start_global: int, count: int = 256, read_len: int = 36) -> ReadBatch:
+    """`count` identical plus-strand reads `read_len`M at global offset `start_global`: the reference window with a C at
+    the first T.  bench.py puts such a cluster on either side of a mid-contig shard cut, so that one cluster spans the
+    cut (open cluster of shard s-1 + head partial of shard s) and the halo merge has real work.  No N calls."""
+    L, T = read_len, abi.PS_TILE_READS
+    pos = np.arange(start_global, start_global + L, dtype=np.int64)
+    codes = ((ref.seq2[pos >> 4] >> ((pos & 15) * 2).astype(np.uint32)) & 3).astype(np.uint8)
+    invalid = ((ref.inv[pos >> 5] >> (pos & 31).astype(np.uint32)) & 1).astype(bool)
+    t = np.nonzero((codes == 3) & ~invalid)[0]
+    if len(t):
+        codes[t[0]] = 1
+    bb = (L + 3) // 4
+    padded = np.zeros(bb * 4, dtype=np.uint8)
+    padded[:L] = codes
+    row = (padded[0::4] | (padded[1::4] << 2) | (padded[2::4] << 4) | (padded[3::4] << 6)).astype(np.uint8)
+    nt = (count + T - 1) // T
+    edges = np.minimum(np.arange(nt + 1, dtype=np.uint64) * np.uint64(T), np.uint64(count))
+    return ReadBatch(
+        count, np.full(count, L | (1 << 16), dtype=np.uint32), np.full(count, start_global, dtype=np.uint32),
+        np.concatenate((np.tile(row, count), np.zeros(64, np.uint8))),
+        np.concatenate((np.full(count * L, 30, dtype=np.uint8), np.zeros(64, np.uint8))),
+        np.concatenate((np.full(count, L << 4, dtype=np.uint32), np.zeros(16, np.uint32))), edges * np.uint64(bb),
+        edges * np.uint64(L), edges.copy(), np.zeros(nt + 1, dtype=np.uint32), np.zeros(16, dtype=np.uint32),
+        uniform_len=L, uniform_ncigar=1, bases_bytes=count * bb, qual_bytes=count * L, cigar_count=count, exc_count=0)
+
+
+def concat_uniform(head, body: ReadBatch, tail=None) -> ReadBatch:
+    """head ++ body ++ tail for uniform batches (one length, one cigar op per read).  head and tail hold no N calls and
+    head is a whole number of tiles, so the body's exception list keeps its (read in tile, position) keys."""
+    T = abi.PS_TILE_READS
+    L, bb = body.uniform_len, (body.uniform_len + 3) // 4
+    parts = [p for p in (head, body, tail) if p is not None]
+    for p in parts:
+        if p.uniform_len != L or p.uniform_ncigar != 1 or (p is not body and p.exc_count):
+            raise ValueError("concat_uniform: parts must be uniform, head / tail without N calls")
+    if head is not None and head.n_reads % T:
+        raise ValueError("concat_uniform: head must be a whole number of tiles")
+    n = sum(p.n_reads for p in parts)
+    nt = (n + T - 1) // T
+    edges = np.minimum(np.arange(nt + 1, dtype=np.uint64) * np.uint64(T), np.uint64(n))
+    k_head = head.n_reads // T if head is not None else 0
+    nt_body = (body.n_reads + T - 1) // T
+    teo = np.zeros(nt + 1, dtype=np.uint32)
+    teo[k_head:k_head + nt_body + 1] = body.tile_exc_off[:nt_body + 1]
+    teo[k_head + nt_body + 1:] = body.tile_exc_off[nt_body]
+    pad8, pad32 = np.zeros(64, np.uint8), np.zeros(16, np.uint32)
+    return ReadBatch(
+        n, np.concatenate([p.meta[:p.n_reads] for p in parts]), np.concatenate([p.ref_start[:p.n_reads] for p in parts]),
+        np.concatenate([p.bases2[:p.n_reads * bb] for p in parts] + [pad8]),
+        np.concatenate([p.qual[:p.n_reads * L] for p in parts] + [pad8]),
+        np.concatenate([p.cigar[:p.n_reads] for p in parts] + [pad32]), edges * np.uint64(bb), edges * np.uint64(L),
+        edges.copy(), teo, np.concatenate((body.exc[:body.exc_count], pad32)), uniform_len=L, uniform_ncigar=1,
+        bases_bytes=n * bb, qual_bytes=n * L, cigar_count=n, exc_count=body.exc_count)

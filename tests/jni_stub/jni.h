@@ -30,6 +30,7 @@ struct JNINativeInterface_ {
   void (*ReleaseIntArrayElements)(JNIEnv*, jintArray, jint*, jint);
   void (*ReleaseLongArrayElements)(JNIEnv*, jlongArray, jlong*, jint);
   void (*ReleaseDoubleArrayElements)(JNIEnv*, jdoubleArray, jdouble*, jint);
+  jsize (*GetArrayLength)(JNIEnv*, jarray);
   jlongArray (*NewLongArray)(JNIEnv*, jsize);
   void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jsize, jsize, const jlong*);
 };

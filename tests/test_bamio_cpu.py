@@ -163,3 +163,20 @@ def test_reference_fixture_fasta(tmp_path):
     assert got.lengths == [483300]
     assert np.array_equal(got.seq2, exp.seq2) and np.array_equal(got.inv, exp.inv)
     assert int(np.unpackbits(got.inv.view(np.uint8)).sum()) == seq.upper().count(b"N")
+
+
+def test_more_than_255_cigar_ops_is_refused_by_name(tmp_path):
+    """htsjdk takes any number of CIGAR elements (ErrorProfiling.java:206-207); the SoA keeps 8 bits per record.  The
+    batcher refuses such a file with PS_ERR_UNSUPPORTED and the ordinal of the record instead of dropping its CIGAR."""
+    contigs = [("chr1", b"ACGT" * 400)]
+    cig = "".join("1M1I" for _ in range(130)) + "1M"
+    recs = [Record(0, "chr1", 5, "20M", b"ACGT" * 5, bytes([30] * 20)),
+            Record(0, "chr1", 10, cig, b"A" * 261, bytes([30] * 261))]
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "x.bam")
+    write_fasta(fa, contigs)
+    write_bam(bam, [("chr1", 1600)], recs)
+    pf = PackedFasta(fa)
+    with pytest.raises(abi.PsError) as e:
+        list(BamBatcher(bam, pf))
+    assert e.value.status == abi.PS_ERR_UNSUPPORTED and "record 1 " in str(e.value)
+    pf.close()

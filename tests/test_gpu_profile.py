@@ -207,8 +207,8 @@ def test_long_reads_dense_cigar(ctx, oracle, infer_q):
 
 
 def test_more_than_255_cigar_ops_is_flagged(ctx, oracle):
-    """A record with > 255 cigar ops cannot be represented (PS_RF_CIGAR_OVERFLOW): it reaches the kernels without ops,
-    i.e. as an empty-CIGAR mapped read, on which the JVM dies (refSequenceForRead[0] of an empty array)."""
+    """A record with > 255 cigar ops cannot be held by the SoA (PS_RF_CIGAR_OVERFLOW; htsjdk takes any number,
+    ErrorProfiling.java:206-207): both tools refuse the batch by name (PS_ERR_UNSUPPORTED) instead of inventing a result."""
     contigs = [("chr1", b"ACGT" * 400)]
     cig = "".join("1M1I" for _ in range(130)) + "1M"          # 261 ops, 261 read bases... 131 M + 130 I
     seq = b"A" * 261
@@ -217,8 +217,14 @@ def test_more_than_255_cigar_ops_is_flagged(ctx, oracle):
     batch = ReadBatch.from_records([rec], ref)
     assert (int(batch.meta[0]) >> 24) & abi.PS_RF_CIGAR_OVERFLOW
     ctx.upload_reference(ref)
-    with pytest.raises(abi.ReferenceWouldThrow) as e:
+    with pytest.raises(abi.PsError) as e:
         ctx.profile(batch, 600)
-    with pytest.raises(oracle.OracleFault) as eo:
-        oracle.profile(ref, batch, 600)
-    assert e.value.fault == (eo.value.code, eo.value.ordinal)
+    assert e.value.status == abi.PS_ERR_UNSUPPORTED and not isinstance(e.value, abi.ReferenceWouldThrow)
+    with pytest.raises(abi.PsError) as e:
+        ctx.pileup(batch)
+    assert e.value.status == abi.PS_ERR_UNSUPPORTED
+    # a good read in front of it: the fault names the offending record, earlier records are not affected
+    good = Record(0, "chr1", 5, "20M", b"ACGT" * 5, bytes([30] * 20))
+    with pytest.raises(abi.PsError) as e:
+        ctx.profile(ReadBatch.from_records([good, rec], ref), 600)
+    assert e.value.status == abi.PS_ERR_UNSUPPORTED and "record 1 " in str(e.value)
