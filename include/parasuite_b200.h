@@ -353,6 +353,32 @@ int ps_flush_totals_get(const ps_flush* f, ps_flush_totals* out, double* allele_
 const char* ps_flush_error(const ps_flush* f);
 void ps_flush_destroy(ps_flush* f);
 
+/* ---- output files of the clust tool (host code, usable without a GPU) --------------------------------------
+ * What PileupClusters.java writes: <out> (cluster rows with the cluster sequence assembled read by read, :317-343 and
+ * :367-487), <out>.ccr.fasta / <out>.ccr.tsv (:262-315), <out>.report (:502-514), <bam>.sitefrequency.tsv and
+ * <bam>.sitepositions.tsv (:529-545) -- byte for byte, doubles printed as Double.toString prints them.
+ * The writer is fed, batch by batch and in file order, with the host SoA of the records (it walks their CIGARs for the
+ * cluster sequence) and with the clusters that closed with that batch (ps_pileup_next; after the halo merge when the
+ * file is taken in windows); it flushes them through `flush` (ps_flush_clusters must not be called for them again).
+ * A read opens a cluster iff its ordinal is the first_read of the next record: boundaries are never re-derived here.
+ * fasta_path needs <fasta>.fai; contigs must be those of the packed reference, in the same order. */
+typedef struct ps_clust_writer ps_clust_writer;
+int ps_clust_writer_open(ps_clust_writer** out, ps_flush* flush, const char* fasta_path, const char* out_path,
+                         const char* bam_path);
+int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* host_batch, uint64_t first_ordinal,
+                         const ps_cluster* closed, uint64_t n_closed, const ps_site* sites, int has_open,
+                         uint64_t open_first_read);
+/* end of the run: the last cluster is never flushed (:528-529); writes .report / sitefrequency / sitepositions and
+ * closes every file.  totals: skipped_due_indel and double_stranded of the whole run are used. */
+int ps_clust_writer_finish(ps_clust_writer* w, const ps_pileup_counters* totals);
+/* PS_ERR_REFERENCE_WOULD_THROW from ps_clust_writer_feed: the record on whose FASTA fetch the JVM would have died */
+int ps_clust_writer_fault(const ps_clust_writer* w, ps_fault* out);
+/* rows written so far; CCR windows that begin in front of their contig (anchor within 20 bases of its start: htsjdk
+ * then reads file bytes in front of the contig -- not emulated, the window is written empty) */
+void ps_clust_writer_stats(const ps_clust_writer* w, uint64_t* rows, uint64_t* ccr_rows, uint64_t* ccr_start_before_contig);
+const char* ps_clust_writer_error(const ps_clust_writer* w);
+void ps_clust_writer_close(ps_clust_writer* w);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 uint64_t ps_kernel_launches(const ps_ctx* ctx);

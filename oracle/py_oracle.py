@@ -771,3 +771,213 @@ def profile_outputs(st: ProfileState, infer_qual: bool, fmt) -> Dict[str, str]:
     out["indelprofile"] = fmt(ins_all) + "\t" + fmt(del_all)
     out["averaged_t2c_epr"] = fmt(avg)
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# Output files of the `clust` tool, literally (PileupClusters.java:62-545): the record loop again, this time WITH the
+# cluster sequence (tempClusterBytes :367-414, :421-487) and every writer.  TEST INFRASTRUCTURE: the native writer
+# (csrc/clust_writer.cpp) is compared with these texts byte for byte.
+# ------------------------------------------------------------------------------------------
+def java_double_str(x: float) -> str:
+    """Double.toString (shortest round-trip digits; decimal for 1e-3 <= |x| < 1e7, else d.dddE<exp>)."""
+    if x != x:
+        return "NaN"
+    if x == float("inf"):
+        return "Infinity"
+    if x == float("-inf"):
+        return "-Infinity"
+    if x == 0:
+        return "-0.0" if math.copysign(1.0, x) < 0 else "0.0"
+    sign = "-" if x < 0 else ""
+    a = abs(x)
+    mant, exp = f"{a:.17e}".split("e")
+    # shortest repr digits
+    r = repr(a)
+    if "e" in r:
+        m, e = r.split("e")
+        e10 = int(e)
+    else:
+        m, e10 = r, 0
+    ip, _, fp = m.partition(".")
+    raw = ip + fp
+    lead = len(raw) - len(raw.lstrip("0"))
+    digits = raw.lstrip("0").rstrip("0") or "0"
+    point = len(ip) + e10 - lead            # number of digits in front of the decimal point
+    if 1e-3 <= a < 1e7:
+        if point <= 0:
+            return sign + "0." + "0" * (-point) + digits
+        if point >= len(digits):
+            return sign + digits + "0" * (point - len(digits)) + ".0"
+        return sign + digits[:point] + "." + digits[point:]
+    return sign + digits[0] + "." + (digits[1:] or "0") + "E" + str(point - 1)
+
+
+def _rc_bytes(b: bytearray) -> bytearray:
+    a = JArray(list(b))
+    reverse_complement(a)
+    return bytearray(a.a)
+
+
+class JvmWouldDie(Exception):
+    """An exception the Java code does not catch (SAMException outside a try block)."""
+
+
+def clust_files(records: List[Rec], genome: Genome, snps: SnpDb, min_cov: int) -> Dict[str, str]:
+    """Returns the text of <out>, <out>.ccr.fasta, <out>.ccr.tsv, <out>.report, <bam>.sitefrequency.tsv and
+    <bam>.sitepositions.tsv as the Java tool writes them."""
+    nl = "\n"
+    fmt = java_double_str
+    out = {"pileup": "ClusterID\tChr\tStart\tEnd\tStrand\t#reads\t#T2C\t#T2C sites\tT2C Fraction\tSeqenece\tCombStrand\tSeqLength" + nl,
+           "ccr.fasta": "",
+           "ccr.tsv": "Protein_Group\tCluster ID\tStrand\tChromosome\tCluster_Begin\tCluster_End\tAnchor_FlankSeq_Begin"
+                      "\tAnchor_FlankSeq_End\tAnchor_FlankSeq\tAnchor_Position\tCluster_Clone_Count\tNumber_of_T2C_Positions"
+                      "\tT2C_Freq_at_Anchor_Position\tT2C_Fract_at_Anchor_Position\tT2C_Freq_Whole_Cluster"
+                      "\tT2C_Fract_Whole_Cluster" + nl,
+           "report": "", "sitefrequency": "", "sitepositions": ""}
+    num_crosslinked = 0
+    num_allele_positions = 0
+    afi: List[float] = []
+    allele_positions = [0] * 51
+    mask = JArray(51)
+    t_start = t_end = 0
+    t_chr = ""
+    t_bytes = bytearray()
+    n_reads = n_t2c = n_t2c_sites = 0
+    double_stranded = 0
+    mutation_map = JHashMap()
+    covered_map = JHashMap()
+    is_reverse = [False]
+    t_is_reverse = False
+    cluster_id = ""
+    running_id = 1
+    snp_count = 0                      # `SNPs`: declared, printed, never incremented (:135, :504)
+    snp_hit = high_frequent_error = skipped_due_indel = 0
+
+    def fetch(chrom, a, b):
+        try:
+            return genome.fetch(chrom, a, b)
+        except KeyError as e:
+            raise JvmWouldDie(str(e))
+
+    for ordinal, r in enumerate(records):
+        if r.unmapped:
+            continue
+        cs = r.cigar_string()
+        if (("I" in cs) or ("D" in cs)) and ("N" in cs):
+            skipped_due_indel += 1
+            continue
+        if (t_end - r.pos) < 5 or r.rname != t_chr:
+            fraction = 0.0
+            if n_reads >= min_cov:                                              # :180
+                n_t2c_sites = mutation_map.size
+                best_pos, best_val = -1, 0.0
+                tmp = JHashMap()
+                tmp.put_all(mutation_map)
+                for key in mutation_map.keys():
+                    if snps.query(t_chr, key, "T", "C"):
+                        tmp.remove(key)
+                        snp_hit += 1
+                    if mutation_map.get(key) == 1:
+                        high_frequent_error += 1
+                mutation_map.clear()
+                mutation_map.put_all(tmp)
+                if n_t2c_sites > 0:
+                    amounts: List[float] = []
+                    for key in mutation_map.keys():
+                        v = float(mutation_map.get(key)) / covered_map.get(key)
+                        if v >= best_val:
+                            best_val, best_pos = v, key
+                        amounts.append(v)
+                    amounts.sort(reverse=True)
+                    if amounts:
+                        s = 0.0
+                        for v in amounts:
+                            s += v
+                        if s >= 0.2:
+                            for k in range(len(amounts)):
+                                if len(afi) > k:
+                                    afi[k] = afi[k] + amounts[k]
+                                elif len(afi) == 0:
+                                    afi.extend(amounts)
+                                else:
+                                    afi.append(amounts[k])
+                            num_crosslinked += 1
+                            for j in range(51):
+                                if mask[j]:
+                                    allele_positions[j] += 1
+                                    num_allele_positions += 1
+                    for v in amounts:
+                        fraction += v
+                    if best_pos > 0:                                            # :262
+                        strand = _strand_str(is_reverse[0])
+                        try:
+                            ccr = bytearray(genome.fetch(t_chr, best_pos - 20, best_pos + 20))
+                            if strand == "-":
+                                ccr = _rc_bytes(ccr)
+                        except KeyError:                                        # catch (SAMException e)
+                            ccr = bytearray()
+                        ccr_seq = "".join(chr(c).upper() for c in ccr)
+                        out["ccr.fasta"] += (">" + cluster_id + " 20-anchor-20 " + t_chr + ":" + strand + ":" +
+                                             str(best_pos - 20) + "-" + str(best_pos + 20) + nl + ccr_seq + nl)
+                        out["ccr.tsv"] += ("Gene\t" + cluster_id + "\t" + strand + "\t" + t_chr + "\t" + str(t_start) + "\t" +
+                                           str(t_end) + "\t" + str(best_pos - 20) + "\t" + str(best_pos + 20) + "\t" + ccr_seq +
+                                           "\t" + str(best_pos) + "\t" + str(n_reads) + "\t" + str(n_t2c_sites) + "\t" +
+                                           str(mutation_map.get(best_pos)) + "\t" + fmt(best_val) + "\t" + str(n_t2c) + "\t" +
+                                           fmt(fraction) + nl)
+                seq = _rc_bytes(t_bytes) if t_is_reverse else t_bytes           # :318-321
+                seq_s = "".join(chr(c) for c in seq)
+                out["pileup"] += (cluster_id + "\t" + t_chr + "\t" + str(t_start) + "\t" + str(t_end) + "\t" +
+                                  ("-" if t_is_reverse else "+") + "\t" + str(n_reads) + "\t" + str(n_t2c) + "\t" +
+                                  str(n_t2c_sites) + "\t" + fmt(fraction) + "\t" + seq_s + "\t" + _strand_str(is_reverse[0]) +
+                                  "\t" + str(len(seq_s)) + nl)
+            t_start, t_end, t_chr = r.pos, r.end(), r.rname                     # :346-357
+            n_reads, n_t2c, n_t2c_sites = 1, 0, 0
+            is_reverse[0] = False
+            mutation_map.clear()
+            covered_map.clear()
+            running_id += 1
+            cluster_id = "cl_" + str(running_id) + "_" + t_chr
+            mask = JArray(51)
+            n_t2c = _cluster_information(ordinal, r, genome, is_reverse, mutation_map, covered_map, mask, n_t2c)
+            t_is_reverse = is_reverse[0]
+            t_bytes = bytearray()                                               # :367
+            cur = r.pos
+            for op, n in r.cigar:                                               # :374-414
+                if op == "D" or op == "M":
+                    t_bytes = t_bytes + bytearray(fetch(r.rname, cur, cur + n - 1))
+                if op != "I":
+                    cur += n
+        else:
+            t_chr = r.rname                                                     # :419
+            if r.end() > t_end:                                                 # :421
+                cur = r.pos
+                for op, n in r.cigar:
+                    if (cur + n - 1) < t_end:                                   # :429-436
+                        if op != "I":
+                            cur += n
+                        continue
+                    if op == "D" or op == "M":
+                        add = bytearray(fetch(r.rname, cur, cur + n - 1))
+                        overhang = t_end - cur + 1
+                        if overhang > 0:                                        # mergeByteSubArrays (:453-457)
+                            t_bytes = t_bytes + add[overhang:n]
+                        else:                                                   # mergeByteArrays(additionalNucs, tempClusterBytes)
+                            t_bytes = add + t_bytes
+                    t_end = r.end()                                             # :480
+                    if op != "I":
+                        cur += n
+            n_reads += 1
+            n_t2c = _cluster_information(ordinal, r, genome, is_reverse, mutation_map, covered_map, mask, n_t2c)
+            if is_reverse[0] is not None and t_is_reverse != is_reverse[0]:
+                double_stranded += 1
+                is_reverse[0] = None
+    out["report"] = ("Double stranded clusters found: " + str(double_stranded) + nl +
+                     "Loci found that are SNPs: " + str(snp_count) + nl +
+                     str(skipped_due_indel) + " insertion or deletion skipped" + nl +
+                     "T-C mutations identified as SNPs: " + str(snp_hit) + nl +
+                     "T-C mutations identified as SNVs (100% T-C in 1 site): " + str(high_frequent_error) + nl)
+    for v in afi:                                                               # :531-536
+        out["sitefrequency"] += fmt(_jdiv(v, num_crosslinked)) + nl
+    for j in range(51):                                                         # :538-543
+        out["sitepositions"] += fmt(_jdiv(float(allele_positions[j]), num_allele_positions)) + nl
+    return out

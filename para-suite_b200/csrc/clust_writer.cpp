@@ -1,0 +1,360 @@
+// Output files of the `clust` tool, natively: what PileupClusters.java does with every closed cluster AFTER the
+// arithmetic of the flush (flush.cpp) -- the cluster sequence it assembles read by read (:367-414 initial, :421-487
+// extension, mergeByteArrays / mergeByteSubArrays :723-748), the cluster row (:317-343), the CCR FASTA / TSV rows
+// (:262-315) -- and the end-of-run files (.report :502-514, sitefrequency / sitepositions :529-545).
+// (reference: /root/reference/src/src/utils/pileupclusters/PileupClusters.java)
+//
+// Host code, no GPU needed.  The record loop itself stays on the GPU: this writer is FED with the SoA batches the
+// kernels saw (for the CIGARs the sequence assembly walks) and with the closed cluster records they produced; it never
+// decides a cluster boundary itself -- a read opens a cluster iff its ordinal is the first_read of the next record.
+// The sequence quirks are kept: only M and D elements fetch reference bytes, every non-I element (S, H, N, P, =, X too)
+// advances the fetch cursor, an element that starts behind the cluster end is PREPENDED, raw FASTA case is kept,
+// the strand of the first read reverse-complements the sequence at flush.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "parasuite_b200.h"
+
+namespace {
+
+// Double.toString: shortest digit string that round-trips (JDK 19+; older JDKs print a longer string in rare cases),
+// decimal notation for 1e-3 <= |x| < 1e7, computerised scientific notation otherwise
+std::string java_double(double x) {
+  if (x != x) return "NaN";
+  if (x == 1.0 / 0.0) return "Infinity";
+  if (x == -1.0 / 0.0) return "-Infinity";
+  if (x == 0.0) return std::signbit(x) ? "-0.0" : "0.0";
+  char buf[64];
+  auto r = std::to_chars(buf, buf + sizeof buf, x < 0 ? -x : x, std::chars_format::scientific);
+  std::string s(buf, r.ptr);                  // d.ddddde[+-]xx (shortest)
+  const size_t e = s.find('e');
+  std::string digits;
+  for (size_t k = 0; k < e; ++k)
+    if (s[k] != '.') digits.push_back(s[k]);
+  const int exp10 = atoi(s.c_str() + e + 1);  // value = d.ddd * 10^exp10
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  const double a = x < 0 ? -x : x;
+  std::string out = x < 0 ? "-" : "";
+  if (a >= 1e-3 && a < 1e7) {
+    const int point = exp10 + 1;              // digits before the decimal point
+    if (point <= 0) out += "0." + std::string((size_t)(-point), '0') + digits;
+    else if ((size_t)point >= digits.size()) out += digits + std::string((size_t)point - digits.size(), '0') + ".0";
+    else out += digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+  } else {
+    out += digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : std::string("0")) + "E" + std::to_string(exp10);
+  }
+  return out;
+}
+
+struct RawFasta {      // IndexedFastaSequenceFile: raw bytes (case kept) by contig and 1-based inclusive range
+  struct Entry { std::string name; uint64_t len, offset, linebases, linewidth; };
+  std::vector<Entry> e;
+  std::vector<uint64_t> off;     // cumulative lengths = the global coordinate space of the packed reference
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  int fd = -1;
+  ~RawFasta() {
+    if (p) munmap((void*)p, n);
+    if (fd >= 0) close(fd);
+  }
+  bool open(const char* path, std::string& err) {
+    const std::string fp = std::string(path) + ".fai";
+    FILE* f = fopen(fp.c_str(), "r");
+    if (!f) { err = "cannot open " + fp; return false; }
+    char line[4096];
+    while (fgets(line, sizeof line, f)) {
+      char name[2048];
+      unsigned long long a, b, c, d;
+      if (sscanf(line, "%2047[^\t]\t%llu\t%llu\t%llu\t%llu", name, &a, &b, &c, &d) != 5) continue;
+      if (c == 0 || d < c) { fclose(f); err = "malformed .fai line"; return false; }
+      e.push_back({name, a, b, c, d});
+    }
+    fclose(f);
+    if (e.empty()) { err = "empty FASTA index"; return false; }
+    fd = ::open(path, O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) { err = std::string("cannot open ") + path; return false; }
+    n = (size_t)st.st_size;
+    void* m = n ? mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    if (n && m == MAP_FAILED) { err = std::string("cannot map ") + path; return false; }
+    p = (const uint8_t*)m;
+    off.assign(1, 0);
+    for (auto& x : e) off.push_back(off.back() + x.len);
+    return true;
+  }
+  // 0: ok; 1: SAMException (start > stop + 1, stop past the contig, unknown contig); 2: start < 1 -- htsjdk then reads
+  // file bytes in front of the contig (or dies on a negative file position), which is not emulated
+  int fetch(int64_t contig, int64_t start, int64_t stop, std::string& out) const {
+    out.clear();
+    if (contig < 0 || contig >= (int64_t)e.size()) return 1;
+    if (start > stop + 1) return 1;
+    const Entry& x = e[(size_t)contig];
+    if (stop > (int64_t)x.len) return 1;
+    if (start < 1) return 2;
+    out.resize((size_t)(stop - start + 1));
+    for (int64_t b = start - 1, k = 0; b < stop; ++b, ++k) {
+      const uint64_t at = x.offset + (uint64_t)b / x.linebases * x.linewidth + (uint64_t)b % x.linebases;
+      out[(size_t)k] = at < n ? (char)p[at] : 'N';
+    }
+    return 0;
+  }
+};
+
+void reverse_complement(std::string& s) {   // htsjdk SequenceUtil.reverseComplement: only ACGTacgt are mapped
+  auto comp = [](char c) {
+    switch (c) {
+      case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+      case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+      default: return c;
+    }
+  };
+  const size_t n = s.size();
+  for (size_t i = 0; i < n / 2; ++i) { const char a = comp(s[i]), b = comp(s[n - 1 - i]); s[i] = b; s[n - 1 - i] = a; }
+  if (n & 1) s[n / 2] = comp(s[n / 2]);
+}
+
+const char* kStrand[3] = {"+", "-", "+/-"};
+
+}  // namespace
+
+struct ps_clust_writer {
+  ps_flush* flush = nullptr;
+  RawFasta fa;
+  FILE *f_pileup = nullptr, *f_ccr_fa = nullptr, *f_ccr_tsv = nullptr, *f_report = nullptr, *f_sitefreq = nullptr,
+       *f_sitepos = nullptr;
+  std::string err;
+  ps_fault fault{};
+  // the cluster being assembled (Java: tempClusterBytes, tempClusterEnd)
+  bool have = false;
+  std::string bytes;
+  int64_t cluster_end = 0;
+  uint64_t cluster_first = 0;
+  // closed records waiting for their cluster to end in the read stream
+  struct Pending { ps_cluster c; ps_flush_row row; };
+  std::deque<Pending> pending;
+  std::deque<uint64_t> starts;        // first_read ordinals of clusters that have not begun yet
+  uint64_t reads_fed = 0, rows_written = 0, ccr_written = 0, ccr_start_before_contig = 0;
+};
+
+static int cw_fail(ps_clust_writer* w, int st, const std::string& m) { w->err = m; return st; }
+
+static void cw_close_files(ps_clust_writer* w) {
+  for (FILE** f : {&w->f_pileup, &w->f_ccr_fa, &w->f_ccr_tsv, &w->f_report, &w->f_sitefreq, &w->f_sitepos})
+    if (*f) { fclose(*f); *f = nullptr; }
+}
+
+// rows of one closed cluster (PileupClusters.java:262-343)
+static int cw_write_cluster(ps_clust_writer* w, const ps_cluster& c, const ps_flush_row& row) {
+  if (!row.emitted) return PS_OK;                                            // numReadsPerCluster < minReadCoverage (:180)
+  const std::string chr = c.contig < w->fa.e.size() ? w->fa.e[c.contig].name : std::string("?");
+  const std::string id = "cl_" + std::to_string(c.running_id) + "_" + chr;   // :356
+  const char* comb = kStrand[c.combined_strand < 3 ? c.combined_strand : 2];
+  const std::string fraction = java_double(row.fraction);
+  if (row.has_ccr) {                                                         // tempBestMutationPos > 0 (:262)
+    std::string ccr;
+    const int rc = w->fa.fetch(c.contig, (int64_t)row.best_pos - 20, (int64_t)row.best_pos + 20, ccr);
+    if (rc == 2) w->ccr_start_before_contig++;
+    if (rc != 0) ccr.clear();                                                // catch (SAMException) -> new byte[0] (:278)
+    else if (c.combined_strand == 1) reverse_complement(ccr);                // getStrandOrientation().equals("-") (:271)
+    for (char& ch : ccr) ch = (char)toupper((unsigned char)ch);              // :283-288
+    fprintf(w->f_ccr_fa, ">%s 20-anchor-20 %s:%s:%d-%d\n%s\n", id.c_str(), chr.c_str(), comb, row.best_pos - 20,
+            row.best_pos + 20, ccr.c_str());
+    fprintf(w->f_ccr_tsv, "Gene\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%d\t%u\t%u\t%u\t%s\t%u\t%s\n", id.c_str(), comb, chr.c_str(),
+            c.start, c.end, row.best_pos - 20, row.best_pos + 20, ccr.c_str(), row.best_pos, c.num_reads, row.num_t2c_sites,
+            row.best_count, java_double(row.best_value).c_str(), c.num_t2c, fraction.c_str());
+    w->ccr_written++;
+  }
+  std::string seq = w->bytes;
+  if (c.first_reverse) reverse_complement(seq);                              // :318-321
+  fprintf(w->f_pileup, "%s\t%s\t%d\t%d\t%s\t%u\t%u\t%u\t%s\t%s\t%s\t%zu\n", id.c_str(), chr.c_str(), c.start, c.end,
+          c.first_reverse ? "-" : "+", c.num_reads, c.num_t2c, row.num_t2c_sites, fraction.c_str(), seq.c_str(), comb,
+          seq.size());
+  w->rows_written++;
+  return PS_OK;
+}
+
+extern "C" {
+
+int ps_clust_writer_open(ps_clust_writer** out, ps_flush* flush, const char* fasta_path, const char* out_path,
+                         const char* bam_path) {
+  if (!out) return PS_ERR_INVALID_ARG;
+  ps_clust_writer* w = new ps_clust_writer();
+  *out = w;                       // returned even on failure so the caller can read the message
+  if (!flush || !fasta_path || !out_path || !bam_path) return cw_fail(w, PS_ERR_INVALID_ARG, "NULL argument");
+  w->flush = flush;
+  if (!w->fa.open(fasta_path, w->err)) return PS_ERR_IO;
+  const std::string o = out_path, b = bam_path;
+  struct { FILE** f; std::string path; } files[] = {
+      {&w->f_pileup, o}, {&w->f_sitefreq, b + ".sitefrequency.tsv"}, {&w->f_ccr_fa, o + ".ccr.fasta"},
+      {&w->f_ccr_tsv, o + ".ccr.tsv"}, {&w->f_sitepos, b + ".sitepositions.tsv"}, {&w->f_report, o + ".report"}};   // :73-83
+  for (auto& f : files) {
+    *f.f = fopen(f.path.c_str(), "w");
+    if (!*f.f) { cw_close_files(w); return cw_fail(w, PS_ERR_IO, "cannot create " + f.path); }
+  }
+  fputs("ClusterID\tChr\tStart\tEnd\tStrand\t#reads\t#T2C\t#T2C sites\tT2C Fraction\tSeqenece\tCombStrand\tSeqLength\n",
+        w->f_pileup);                                                                                                  // :94-96
+  fputs("Protein_Group\tCluster ID\tStrand\tChromosome\tCluster_Begin\tCluster_End\tAnchor_FlankSeq_Begin\tAnchor_FlankSeq_End"
+        "\tAnchor_FlankSeq\tAnchor_Position\tCluster_Clone_Count\tNumber_of_T2C_Positions\tT2C_Freq_at_Anchor_Position"
+        "\tT2C_Fract_at_Anchor_Position\tT2C_Freq_Whole_Cluster\tT2C_Fract_Whole_Cluster\n", w->f_ccr_tsv);            // :98-104
+  return PS_OK;
+}
+
+const char* ps_clust_writer_error(const ps_clust_writer* w) { return w ? w->err.c_str() : "no object"; }
+
+int ps_clust_writer_fault(const ps_clust_writer* w, ps_fault* out) {
+  if (!w || !out) return PS_ERR_INVALID_ARG;
+  *out = w->fault;
+  return PS_OK;
+}
+
+// One batch of records in file order (host SoA, ordinals first_ordinal ...), the clusters that closed with it -- in
+// order, flushed here through ps_flush_clusters -- and the first read of the cluster still open behind it.
+int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t first_ordinal, const ps_cluster* closed,
+                         uint64_t n_closed, const ps_site* sites, int has_open, uint64_t open_first_read) {
+  if (!w || !hb || (n_closed && !closed)) return PS_ERR_INVALID_ARG;
+  if (!w->f_pileup) return cw_fail(w, PS_ERR_STATE, "writer is closed");
+  // ---- arithmetic of the flush for the new records, in order (running state lives in the flush object) ----------
+  std::vector<ps_flush_row> rows(n_closed);
+  if (n_closed) {
+    const int st = ps_flush_clusters(w->flush, closed, n_closed, sites, rows.data());
+    if (st != PS_OK) return cw_fail(w, st, ps_flush_error(w->flush));
+  }
+  // a record whose cluster begins in this batch announces a start; so does the cluster still open behind the batch.  (A
+  // record of a cluster that began in an earlier batch was announced then, as that batch's open cluster.)
+  for (uint64_t k = 0; k < n_closed; ++k) {
+    w->pending.push_back({closed[k], rows[k]});
+    if (closed[k].first_read >= first_ordinal) w->starts.push_back(closed[k].first_read);
+  }
+  if (has_open && open_first_read >= first_ordinal) w->starts.push_back(open_first_read);
+
+  // ---- the records: cluster sequence read by read -------------------------------------------------------------------
+  const uint64_t n = hb->n_reads;
+  uint64_t coff = (!hb->uniform_ncigar && hb->tile_cigar_off) ? hb->tile_cigar_off[0] : 0;
+  std::string piece;
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint32_t meta = hb->meta[r], flags = PS_META_FLAGS(meta), ncig = PS_META_NCIGAR(meta);
+    const uint32_t* cig = hb->cigar + coff;
+    coff += ncig;
+    if (flags & PS_RF_UNMAPPED) continue;                                   // :146
+    bool hasI = false, hasD = false, hasN = false;
+    int64_t R = 0;
+    for (uint32_t e = 0; e < ncig; ++e) {
+      const uint32_t op = cig[e] & 15u;
+      hasI |= op == 1u; hasD |= op == 2u; hasN |= op == 3u;
+      if ((0x18Du >> op) & 1u) R += cig[e] >> 4;
+    }
+    if ((hasI || hasD) && hasN) continue;                                   // :152-157
+    const uint64_t ordinal = first_ordinal + r;
+    // contig and 1-based start from the global offset (same coordinate space as the packed reference)
+    const uint64_t g = hb->ref_start[r];
+    size_t ci = 0;
+    {
+      size_t lo = 0, hi = w->fa.e.size();
+      while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (w->fa.off[mid] <= g) lo = mid; else hi = mid; }
+      ci = lo;
+    }
+    const int64_t start = (int64_t)(g - w->fa.off[ci]) + 1, end = start + R - 1;
+    const bool opens = !w->starts.empty() && w->starts.front() == ordinal;
+    if (opens) {
+      w->starts.pop_front();
+      if (w->have) {                                                        // the previous cluster is flushed (:178)
+        if (w->pending.empty() || w->pending.front().c.first_read != w->cluster_first)
+          return cw_fail(w, PS_ERR_STATE, "cluster records and read stream disagree (records must be fed in order)");
+        const int st = cw_write_cluster(w, w->pending.front().c, w->pending.front().row);
+        w->pending.pop_front();
+        if (st) return st;
+      }
+      w->have = true;
+      w->cluster_first = ordinal;
+      w->cluster_end = end;                                                 // :347
+      w->bytes.clear();                                                     // :367
+      int64_t cur = start;
+      for (uint32_t e = 0; e < ncig; ++e) {
+        const uint32_t op = cig[e] & 15u;
+        const int64_t len = cig[e] >> 4;
+        if (op == 2u || op == 0u) {                                         // D or M only (:383-386)
+          const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
+          if (rc != 0) {      // SAMException outside any try block: the JVM dies here
+            w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
+            return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)");
+          }
+          w->bytes += piece;
+        }
+        if (op != 1u) cur += len;                                           // every non-I element advances (:402-404)
+      }
+    } else {
+      if (!w->have) return cw_fail(w, PS_ERR_STATE, "a kept read in front of the first cluster start");
+      if (end > w->cluster_end) {                                           // :421
+        int64_t cur = start;
+        for (uint32_t e = 0; e < ncig; ++e) {
+          const uint32_t op = cig[e] & 15u;
+          const int64_t len = cig[e] >> 4;
+          if (cur + len - 1 < w->cluster_end) {                             // :429-436
+            if (op != 1u) cur += len;
+            continue;
+          }
+          if (op == 2u || op == 0u) {
+            const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
+            if (rc != 0) {
+              w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
+              return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)");
+            }
+            const int64_t overhang = w->cluster_end - cur + 1;               // :449
+            if (overhang > 0) w->bytes.append(piece, (size_t)overhang, std::string::npos);   // mergeByteSubArrays (:453-457)
+            else w->bytes.insert(0, piece);                                 // mergeByteArrays(additionalNucs, tempClusterBytes) (:462)
+          }
+          w->cluster_end = end;                                             // :480, inside the element loop
+          if (op != 1u) cur += len;
+        }
+      }
+    }
+  }
+  w->reads_fed += n;
+  return PS_OK;
+}
+
+// End of the run (PileupClusters.java:502-545): the last cluster is never flushed; .report, sitefrequency and
+// sitepositions are written, every file is closed.
+int ps_clust_writer_finish(ps_clust_writer* w, const ps_pileup_counters* totals) {
+  if (!w || !totals) return PS_ERR_INVALID_ARG;
+  if (!w->f_pileup) return cw_fail(w, PS_ERR_STATE, "writer is closed");
+  ps_flush_totals t;
+  ps_flush_totals_get(w->flush, &t, nullptr, 0);
+  std::vector<double> afi(t.n_allele_frequency);
+  ps_flush_totals_get(w->flush, &t, afi.data(), afi.size());
+  fprintf(w->f_report, "Double stranded clusters found: %llu\n", (unsigned long long)totals->double_stranded);
+  fprintf(w->f_report, "Loci found that are SNPs: 0\n");                                  // `SNPs` is never incremented (:135)
+  fprintf(w->f_report, "%llu insertion or deletion skipped\n", (unsigned long long)totals->skipped_due_indel);
+  fprintf(w->f_report, "T-C mutations identified as SNPs: %llu\n", (unsigned long long)t.snp_hit);
+  fprintf(w->f_report, "T-C mutations identified as SNVs (100%% T-C in 1 site): %llu\n", (unsigned long long)t.high_frequent_error);
+  for (double v : afi) fprintf(w->f_sitefreq, "%s\n", java_double(v / (double)t.num_crosslinked_clusters).c_str());   // :531-536
+  for (int j = 0; j < 51; ++j)
+    fprintf(w->f_sitepos, "%s\n", java_double((double)t.allele_positions[j] / (double)t.num_allele_positions).c_str());   // :538-543
+  cw_close_files(w);
+  return PS_OK;
+}
+
+void ps_clust_writer_stats(const ps_clust_writer* w, uint64_t* rows, uint64_t* ccr_rows, uint64_t* ccr_start_before_contig) {
+  if (!w) return;
+  if (rows) *rows = w->rows_written;
+  if (ccr_rows) *ccr_rows = w->ccr_written;
+  if (ccr_start_before_contig) *ccr_start_before_contig = w->ccr_start_before_contig;
+}
+
+void ps_clust_writer_close(ps_clust_writer* w) {
+  if (!w) return;
+  cw_close_files(w);
+  delete w;
+}
+
+}  // extern "C"

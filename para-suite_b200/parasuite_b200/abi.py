@@ -145,6 +145,13 @@ EXPORTS = {
     "ps_reference_adopt_device": (C.c_int, [VP, C.POINTER(ps_reference), VP]),
     "ps_batch_upload": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_read_batch)]),
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "ps_clust_writer_open": (C.c_int, [C.POINTER(VP), VP, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "ps_clust_writer_feed": (C.c_int, [VP, C.POINTER(ps_read_batch), C.c_uint64, VP, C.c_uint64, VP, C.c_int, C.c_uint64]),
+    "ps_clust_writer_finish": (C.c_int, [VP, C.POINTER(ps_pileup_counters)]),
+    "ps_clust_writer_fault": (C.c_int, [VP, C.POINTER(ps_fault)]),
+    "ps_clust_writer_stats": (None, [VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ps_clust_writer_error": (C.c_char_p, [VP]),
+    "ps_clust_writer_close": (None, [VP]),
     "ps_profile_begin": (C.c_int, [VP, C.POINTER(ps_profile_opts)]),
     "ps_profile_masks_device": (C.c_int, [VP, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "ps_profile_batch": (C.c_int, [VP, C.POINTER(ps_read_batch)]),

@@ -111,3 +111,58 @@ class Flush:
             self.close()
         except Exception:
             pass
+
+
+class ClustWriter:
+    """The output files of the `clust` tool (PileupClusters.java:262-343, :367-487, :502-545) written natively
+    (csrc/clust_writer.cpp): <out>, <out>.ccr.fasta, <out>.ccr.tsv, <out>.report, <bam>.sitefrequency.tsv,
+    <bam>.sitepositions.tsv.  Feed it, in file order, the host batches the kernels saw and the clusters that closed
+    with each of them; it runs them through `flush` itself."""
+
+    def __init__(self, flush: Flush, fasta_path: str, out_path: str, bam_path: str):
+        self.lib = flush.lib
+        self.flush = flush
+        h = C.c_void_p()
+        st = self.lib.ps_clust_writer_open(C.byref(h), flush.h, fasta_path.encode(), out_path.encode(), bam_path.encode())
+        self.h = h
+        if st != abi.PS_OK:
+            msg = self.lib.ps_clust_writer_error(h).decode() if h else ""
+            self.close()
+            raise abi.PsError(st, msg or self.lib.ps_strerror(st).decode())
+
+    def feed(self, batch, first_ordinal: int, clusters: np.ndarray, sites: np.ndarray, open_first_read: Optional[int] = None):
+        s = batch.struct if hasattr(batch, "struct") else batch.as_struct()
+        clusters = np.ascontiguousarray(clusters)
+        sites = np.ascontiguousarray(sites)
+        st = self.lib.ps_clust_writer_feed(self.h, C.byref(s), int(first_ordinal), clusters.ctypes.data if len(clusters) else None,
+                                           len(clusters), sites.ctypes.data if len(sites) else None,
+                                           0 if open_first_read is None else 1, int(open_first_read or 0))
+        if st == abi.PS_ERR_REFERENCE_WOULD_THROW:
+            f = abi.ps_fault()
+            self.lib.ps_clust_writer_fault(self.h, C.byref(f))
+            raise abi.ReferenceWouldThrow(st, self.lib.ps_clust_writer_error(self.h).decode(), (f.code, f.read_ordinal))
+        if st != abi.PS_OK:
+            raise abi.PsError(st, self.lib.ps_clust_writer_error(self.h).decode() or self.lib.ps_strerror(st).decode())
+
+    def finish(self, counters: dict) -> dict:
+        ctr = abi.ps_pileup_counters()
+        ctr.skipped_due_indel = int(counters["skipped_due_indel"])
+        ctr.double_stranded = int(counters["double_stranded"])
+        ctr.num_reads_processed = int(counters.get("num_reads_processed", 0))
+        st = self.lib.ps_clust_writer_finish(self.h, C.byref(ctr))
+        if st != abi.PS_OK:
+            raise abi.PsError(st, self.lib.ps_clust_writer_error(self.h).decode())
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.ps_clust_writer_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"rows": a.value, "ccr_rows": b.value, "ccr_start_before_contig": c.value}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ps_clust_writer_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
