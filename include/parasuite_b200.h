@@ -200,7 +200,7 @@ typedef struct ps_pileup ps_pileup;   /* opaque result handle */
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
 int ps_abi_version(void);
-/* One context per GPU (one process per GPU under torch.distributed; a JVM may hold several). */
+/* One context per GPU (one process per GPU under torch.distributed; a JVM holds several through ps_create_multi). */
 int ps_create(ps_ctx** out, int device);
 void ps_destroy(ps_ctx* ctx);
 const char* ps_last_error(const ps_ctx* ctx);
@@ -300,7 +300,33 @@ int ps_pileup_head_partial(ps_pileup* h, ps_cluster* cluster, ps_site* sites, ui
 int64_t ps_pileup_boundary_coverage(ps_pileup* h, int which, int32_t* first_pos, uint32_t* cov, uint64_t max);
 int ps_pileup_fault(const ps_pileup* h, ps_fault* out);
 void ps_pileup_close(ps_pileup* h);
+/* The file is taken in windows of records (PARASUITE_B200_WINDOW_READS, default 2^23): every window's carry-in is the
+ * maximum (contig, end) over the windows before it, the reads at its head that continue the cluster left open by the
+ * window before are folded into that cluster on the host (halo merge).  The handle holds the merged records of the whole
+ * file on the host; no limit on the number of records. */
 int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);
+/* The whole `clust` tool from files (PileupClusters.calculateReadPileups, :62-584): record loop on the GPU in windows,
+ * flush arithmetic and the six output files natively (ps_flush_*, ps_clust_writer_*).  snp_vcf may be NULL.  The
+ * reference must have been loaded with ps_reference_load_fasta (the raw-case FASTA is read for the sequence columns). */
+int ps_clust_bam(ps_ctx* ctx, const char* bam_path, const char* out_path, const char* snp_vcf, uint32_t min_read_coverage,
+                 ps_pileup_counters* counters_out, ps_fault* fault_out);
+
+/* ---- several GPUs behind one handle (one process, e.g. a JVM; Main.java:595-597, :634-636 enter here) -----------------
+ * devices == NULL or n == 0: the list in PARASUITE_B200_DEVICES ("0,1,2"), else device 0.  The handle owns one context
+ * per device.  The reference is packed once and made resident on every device; the profile sends batches round-robin and
+ * sums the (< 10 KB) accumulator vectors on the host, the pileup sends windows round-robin and merges the boundary
+ * clusters on the host.  Results are bit-identical to the single-context calls. */
+typedef struct ps_multi ps_multi;
+int ps_create_multi(ps_multi** out, const int* devices, int n);
+void ps_destroy_multi(ps_multi* m);
+int ps_multi_device_count(const ps_multi* m);
+ps_ctx* ps_multi_context(ps_multi* m, int i);            /* borrowed: for batch-level calls on one of the devices */
+const char* ps_multi_last_error(const ps_multi* m);
+int ps_multi_load_fasta(ps_multi* m, const char* fasta_path);
+int ps_multi_profile_bam(ps_multi* m, const char* bam_path, const ps_profile_opts* opts, ps_profile_result* out);
+int ps_multi_pileup_bam(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);
+int ps_multi_clust_bam(ps_multi* m, const char* bam_path, const char* out_path, const char* snp_vcf,
+                       uint32_t min_read_coverage, ps_pileup_counters* counters_out, ps_fault* fault_out);
 
 /* ---- host batcher (usable without a GPU) --------------------------------------------------------
  * What htsjdk does for the two loops, as a library: FASTA(+.fai) -> packed reference; BGZF/BAM -> SoA batches in

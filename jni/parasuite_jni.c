@@ -27,6 +27,12 @@ static void throw_status(JNIEnv* env, ps_ctx* ctx, int status) {
   if (cls) (*env)->ThrowNew(env, cls, msg);
 }
 
+static void throw_message(JNIEnv* env, const char* msg, int status) {
+  jclass cls = (*env)->FindClass(env, "java/lang/RuntimeException");
+  if (!msg || !*msg) msg = ps_strerror(status);
+  if (cls) (*env)->ThrowNew(env, cls, msg);
+}
+
 static void throw_illegal(JNIEnv* env, const char* msg) {
   jclass cls = (*env)->FindClass(env, "java/lang/IllegalArgumentException");
   if (cls) (*env)->ThrowNew(env, cls, msg);
@@ -68,12 +74,12 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_loadReference(
  *     startZero, indelRead, skippedReads, longerIndels, totalBasesChecked));
  * The arrays are the Java fields themselves (ErrorProfiling.java:41-55); the loop's post-processing (:410-621)
  * runs unchanged on them. */
-JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
-    JNIEnv* env, jclass c, jlong h, jstring bam, jint maxReadLength, jboolean inferQualities, jintArray positionConversions,
-    jintArray qualityPerMismatch, jintArray qualityPerMismatchCounts, jdoubleArray insertionsPerPos,
-    jdoubleArray deletionsPerPos, jlongArray qualityHist, jintArray counters) {
-  (void)c;
-  ps_ctx* ctx = (ps_ctx*)(intptr_t)h;
+static void profile_bam_common(JNIEnv* env, int multi, jlong h, jstring bam, jint maxReadLength, jboolean inferQualities,
+                               jintArray positionConversions, jintArray qualityPerMismatch, jintArray qualityPerMismatchCounts,
+                               jdoubleArray insertionsPerPos, jdoubleArray deletionsPerPos, jlongArray qualityHist,
+                               jintArray counters) {
+  ps_ctx* ctx = multi ? NULL : (ps_ctx*)(intptr_t)h;
+  ps_multi* mc = multi ? (ps_multi*)(intptr_t)h : NULL;
   const char* path = (*env)->GetStringUTFChars(env, bam, NULL);
   if (!path) return;
   ps_profile_opts opts;
@@ -106,7 +112,7 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
   /* Get*ArrayElements returns NULL (with an OutOfMemoryError pending) when the VM cannot pin or copy */
   const int got_all = r.position_conversions && r.quality_per_mismatch && r.quality_per_mismatch_counts && r.insertions_per_pos &&
                       r.deletions_per_pos && r.counters && (!(inferQualities && qualityHist) || r.quality_hist);
-  int st = got_all ? ps_profile_bam(ctx, path, &opts, &r) : PS_OK;
+  int st = !got_all ? PS_OK : (multi ? ps_multi_profile_bam(mc, path, &opts, &r) : ps_profile_bam(ctx, path, &opts, &r));
   if (r.position_conversions) (*env)->ReleaseIntArrayElements(env, positionConversions, (jint*)r.position_conversions, 0);
   if (r.quality_per_mismatch) (*env)->ReleaseIntArrayElements(env, qualityPerMismatch, (jint*)r.quality_per_mismatch, 0);
   if (r.quality_per_mismatch_counts) (*env)->ReleaseIntArrayElements(env, qualityPerMismatchCounts, (jint*)r.quality_per_mismatch_counts, 0);
@@ -115,7 +121,59 @@ JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
   if (r.counters) (*env)->ReleaseIntArrayElements(env, counters, (jint*)r.counters, 0);
   if (r.quality_hist) (*env)->ReleaseLongArrayElements(env, qualityHist, (jlong*)r.quality_hist, 0);
   (*env)->ReleaseStringUTFChars(env, bam, path);
-  if (got_all && st != PS_OK) throw_status(env, ctx, st);     /* !got_all: the VM's own exception is pending */
+  if (got_all && st != PS_OK) {                                /* !got_all: the VM's own exception is pending */
+    if (multi) throw_message(env, ps_multi_last_error(mc), st);
+    else throw_status(env, ctx, st);
+  }
+}
+
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBam(
+    JNIEnv* env, jclass c, jlong h, jstring bam, jint maxReadLength, jboolean inferQualities, jintArray positionConversions,
+    jintArray qualityPerMismatch, jintArray qualityPerMismatchCounts, jdoubleArray insertionsPerPos,
+    jdoubleArray deletionsPerPos, jlongArray qualityHist, jintArray counters) {
+  (void)c;
+  profile_bam_common(env, 0, h, bam, maxReadLength, inferQualities, positionConversions, qualityPerMismatch,
+                     qualityPerMismatchCounts, insertionsPerPos, deletionsPerPos, qualityHist, counters);
+}
+
+/* ---- several GPUs in one JVM (ps_create_multi): the same calls on a multi handle ---------------------------------
+ * static native long createMulti(int[] devices);   -- null or empty: PARASUITE_B200_DEVICES ("0,1,2"), else device 0
+ * static native void destroyMulti(long multi);
+ * static native void loadReferenceMulti(long multi, String fasta);
+ * static native void profileBamMulti(long multi, String bam, ... as profileBam ...); */
+JNIEXPORT jlong JNICALL Java_utils_errorprofile_NativeErrorProfile_createMulti(JNIEnv* env, jclass c, jintArray devices) {
+  (void)c;
+  ps_multi* m = NULL;
+  jint* d = devices ? (*env)->GetIntArrayElements(env, devices, NULL) : NULL;
+  const jsize n = devices ? (*env)->GetArrayLength(env, devices) : 0;
+  int st = ps_create_multi(&m, (const int*)d, (int)n);
+  if (d) (*env)->ReleaseIntArrayElements(env, devices, d, 0);
+  if (st != PS_OK) { throw_status(env, NULL, st); return 0; }
+  return (jlong)(intptr_t)m;
+}
+
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_destroyMulti(JNIEnv* env, jclass c, jlong m) {
+  (void)env; (void)c;
+  ps_destroy_multi((ps_multi*)(intptr_t)m);
+}
+
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_loadReferenceMulti(JNIEnv* env, jclass c, jlong h, jstring fasta) {
+  (void)c;
+  ps_multi* m = (ps_multi*)(intptr_t)h;
+  const char* path = (*env)->GetStringUTFChars(env, fasta, NULL);
+  if (!path) return;
+  int st = ps_multi_load_fasta(m, path);
+  (*env)->ReleaseStringUTFChars(env, fasta, path);
+  if (st != PS_OK) throw_message(env, ps_multi_last_error(m), st);
+}
+
+JNIEXPORT void JNICALL Java_utils_errorprofile_NativeErrorProfile_profileBamMulti(
+    JNIEnv* env, jclass c, jlong h, jstring bam, jint maxReadLength, jboolean inferQualities, jintArray positionConversions,
+    jintArray qualityPerMismatch, jintArray qualityPerMismatchCounts, jdoubleArray insertionsPerPos,
+    jdoubleArray deletionsPerPos, jlongArray qualityHist, jintArray counters) {
+  (void)c;
+  profile_bam_common(env, 1, h, bam, maxReadLength, inferQualities, positionConversions, qualityPerMismatch,
+                     qualityPerMismatchCounts, insertionsPerPos, deletionsPerPos, qualityHist, counters);
 }
 
 /* ---- T>C pileup ------------------------------------------------------------------------------------------
@@ -181,6 +239,41 @@ JNIEXPORT jint JNICALL Java_utils_pileupclusters_NativePileup_nextClusters(JNIEn
   if (!got_all) return 0;                                       /* the VM's OutOfMemoryError is pending */
   if (n < 0) { throw_status(env, NULL, (int)n); return 0; }
   return (jint)n;
+}
+
+/* static native long[] clustBam(long ctx, boolean multi, String bam, String out, String snpVcf, int minReadCoverage);
+ * The whole body of PileupClusters.calculateReadPileups (:62-584): record loop on the GPU(s) in windows, flush and the six
+ * output files natively.  Returns numReadsProcessed, skippedDueIndel, doubleStranded, nClusters, nSites, hasOpenCluster.
+ * `multi`: ctx is a createMulti handle. */
+JNIEXPORT jlongArray JNICALL Java_utils_pileupclusters_NativePileup_clustBam(JNIEnv* env, jclass c, jlong h, jboolean multi,
+                                                                              jstring bam, jstring out, jstring snpVcf,
+                                                                              jint minReadCoverage) {
+  (void)c;
+  const char* pb = (*env)->GetStringUTFChars(env, bam, NULL);
+  const char* po = pb ? (*env)->GetStringUTFChars(env, out, NULL) : NULL;
+  const char* pv = (po && snpVcf) ? (*env)->GetStringUTFChars(env, snpVcf, NULL) : NULL;
+  jlongArray a = NULL;
+  if (pb && po && (pv || !snpVcf)) {
+    ps_pileup_counters ctr;
+    ps_fault fault;
+    memset(&ctr, 0, sizeof ctr);
+    memset(&fault, 0, sizeof fault);
+    int st = multi ? ps_multi_clust_bam((ps_multi*)(intptr_t)h, pb, po, pv, (uint32_t)minReadCoverage, &ctr, &fault)
+                   : ps_clust_bam((ps_ctx*)(intptr_t)h, pb, po, pv, (uint32_t)minReadCoverage, &ctr, &fault);
+    if (st != PS_OK) {
+      if (multi) throw_message(env, ps_multi_last_error((ps_multi*)(intptr_t)h), st);
+      else throw_status(env, (ps_ctx*)(intptr_t)h, st);
+    } else {
+      jlong v[6] = {(jlong)ctr.num_reads_processed, (jlong)ctr.skipped_due_indel, (jlong)ctr.double_stranded,
+                    (jlong)ctr.n_clusters, (jlong)ctr.n_sites, (jlong)ctr.has_open_cluster};
+      a = (*env)->NewLongArray(env, 6);
+      if (a) (*env)->SetLongArrayRegion(env, a, 0, 6, v);
+    }
+  }
+  if (pv) (*env)->ReleaseStringUTFChars(env, snpVcf, pv);
+  if (po) (*env)->ReleaseStringUTFChars(env, out, po);
+  if (pb) (*env)->ReleaseStringUTFChars(env, bam, pb);
+  return a;
 }
 
 JNIEXPORT void JNICALL Java_utils_pileupclusters_NativePileup_close(JNIEnv* env, jclass c, jlong handle) {

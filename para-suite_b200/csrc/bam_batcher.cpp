@@ -610,12 +610,14 @@ int ps_reference_load_fasta(ps_ctx* ctx, const char* fasta_path) {
   }
   st = ps_reference_upload(ctx, &F->view);
   if (st != PS_OK) { ps_fasta_free(F); return st; }
-  if (ctx->fasta) ps_fasta_free(ctx->fasta);
+  if (ctx->fasta && !ctx->fasta_shared) ps_fasta_free(ctx->fasta);
   ctx->fasta = F;      // contig names for the BAM header; the packed words stay on the host for later uploads
+  ctx->fasta_shared = false;
+  ctx->fasta_path = fasta_path;
   return PS_OK;
 }
 
-static int open_for_ctx(ps_ctx* ctx, const char* bam_path, uint64_t max_batch, ps_bam** B) {
+int open_for_ctx(ps_ctx* ctx, const char* bam_path, uint64_t max_batch, ps_bam** B) {
   if (!ctx->fasta) return set_error(ctx, PS_ERR_STATE, "ps_reference_load_fasta must come first (contig names are needed)");
   int st = ps_bam_open(B, bam_path, ctx->fasta, max_batch, 0);
   if (st != PS_OK) {
@@ -647,30 +649,6 @@ int ps_profile_bam(ps_ctx* ctx, const char* bam_path, const ps_profile_opts* opt
   }
   if (st == PS_OK) st = ps_profile_end(ctx, out);
   else if (ctx->profile_open) { ps_profile_result dump; memset(&dump, 0, sizeof dump); ps_profile_end(ctx, &dump); }
-  ps_bam_close(B);
-  return st;
-}
-
-// PileupClusters.calculateReadPileups up to the end of the record loop (:62-500).  The file is taken as ONE batch
-// (the cluster chain is a prefix scan over all reads); callers that need to stream use ps_pileup_batch with
-// ps_pileup_opts.carry_* per window and merge the boundary clusters (parasuite_b200/sharding.py).
-int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out) {
-  if (!ctx || !bam_path || !out) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
-  *out = nullptr;
-  ps_bam* B = nullptr;
-  int st = open_for_ctx(ctx, bam_path, 0xFFFFFF00ull, &B);
-  if (st) return st;
-  ps_read_batch hb;
-  const int k = ps_bam_next(B, &hb);
-  if (k < 0) st = set_error(ctx, k, B->err);
-  else {
-    if (k == 0) memset(&hb, 0, sizeof hb);
-    st = ps_pileup_batch(ctx, &hb, opts, out);
-    if (st == PS_OK && k == 1) {
-      ps_read_batch more;
-      if (ps_bam_next(B, &more) != 0) st = set_error(ctx, PS_ERR_UNSUPPORTED, "BAM holds more than 2^32-256 records");
-    }
-  }
   ps_bam_close(B);
   return st;
 }

@@ -178,7 +178,7 @@ void ps_destroy(ps_ctx* ctx) {
   if (ctx->early_ev) cudaEventDestroy(ctx->early_ev);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_acc) cudaFreeHost(ctx->h_acc);
-  if (ctx->fasta) ps_fasta_free(ctx->fasta);
+  if (ctx->fasta && !ctx->fasta_shared) ps_fasta_free(ctx->fasta);
   for (auto& e : ctx->staged_done) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->staged_core) if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -390,6 +390,23 @@ int ps_profile_set_stream(ps_ctx* ctx, void* stream) {
   return PS_OK;
 }
 
+}  // extern "C"
+
+void profile_fill_result(const ProfileLayout& l, const int64_t* acc, ps_profile_result* out) {
+  auto wrap = [](int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; };   // Java int two's-complement wrap (Q8)
+  const uint32_t m = l.max_len;
+  if (out->position_conversions) for (uint32_t k = 0; k < 16 * m; ++k) out->position_conversions[k] = wrap(acc[l.conv + k]);
+  if (out->quality_per_mismatch) for (int k = 0; k < 16; ++k) out->quality_per_mismatch[k] = wrap(acc[l.qsum + k]);
+  if (out->quality_per_mismatch_counts) for (int k = 0; k < 16; ++k) out->quality_per_mismatch_counts[k] = wrap(acc[l.qcnt + k]);
+  if (out->insertions_per_pos) for (uint32_t k = 0; k < m; ++k) out->insertions_per_pos[k] = (double)acc[l.ins + k];
+  if (out->deletions_per_pos) for (uint32_t k = 0; k < m; ++k) out->deletions_per_pos[k] = (double)acc[l.del + k];
+  if (out->counters) for (int k = 0; k < PS_PC_COUNT; ++k) out->counters[k] = wrap(acc[l.ctr + k]);
+  if (out->quality_hist && l.infer_q) memcpy(out->quality_hist, &acc[l.qhist], (size_t)256 * m * 8);
+  if (out->wide) memcpy(out->wide, acc, (size_t)l.total * 8);
+}
+
+extern "C" {
+
 int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
   if (!ctx || !out) return PS_ERR_INVALID_ARG;
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
@@ -426,16 +443,7 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
              (int)(fw & 0xFF));
     return set_error(ctx, PS_ERR_REFERENCE_WOULD_THROW, msg);
   }
-  auto wrap = [](int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; };   // Java int two's-complement wrap (Q8)
-  const uint32_t m = l.max_len;
-  if (out->position_conversions) for (uint32_t k = 0; k < 16 * m; ++k) out->position_conversions[k] = wrap(acc[l.conv + k]);
-  if (out->quality_per_mismatch) for (int k = 0; k < 16; ++k) out->quality_per_mismatch[k] = wrap(acc[l.qsum + k]);
-  if (out->quality_per_mismatch_counts) for (int k = 0; k < 16; ++k) out->quality_per_mismatch_counts[k] = wrap(acc[l.qcnt + k]);
-  if (out->insertions_per_pos) for (uint32_t k = 0; k < m; ++k) out->insertions_per_pos[k] = (double)acc[l.ins + k];
-  if (out->deletions_per_pos) for (uint32_t k = 0; k < m; ++k) out->deletions_per_pos[k] = (double)acc[l.del + k];
-  if (out->counters) for (int k = 0; k < PS_PC_COUNT; ++k) out->counters[k] = wrap(acc[l.ctr + k]);
-  if (out->quality_hist && l.infer_q) memcpy(out->quality_hist, &acc[l.qhist], (size_t)256 * m * 8);
-  if (out->wide) memcpy(out->wide, acc, (size_t)l.total * 8);
+  profile_fill_result(l, acc, out);
   return PS_OK;
 }
 

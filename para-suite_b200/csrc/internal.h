@@ -98,6 +98,8 @@ struct ps_ctx {
   std::vector<uint64_t> contig_off;  // host copy
   bool ref_loaded = false;
   ps_packed_fasta* fasta = nullptr;   // set by ps_reference_load_fasta: contig names for BAM headers
+  bool fasta_shared = false;          // the packed FASTA belongs to a ps_multi (several contexts share one)
+  std::string fasta_path;             // raw-case FASTA for the clust output files (cluster sequence, CCR windows)
   // profile state
   bool profile_open = false;
   ProfileLayout layout{};
@@ -148,6 +150,14 @@ struct ps_ctx {
   bool pl_compact_lookback = false;   // PARASUITE_B200_COMPACT_LOOKBACK=1 at ps_create: always order the site runs with the look-back (tests)
   bool pl_exact_flags = false;   // a speculative flag pass failed on this context: keep to the exact look-back kernel
 };
+
+// ---- pileup handles over host-resident records (pileup.cu; used by the windowed file loops in tool_loops.cpp) --------
+ps_pileup* pileup_host_handle(ps_ctx* ctx, std::vector<ps_cluster>&& clusters, std::vector<ps_site>&& sites, bool has_open,
+                              const ps_cluster& open, std::vector<ps_site>&& open_sites, int32_t open_cov_pos0,
+                              std::vector<uint32_t>&& open_cov, const ps_pileup_counters& counters);
+void pileup_set_fault(ps_pileup* h, const ps_fault& f);
+// wrap the int64 accumulator vector of a profile run into the caller's arrays (ctx.cu; Java int wrap-around, Q8)
+void profile_fill_result(const ProfileLayout& l, const int64_t* acc, ps_profile_result* out);
 
 // ---- kernel launchers (defined in the .cu files) ----------------------------------------------------
 // t2c_mask (optional): n_reads words; *mask_written tells whether the batch took the fast kernel, which fills them

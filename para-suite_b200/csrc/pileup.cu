@@ -1502,6 +1502,11 @@ struct ps_pileup {
   bool spec = false;                 // the attempt in flight used the speculative flag pass
   uint64_t cap_cl = 0, cap_sites = 0;   // capacities of the attempt in flight
   PlState hs_fallback{};             // landing place of the run state when the context has no page-locked scratch
+  // host mode (windowed ps_pileup_bam / ps_multi_pileup_bam, tool_loops.cpp): the merged records of all windows live in
+  // host vectors; nothing is resident on a device
+  bool host_mode = false;
+  std::vector<ps_cluster> h_cl;
+  std::vector<ps_site> h_sites, h_open_sites;
 };
 
 template <typename T>
@@ -1765,6 +1770,7 @@ static DeviceBatch pl_view_of(const ps_read_batch* b) {
 
 static void free_handle(ps_pileup* h) {
   if (!h) return;
+  if (h->host_mode) { delete h; return; }
   if (h->ctx) cudaSetDevice(h->ctx->device);
   if (h->pending && h->ctx) pileup_finish(h->ctx, h);     // the kernels in flight use the handle's arrays
   if (h->ctx && h->ctx->pl_pending == h) h->ctx->pl_pending = nullptr;
@@ -1823,6 +1829,31 @@ static int boundary_coverage(ps_pileup* h) {
   h->cov_done = true;
   return PS_OK;
 }
+
+// Handle over records that already sit on the host: closed clusters (site_begin / site_end index `sites`), the open
+// cluster with its sites (site range [0, n)) and its dense coverage, the run's counters.
+ps_pileup* pileup_host_handle(ps_ctx* ctx, std::vector<ps_cluster>&& clusters, std::vector<ps_site>&& sites, bool has_open,
+                              const ps_cluster& open, std::vector<ps_site>&& open_sites, int32_t open_cov_pos0,
+                              std::vector<uint32_t>&& open_cov, const ps_pileup_counters& counters) {
+  ps_pileup* H = new ps_pileup();
+  H->ctx = ctx;
+  H->host_mode = true;
+  H->h_cl = std::move(clusters);
+  H->h_sites = std::move(sites);
+  H->h_open_sites = std::move(open_sites);
+  H->open = open;
+  H->open_cov = std::move(open_cov);
+  H->open_cov_pos0 = open_cov_pos0;
+  H->cov_done = true;
+  H->counters = counters;
+  H->counters.n_clusters = H->h_cl.size();
+  H->counters.n_sites = H->h_sites.size();
+  H->counters.has_open_cluster = has_open ? 1 : 0;
+  H->n_reads = counters.num_reads_processed;
+  return H;
+}
+
+void pileup_set_fault(ps_pileup* h, const ps_fault& f) { h->fault = f; }
 
 extern "C" {
 
@@ -1928,6 +1959,18 @@ int64_t ps_pileup_next(ps_pileup* h, uint64_t first, ps_cluster* clusters, uint6
   if (h->pending) return PS_ERR_STATE;
   const uint64_t n_closed = h->counters.n_clusters;
   if (first >= n_closed || max_clusters == 0) return 0;
+  if (h->host_mode) {
+    const uint64_t cnt0 = std::min<uint64_t>(max_clusters, n_closed - first);
+    const uint64_t sb = h->h_cl[first].site_begin;
+    uint64_t m = 0;
+    while (m < cnt0 && h->h_cl[first + m].site_end - sb <= max_sites) ++m;
+    if (m == 0) return 0;
+    std::memcpy(clusters, h->h_cl.data() + first, m * sizeof(ps_cluster));
+    const uint64_t ns = h->h_cl[first + m - 1].site_end - sb;
+    if (ns) std::memcpy(sites, h->h_sites.data() + sb, ns * sizeof(ps_site));
+    for (uint64_t k = 0; k < m; ++k) { clusters[k].site_begin -= sb; clusters[k].site_end -= sb; }
+    return (int64_t)m;
+  }
   ps_ctx* ctx = h->ctx;
   cudaSetDevice(ctx->device);
   uint64_t cnt = std::min<uint64_t>(max_clusters, n_closed - first);
@@ -1979,6 +2022,17 @@ int ps_pileup_open_cluster(ps_pileup* h, ps_cluster* cluster, ps_site* sites, ui
   if (!h || !cluster) return PS_ERR_INVALID_ARG;
   if (h->pending) return PS_ERR_STATE;
   if (!h->counters.has_open_cluster) return 0;
+  if (h->host_mode) {
+    if (h->h_open_sites.size() > max_sites) return PS_ERR_INVALID_ARG;
+    *cluster = h->open;
+    cluster->site_begin = 0;
+    cluster->site_end = h->h_open_sites.size();
+    if (!h->h_open_sites.empty()) {
+      if (!sites) return PS_ERR_INVALID_ARG;
+      std::memcpy(sites, h->h_open_sites.data(), h->h_open_sites.size() * sizeof(ps_site));
+    }
+    return 1;
+  }
   return copy_boundary(h, h->open, cluster, sites, max_sites);
 }
 

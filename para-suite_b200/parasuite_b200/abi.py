@@ -145,6 +145,18 @@ EXPORTS = {
     "ps_reference_adopt_device": (C.c_int, [VP, C.POINTER(ps_reference), VP]),
     "ps_batch_upload": (C.c_int, [VP, C.POINTER(ps_read_batch), C.POINTER(ps_read_batch)]),
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+    "ps_clust_bam": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(ps_pileup_counters),
+                               C.POINTER(ps_fault)]),
+    "ps_create_multi": (C.c_int, [C.POINTER(VP), C.POINTER(C.c_int), C.c_int]),
+    "ps_destroy_multi": (None, [VP]),
+    "ps_multi_device_count": (C.c_int, [VP]),
+    "ps_multi_context": (VP, [VP, C.c_int]),
+    "ps_multi_last_error": (C.c_char_p, [VP]),
+    "ps_multi_load_fasta": (C.c_int, [VP, C.c_char_p]),
+    "ps_multi_profile_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_profile_opts), C.POINTER(ps_profile_result)]),
+    "ps_multi_pileup_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_pileup_opts), C.POINTER(VP)]),
+    "ps_multi_clust_bam": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(ps_pileup_counters),
+                                     C.POINTER(ps_fault)]),
     "ps_clust_writer_open": (C.c_int, [C.POINTER(VP), VP, C.c_char_p, C.c_char_p, C.c_char_p]),
     "ps_clust_writer_feed": (C.c_int, [VP, C.POINTER(ps_read_batch), C.c_uint64, VP, C.c_uint64, VP, C.c_int, C.c_uint64]),
     "ps_clust_writer_finish": (C.c_int, [VP, C.POINTER(ps_pileup_counters)]),

@@ -140,6 +140,15 @@ class Context:
             raise
         return res
 
+    def clust_bam(self, bam_path: str, out_path: str, snp_vcf: Optional[str] = None, min_read_coverage: int = 1) -> dict:
+        """The whole `clust` tool from files (PileupClusters.java:62-584): writes <out>, <out>.ccr.fasta, <out>.ccr.tsv,
+        <out>.report, <bam>.sitefrequency.tsv and <bam>.sitepositions.tsv; returns the run's counters."""
+        ctr, f = abi.ps_pileup_counters(), abi.ps_fault()
+        st = self.lib.ps_clust_bam(self.h, bam_path.encode(), out_path.encode(), snp_vcf.encode() if snp_vcf else None,
+                                   min_read_coverage, C.byref(ctr), C.byref(f))
+        _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
+        return {k: getattr(ctr, k) for k, _ in abi.ps_pileup_counters._fields_}
+
     # ---- batches ---------------------------------------------------------------------------------
     def upload(self, batch) -> UploadedBatch:
         """One H2D copy of a host batch (ReadBatch / PinnedBatch); both tools can then run on the device view
@@ -427,3 +436,79 @@ class PileupResult:
             "head_sites": head_s[:int(head_c[0]["site_end"])].copy() if kh > 0 else head_s[:0],
         })
         return out
+
+
+class MultiContext:
+    """Several GPUs behind one handle in ONE process (what a JVM uses: ps_create_multi): the file loops of both tools,
+    batches / windows round-robin over the devices, results merged on the host."""
+
+    def __init__(self, devices=None):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            st = self.lib.ps_create_multi(C.byref(h), arr, len(devices))
+        else:
+            st = self.lib.ps_create_multi(C.byref(h), None, 0)          # PARASUITE_B200_DEVICES or device 0
+        if st != abi.PS_OK:
+            raise abi.PsError(st, self.lib.ps_strerror(st).decode())
+        self.h = h
+
+    def _check(self, st, fault=None):
+        if st == abi.PS_OK:
+            return
+        msg = self.lib.ps_multi_last_error(self.h).decode() or self.lib.ps_strerror(st).decode()
+        if st == abi.PS_ERR_REFERENCE_WOULD_THROW:
+            raise abi.ReferenceWouldThrow(st, msg, fault)
+        raise abi.PsError(st, msg, fault)
+
+    @property
+    def n_devices(self) -> int:
+        return int(self.lib.ps_multi_device_count(self.h))
+
+    def load_fasta(self, path: str):
+        self._check(self.lib.ps_multi_load_fasta(self.h, path.encode()))
+
+    def profile_bam(self, bam_path: str, max_read_length: int, infer_qualities: bool = False) -> dict:
+        tmp = Context.__new__(Context)
+        tmp.lib, tmp._max_len, tmp._infer_q, tmp._result_plans = self.lib, max_read_length, infer_qualities, {}
+        out, r = Context._profile_result_arrays(tmp)
+        o = abi.ps_profile_opts(max_read_length, int(infer_qualities), 0, 0)
+        st = self.lib.ps_multi_profile_bam(self.h, bam_path.encode(), C.byref(o), C.byref(r))
+        self._check(st, fault=(r.fault.code, r.fault.read_ordinal))
+        return out
+
+    def pileup_bam(self, bam_path: str, first_running_id: int = 1) -> "PileupResult":
+        opts = abi.ps_pileup_opts(first_running_id, 0, 0, 0, 0, None, None)
+        h = C.c_void_p()
+        st = self.lib.ps_multi_pileup_bam(self.h, bam_path.encode(), C.byref(opts), C.byref(h))
+        fault = None
+        if st in (abi.PS_ERR_REFERENCE_WOULD_THROW, abi.PS_ERR_UNSUPPORTED) and h:
+            f = abi.ps_fault()
+            self.lib.ps_pileup_fault(h, C.byref(f))
+            fault = (f.code, f.read_ordinal)
+            self.lib.ps_pileup_close(h)
+        self._check(st, fault=fault)
+        holder = Context.__new__(Context)
+        holder.lib, holder.h = self.lib, self.lib.ps_multi_context(self.h, 0)
+        holder._pinned_bufs = {}
+        holder.close = lambda: None
+        return PileupResult(holder, h, None)
+
+    def clust_bam(self, bam_path: str, out_path: str, snp_vcf: Optional[str] = None, min_read_coverage: int = 1) -> dict:
+        ctr, f = abi.ps_pileup_counters(), abi.ps_fault()
+        st = self.lib.ps_multi_clust_bam(self.h, bam_path.encode(), out_path.encode(), snp_vcf.encode() if snp_vcf else None,
+                                         min_read_coverage, C.byref(ctr), C.byref(f))
+        self._check(st, fault=(f.code, f.read_ordinal))
+        return {k: getattr(ctr, k) for k, _ in abi.ps_pileup_counters._fields_}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ps_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
