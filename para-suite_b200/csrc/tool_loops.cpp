@@ -257,6 +257,10 @@ int pileup_windows(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts
     if (k < 0) { st = multi_fail(m, k, ps_bam_error(B)); break; }
     if (k == 0) break;
     ps_ctx* c = m->ctx[window % m->ctx.size()];
+    // a context takes one submitted call at a time (its scratch belongs to it): with a single context the window before
+    // -- whose kernels ran while this one was being decoded -- completes before this one is launched
+    InFlight& prev = fl[(window & 1) ^ 1];
+    if (prev.live && prev.ctx == c) { st = complete(prev); if (st) break; }
     cudaSetDevice(c->device);
     // cluster ids are numbered from the window's own first cluster; the clusters opened by earlier windows are added
     // when the window completes (they are not known yet: those windows may still be running)
