@@ -232,6 +232,12 @@ struct ps_bam {
   uint64_t ordinal = 0;
   std::string err;
   std::vector<uint64_t> rec_off;   // scratch: offsets of the records of the batch being built
+  // SAM text input (htsjdk opens SAM and BAM through one factory, ErrorProfiling.java:104-107): the text is turned into
+  // the byte stream an inflated BAM would give -- header, then records in BAM encoding -- so everything behind
+  // bam_fill is shared
+  bool sam_text = false;
+  size_t sam_at = 0;               // next unread byte of the text
+  std::unordered_map<std::string, int32_t> sam_ref_id;
   double t_fill = 0, t_locate = 0, t_pass1 = 0, t_pass2 = 0;   // seconds (PARASUITE_B200_BATCHER_TIMING=1 prints them)
 };
 
@@ -266,9 +272,139 @@ static int bam_scan_blocks(ps_bam* B) {
 // inflate blocks until at least `want` unconsumed bytes are buffered (or the file ends)
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// ---- SAM text ---------------------------------------------------------------------------------------------------
+static void put32(ByteBuf& b, size_t at, uint32_t v) { memcpy(b.data() + at, &v, 4); }
+
+// header lines ('@...') -> "BAM\1" l_text text n_ref (l_name name l_ref)*
+static int sam_header(ps_bam* B) {
+  const uint8_t* p = B->mf.p;
+  const size_t n = B->mf.n;
+  size_t o = 0;
+  std::vector<std::pair<std::string, uint32_t>> refs;
+  while (o < n && p[o] == '@') {
+    size_t e = o;
+    while (e < n && p[e] != '\n') ++e;
+    const std::string line((const char*)p + o, e - o);
+    if (line.compare(0, 3, "@SQ") == 0) {
+      std::string name;
+      uint32_t len = 0;
+      size_t a = 0;
+      while (a < line.size()) {
+        size_t b = line.find('\t', a);
+        if (b == std::string::npos) b = line.size();
+        if (line.compare(a, 3, "SN:") == 0) name = line.substr(a + 3, b - a - 3);
+        if (line.compare(a, 3, "LN:") == 0) len = (uint32_t)strtoul(line.c_str() + a + 3, nullptr, 10);
+        a = b + 1;
+      }
+      while (!name.empty() && name.back() == '\r') name.pop_back();
+      B->sam_ref_id.emplace(name, (int32_t)refs.size());
+      refs.emplace_back(name, len);
+    }
+    o = e < n ? e + 1 : e;
+  }
+  const std::string text((const char*)p, o);
+  size_t bytes = 12 + text.size();
+  for (auto& r : refs) bytes += 8 + r.first.size() + 1;
+  if (!B->buf.grow_to(bytes)) return bam_fail(B, PS_ERR_OOM, "out of host memory");
+  uint8_t* d = B->buf.data();
+  memcpy(d, "BAM\1", 4);
+  put32(B->buf, 4, (uint32_t)text.size());
+  memcpy(d + 8, text.data(), text.size());
+  size_t at = 8 + text.size();
+  put32(B->buf, at, (uint32_t)refs.size());
+  at += 4;
+  for (auto& r : refs) {
+    put32(B->buf, at, (uint32_t)r.first.size() + 1);
+    memcpy(d + at + 4, r.first.c_str(), r.first.size() + 1);
+    put32(B->buf, at + 4 + r.first.size() + 1, r.second);
+    at += 8 + r.first.size() + 1;
+  }
+  B->sam_at = o;
+  return PS_OK;
+}
+
+// alignment lines -> BAM records, until `want` unconsumed bytes are buffered or the text ends.  What SAMLineParser hands
+// the loops: FLAG, RNAME, POS, CIGAR, SEQ (upper-cased, '.' -> N: SAMRecord.setReadString), QUAL - 33 ('*' -> none).
+static int sam_fill(ps_bam* B, size_t want) {
+  auto nib = [](uint8_t c) -> uint8_t {
+    switch (c >= 'a' && c <= 'z' ? c - 32 : c) {
+      case '=': return 0; case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5;
+      case 'S': return 6; case 'V': return 7; case 'T': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11;
+      case 'K': return 12; case 'D': return 13; case 'B': return 14; default: return 15;          // N, '.', anything else
+    }
+  };
+  const uint8_t* p = B->mf.p;
+  const size_t n = B->mf.n;
+  while (B->buf.size() - B->head < want && B->sam_at < n) {
+    size_t o = B->sam_at, e = o;
+    while (e < n && p[e] != '\n') ++e;
+    B->sam_at = e < n ? e + 1 : e;
+    size_t le = e;
+    while (le > o && (p[le - 1] == '\r')) --le;
+    if (le == o) continue;                                                       // blank line
+    const char* f[11];
+    size_t fl[11];
+    int nf = 0;
+    for (size_t a = o; nf < 11;) {
+      size_t b = a;
+      while (b < le && p[b] != '\t') ++b;
+      f[nf] = (const char*)p + a; fl[nf] = b - a; ++nf;
+      if (b >= le) break;
+      a = b + 1;
+    }
+    if (nf < 11) return bam_fail(B, PS_ERR_FORMAT, "SAM alignment line with fewer than 11 fields");
+    const uint32_t flag = (uint32_t)strtoul(std::string(f[1], fl[1]).c_str(), nullptr, 10);
+    const std::string rname(f[2], fl[2]);
+    int32_t ref_id = -1;
+    if (rname != "*") { auto it = B->sam_ref_id.find(rname); if (it != B->sam_ref_id.end()) ref_id = it->second; }
+    const int32_t pos = (int32_t)strtol(std::string(f[3], fl[3]).c_str(), nullptr, 10) - 1;
+    std::vector<uint32_t> cig;
+    if (!(fl[5] == 1 && f[5][0] == '*')) {
+      uint32_t num = 0;
+      for (size_t k = 0; k < fl[5]; ++k) {
+        const char c = f[5][k];
+        if (c >= '0' && c <= '9') { num = num * 10 + (uint32_t)(c - '0'); continue; }
+        const char* ops = "MIDNSHP=X";
+        const char* w = strchr(ops, c);
+        if (!w || !c) return bam_fail(B, PS_ERR_FORMAT, "SAM: unknown CIGAR operator");
+        cig.push_back((num << 4) | (uint32_t)(w - ops));
+        num = 0;
+      }
+    }
+    if (cig.size() > 0xFFFFu) return bam_fail(B, PS_ERR_UNSUPPORTED, "SAM: more than 65535 CIGAR operations");
+    const bool no_seq = fl[9] == 1 && f[9][0] == '*';
+    const uint32_t l_seq = no_seq ? 0u : (uint32_t)fl[9];
+    const bool no_qual = (fl[10] == 1 && f[10][0] == '*') || fl[10] != l_seq;
+    const uint32_t bs = 32 + 2 + 4 * (uint32_t)cig.size() + (l_seq + 1) / 2 + l_seq;
+    const size_t at = B->buf.size();
+    if (!B->buf.grow_to(at + 4 + bs)) return bam_fail(B, PS_ERR_OOM, "out of host memory for the records");
+    uint8_t* d = B->buf.data() + at;
+    memset(d, 0, 4 + bs);
+    put32(B->buf, at, bs);
+    put32(B->buf, at + 4, (uint32_t)ref_id);
+    put32(B->buf, at + 8, (uint32_t)pos);
+    d[12] = 2;                                                                   // l_read_name ("r\0": names are never read)
+    const uint16_t ncg = (uint16_t)cig.size(), fl16 = (uint16_t)flag;
+    memcpy(d + 16, &ncg, 2);
+    memcpy(d + 18, &fl16, 2);
+    put32(B->buf, at + 20, l_seq);
+    put32(B->buf, at + 24, 0xFFFFFFFFu);
+    put32(B->buf, at + 28, 0xFFFFFFFFu);
+    d[36] = 'r';
+    uint8_t* q = d + 38;
+    if (!cig.empty()) memcpy(q, cig.data(), 4 * cig.size());
+    q += 4 * cig.size();
+    for (uint32_t k = 0; k < l_seq; ++k) q[k >> 1] |= (uint8_t)(nib((uint8_t)f[9][k]) << ((~k & 1) * 4));
+    q += (l_seq + 1) / 2;
+    for (uint32_t k = 0; k < l_seq; ++k) q[k] = no_qual ? 0xFF : (uint8_t)((uint8_t)f[10][k] - 33);
+  }
+  return PS_OK;
+}
+
 static int bam_fill(ps_bam* B, size_t want) {
   const double t0 = now_s();
   struct Acc { ps_bam* b; double t0; ~Acc() { b->t_fill += now_s() - t0; } } acc{B, t0};
+  if (B->sam_text) return sam_fill(B, want);
   while (B->buf.size() - B->head < want && B->next_block < B->blocks.size()) {
     // a window of blocks: enough for `want`, at least 64 MB when a big batch is being assembled
     size_t b1 = B->next_block, total = 0;
@@ -383,7 +519,9 @@ int ps_bam_open(ps_bam** out, const char* bam_path, const ps_packed_fasta* ref, 
   }
   B->threads = threads;
   if (!B->mf.open(bam_path)) return bam_fail(B, PS_ERR_IO, std::string("cannot open ") + bam_path);
-  int st = bam_scan_blocks(B);
+  int st;
+  if (B->mf.n >= 2 && B->mf.p[0] == 0x1f && B->mf.p[1] == 0x8b) st = bam_scan_blocks(B);      // BGZF: a BAM
+  else { B->sam_text = true; st = sam_header(B); }                                             // anything else: SAM text
   if (st) return st;
   st = bam_header(B);
   if (st) return st;

@@ -96,6 +96,21 @@ def write_bam(path: str, contigs: Sequence[Tuple[str, int]], records: Iterable[R
     return count
 
 
+def write_sam(path: str, contigs: Sequence[Tuple[str, int]], records: Iterable[Record], sort_order: str = "coordinate") -> None:
+    """The same records as SAM text (htsjdk opens SAM and BAM through one factory, ErrorProfiling.java:104-107)."""
+    with open(path, "w") as f:
+        f.write(f"@HD\tVN:1.4\tSO:{sort_order}\n")
+        for name, length in contigs:
+            f.write(f"@SQ\tSN:{name}\tLN:{length}\n")
+        for k, r in enumerate(records):
+            q = bytes(r.qual)
+            missing = len(q) == 0 or q[0] == 0xFF
+            qual = "*" if missing else "".join(chr(33 + (b & 0xFF)) if (b & 0xFF) + 33 < 127 else "~" for b in q)
+            seq = r.seq.decode() if len(r.seq) else "*"
+            f.write("\t".join([f"r{k}", str(r.flag), r.rname, str(r.pos), "30", r.cigar if r.cigar else "*", "*", "0", "0", seq,
+                               qual]) + "\n")
+
+
 def batch_to_records(batch: ReadBatch, ref: PackedReference) -> List[Record]:
     """Inverse of the packers for uniform or ragged batches (used to write synthetic workloads as BAM files)."""
     out = []

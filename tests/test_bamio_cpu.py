@@ -180,3 +180,78 @@ def test_more_than_255_cigar_ops_is_refused_by_name(tmp_path):
         list(BamBatcher(bam, pf))
     assert e.value.status == abi.PS_ERR_UNSUPPORTED and "record 1 " in str(e.value)
     pf.close()
+
+
+def test_sam_text_gives_the_same_batches_as_bam(tmp_path):
+    """htsjdk opens SAM and BAM through one factory (ErrorProfiling.java:104-107): the batcher takes SAM text too and
+    hands the loops the same SoA (bases upper-cased, '.' as N, QUAL '*' as missing, POS 0 as getAlignmentStart() == 0)."""
+    from parasuite_b200.bamio import write_sam
+    rng = random.Random(77)
+    contigs = random_genome(rng, n_contigs=3, length=4000, n_frac=0.01, lower_frac=0.1)
+    # (reads of one base are left out: a lone quality 9 is "*" in SAM text, which means "no qualities")
+    recs = random_records(rng, contigs, 1500, kinds=("M", "clip", "indel", "splice", "wild"), Lrange=(2, 50), flags_special=0.08)
+    recs.append(Record(4, "*", 0, "*", b"", b""))
+    recs.append(Record(16, contigs[2][0], 10, "3M", b"ACN", b"\xff\xff\xff"))
+    fa, bam, sam = str(tmp_path / "ref.fa"), str(tmp_path / "x.bam"), str(tmp_path / "x.sam")
+    write_fasta(fa, contigs)
+    hdr = [(n, len(s)) for n, s in contigs]
+    write_bam(bam, hdr, recs)
+    write_sam(sam, hdr, recs)
+    pf = PackedFasta(fa)
+    a = list(BamBatcher(bam, pf, max_batch_reads=400, threads=2))
+    b = list(BamBatcher(sam, pf, max_batch_reads=400, threads=2))
+    assert len(a) == len(b) == 4
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert_batch_equal(y, x, f"SAM vs BAM, batch {k}")
+    # lower-case bases and '.' in the text are what SAMRecord.setReadString normalises
+    low = str(tmp_path / "low.sam")
+    with open(low, "w") as f:
+        f.write("@HD\tVN:1.4\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n" % hdr[0])
+        f.write("r\t0\t%s\t5\t30\t6M\t*\t0\t0\tac.gtN\tIIIIII\n" % hdr[0][0])
+    got = list(BamBatcher(low, pf))[0]
+    exp = ReadBatch.from_records([Record(0, hdr[0][0], 5, "6M", b"ACNGTN", bytes([40] * 6))], pf.reference())
+    assert_batch_equal(got, exp, "lower case / dot")
+    with open(low, "w") as f:
+        f.write("@HD\tVN:1.4\tSO:unsorted\n@SQ\tSN:%s\tLN:%d\n" % hdr[0])
+    with pytest.raises(abi.PsError) as e:
+        BamBatcher(low, pf)
+    assert e.value.status == abi.PS_ERR_UNSORTED
+    pf.close()
+
+
+def test_hand_encoded_bam_bytes(tmp_path):
+    """A BAM assembled here byte by byte from the SAM specification (section 4.2), NOT by bamio.write_bam: magic, header
+    text, one reference, two records with hand-packed nibbles, two BGZF members plus the EOF marker, written with zlib at
+    raw-deflate level 0 (stored blocks) -- a reader that shares a misreading with our writer would not survive this."""
+    import struct
+    import zlib
+
+    def bgzf(data: bytes) -> bytes:
+        c = zlib.compressobj(0, zlib.DEFLATED, -15)
+        comp = c.compress(data) + c.flush()
+        bsize = len(comp) + 25
+        return (b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) + comp +
+                struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+    text = b"@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:chrQ\tLN:40\n"
+    head = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chrQ\x00" + struct.pack("<i", 40)
+
+    def rec(pos0, flag, cigar, seq_nibbles, l_seq, qual, name=b"q1\x00"):
+        body = struct.pack("<iiBBHHHiiii", 0, pos0, len(name), 30, 4680, len(cigar), flag, l_seq, -1, -1, 0) + name
+        body += b"".join(struct.pack("<I", (n << 4) | op) for n, op in cigar) + seq_nibbles + qual
+        return struct.pack("<i", len(body)) + body
+
+    # read 1: pos 3 (0-based 2), 5M, ACGTN -> nibbles 1,2,4,8,15 ; read 2: reverse, 2S3M, GGTCA, qualities missing
+    r1 = rec(2, 0, [(5, 0)], bytes([0x12, 0x48, 0xF0]), 5, bytes([10, 20, 30, 40, 41]))
+    r2 = rec(6, 16, [(2, 4), (3, 0)], bytes([0x44, 0x82, 0x10]), 5, b"\xff" * 5)
+    blob = bgzf(head + r1[:7]) + bgzf(r1[7:] + r2) + bgzf(b"")          # a record split across two BGZF members
+    fa, bam = str(tmp_path / "q.fa"), str(tmp_path / "hand.bam")
+    write_fasta(fa, [("chrQ", b"ACGTACGTAC" * 4)])
+    open(bam, "wb").write(blob)
+    pf = PackedFasta(fa)
+    got = list(BamBatcher(bam, pf))
+    assert len(got) == 1
+    exp = ReadBatch.from_records([Record(0, "chrQ", 3, "5M", b"ACGTN", bytes([10, 20, 30, 40, 41])),
+                                  Record(16, "chrQ", 7, "2S3M", b"GGTCA", b"")], pf.reference())
+    assert_batch_equal(got[0], exp, "hand-encoded BAM")
+    pf.close()
