@@ -14,7 +14,7 @@ rank r holds region r of an N x 100 Mb genome whose contigs span two regions eac
 contig, and a cluster of 256 reads on either side of such a cut makes one cluster span it (open cluster of shard s-1 +
 head partial of shard s).  One NCCL all-reduce of the profile count vector and one all-gather of a (contig, end) key per
 rank and step; the e2e leg adds one small all-gather of the boundary-cluster pieces.
---impl reference times the CPU restatement of the Java loops (oracle/; the jar cannot run: no JVM) on the host cores, on
+--impl reference times the CPU restatement of the Java loops (oracle/; plus the jar itself on a sample when `java` is on PATH) on the host cores, on
 the whole batch.
 """
 import argparse
@@ -199,6 +199,11 @@ def run_reference(args):
         cpu.step()
     dt = time.perf_counter() - t0
     v = batch.n_reads * args.steps / dt
+    try:                    # the jar itself, when this host has a JVM (it does not in the build image or on the GPU box)
+        import java_ref
+        java = java_ref.time_sample(ref, batch, max_len)
+    except Exception as e:  # never let the optional leg break the arm
+        java = {"available": False, "why": f"{type(e).__name__}: {e}"}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -206,7 +211,7 @@ def run_reference(args):
         "config": {"workload": name, "stages": ["profile", "pileup"], "reads_per_step": batch.n_reads,
                    "note": "one rank's batch per step on all host cores (the Java tools are single-threaded; at N > 1 the "
                            "GPU arm processes N such batches per step)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe()},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu.describe(), "java": java},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

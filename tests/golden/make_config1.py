@@ -16,7 +16,7 @@ FASTA, so no T>C site can ever be at those positions and snpHit stays 0 on this 
 own files (the filter's hits are covered by tests/test_flush_cpu.py and tests/test_gpu_stream.py).
 Expected outputs come from the literal Python restatement of the Java loops (oracle/py_oracle.py):
   config1/reference_chr1.fa.gz   the FASTA as shipped (gzip; the test writes it back with its .fai)
-  config1/snp_db.vcf.gz          the SNP file as shipped (bgzip)
+  config1/snp_db.vcf.gz(.tbi)    the SNP file as shipped (bgzip + tabix index)
   config1/reads.json.gz          the records (flag, contig, pos, cigar, seq, qual)
   config1/expected.json.gz       profile arrays + the six clust output files + counters
 """
@@ -131,8 +131,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     with gzip.GzipFile(os.path.join(OUT, "reference_chr1.fa.gz"), "wb", mtime=0) as f:
         f.write(open(f"{EX}/references/reference_chr1.fa", "rb").read())
-    with open(os.path.join(OUT, "snp_db.vcf.gz"), "wb") as f:
-        f.write(open(f"{EX}/references/snp_db.vcf.gz", "rb").read())
+    for name in ("snp_db.vcf.gz", "snp_db.vcf.gz.tbi"):     # the tabix index is what the reference's TabixReader opens
+        with open(os.path.join(OUT, name), "wb") as f:
+            f.write(open(f"{EX}/references/{name}", "rb").read())
     with gzip.GzipFile(os.path.join(OUT, "reads.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps([[r.flag, r.rname, r.pos, r.cigar, r.seq.decode(), list(r.qual)] for r in keep]).encode())
     exp = {"max_len": MAX_LEN, "min_cov": 1, "n_records": len(keep), "snps": snps,
