@@ -109,6 +109,9 @@ typedef struct ps_read_batch {
   uint64_t qual_bytes;
   uint64_t cigar_count;
   uint64_t exc_count;
+  uint32_t max_len;               /* longest read of the batch when the producer knows it, else 0 (a hint: ragged batches of
+                                     short reads are re-laid in rows of 16*ceil(min(max_len, max_read_length)/16) positions) */
+  uint32_t reserved;
 } ps_read_batch;
 
 /* ---- error profile ------------------------------------------------------------------------ */
@@ -310,6 +313,25 @@ int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts,
  * reference must have been loaded with ps_reference_load_fasta (the raw-case FASTA is read for the sequence columns). */
 int ps_clust_bam(ps_ctx* ctx, const char* bam_path, const char* out_path, const char* snp_vcf, uint32_t min_read_coverage,
                  ps_pileup_counters* counters_out, ps_fault* fault_out);
+
+/* ---- `comb` tool (host only): transcript hits lifted to genomic coordinates, merged with the genomic hits ---------------
+ * Replaces CombineGenomeTranscript.combine / printReadsToBamFile (utils/postprocessing/CombineGenomeTranscript.java:36-666;
+ * Main.java:438-486 `comb -g <genomic.bam> -t <transcript.bam> -o <combined.bam>`): the step that writes the `aMbNcM`
+ * cigars both kernels must tolerate.  The transcript BAM must be queryname-sorted and its reference names must be
+ * gene|transcript|chr|exonStarts;..|exonEnds;..|strand (PS_ERR_UNSORTED / PS_ERR_REFERENCE_WOULD_THROW otherwise). */
+typedef struct ps_comb_stats {
+  uint64_t genomic_records;                /* copied through from the genomic BAM */
+  uint64_t transcript_records;             /* read from the transcript BAM */
+  uint64_t lifted_records;                 /* written with genomic coordinates */
+  uint64_t mapped_reads;                   /* mappedReads (:59, :662) */
+  uint64_t spliced_reads;                  /* splicedReads (:479) */
+  uint64_t missed_transcript_alignments;   /* indel + splice junction (:294, :431, :447) */
+} ps_comb_stats;
+/* One hit (:146-474).  *new_start = -1: the hit does not lift.  On PS_ERR_REFERENCE_WOULD_THROW new_cigar holds the message. */
+int ps_liftover_hit(const char* transcript_name, int32_t aln_start, int32_t aln_end, int32_t read_len, const char* cigar,
+                    int32_t* new_start, char* new_cigar, size_t new_cigar_cap, uint32_t* missed);
+int ps_comb_bam(const char* genomic_bam, const char* transcript_bam, const char* out_bam, ps_comb_stats* stats, char* err,
+                size_t err_cap);
 
 /* ---- several GPUs behind one handle (one process, e.g. a JVM; Main.java:595-597, :634-636 enter here) -----------------
  * devices == NULL or n == 0: the list in PARASUITE_B200_DEVICES ("0,1,2"), else device 0.  The handle owns one context

@@ -981,3 +981,184 @@ def clust_files(records: List[Rec], genome: Genome, snps: SnpDb, min_cov: int) -
     for j in range(51):                                                         # :538-543
         out["sitepositions"] += fmt(_jdiv(float(allele_positions[j]), num_allele_positions)) + nl
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CombineGenomeTranscript (utils/postprocessing/CombineGenomeTranscript.java): transcript hits lifted to genomic
+# coordinates (cigars with N across introns) and merged with the genomic hits.  Literal restatement, statement by
+# statement; test infrastructure like everything in this file.
+# ---------------------------------------------------------------------------------------------------------
+def java_split(s: str, sep: str) -> List[str]:
+    """String.split(regex) for a one-character literal separator: trailing empty strings are removed."""
+    parts = s.split(sep)
+    while parts and parts[-1] == "":
+        parts.pop()
+    return parts if parts else ([""] if s == "" else [])
+
+
+def java_parse_int(s: str) -> int:
+    """Integer.parseInt: optional sign, decimal digits only, 32-bit range; anything else kills the tool."""
+    body = s[1:] if s[:1] in "+-" else s
+    if not body or not all("0" <= c <= "9" for c in body):
+        raise ReferenceWouldThrow(f"NumberFormatException: {s!r}")
+    v = int(s)
+    if not -2 ** 31 <= v < 2 ** 31:
+        raise ReferenceWouldThrow(f"NumberFormatException: {s!r}")
+    return v
+
+
+def liftover_hit(ref_name: str, aln_start: int, aln_end: int, read_len: int, cigar: str):
+    """One transcript hit (CombineGenomeTranscript.java:146-474).  -> (newGenomicPositionStart or -1, newGenomicCigar,
+    missedTranscriptAlignments increment)."""
+    f = java_split(ref_name, "|")                                          # :148
+    if len(f) < 6:
+        raise ReferenceWouldThrow("ArrayIndexOutOfBoundsException: transcript name without six |-separated fields")
+    exon_starts = sorted(java_split(f[3], ";"))                            # :172-175 Arrays.sort on STRINGS
+    exon_ends = sorted(java_split(f[4], ";"))
+    strand = f[5]
+    new_start, new_cigar, missed = -1, "", 0
+    length_passed = 0
+    has_indel = "D" in cigar or "I" in cigar
+    n = len(exon_starts)
+
+    def st(i):
+        return java_parse_int(exon_starts[i])
+
+    def en(i):
+        if i >= len(exon_ends):
+            raise ReferenceWouldThrow("ArrayIndexOutOfBoundsException: fewer exon ends than starts")
+        return java_parse_int(exon_ends[i])
+
+    if strand == "1":                                                      # :219-391
+        for i in range(n):
+            tmp = length_passed
+            length_passed += en(i) - st(i) + 1
+            if aln_start <= length_passed:
+                if new_start == -1:
+                    new_start = st(i) + (aln_start - tmp) - 1
+            if aln_end <= length_passed:
+                if new_start >= st(i):
+                    new_cigar = cigar
+                else:
+                    new_cigar += str(aln_end - tmp) + "M"
+                break
+            elif new_start != -1:
+                if has_indel:
+                    missed += 1
+                    break
+                if new_start >= st(i):
+                    new_cigar += str(en(i) - new_start + 1) + "M"
+                else:
+                    new_cigar += str(en(i) - st(i) + 1) + "M"
+                if i < n - 1:
+                    intron = st(i + 1) - en(i) - 1
+                    if intron <= 0:
+                        break
+                    new_cigar += str(intron) + "N"
+                else:
+                    break
+    elif strand == "-1":                                                   # :392-473
+        new_end = -1
+        for i in range(n - 1, -1, -1):
+            tmp = length_passed
+            length_passed += en(i) - st(i) + 1
+            if aln_start <= length_passed:
+                if new_end == -1:
+                    new_end = en(i) - (aln_start - tmp) + 1
+            if aln_end <= length_passed:
+                if new_end <= en(i):
+                    new_cigar = cigar
+                    new_start = new_end - read_len + 1
+                else:
+                    if has_indel:
+                        missed += 1
+                        break
+                    new_cigar = str(aln_end - tmp) + "M" + new_cigar
+                    new_start = en(i) - (aln_end - tmp) + 1
+                break
+            elif new_end != -1:
+                if has_indel:
+                    missed += 1
+                    break
+                if new_end < en(i):
+                    new_cigar = str(new_end - st(i) + 1) + "M" + new_cigar
+                else:
+                    new_cigar = str(en(i) - st(i) + 1) + "M" + new_cigar
+                if i >= 1:
+                    intron = st(i) - en(i - 1) - 1
+                    if intron <= 0:
+                        break
+                    new_cigar = str(intron) + "N" + new_cigar
+                else:
+                    break
+    return new_start, new_cigar, missed
+
+
+_RC = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")          # SequenceUtil.complement: other symbols stay as they are
+
+
+def combine(genome_names: List[str], sort_order: str, genome_recs: List[dict], transcript_recs: List[dict]):
+    """combine() + printReadsToBamFile (CombineGenomeTranscript.java:36-666) on records given as dicts
+    {name, flag, rname, pos, cigar, seq, qual, mapq}; the transcript records are name-grouped as in a queryname-sorted
+    BAM.  -> (output records in the order htsjdk's writer emits them, stats dict)."""
+    out = [dict(r) for r in genome_recs]                                   # :53-60
+    mapped, spliced, missed_total = len(out), 0, 0
+    index = {n: i for i, n in enumerate(genome_names)}
+    lifted = []
+
+    def flush(group):                                                      # printReadsToBamFile :598-666
+        nonlocal mapped
+        if not group:
+            return
+        if any(p != group["pos"][0] for p in group["pos"]):
+            return
+        rec = dict(group["recs"][group["primary"]])
+        f = java_split(rec["rname"], "|")
+        if "chr" + f[2] not in index:
+            return
+        chrom = "M" if f[2] == "MT" else f[2]
+        rec["rname"] = "chr" + chrom if "chr" + chrom in index else "*"
+        rec["pos"] = group["pos"][group["primary"]]
+        rec["cigar"] = group["cigars"][group["primary"]]
+        rec["mapq"] = 10
+        if f[5] == "-1":
+            rec["flag"] = rec["flag"] - 16 if rec["flag"] & 16 else rec["flag"] + 16
+            rec["seq"] = rec["seq"].translate(_RC)[::-1]
+        lifted.append(rec)
+        mapped += 1
+
+    group, name_tmp = None, ""
+    for r in transcript_recs:
+        if r["rname"] == "*":                                              # :105
+            continue
+        if name_tmp != r["name"]:                                          # :137-144
+            flush(group)
+            group, name_tmp = None, r["name"]
+        aln_end = r["pos"] + ref_length(r["cigar"]) - 1 if not (r["flag"] & 4) else 0
+        new_start, new_cigar, missed = liftover_hit(r["rname"], r["pos"], aln_end, len(r["seq"]), r["cigar"])
+        missed_total += missed
+        if new_start == -1:                                                # :476
+            continue
+        if "N" in new_cigar:
+            spliced += 1
+        if group is None:
+            group = {"genes": [], "pos": [], "cigars": [], "recs": [], "primary": 0}
+        if not (r["flag"] & 0x100):
+            group["primary"] = len(group["genes"])
+        group["genes"].append(java_split(r["rname"], "|")[0])
+        group["pos"].append(new_start)
+        group["cigars"].append(new_cigar)
+        group["recs"].append(r)
+    flush(group)
+    out += lifted
+    if sort_order == "coordinate":
+        def key(r):       # SAMRecordCoordinateComparator: reference index (unmapped last), start, strand, name, flags, mapq
+            ri = index.get(r["rname"], -1)
+            return (ri if ri >= 0 else 1 << 31, r["pos"], 1 if r["flag"] & 16 else 0, r["name"], r["flag"], r["mapq"])
+        out.sort(key=key)
+    return out, {"mapped_reads": mapped, "spliced_reads": spliced, "missed_transcript_alignments": missed_total,
+                 "lifted": len(lifted)}
+
+
+def ref_length(cigar: str) -> int:
+    return sum(n for op, n in parse_cigar(cigar) if op in "MDN=X") if cigar and cigar != "*" else 0

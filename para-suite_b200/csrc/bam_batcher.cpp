@@ -732,6 +732,8 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   out->qual_bytes = qual_bytes;
   out->cigar_count = cigar_count;
   out->exc_count = exc_count;
+  out->max_len = lens_max.load();
+  out->reserved = 0;
   B->ordinal += n;
   return 1;
 }

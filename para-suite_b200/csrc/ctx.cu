@@ -31,6 +31,8 @@ static DeviceBatch view_of(const ps_read_batch* b) {
   v.exc = b->exc;
   v.uniform_len = b->uniform_len;
   v.uniform_ncigar = b->uniform_ncigar;
+  v.cigar_count = b->cigar_count;
+  v.max_len = b->max_len;
   return v;
 }
 
@@ -91,6 +93,8 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
   v.exc = (const uint32_t*)s.exc.p;
   v.uniform_len = hb->uniform_len;
   v.uniform_ncigar = hb->uniform_ncigar;
+  v.cigar_count = hb->cigar_count;
+  v.max_len = hb->max_len;
   *out = &s;
   return PS_OK;
 }
@@ -184,6 +188,7 @@ void ps_destroy(ps_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release(); ctx->t2c_mask.release();
+  ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
     s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();

@@ -36,6 +36,8 @@ struct DeviceBatch {
   const uint32_t* exc;
   uint32_t uniform_len;
   uint32_t uniform_ncigar;
+  uint64_t cigar_count;    // total cigar elements (0: not known)
+  uint32_t max_len;        // longest read (0: not known)
 };
 
 struct ProfileLayout {   // offsets (in int64 elements) inside the accumulator vector
@@ -106,6 +108,7 @@ struct ps_ctx {
   DevBuf acc;        // int64[layout.total]
   DevBuf fault;      // uint64 fault word + debug / deferred-count words (64 bytes)
   DevBuf deferred;   // uint32 read indices the fast profile kernel hands to the generic routine
+  DevBuf rg_off, rg_bases, rg_qual, rg_op0;   // ragged batches re-laid for the fast profile kernel (profile.cu: repack)
   uint64_t reads_seen = 0;
   uint32_t profile_batches = 0;   // fast-path batches of the open run (selects the deferred-read counter)
   cudaStream_t profile_stream = nullptr;   // stream of the last profile batch

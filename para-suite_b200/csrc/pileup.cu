@@ -1764,7 +1764,7 @@ static DeviceBatch pl_view_of(const ps_read_batch* b) {
   v.n_reads = b->n_reads; v.meta = b->meta; v.ref_start = b->ref_start; v.bases2 = b->bases2; v.qual = b->qual;
   v.cigar = b->cigar; v.tile_base_off = b->tile_base_off; v.tile_qual_off = b->tile_qual_off;
   v.tile_cigar_off = b->tile_cigar_off; v.tile_exc_off = b->tile_exc_off; v.exc = b->exc;
-  v.uniform_len = b->uniform_len; v.uniform_ncigar = b->uniform_ncigar;
+  v.uniform_len = b->uniform_len; v.uniform_ncigar = b->uniform_ncigar; v.cigar_count = b->cigar_count; v.max_len = b->max_len;
   return v;
 }
 

@@ -18,6 +18,7 @@
 // Counts land in per-block shared-memory histograms and are flushed once per block with 64-bit global atomics
 // into the accumulator vector (internal.h ProfileLayout) -- the unit of the multi-GPU all-reduce.
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_common.cuh"
 
@@ -37,6 +38,8 @@ struct ProfileParams {
   unsigned int* deferred_count_next;   // the counter of the run's next batch: cleared by this batch's deferred kernel
                                        // (two counters take turns, so no memset sits in front of the fast kernel)
   unsigned long long* t2c_mask;        // fast kernel, optional: one T>C mask word per read (profile_fast.cuh), for the pileup
+  const uint32_t* off3;                // deferred kernel on a re-laid ragged batch: [3][n_reads] in-tile offsets of every read
+                                       // (bytes of bases, bytes of qualities, cigar elements), written by the repack kernel
 };
 
 // shared-memory histograms of the generic path
@@ -504,13 +507,108 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS) profile_deferred_kernel(cons
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint64_t r = P.deferred[k];
     ReadOffsets off;
-    off.base = r * (uint64_t)bpr;
-    off.qual = r * (uint64_t)P.b.uniform_len;
-    off.cigar = r * (uint64_t)P.b.uniform_ncigar;
+    if (P.off3 != nullptr) {      // ragged batch: tile offset + the in-tile offset the repack kernel left
+      const uint64_t t = r / PS_TILE_READS, n_all = P.b.n_reads;
+      off.base = (P.b.uniform_len ? t * PS_TILE_READS * bpr : __ldg(P.b.tile_base_off + t)) + __ldg(P.off3 + r);
+      off.qual = (P.b.uniform_len ? t * PS_TILE_READS * (uint64_t)P.b.uniform_len : __ldg(P.b.tile_qual_off + t)) + __ldg(P.off3 + n_all + r);
+      off.cigar = (P.b.uniform_ncigar ? t * PS_TILE_READS * (uint64_t)P.b.uniform_ncigar : __ldg(P.b.tile_cigar_off + t)) +
+                  __ldg(P.off3 + 2 * n_all + r);
+    } else {
+      off.base = r * (uint64_t)bpr;
+      off.qual = r * (uint64_t)P.b.uniform_len;
+      off.cigar = r * (uint64_t)P.b.uniform_ncigar;
+    }
     profile_read_generic(P, S, r / PS_TILE_READS, (uint32_t)(r % PS_TILE_READS), r, __ldg(P.b.meta + r), off);
   }
   __syncthreads();
   flush_generic(P, S);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ragged batch -> rows of S positions for the fast kernel (profile_fast.cuh, RG): one block per tile of 256 reads.
+// A block scan over the metas gives every read's place in the three streams (left in `off3` for the deferred kernel);
+// then every thread moves its own read: aligned word loads + funnel shifts out of the streams (neighbouring lanes read
+// neighbouring rows, so the loads hit the same lines), 16-byte stores into its row, zero beyond the read's end.  Reads
+// longer than S get a zero row: the fast kernel hands them to the deferred kernel, which works on the original streams.
+// ---------------------------------------------------------------------------------------------------------
+struct RepackParams {
+  DeviceBatch b;          // the batch as uploaded
+  uint64_t first_read;    // chunk [first_read, first_read + n_reads), first_read a multiple of PS_TILE_READS
+  uint64_t n_reads;
+  uint32_t S;             // row length in positions: a multiple of 16, <= 64
+  uint32_t* bases_out;    // [n_reads][S/16] words
+  uint32_t* qual_out;     // [n_reads][S/4] words
+  uint32_t* op0_out;      // [n_reads] the read's cigar op when it has exactly one, else ~0
+  uint32_t* off3;         // [3][b.n_reads]
+};
+
+// One stream row -> NWORDS output words: bytes [a, a + len) of `stream`, zero behind them.  The row starts at any byte:
+// aligned word loads, funnel shifts; a word is only requested when it holds a wanted byte.
+template <int NWORDS>
+__device__ __forceinline__ void repack_row(const uint8_t* stream, uint64_t a, uint32_t len, uint32_t (&o)[NWORDS]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(stream) + (a >> 2);
+  const uint32_t sk = (uint32_t)(a & 3u), need = sk + len;      // bytes counted from the aligned start
+  uint32_t prev = len ? __ldg(w) : 0u;
+#pragma unroll
+  for (int k = 0; k < NWORDS; ++k) {
+    const uint32_t nxt = 4u * (uint32_t)(k + 1) < need ? __ldg(w + k + 1) : 0u;
+    const uint32_t v = __funnelshift_r(prev, nxt, sk * 8u);
+    const int have = (int)len - 4 * k;
+    o[k] = have >= 4 ? v : (have <= 0 ? 0u : (v & ((1u << (8 * have)) - 1u)));
+    prev = nxt;
+  }
+}
+
+template <int NW>     // S = 16 * NW
+__global__ void __launch_bounds__(PS_TILE_READS) profile_repack_kernel(const __grid_constant__ RepackParams P) {
+  __shared__ unsigned long long s_wsum[PS_TILE_READS / 32];
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint64_t tile = P.first_read / PS_TILE_READS + blockIdx.x;
+  const uint64_t r = tile * PS_TILE_READS + t, r_end = P.first_read + P.n_reads;
+  const bool in = r < r_end;
+  const uint32_t meta = in ? __ldg(P.b.meta + r) : 0u;
+  const uint32_t L = PS_META_LEN(meta), nc = PS_META_NCIGAR(meta);
+  // L | bytes of bases << 25 | cigar ops << 48, like warp_read_offsets
+  const unsigned long long mine = (unsigned long long)L | ((unsigned long long)((L + 3) >> 2) << 25) | ((unsigned long long)nc << 48);
+  unsigned long long inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  unsigned long long pre = 0;
+  for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
+  if (!in) return;
+  const unsigned long long ex = pre + inc - mine;
+  const uint32_t relq = (uint32_t)(ex & 0x1FFFFFFu), relb = (uint32_t)((ex >> 25) & 0x7FFFFFu), relc = (uint32_t)(ex >> 48);
+  const uint64_t B0 = P.b.uniform_len ? tile * PS_TILE_READS * (uint64_t)((P.b.uniform_len + 3) >> 2) : __ldg(P.b.tile_base_off + tile);
+  const uint64_t Q0 = P.b.uniform_len ? tile * PS_TILE_READS * (uint64_t)P.b.uniform_len : __ldg(P.b.tile_qual_off + tile);
+  const uint64_t C0 = P.b.uniform_ncigar ? tile * PS_TILE_READS * (uint64_t)P.b.uniform_ncigar : __ldg(P.b.tile_cigar_off + tile);
+  P.off3[r] = relb;
+  P.off3[P.b.n_reads + r] = relq;
+  P.off3[2 * P.b.n_reads + r] = relc;
+  const uint64_t row = r - P.first_read;
+  P.op0_out[row] = nc == 1u ? __ldg(P.b.cigar + C0 + relc) : 0xFFFFFFFFu;
+  const uint32_t Lr = L <= 16u * NW ? L : 0u;              // longer reads: a zero row (the deferred kernel takes them)
+  {  // qualities: one row of 16 * NW bytes, written as NW 16-byte stores
+    uint4* dst = reinterpret_cast<uint4*>(P.qual_out) + row * NW;
+#pragma unroll
+    for (int g = 0; g < NW; ++g) {
+      uint32_t o[4];
+      const uint32_t done = 16u * (uint32_t)g;
+      repack_row<4>(P.b.qual, Q0 + relq + done, Lr > done ? Lr - done : 0u, o);
+      dst[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  {  // bases: NW words
+    uint32_t o[NW];
+    repack_row<NW>(P.b.bases2, B0 + relb, (Lr + 3u) >> 2, o);
+    uint32_t* dst = P.bases_out + row * NW;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) dst[k] = o[k];
+  }
 }
 
 #include "profile_fast.cuh"
@@ -567,6 +665,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   P.n_tiles = 0;
   P.deferred = nullptr;
   P.t2c_mask = nullptr;
+  P.off3 = nullptr;
   // both counters are zero at the start of a run (ps_profile_begin clears the words behind the fault word)
   P.deferred_count = reinterpret_cast<unsigned int*>(P.fault + 2) + (ctx->profile_batches & 1u);
   P.deferred_count_next = reinterpret_cast<unsigned int*>(P.fault + 2) + ((ctx->profile_batches + 1u) & 1u);
@@ -592,6 +691,68 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     else if (nw == 3) e = launch_fast<3, 5, 0>(ctx, P, n_wt, stream);
     else e = launch_fast<4, 5, 0>(ctx, P, n_wt, stream);
     if (e != cudaSuccess) return e;
+    return launch_deferred(ctx, P, stream);
+  }
+  // Ragged batches of short reads (adapter-trimmed PAR-CLIP reads as an aligner leaves them): re-lay them as rows of
+  // S = 16 * ceil(max_read_length / 16) positions and run the fast kernel with per-read lengths.  Reads of another
+  // shape (several cigar ops, clips, longer than S) go to the deferred kernel on the original streams; the test on the
+  // op count keeps batches of mostly gapped alignments on the warp-per-read kernel.
+  const uint32_t max_len = ctx->layout.max_len;
+  const bool ragged_ok = !ctx->layout.infer_q && max_len >= 1 && max_len <= 64 && b.n_reads < 0xFFFFFFFFull &&
+                         aligned16(b.meta) && aligned16(b.ref_start) && (b.uniform_len == 0 || b.uniform_len <= 64) &&
+                         (reinterpret_cast<uintptr_t>(b.bases2) & 3u) == 0 && (reinterpret_cast<uintptr_t>(b.qual) & 3u) == 0 &&
+                         b.cigar_count * 2 <= b.n_reads * 3 && getenv("PARASUITE_B200_NO_RAGGED_FAST") == nullptr;
+  if (ragged_ok) {
+    // rows as short as the batch allows when its producer says how long the longest read is
+    const uint32_t Lmax = b.max_len ? std::min(b.max_len, max_len) : max_len;
+    const uint32_t S = (Lmax + 15u) / 16u * 16u, nw = S / 16u;
+    uint64_t chunk = 1ull << 23;                              // reads re-laid per pass (bounds the scratch rows)
+    if (const char* ev = getenv("PARASUITE_B200_RAGGED_CHUNK")) {
+      const uint64_t v = strtoull(ev, nullptr, 10) / PS_TILE_READS * PS_TILE_READS;
+      if (v >= PS_TILE_READS && v <= (1ull << 26)) chunk = v;
+    }
+    chunk = std::min<uint64_t>((b.n_reads + PS_TILE_READS - 1) / PS_TILE_READS * PS_TILE_READS, chunk);
+    cudaError_t e;
+    if ((e = ctx->deferred.reserve((size_t)b.n_reads * 4)) != cudaSuccess) return e;
+    if ((e = ctx->rg_off.reserve((size_t)b.n_reads * 12)) != cudaSuccess) return e;
+    if ((e = ctx->rg_bases.reserve((size_t)chunk * (S / 4) + 64)) != cudaSuccess) return e;
+    if ((e = ctx->rg_qual.reserve((size_t)chunk * S + 64)) != cudaSuccess) return e;
+    if ((e = ctx->rg_op0.reserve((size_t)chunk * 4 + 64)) != cudaSuccess) return e;
+    P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
+    P.off3 = static_cast<const uint32_t*>(ctx->rg_off.p);
+    ctx->profile_batches++;
+    for (uint64_t c0 = 0; c0 < b.n_reads; c0 += chunk) {
+      const uint64_t cn = std::min<uint64_t>(chunk, b.n_reads - c0);
+      RepackParams R;
+      R.b = b; R.first_read = c0; R.n_reads = cn; R.S = S;
+      R.bases_out = static_cast<uint32_t*>(ctx->rg_bases.p);
+      R.qual_out = static_cast<uint32_t*>(ctx->rg_qual.p);
+      R.op0_out = static_cast<uint32_t*>(ctx->rg_op0.p);
+      R.off3 = static_cast<uint32_t*>(ctx->rg_off.p);
+      const uint32_t rgrid = (uint32_t)((cn + PS_TILE_READS - 1) / PS_TILE_READS);
+      if (nw == 1) profile_repack_kernel<1><<<rgrid, PS_TILE_READS, 0, stream>>>(R);
+      else if (nw == 2) profile_repack_kernel<2><<<rgrid, PS_TILE_READS, 0, stream>>>(R);
+      else if (nw == 3) profile_repack_kernel<3><<<rgrid, PS_TILE_READS, 0, stream>>>(R);
+      else profile_repack_kernel<4><<<rgrid, PS_TILE_READS, 0, stream>>>(R);
+      ctx->launches++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      ProfileParams Q = P;
+      Q.b.n_reads = cn;
+      Q.b.meta = b.meta + c0; Q.b.ref_start = b.ref_start + c0;
+      Q.b.cigar = R.op0_out;
+      Q.b.bases2 = reinterpret_cast<const uint8_t*>(R.bases_out);
+      Q.b.qual = reinterpret_cast<const uint8_t*>(R.qual_out);
+      Q.b.tile_exc_off = b.tile_exc_off + c0 / PS_TILE_READS;
+      Q.b.uniform_len = S; Q.b.uniform_ncigar = 1;
+      Q.first_read = c0;
+      Q.off3 = nullptr;
+      const uint32_t n_wt = (uint32_t)((cn + WT_READS - 1) / WT_READS);
+      if (nw == 1) e = launch_fast<1, 6, 0, true>(ctx, Q, n_wt, stream);
+      else if (nw == 2) e = launch_fast<2, 6, 0, true>(ctx, Q, n_wt, stream);
+      else if (nw == 3) e = launch_fast<3, 5, 0, true>(ctx, Q, n_wt, stream);
+      else e = launch_fast<4, 5, 0, true>(ctx, Q, n_wt, stream);
+      if (e != cudaSuccess) return e;
+    }
     return launch_deferred(ctx, P, stream);
   }
   return launch_generic(ctx, P, done, stream);

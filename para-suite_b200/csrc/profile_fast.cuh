@@ -23,6 +23,12 @@
 //                  consumes it instead of decoding the read again (ps_profile_pileup_batch_device).
 // Reads outside the shape (flags, other cigars, contig edges) are appended to a dense list for
 // profile_deferred_kernel instead of being walked inline (one slow lane would stall the other 31).
+//
+// RG (ragged) instantiation: batches whose reads differ in length or cigar (what an aligner leaves of adapter-trimmed
+// PAR-CLIP reads) are first re-laid by profile_repack_kernel into rows of S = 16 * ceil(max_read_length / 16) <= 64
+// positions (bases and qualities zero-padded, first cigar op per read).  The kernel then runs with L = S as the row
+// geometry and takes every length-dependent mask (read extent, reference-window extent, reversal shift, cigar shape)
+// from the read's own length in its meta word; zero-padded qualities add nothing to the sums.
 
 #define FAST_STAGES 2
 #define WT_READS 64            // reads per warp-tile
@@ -205,8 +211,34 @@ __device__ __forceinline__ void fast_reverse(uint32_t (&v)[NW], uint32_t L, cons
   }
 }
 
-template <int NW, int NPL, int LT>
-__global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast_kernel(const ProfileParams P) {
+// the same for a read of any length Lr <= 16 * NW: the shift may span whole words
+template <int NW, bool CODES>
+__device__ __forceinline__ void fast_reverse_any(uint32_t (&v)[NW], uint32_t Lr, const uint32_t (&lenmask)[NW]) {
+  const uint32_t s = 2u * (16u * NW - Lr);   // < 32 * NW
+  uint32_t a[NW + 1];
+#pragma unroll
+  for (int k = 0; k < NW; ++k) a[k] = __brev(v[NW - 1 - k]);
+  a[NW] = 0u;
+  if (NW > 2) {                              // whole-word part of the shift, two words then one
+    const bool w2 = (s & 64u) != 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) a[k] = w2 ? (k + 2 < NW ? a[k + 2 < NW ? k + 2 : 0] : 0u) : a[k];
+  }
+  if (NW > 1) {
+    const bool w1 = (s & 32u) != 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) a[k] = w1 ? a[k + 1] : a[k];
+  }
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    const uint32_t x = __funnelshift_r(a[k], a[k + 1], s & 31u);
+    const uint32_t y = ((x << 1) & 0xAAAAAAAAu) | ((x >> 1) & 0x55555555u);
+    v[k] = (CODES ? ~y : y) & lenmask[k];
+  }
+}
+
+template <int NW, int NPL, int LT, bool RG>
+__global__ void __launch_bounds__(FAST_THREADS, RG ? 3 : FAST_BLOCKS_PER_SM) profile_fast_kernel(const ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NC = fast_nc(NW, LT);
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -283,6 +315,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
   const uint32_t ivmask1 = L > 32 ? (L >= 64 ? 0xFFFFFFFFu : ((1u << (L - 32)) - 1u)) : 0u;
   const uint32_t metaE = PS_MAKE_META(L, 1, 0), cgE = L << 4;      // the shape: length L, one op, L x M
   constexpr uint32_t kMetaMask = ~((uint32_t)(PS_RF_REVERSE | PS_RF_HAS_INVALID) << 24);
+  const uint32_t Lcap = RG ? min(L, max_len) : L;                  // RG: longest read the rows and the histogram take
 
   Planes<NPL> pl[NC];
   uint32_t tot[NC];
@@ -387,8 +420,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
       }
     }
     // one unsigned compare per read: lo <= g0 and g0 + L <= hi  <=>  g0 - lo <= hi - lo - L  (offsets fit 32 bits)
-    const bool span_ok = c_hi >= c_lo + L && L <= max_len;
-    const uint32_t lo32 = (uint32_t)c_lo, span32 = span_ok ? (uint32_t)(c_hi - c_lo - L) : 0u;
+    // (RG: span32 is the contig length and every read brings its own length to the test)
+    const bool span_ok = RG ? c_hi > c_lo : (c_hi >= c_lo + L && L <= max_len);
+    const uint32_t lo32 = (uint32_t)c_lo, span32 = span_ok ? (uint32_t)(c_hi - c_lo - (RG ? 0u : L)) : 0u;
     // scatter this warp-tile's N calls into the per-read invalid map
     if (cur_hi > cur_lo) {
       const uint32_t quarter = wt & 3u;
@@ -397,13 +431,15 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
         if (e != cur_lo) x = (e + lane < cur_hi) ? __ldg(P.b.exc + e + lane) : 0xFFFFFFFFu;
         if (x != 0xFFFFFFFFu && ((x >> 22) & 3u) == quarter) {
           const uint32_t rit = (x >> 16) & 63u, p = x & 0xFFFFu;
-          if (p < L) {
+          const uint32_t mrit = lds32(a_sb + lay.meta + rit * 4);
+          const uint32_t Lx = RG ? min(PS_META_LEN(mrit), L) : L;     // RG: rows hold the first L bases at most
+          if (p < Lx) {
             atomicOr(&s_inv[rit * NW + (p >> 4)], 1u << (2u * (p & 15u)));
             // An N call is never counted, but the quality sums below run over ALL positions: clear the byte that pairs
             // with this base in the warp's copy of the qualities (index = distance from the 5' end: qualities are not
             // reversed with the bases, Q10), so that nothing has to be taken out again afterwards.
-            const bool minus = (lds32(a_sb + lay.meta + rit * 4) & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_sb + lay.qual + rit * L + (minus ? L - 1u - p : p)), "r"(0u) : "memory");
+            const bool minus = (mrit & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_sb + lay.qual + rit * L + (minus ? Lx - 1u - p : p)), "r"(0u) : "memory");
           }
         }
       }
@@ -414,15 +450,35 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
     bool ok[2], rev[2], hasn[2], anyinv[2], punct[2];
     uint32_t rf[2][NW], iv[2][2], rd[2][NW], ve[2][NW];
     uint32_t a_qrow[2];
+    uint32_t Lr[2], lm[2][RG ? NW : 1];          // RG: the read's own length and extent masks
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t rit = lane + h * 32;
 #pragma unroll
       for (int k = 0; k < NW; ++k) rf[h][k] = __funnelshift_r(rw[h][k], rw[h][k + 1], (rsh[h] & 15u) * 2u);
-      iv[h][0] = __funnelshift_r(ri[h][0], ri[h][1], rsh[h]) & ivmask0;
-      iv[h][1] = (LT == 0 || LT > 32) ? (__funnelshift_r(ri[h][1], ri[h][2], rsh[h]) & ivmask1) : 0u;
-      const bool shaped = ((meta[h] ^ metaE) & kMetaMask) == 0 && cg[h] == cgE;
-      ok[h] = shaped && (g0[h] - lo32) <= span32 && span_ok && rit < n_here;
+      bool shaped;
+      if (RG) {
+        Lr[h] = PS_META_LEN(meta[h]);
+        // one cigar op, no flag but strand / N calls, 1 <= Lr <= Lcap, the op is Lr x M
+        shaped = (meta[h] & kMetaMask & 0xFFFF0000u) == (1u << 16) && Lr[h] - 1u < Lcap && cg[h] == (Lr[h] << 4);
+        if (!shaped) Lr[h] = 1u;                    // keeps every shift below in range; the read adds nothing
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          const int rem = min(max((int)Lr[h] - 16 * k, 0), 16);
+          lm[h][k] = shl_clamp(1u, 2u * (uint32_t)rem) - 1u;        // rem == 16: shl by 32 gives 0, minus one = all ones
+        }
+        iv[h][0] = __funnelshift_r(ri[h][0], ri[h][1], rsh[h]) & (shl_clamp(1u, Lr[h]) - 1u);
+        iv[h][1] = Lr[h] > 32u ? (__funnelshift_r(ri[h][1], ri[h][2], rsh[h]) & (shl_clamp(1u, Lr[h] - 32u) - 1u)) : 0u;
+        // lo <= g0 and g0 + Lr <= hi with 32-bit offsets: d = g0 - lo may wrap to a huge value, which fails d <= span
+        const uint32_t d = g0[h] - lo32;
+        ok[h] = shaped && span_ok && d <= span32 && Lr[h] <= span32 - d && rit < n_here;
+      } else {
+        Lr[h] = L;
+        iv[h][0] = __funnelshift_r(ri[h][0], ri[h][1], rsh[h]) & ivmask0;
+        iv[h][1] = (LT == 0 || LT > 32) ? (__funnelshift_r(ri[h][1], ri[h][2], rsh[h]) & ivmask1) : 0u;
+        shaped = ((meta[h] ^ metaE) & kMetaMask) == 0 && cg[h] == cgE;
+        ok[h] = shaped && (g0[h] - lo32) <= span32 && span_ok && rit < n_here;
+      }
       rev[h] = ok[h] && (meta[h] & ((uint32_t)PS_RF_REVERSE << 24)) != 0;
       hasn[h] = (meta[h] & ((uint32_t)PS_RF_HAS_INVALID << 24)) != 0 && rit < n_here;
       anyinv[h] = ok[h] && (iv[h][0] | iv[h][1]) != 0;
@@ -436,8 +492,9 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
       const uint32_t vmask = ok[h] ? 0x55555555u : 0u;
 #pragma unroll
       for (int k = 0; k < NW; ++k) {
-        rd[h][k] = __funnelshift_r(bw[k], bw[k + 1], bshift) & lenmask[k];
-        ve[h][k] = lenmask[k] & vmask;
+        const uint32_t lmk = RG ? lm[h][k] : lenmask[k];
+        rd[h][k] = __funnelshift_r(bw[k], bw[k + 1], bshift) & lmk;
+        ve[h][k] = lmk & vmask;
       }
       a_qrow[h] = ok[h] ? a_sb + lay.qual + rit * L : a_zero;    // a read outside the shape adds zeros
       n_fast += ok[h] ? 1u : 0u;
@@ -465,15 +522,30 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
         uint32_t a[NW], b[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) { a[k] = rf[h][k]; b[k] = rd[h][k]; }
-        fast_reverse<NW, true>(a, L, lenmask);
-        fast_reverse<NW, true>(b, L, lenmask);
+        if (RG) {
+          uint32_t lmh[NW];
+#pragma unroll
+          for (int k = 0; k < NW; ++k) lmh[k] = lm[h][RG ? k : 0];
+          fast_reverse_any<NW, true>(a, Lr[h], lmh);
+          fast_reverse_any<NW, true>(b, Lr[h], lmh);
+        } else {
+          fast_reverse<NW, true>(a, L, lenmask);
+          fast_reverse<NW, true>(b, L, lenmask);
+        }
 #pragma unroll
         for (int k = 0; k < NW; ++k) { rf[h][k] = rev[h] ? a[k] : rf[h][k]; rd[h][k] = rev[h] ? b[k] : rd[h][k]; }
         if (punct[h] && rev[h]) {   // the plain length mask is its own mirror image; only a punctured one needs reversing
           uint32_t v[NW];
 #pragma unroll
           for (int k = 0; k < NW; ++k) v[k] = ve[h][k];
-          fast_reverse<NW, false>(v, L, lenmask);
+          if (RG) {
+            uint32_t lmh[NW];
+#pragma unroll
+            for (int k = 0; k < NW; ++k) lmh[k] = lm[h][RG ? k : 0];
+            fast_reverse_any<NW, false>(v, Lr[h], lmh);
+          } else {
+            fast_reverse<NW, false>(v, L, lenmask);
+          }
 #pragma unroll
           for (int k = 0; k < NW; ++k) ve[h][k] = v[k] & 0x55555555u;
         }
@@ -505,7 +577,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
     // ---- quality sums by read base over ALL positions < L (corrected for mismatches / invalid at the end) ---------
     {
       constexpr int NCH = 2 * NW;                 // chunks of 8 positions
-      const bool unaligned = LT == 0 || (LT & 3);   // rows start at any byte unless L is a multiple of 4
+      const bool unaligned = !RG && (LT == 0 || (LT & 3));   // rows start at any byte unless L is a multiple of 4 (RG: of 16)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (8 * c >= (int)L) break;               // L is uniform over the launch: no divergence
@@ -581,7 +653,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
         if (!anyinv[h]) continue;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-          uint32_t mi = (lenmask[k] & 0x55555555u) & ~ve[h][k];
+          uint32_t mi = ((RG ? lm[h][RG ? k : 0] : lenmask[k]) & 0x55555555u) & ~ve[h][k];
           while (mi) {
             const uint32_t b = (uint32_t)__ffs((int)mi) - 1u;
             mi &= mi - 1u;
@@ -678,10 +750,10 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_BLOCKS_PER_SM) profile_fast
 // (64 positions x |q| <= 128 x 2^17 reads = 2^30)
 #define FAST_MAX_READS_PER_BLOCK (1u << 17)
 
-template <int NW, int NPL, int LT>
+template <int NW, int NPL, int LT, bool RG = false>
 cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cudaStream_t stream) {
   const size_t smem = fast_layout(P.lay.max_len, P.b.uniform_len, NW).total + 128;
-  auto kern = profile_fast_kernel<NW, NPL, LT>;
+  auto kern = profile_fast_kernel<NW, NPL, LT, RG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
@@ -703,7 +775,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
     Q.b.qual += r0 * P.b.uniform_len;
     Q.b.tile_exc_off += r0 / PS_TILE_READS;
     Q.b.n_reads = std::min<uint64_t>(P.b.n_reads - r0, cnt * WT_READS);
-    Q.first_read = r0;    // offset added to deferred read indices
+    Q.first_read = P.first_read + r0;    // offset added to deferred read indices
     if (Q.t2c_mask) Q.t2c_mask += r0;
     kern<<<grid, FAST_THREADS, smem, stream>>>(Q);
     ctx->launches++;

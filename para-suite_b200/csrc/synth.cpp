@@ -400,6 +400,7 @@ Synth* ps_synth_reads(const ps_synth_params* P, const ps_reference* ref) {
   B.qual_bytes = n * (uint64_t)L;
   B.cigar_count = coff[n];
   B.exc_count = S->tile_exc_off[n_tiles];
+  B.max_len = L;
   return S;
 }
 

@@ -72,7 +72,12 @@ class ps_read_batch(C.Structure):
                 ("tile_qual_off", C.c_void_p), ("tile_cigar_off", C.c_void_p), ("tile_exc_off", C.c_void_p),
                 ("exc", C.c_void_p), ("uniform_len", C.c_uint32), ("uniform_ncigar", C.c_uint32),
                 ("bases_bytes", C.c_uint64), ("qual_bytes", C.c_uint64), ("cigar_count", C.c_uint64),
-                ("exc_count", C.c_uint64)]
+                ("exc_count", C.c_uint64), ("max_len", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class ps_comb_stats(C.Structure):
+    _fields_ = [("genomic_records", C.c_uint64), ("transcript_records", C.c_uint64), ("lifted_records", C.c_uint64),
+                ("mapped_reads", C.c_uint64), ("spliced_reads", C.c_uint64), ("missed_transcript_alignments", C.c_uint64)]
 
 
 class ps_profile_opts(C.Structure):
@@ -147,6 +152,9 @@ EXPORTS = {
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "ps_clust_bam": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(ps_pileup_counters),
                                C.POINTER(ps_fault)]),
+    "ps_liftover_hit": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p,
+                                  C.c_size_t, C.POINTER(C.c_uint32)]),
+    "ps_comb_bam": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ps_comb_stats), C.c_char_p, C.c_size_t]),
     "ps_create_multi": (C.c_int, [C.POINTER(VP), C.POINTER(C.c_int), C.c_int]),
     "ps_destroy_multi": (None, [VP]),
     "ps_multi_device_count": (C.c_int, [VP]),

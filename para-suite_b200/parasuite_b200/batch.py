@@ -133,6 +133,8 @@ class ReadBatch:
         self.qual_bytes = int(tile_qual_off[-1]) if qual_bytes is None else int(qual_bytes)
         self.cigar_count = int(tile_cigar_off[-1]) if cigar_count is None else int(cigar_count)
         self.exc_count = int(tile_exc_off[-1]) if exc_count is None else int(exc_count)
+        # longest read: a hint for the kernels' choice of row geometry on ragged batches
+        self.max_len = self.uniform_len or (int((np.asarray(meta[:self.n_reads]) & 0xFFFF).max()) if self.n_reads else 0)
 
     @property
     def n_tiles(self) -> int:
@@ -149,6 +151,7 @@ class ReadBatch:
         s.qual_bytes = self.qual_bytes
         s.cigar_count = self.cigar_count
         s.exc_count = self.exc_count
+        s.max_len = self.max_len
         return s
 
     def algorithmic_bytes(self, with_qual: bool = True) -> int:

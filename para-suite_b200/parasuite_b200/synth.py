@@ -160,3 +160,47 @@ def concat_uniform(head, body: ReadBatch, tail=None) -> ReadBatch:
         np.concatenate([p.cigar[:p.n_reads] for p in parts] + [pad32]), edges * np.uint64(bb), edges * np.uint64(L),
         edges.copy(), teo, np.concatenate((body.exc[:body.exc_count], pad32)), uniform_len=L, uniform_ncigar=1,
         bases_bytes=n * bb, qual_bytes=n * L, cigar_count=n, exc_count=body.exc_count)
+
+
+def trim_uniform(batch: ReadBatch, min_len: int, seed: int = 1) -> ReadBatch:
+    """A uniform single-M batch with every read cut to its own length in [min_len, L], 3' end of the stored sequence
+    removed (what adapter trimming leaves): a ragged batch, still one `xM` op per read, same starts.  Special reads
+    (unmapped, POS 0, duplicates) keep their flags.  Vectorised, for workloads of millions of reads."""
+    if not (batch.uniform_len and batch.uniform_ncigar == 1):
+        raise ValueError("trim_uniform: uniform single-op batch expected")
+    n, L, T = batch.n_reads, batch.uniform_len, abi.PS_TILE_READS
+    bb = (L + 3) // 4
+    rng = np.random.default_rng(seed)
+    Lr = rng.integers(min_len, L + 1, size=n, dtype=np.int64)
+    meta = (batch.meta[:n] & np.uint32(0xFFFF0000)) | Lr.astype(np.uint32)
+    cigar = (Lr.astype(np.uint32) << np.uint32(4))
+    q2 = batch.qual[:n * L].reshape(n, L)
+    qual = q2[np.arange(L)[None, :] < Lr[:, None]]
+    nb = (Lr + 3) // 4
+    b2 = batch.bases2[:n * bb].reshape(n, bb).copy()
+    last = nb - 1                                       # clear the bits behind the last kept base
+    keep_bits = ((Lr - 1) % 4 + 1) * 2
+    rows = np.arange(n)
+    b2[rows, last] &= ((1 << keep_bits) - 1).astype(np.uint8)
+    bases = b2[np.arange(bb)[None, :] < nb[:, None]]
+    nt = (n + T - 1) // T
+    edges = np.minimum(np.arange(nt + 1, dtype=np.int64) * T, n)
+    cq = np.concatenate(([0], np.cumsum(Lr)))
+    cb = np.concatenate(([0], np.cumsum(nb)))
+    # N calls: keep those inside the kept part; the list stays sorted by (read in tile, position) within each tile
+    exc = batch.exc[:batch.exc_count]
+    teo = batch.tile_exc_off[:nt + 1].astype(np.int64)
+    tile_of = np.repeat(np.arange(nt), np.diff(teo))
+    read_of = tile_of * T + (exc >> np.uint32(16)).astype(np.int64)
+    keep = (exc & np.uint32(0xFFFF)).astype(np.int64) < Lr[read_of] if len(exc) else np.zeros(0, dtype=bool)
+    new_teo = np.concatenate(([0], np.cumsum(np.bincount(tile_of[keep], minlength=nt)))).astype(np.uint32)
+    has = np.zeros(n, dtype=bool)
+    has[read_of[keep]] = True
+    inv_bit = np.uint32(abi.PS_RF_HAS_INVALID << 24)
+    meta = np.where(has, meta | inv_bit, meta & ~inv_bit).astype(np.uint32)
+    pad8, pad32 = np.zeros(64, np.uint8), np.zeros(16, np.uint32)
+    return ReadBatch(
+        n, meta, batch.ref_start[:n].copy(), np.concatenate((bases, pad8)), np.concatenate((qual, pad8)),
+        np.concatenate((cigar, pad32)), cb[edges].astype(np.uint64), cq[edges].astype(np.uint64), edges.astype(np.uint64),
+        new_teo, np.concatenate((exc[keep], pad32)), uniform_len=0, uniform_ncigar=1, bases_bytes=int(cb[-1]),
+        qual_bytes=int(cq[-1]), cigar_count=n, exc_count=int(keep.sum()))

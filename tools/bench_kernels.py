@@ -18,6 +18,7 @@ ap.add_argument("--iters", type=int, default=12)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--max-len", type=int, default=51)
+ap.add_argument("--trim", type=int, default=0, help="cut every read to its own length in [TRIM, len]: ragged batch")
 args = ap.parse_args()
 peak = 6552.0
 try:
@@ -28,8 +29,36 @@ ctx = Context(0)
 ref = synth.synth_reference(0x5EED0001, [args.ref])
 ctx.upload_reference(ref)
 b = synth.synth_reads(ref, args.reads, args.len, seed=0x5EED0002, mode=args.mode)
-d = DeviceBatch(b, "cuda:0")
 st = torch.cuda.current_stream().cuda_stream
+if args.trim:      # ragged single-M batch: repack + per-read-length fast kernel against the warp-per-read kernel
+    b = synth.trim_uniform(b, args.trim, seed=3)
+    d = DeviceBatch(b, "cuda:0")
+    out = {"reads": args.reads, "len": [args.trim, args.len], "ragged": True}
+    by = b.algorithmic_bytes(with_qual=True)
+    res = {}
+    for name, off in (("ragged_fast", False), ("warp_per_read", True)):
+        if off:
+            os.environ["PARASUITE_B200_NO_RAGGED_FAST"] = "1"
+        else:
+            os.environ.pop("PARASUITE_B200_NO_RAGGED_FAST", None)
+        ctx.kernel_times_reset(True)
+        for _ in range(args.iters if not off else max(3, args.iters // 4)):
+            ctx.profile_begin(args.max_len)
+            ctx.profile_batch_device(d, st)
+            res[name] = ctx.profile_end()
+        t = ctx.kernel_times_ms()
+        ms = float(np.mean(t[1:] if off else t[3:]))
+        out[name] = {"ms": ms, "reads_per_s": args.reads / ms * 1e3, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak}
+    out["equal"] = bool(np.array_equal(res["ragged_fast"]["wide"], res["warp_per_read"]["wide"]))
+    if args.check:
+        import oracle_lib
+        oracle_lib.build()
+        acc = oracle_lib.profile_acc(ref, b, args.max_len, threads=os.cpu_count() or 1)
+        out["parity"] = bool(np.array_equal(acc, res["ragged_fast"]["wide"]))
+    print(json.dumps(out), flush=True)
+    ctx.close()
+    sys.exit(0)
+d = DeviceBatch(b, "cuda:0")
 out = {"lib": os.environ.get("PARASUITE_B200_LIB", "default"), "reads": args.reads, "len": args.len, "mode": args.mode}
 by = b.algorithmic_bytes(with_qual=True)
 res = {}

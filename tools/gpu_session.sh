@@ -1,8 +1,10 @@
+#!/bin/bash
+# scratch: one gpurun call
 set -x
-cd $GRAFT_REPO_ROOT
+cd /root/repo
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/r2_n8_topo.txt 2>&1
-nproc > gpurun_out/r2_n8_nproc.txt; free -g >> gpurun_out/r2_n8_nproc.txt
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-timeout 900 $TR --master-port 29501 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_n8_bench.json 2> gpurun_out/r2_n8_bench.err
-timeout 1500 $TR --master-port 29502 tools/run_config.py --configs 3,4,5 > gpurun_out/r2_n8_configs.json 2> gpurun_out/r2_n8_configs.err
+timeout 1200 python -m pytest tests/test_gpu_ragged.py tests/test_gpu_bam.py -x -q > gpurun_out/r2_ragged_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_ragged_tests.log
+timeout 600 python tools/bench_kernels.py --reads 4000000 --len 44 --trim 18 --check > gpurun_out/r2_ragged_bench.json 2> gpurun_out/r2_ragged_bench.err
+timeout 600 python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 > gpurun_out/r2_ragged_bench36.json 2>> gpurun_out/r2_ragged_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ragged_launches.csv python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --iters 4 > gpurun_out/r2_ragged_ncu.log 2>&1
