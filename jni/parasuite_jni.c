@@ -280,3 +280,31 @@ JNIEXPORT void JNICALL Java_utils_pileupclusters_NativePileup_close(JNIEnv* env,
   (void)env; (void)c;
   ps_pileup_close((ps_pileup*)(intptr_t)handle);
 }
+
+/* package utils.postprocessing;  class NativeCombine { static native long[] combine(String genomicBam, String transcriptBam,
+ * String combinedBam); }  -- the whole body of CombineGenomeTranscript.combine (:36-596).  Returns mappedReads,
+ * splicedReads, missedTranscriptAlignments, liftedRecords.  Host only: no context needed. */
+JNIEXPORT jlongArray JNICALL Java_utils_postprocessing_NativeCombine_combine(JNIEnv* env, jclass c, jstring genomic,
+                                                                             jstring transcript, jstring combined) {
+  (void)c;
+  if (!genomic || !transcript || !combined) { throw_illegal(env, "combine: file names must not be null"); return NULL; }
+  const char* pg = (*env)->GetStringUTFChars(env, genomic, NULL);
+  const char* pt = pg ? (*env)->GetStringUTFChars(env, transcript, NULL) : NULL;
+  const char* po = pt ? (*env)->GetStringUTFChars(env, combined, NULL) : NULL;
+  jlongArray a = NULL;
+  if (pg && pt && po) {
+    ps_comb_stats s;
+    char err[512];
+    const int st = ps_comb_bam(pg, pt, po, &s, err, sizeof err);
+    if (st != PS_OK) throw_message(env, err, st);
+    else {
+      jlong v[4] = {(jlong)s.mapped_reads, (jlong)s.spliced_reads, (jlong)s.missed_transcript_alignments, (jlong)s.lifted_records};
+      a = (*env)->NewLongArray(env, 4);
+      if (a) (*env)->SetLongArrayRegion(env, a, 0, 4, v);
+    }
+  }
+  if (po) (*env)->ReleaseStringUTFChars(env, combined, po);
+  if (pt) (*env)->ReleaseStringUTFChars(env, transcript, pt);
+  if (pg) (*env)->ReleaseStringUTFChars(env, genomic, pg);
+  return a;
+}

@@ -86,3 +86,8 @@ def time_sample(ref, batch, max_len, n_reads=200_000, vcf=None):
     return {"available": True, "jar": jar, "reads": len(recs), "error_s": t_err, "clust_s": t_cl,
             "reads_per_s": len(recs) / (t_err + t_cl), "exit_codes": [p1.returncode, p2.returncode],
             "note": "single-threaded Java tools on a BAM + FASTA of the sample; JVM start-up and file I/O included"}
+
+
+def run_comb(java, jar, genomic_bam, transcript_bam, out_bam, timeout=1800):
+    """Main.java:438-486: comb -g <genomic.bam> -t <transcript.bam> -o <combined.bam>."""
+    return _run(java, jar, ["comb", "-g", genomic_bam, "-t", transcript_bam, "-o", out_bam], timeout)

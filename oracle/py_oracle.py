@@ -1000,10 +1000,10 @@ def java_parse_int(s: str) -> int:
     """Integer.parseInt: optional sign, decimal digits only, 32-bit range; anything else kills the tool."""
     body = s[1:] if s[:1] in "+-" else s
     if not body or not all("0" <= c <= "9" for c in body):
-        raise ReferenceWouldThrow(f"NumberFormatException: {s!r}")
+        raise ReferenceWouldThrow(-1, f"NumberFormatException: {s!r}")
     v = int(s)
     if not -2 ** 31 <= v < 2 ** 31:
-        raise ReferenceWouldThrow(f"NumberFormatException: {s!r}")
+        raise ReferenceWouldThrow(-1, f"NumberFormatException: {s!r}")
     return v
 
 
@@ -1012,7 +1012,7 @@ def liftover_hit(ref_name: str, aln_start: int, aln_end: int, read_len: int, cig
     missedTranscriptAlignments increment)."""
     f = java_split(ref_name, "|")                                          # :148
     if len(f) < 6:
-        raise ReferenceWouldThrow("ArrayIndexOutOfBoundsException: transcript name without six |-separated fields")
+        raise ReferenceWouldThrow(-1, "ArrayIndexOutOfBoundsException: transcript name without six |-separated fields")
     exon_starts = sorted(java_split(f[3], ";"))                            # :172-175 Arrays.sort on STRINGS
     exon_ends = sorted(java_split(f[4], ";"))
     strand = f[5]
@@ -1026,7 +1026,7 @@ def liftover_hit(ref_name: str, aln_start: int, aln_end: int, read_len: int, cig
 
     def en(i):
         if i >= len(exon_ends):
-            raise ReferenceWouldThrow("ArrayIndexOutOfBoundsException: fewer exon ends than starts")
+            raise ReferenceWouldThrow(-1, "ArrayIndexOutOfBoundsException: fewer exon ends than starts")
         return java_parse_int(exon_ends[i])
 
     if strand == "1":                                                      # :219-391

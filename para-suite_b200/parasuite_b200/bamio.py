@@ -52,7 +52,7 @@ def _reg2bin(beg: int, end: int) -> int:
     return 0
 
 
-def encode_bam_record(rec: Record, ref_ids: dict, name: bytes = b"r") -> bytes:
+def encode_bam_record(rec: Record, ref_ids: dict, name: bytes = b"r", mapq: int = 255) -> bytes:
     ops = parse_cigar(rec.cigar)
     L = len(rec.seq)
     ref_id = ref_ids.get(rec.rname, -1)
@@ -64,14 +64,15 @@ def encode_bam_record(rec: Record, ref_ids: dict, name: bytes = b"r") -> bytes:
         nib = _NIB.get(chr(ch).upper(), 15)
         seq[k >> 1] |= nib << (4 if k % 2 == 0 else 0)
     qual = bytes(rec.qual) if len(rec.qual) == L else b"\xff" * L
-    body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(name) + 1, 255, bin_, len(ops), rec.flag & 0xFFFF, L, -1, -1, 0)
+    body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(name) + 1, mapq, bin_, len(ops), rec.flag & 0xFFFF, L, -1, -1, 0)
     body += name + b"\0" + b"".join(struct.pack("<I", (n << 4) | op) for op, n in ops) + bytes(seq) + qual
     return struct.pack("<I", len(body)) + body
 
 
 def write_bam(path: str, contigs: Sequence[Tuple[str, int]], records: Iterable[Record], sort_order: str = "coordinate",
-              block_bytes: int = 0xFF00, level: int = 1) -> int:
-    """Minimal BAM writer (one read group-less header; records in the order given).  Returns the record count."""
+              block_bytes: int = 0xFF00, level: int = 1, names: Optional[Sequence[bytes]] = None) -> int:
+    """Minimal BAM writer (one read group-less header; records in the order given; read names r<k> unless `names` gives
+    them).  Returns the record count."""
     text = f"@HD\tVN:1.4\tSO:{sort_order}\n" + "".join(f"@SQ\tSN:{n}\tLN:{ln}\n" for n, ln in contigs)
     hdr = b"BAM\1" + struct.pack("<I", len(text)) + text.encode() + struct.pack("<I", len(contigs))
     for n, ln in contigs:
@@ -88,12 +89,52 @@ def write_bam(path: str, contigs: Sequence[Tuple[str, int]], records: Iterable[R
                 del pend[:block_bytes]
 
         for k, rec in enumerate(records):
-            pend += encode_bam_record(rec, ref_ids, b"r%d" % k)
+            pend += encode_bam_record(rec, ref_ids, names[k] if names is not None else b"r%d" % k)
             count += 1
             flush()
         flush(final=True)
         f.write(_bgzf_block(b""))       # EOF marker
     return count
+
+
+def read_bam_records(path: str):
+    """Pure-Python BAM decoder for tests and small files: -> (header text, [(name, length)], [record dict]).  A record
+    dict holds name, flag, rname, pos (1-based), mapq, cigar, seq, qual (bytes), mate fields and the raw tag bytes."""
+    import gzip
+    data = gzip.open(path, "rb").read()
+    assert data[:4] == b"BAM\1"
+    l_text, = struct.unpack_from("<I", data, 4)
+    text = data[8:8 + l_text].rstrip(b"\0").decode()
+    o = 8 + l_text
+    n_ref, = struct.unpack_from("<I", data, o)
+    o += 4
+    refs = []
+    for _ in range(n_ref):
+        ln, = struct.unpack_from("<I", data, o)
+        name = data[o + 4:o + 4 + ln - 1].decode()
+        length, = struct.unpack_from("<I", data, o + 4 + ln)
+        refs.append((name, length))
+        o += 8 + ln
+    nib = "=ACMGRSVTWYHKDBN"
+    recs = []
+    while o + 4 <= len(data):
+        bs, = struct.unpack_from("<I", data, o)
+        ref_id, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nref, npos, tlen = struct.unpack_from("<iiBBHHHIiii", data, o + 4)
+        q = o + 36
+        name = data[q:q + l_name - 1].decode()
+        q += l_name
+        ops = struct.unpack_from("<%dI" % n_cig, data, q)
+        q += 4 * n_cig
+        sb = data[q:q + (l_seq + 1) // 2]
+        q += (l_seq + 1) // 2
+        seq = "".join(nib[(sb[k >> 1] >> (4 if k % 2 == 0 else 0)) & 15] for k in range(l_seq))
+        qual = data[q:q + l_seq]
+        q += l_seq
+        recs.append({"name": name, "flag": flag, "rname": refs[ref_id][0] if ref_id >= 0 else "*", "pos": pos + 1, "mapq": mapq,
+                     "cigar": "".join(f"{c >> 4}{CIGAR_OPS[c & 15]}" for c in ops) or "*", "seq": seq.encode(), "qual": qual,
+                     "next_ref": nref, "next_pos": npos + 1, "tlen": tlen, "tags": data[q:o + 4 + bs]})
+        o += 4 + bs
+    return text, refs, recs
 
 
 def write_sam(path: str, contigs: Sequence[Tuple[str, int]], records: Iterable[Record], sort_order: str = "coordinate") -> None:

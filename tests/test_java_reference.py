@@ -139,3 +139,39 @@ def test_config1_fixture(tmp_path):
     assert proc.returncode == 0, proc.stderr[-2000:]
     for k in java_ref.CLUST_FILES:
         assert got[k] == exp["clust_files"][k], k
+
+
+def test_comb_tool(tmp_path):
+    """`comb` (CombineGenomeTranscript): the jar's combined BAM against the Python restatement, record by record."""
+    from parasuite_b200.bamio import read_bam_records
+    from test_liftover_cpu import random_hit_cigar, random_transcript
+    rng = random.Random(3)
+    genome = [("chr1", 200000), ("chr2", 150000)]
+    transcripts = list(dict.fromkeys(random_transcript(rng, chrom=rng.choice(["1", "2", "7"])) for _ in range(20)))
+    g_recs = [Record(rng.choice([0, 16]), "chr1", 100 + 37 * k, "30M", bytes(rng.choice(b"ACGT") for _ in range(30)), bytes([30] * 30))
+              for k in range(200)]
+    g_names = [b"g%d" % k for k in range(len(g_recs))]
+    t_recs, t_names = [], []
+    for k in range(300):
+        tr = rng.choice(transcripts)
+        L = rng.randint(18, 45)
+        cigar, R = random_hit_cigar(rng, L)
+        t_recs.append(Record(rng.choice([0, 16]), tr[0], rng.randint(1, max(1, tr[1] - R + 3)), cigar,
+                             bytes(rng.choice(b"ACGT") for _ in range(L)), bytes(rng.randint(2, 40) for _ in range(L))))
+        t_names.append(b"t%04d" % k)
+    gb, tb, ob = str(tmp_path / "g.bam"), str(tmp_path / "t.bam"), str(tmp_path / "o.bam")
+    write_bam(gb, genome, g_recs, names=g_names)
+    write_bam(tb, [(t[0], t[1]) for t in transcripts], t_recs, sort_order="queryname", names=t_names)
+    proc, _ = java_ref.run_comb(JAVA, JAR, gb, tb, ob)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    _, _, got = read_bam_records(ob)
+
+    def as_dicts(recs, names):
+        return [{"name": n.decode(), "flag": r.flag, "rname": r.rname, "pos": r.pos, "cigar": r.cigar, "seq": r.seq, "qual": bytes(r.qual),
+                 "mapq": 255} for r, n in zip(recs, names)]
+    want, _ = po.combine([n for n, _ in genome], "coordinate", as_dicts(g_recs, g_names), as_dicts(t_recs, t_names))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        for k in ("name", "flag", "rname", "pos", "mapq", "seq", "qual"):
+            assert a[k] == b[k], (k, a, b)
+        assert a["cigar"] == (b["cigar"] or "*")
