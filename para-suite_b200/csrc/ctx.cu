@@ -188,7 +188,7 @@ void ps_destroy(ps_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release(); ctx->t2c_mask.release();
-  ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
+  ctx->rg_okmap.release(); ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
     s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();

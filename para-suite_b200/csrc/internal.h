@@ -108,6 +108,7 @@ struct ps_ctx {
   DevBuf acc;        // int64[layout.total]
   DevBuf fault;      // uint64 fault word + debug / deferred-count words (64 bytes)
   DevBuf deferred;   // uint32 read indices the fast profile kernel hands to the generic routine
+  DevBuf rg_okmap;                            // -q on the fast path: which reads the fast kernel counted
   DevBuf rg_off, rg_bases, rg_qual, rg_op0;   // ragged batches re-laid for the fast profile kernel (profile.cu: repack)
   uint64_t reads_seen = 0;
   uint32_t profile_batches = 0;   // fast-path batches of the open run (selects the deferred-read counter)

@@ -38,6 +38,7 @@ struct ProfileParams {
   unsigned int* deferred_count_next;   // the counter of the run's next batch: cleared by this batch's deferred kernel
                                        // (two counters take turns, so no memset sits in front of the fast kernel)
   unsigned long long* t2c_mask;        // fast kernel, optional: one T>C mask word per read (profile_fast.cuh), for the pileup
+  uint32_t* okmap;                     // fast kernel, optional (-q): bit r%32 of word r/32 = read r took the fast path
   const uint32_t* off3;                // deferred kernel on a re-laid ragged batch: [3][n_reads] in-tile offsets of every read
                                        // (bytes of bases, bytes of qualities, cigar elements), written by the repack kernel
 };
@@ -648,6 +649,65 @@ static cudaError_t launch_deferred(ps_ctx* ctx, const ProfileParams& P, cudaStre
   return cudaGetLastError();
 }
 
+// `-q` on the fast path: baseQualitiesPerPos[i].add(readQualities[i]) for every i < L (ErrorProfiling.java:402-407) of the
+// reads the fast kernel counted (its ok-map), as a histogram [position][byte] in shared memory.  Rows of `stride` bytes
+// (the uniform batch itself, or the re-laid rows of a ragged one); lane = read, so a warp walks 32 neighbouring rows.
+// Rows of the histogram are 257 words apart: equal qualities at neighbouring positions fall into different banks.
+namespace {
+__global__ void __launch_bounds__(256) profile_qhist_kernel(const uint8_t* __restrict__ qual, const uint32_t* __restrict__ meta,
+                                                            const uint32_t* __restrict__ okmap, uint64_t n_reads, uint32_t stride,
+                                                            uint32_t uniform_L, uint32_t max_len, unsigned long long* acc_qhist) {
+  extern __shared__ uint32_t s_hist[];          // [max_len][257]
+  for (uint32_t k = threadIdx.x; k < max_len * 257u; k += blockDim.x) s_hist[k] = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t n_groups = (n_reads + 31) / 32;
+  for (uint64_t g = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); g < n_groups; g += (uint64_t)gridDim.x * (blockDim.x / 32)) {
+    const uint64_t r = g * 32 + lane;
+    const uint32_t okw = __ldg(okmap + g);
+    if (r >= n_reads || !((okw >> lane) & 1u)) continue;
+    const uint32_t L = uniform_L ? uniform_L : PS_META_LEN(__ldg(meta + r));
+    const uint8_t* row = qual + r * (uint64_t)stride;
+    if ((stride & 3u) == 0) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
+      for (uint32_t i = 0; i < L; i += 4) {
+        const uint32_t v = __ldg(w + (i >> 2));
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+          if (i + j < L) atomicAdd(&s_hist[(i + j) * 257u + ((v >> (8u * j)) & 255u)], 1u);
+      }
+    } else {
+      for (uint32_t i = 0; i < L; ++i) atomicAdd(&s_hist[i * 257u + __ldg(row + i)], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < max_len * 256u; k += blockDim.x) {
+    const uint32_t v = s_hist[(k >> 8) * 257u + (k & 255u)];
+    if (v) atomicAdd(acc_qhist + k, (unsigned long long)v);
+  }
+}
+}  // namespace
+
+static cudaError_t launch_qhist(ps_ctx* ctx, const uint8_t* qual, const uint32_t* meta, const uint32_t* okmap, uint64_t n_reads,
+                                uint32_t stride, uint32_t uniform_L, unsigned long long* acc, cudaStream_t stream) {
+  const uint32_t max_len = ctx->layout.max_len;
+  const size_t smem = (size_t)max_len * 257 * 4;
+  cudaError_t e = cudaFuncSetAttribute(profile_qhist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, profile_qhist_kernel, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  const uint64_t need = (n_reads + 255) / 256;
+  // a block's 32-bit cells see at most n_reads / grid reads each: keep that below 2^31
+  uint32_t grid = (uint32_t)std::min<uint64_t>(need, (uint64_t)ctx->sm_count * per_sm);
+  grid = std::max<uint32_t>(grid, (uint32_t)std::min<uint64_t>(need, n_reads / (1ull << 31) + 1));
+  profile_qhist_kernel<<<grid, 256, smem, stream>>>(qual, meta, okmap, n_reads, stride, uniform_L, max_len,
+                                                      acc + ctx->layout.qhist);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0, cudaStream_t stream,
@@ -666,12 +726,16 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   P.deferred = nullptr;
   P.t2c_mask = nullptr;
   P.off3 = nullptr;
+  P.okmap = nullptr;
   // both counters are zero at the start of a run (ps_profile_begin clears the words behind the fault word)
   P.deferred_count = reinterpret_cast<unsigned int*>(P.fault + 2) + (ctx->profile_batches & 1u);
   P.deferred_count_next = reinterpret_cast<unsigned int*>(P.fault + 2) + ((ctx->profile_batches + 1u) & 1u);
   uint64_t done = 0;
   const uint32_t L = b.uniform_len;
-  const bool fast_ok = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && !ctx->layout.infer_q && ctx->layout.max_len <= 256 &&
+  // -q: the fast kernels count as usual and leave a map of the reads they took; profile_qhist_kernel adds those reads'
+  // qualities to the per-position histogram (the deferred kernel does it for the others)
+  const bool q_ok = !ctx->layout.infer_q || ctx->layout.max_len <= 64;
+  const bool fast_ok = L >= 1 && L <= 64 && b.uniform_ncigar == 1 && q_ok && ctx->layout.max_len <= 256 &&
                        aligned16(b.meta) && aligned16(b.ref_start) && aligned16(b.cigar) && aligned16(b.bases2) &&
                        aligned16(b.qual) && b.n_reads < 0xFFFFFFFFull;
   if (fast_ok) {
@@ -680,6 +744,10 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
     // bits 62 and 63 of a mask word are flags: the mask is offered for L <= 62 only
     if (t2c_mask && L <= 62) { P.t2c_mask = t2c_mask; if (mask_written) *mask_written = true; }
+    if (ctx->layout.infer_q) {
+      if ((ee = ctx->rg_okmap.reserve(((size_t)b.n_reads + 63) / 64 * 8 + 64)) != cudaSuccess) return ee;
+      P.okmap = static_cast<uint32_t*>(ctx->rg_okmap.p);
+    }
     ctx->profile_batches++;
     const uint32_t n_wt = (uint32_t)((b.n_reads + WT_READS - 1) / WT_READS);   // the fast kernel takes every read
     const uint32_t nw = (L + 15) / 16;
@@ -691,6 +759,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     else if (nw == 3) e = launch_fast<3, 5, 0>(ctx, P, n_wt, stream);
     else e = launch_fast<4, 5, 0>(ctx, P, n_wt, stream);
     if (e != cudaSuccess) return e;
+    if (P.okmap && (e = launch_qhist(ctx, b.qual, b.meta, P.okmap, b.n_reads, L, L, P.acc, stream)) != cudaSuccess) return e;
     return launch_deferred(ctx, P, stream);
   }
   // Ragged batches of short reads (adapter-trimmed PAR-CLIP reads as an aligner leaves them): re-lay them as rows of
@@ -698,7 +767,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
   // shape (several cigar ops, clips, longer than S) go to the deferred kernel on the original streams; the test on the
   // op count keeps batches of mostly gapped alignments on the warp-per-read kernel.
   const uint32_t max_len = ctx->layout.max_len;
-  const bool ragged_ok = !ctx->layout.infer_q && max_len >= 1 && max_len <= 64 && b.n_reads < 0xFFFFFFFFull &&
+  const bool ragged_ok = max_len >= 1 && max_len <= 64 && b.n_reads < 0xFFFFFFFFull &&
                          aligned16(b.meta) && aligned16(b.ref_start) && (b.uniform_len == 0 || b.uniform_len <= 64) &&
                          (reinterpret_cast<uintptr_t>(b.bases2) & 3u) == 0 && (reinterpret_cast<uintptr_t>(b.qual) & 3u) == 0 &&
                          b.cigar_count * 2 <= b.n_reads * 3 && getenv("PARASUITE_B200_NO_RAGGED_FAST") == nullptr;
@@ -720,6 +789,10 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     if ((e = ctx->rg_op0.reserve((size_t)chunk * 4 + 64)) != cudaSuccess) return e;
     P.deferred = static_cast<uint32_t*>(ctx->deferred.p);
     P.off3 = static_cast<const uint32_t*>(ctx->rg_off.p);
+    if (ctx->layout.infer_q) {
+      if ((e = ctx->rg_okmap.reserve(((size_t)chunk + 63) / 64 * 8 + 64)) != cudaSuccess) return e;
+      P.okmap = static_cast<uint32_t*>(ctx->rg_okmap.p);
+    }
     ctx->profile_batches++;
     for (uint64_t c0 = 0; c0 < b.n_reads; c0 += chunk) {
       const uint64_t cn = std::min<uint64_t>(chunk, b.n_reads - c0);
@@ -752,6 +825,7 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
       else if (nw == 3) e = launch_fast<3, 5, 0, true>(ctx, Q, n_wt, stream);
       else e = launch_fast<4, 5, 0, true>(ctx, Q, n_wt, stream);
       if (e != cudaSuccess) return e;
+      if (P.okmap && (e = launch_qhist(ctx, Q.b.qual, Q.b.meta, P.okmap, cn, S, 0, P.acc, stream)) != cudaSuccess) return e;
     }
     return launch_deferred(ctx, P, stream);
   }

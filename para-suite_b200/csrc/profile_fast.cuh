@@ -38,6 +38,9 @@
 #define FAST_BLOCKS_PER_SM 4
 #endif
 #define FAST_QCOPIES 8         // copies of the per-pair mismatch quality cells (spreads same-address reductions)
+#ifndef FAST_REV_SPLIT
+#define FAST_REV_SPLIT 1       // test "any minus-strand read" per half of the warp-tile instead of once per tile
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -516,9 +519,11 @@ __global__ void __launch_bounds__(FAST_THREADS, RG ? 3 : FAST_BLOCKS_PER_SM) pro
       }
     }
     // ---- minus strand: reverse-complement both arrays (qualities stay forward, Q10) ------------------------------
-    if (__any_sync(FULL, rev[0] | rev[1])) {
+    // (tested per half of the tile: clusters are single-stranded and reads come cluster by cluster, so 32 consecutive
+    //  reads are on one strand far more often than 64)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h) {
+      if (__any_sync(FULL, FAST_REV_SPLIT ? rev[h] : (rev[0] | rev[1]))) {
         uint32_t a[NW], b[NW];
 #pragma unroll
         for (int k = 0; k < NW; ++k) { a[k] = rf[h][k]; b[k] = rd[h][k]; }
@@ -672,6 +677,10 @@ __global__ void __launch_bounds__(FAST_THREADS, RG ? 3 : FAST_BLOCKS_PER_SM) pro
       if (lane < n_here) mp[0] = ((unsigned long long)hi0 << 32) | tc_lo[0];        // !ok: tc_lo is 0 (no events)
       if (lane + 32 < n_here) mp[32] = ((unsigned long long)hi1 << 32) | tc_lo[1];
     }
+    if (P.okmap != nullptr) {          // -q: the histogram pass adds the qualities of exactly these reads
+      const uint32_t b0 = __ballot_sync(FULL, ok[0]), b1 = __ballot_sync(FULL, ok[1]);
+      if (lane == 0) { P.okmap[2 * (size_t)wt] = b0; P.okmap[2 * (size_t)wt + 1] = b1; }
+    }
     if (__any_sync(FULL, (!ok[0] && lane < n_here) | (!ok[1] && lane + 32 < n_here))) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -777,6 +786,7 @@ cudaError_t launch_fast(ps_ctx* ctx, const ProfileParams& P, uint32_t n_wt, cuda
     Q.b.n_reads = std::min<uint64_t>(P.b.n_reads - r0, cnt * WT_READS);
     Q.first_read = P.first_read + r0;    // offset added to deferred read indices
     if (Q.t2c_mask) Q.t2c_mask += r0;
+    if (Q.okmap) Q.okmap += r0 / 32;
     kern<<<grid, FAST_THREADS, smem, stream>>>(Q);
     ctx->launches++;
     e = cudaGetLastError();

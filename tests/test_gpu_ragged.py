@@ -172,3 +172,23 @@ def test_trimmed_synthetic_at_scale(ctx, oracle):
     got, fast = profile_counting_fast(ctx, ref, batch, 51)
     assert_profile_equal(got, oracle.profile(ref, batch, 51, threads=8), "trimmed synthetic")
     assert fast > 590_000
+
+
+@pytest.mark.parametrize("trim", [0, 20])
+def test_quality_histogram_on_the_fast_path(ctx, oracle, trim):
+    """-q (ErrorProfiling.java:402-407) with the fast kernels: their ok-map + the histogram kernel for the reads they took,
+    the deferred kernel for the others; uniform 36-nt batch and the same batch trimmed to 20..36 nt."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(33, [2_000_000, 500_000], n_run=1500)
+    batch = synth.synth_reads(ref, 300_001, 36, seed=12, special_ppm=3000, n_ppm=4000)
+    if trim:
+        batch = synth.trim_uniform(batch, trim, seed=13)
+    ctx.upload_reference(ref)
+    ctx.profile_begin(51, infer_qualities=True)
+    ctx.profile_batch(batch)
+    fast = int(ctx.lib.ps_debug_word(ctx.h, 1))
+    got = ctx.profile_end()
+    exp = oracle.profile(ref, batch, 51, True, threads=8)
+    assert_profile_equal(got, exp, f"-q trim {trim}")
+    assert np.array_equal(got["quality_hist"], exp["quality_hist"])
+    assert fast > 290_000 and int(got["quality_hist"].sum()) > 290_000 * 20
