@@ -676,7 +676,10 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
         if (flag & 0x4) fl |= PS_RF_UNMAPPED;
         if (flag & 0x10) fl |= PS_RF_REVERSE;
         if (flag & 0x400) fl |= PS_RF_DUPLICATE;
-        if (pos < 0) fl |= PS_RF_POS_ZERO;                       // getAlignmentStart() == 0
+        // getAlignmentStart() == 0 <=> stored pos == -1.  A stored pos < -1 is outside the BAM format (htsjdk would hand the
+        // Java a negative start, which passes the == 0 filters and dies in the FASTA fetch); such records are folded into
+        // the same class here instead of modelling a malformed file.
+        if (pos < 0) fl |= PS_RF_POS_ZERO;
         if (l_seq == 0 || ql[0] == 0xFF) fl |= PS_RF_QUAL_MISSING;
         uint32_t nc = n_cig;
         if (n_cig > 255) { fl |= PS_RF_CIGAR_OVERFLOW; nc = 0; }
