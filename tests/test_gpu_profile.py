@@ -228,3 +228,43 @@ def test_more_than_255_cigar_ops_is_flagged(ctx, oracle):
     with pytest.raises(abi.PsError) as e:
         ctx.profile(ReadBatch.from_records([good, rec], ref), 600)
     assert e.value.status == abi.PS_ERR_UNSUPPORTED and "record 1 " in str(e.value)
+
+
+@pytest.mark.parametrize("L,ragged", [(36, False), (50, False), (40, True)])
+def test_tiles_with_more_events_than_the_queue_holds(ctx, oracle, L, ragged):
+    """Reads unrelated to the reference (three mismatches in four bases): a warp-tile of 64 such reads holds far more
+    mismatch events than the per-warp event queue of the fast kernel (FAST_QCAP), which then drains lane by lane; mixed
+    with clean reads so that both ways run in one launch, with and without T>C mask words."""
+    rng = random.Random(4242 + L)
+    contigs = random_genome(rng, n_contigs=2, length=30_000, n_frac=0.002)
+    recs = []
+    for k in range(6000):
+        name, seq = contigs[k % 2]
+        Lr = rng.randint(12, L) if ragged else L
+        pos = rng.randint(1, len(seq) - Lr - 1)
+        noisy = (k // 300) % 2 == 0                     # runs of 300 noisy reads, then 300 clean ones
+        if noisy:
+            b = bytes(rng.choice(b"ACGT") for _ in range(Lr))
+        else:
+            b = bytes(c if c in b"ACGT" else ord("A") for c in bytes(seq[pos - 1:pos - 1 + Lr]).upper())
+        recs.append(Record(16 if rng.random() < 0.5 else 0, name, pos, f"{Lr}M", b, bytes(rng.randint(2, 41) for _ in range(Lr))))
+    order = {n: i for i, (n, _) in enumerate(contigs)}
+    recs.sort(key=lambda r: (order[r.rname], r.pos))
+    ref = PackedReference.from_contigs(contigs)
+    batch = ReadBatch.from_records(recs, ref)
+    exp = oracle.profile(ref, batch, 51)
+    assert_profile_equal(run_gpu(ctx, ref, batch, 51), exp, f"noisy tiles L {L}")
+    if not ragged:          # the mask-emitting variant of the same kernel, and the pileup fed by its masks
+        import torch
+        from parasuite_b200.runtime import DeviceBatch
+        d = DeviceBatch(batch, "cuda:0")
+        st = torch.cuda.current_stream().cuda_stream
+        ctx.profile_begin(51, emit_t2c_masks=True)
+        ctx.profile_batch_device(d, st)
+        masks = ctx.profile_masks()
+        with ctx.pileup_run(d, stream=st, masks=masks) as h:
+            got_m = h.fetch(boundary=False)
+        assert_profile_equal(ctx.profile_end(), exp, "noisy tiles, masks")
+        with ctx.pileup_run(d, stream=st) as h:
+            got_d = h.fetch(boundary=False)
+        assert np.array_equal(got_m["clusters"], got_d["clusters"]) and np.array_equal(got_m["sites"], got_d["sites"])

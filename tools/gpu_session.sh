@@ -1,13 +1,14 @@
 #!/bin/bash
-# scratch: one gpurun call -- final single-GPU records of the round
+# scratch: one gpurun call
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > gpurun_out/r2_final_smi.txt
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_final_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/r2_final_tests.log
-timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_final_reference.json 2> gpurun_out/r2_final_reference.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_final_smoke.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_final_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2_final_ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_fast_kernel|pl_flag_kernel|pl_flag_expand_kernel|pl_cluster_kernel|pl_compact_kernel' -s 25 -c 5 -o gpurun_out/r2_final_full python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2_final_ncu_full.log 2>&1
+rm -f gpurun_out/r2_coop_variants.json
+for v in coop0 coop1; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --check >> gpurun_out/r2_coop_variants.json 2>> gpurun_out/r2_coop_variants.err
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --len 50 --check >> gpurun_out/r2_coop_variants.json 2>> gpurun_out/r2_coop_variants.err
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --check >> gpurun_out/r2_coop_variants.json 2>> gpurun_out/r2_coop_variants.err
+done
+timeout 1200 python -m pytest tests/test_gpu_profile.py tests/test_gpu_ragged.py tests/test_gpu_fused.py tests/test_gpu_golden.py -x -q > gpurun_out/r2_coop_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_coop_tests.log
