@@ -38,10 +38,6 @@
 #define FAST_BLOCKS_PER_SM 4
 #endif
 #define FAST_QCOPIES 8         // copies of the per-pair mismatch quality cells (spreads same-address reductions)
-#ifndef FAST_COOP_DRAIN
-#define FAST_COOP_DRAIN 1      // mismatch events of a warp-tile go through a per-warp queue: one event per lane and round
-#endif
-#define FAST_QCAP 256          // events the queue holds; a tile with more drains the old way (every lane its own)
 #ifndef FAST_REV_SPLIT
 #define FAST_REV_SPLIT 1       // test "any minus-strand read" per half of the warp-tile instead of once per tile
 #endif
@@ -111,7 +107,7 @@ __host__ __device__ inline FastStage fast_stage_layout(uint32_t L) {
 }
 
 struct FastLayout {     // byte offsets of the block's shared memory
-  uint32_t misc, zero, tbl, mm_cnt, mm_q, fast, warp0, warp_stride, inv, park, evq, tcm, bars, stage0, total;
+  uint32_t misc, zero, tbl, mm_cnt, mm_q, fast, warp0, warp_stride, inv, park, bars, stage0, total;
 };
 __host__ __device__ inline FastLayout fast_layout(uint32_t max_len, uint32_t L, uint32_t nw) {
   FastLayout f;
@@ -125,9 +121,7 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t max_len, uint32_t L, 
   f.bars = 0;                                   // per warp: u64[FAST_STAGES] (+pad to 32)
   f.inv = 32;                                   // per warp: u32[WT_READS*nw] N calls of the tile's reads
   f.park = f.inv + WT_READS * nw * 4;           // per warp: u32[2 reads][rf|rd][nw][32 lanes]
-  f.evq = f.park + 2 * 2 * nw * 32 * 4;         // per warp: u16[FAST_QCAP] mismatch events (read in tile << 6 | position)
-  f.tcm = f.evq + FAST_QCAP * 2;                // per warp: u32[WT_READS][2] T>C masks collected from the events
-  f.stage0 = (f.tcm + WT_READS * 8 + 127) & ~127u;
+  f.stage0 = (f.park + 2 * 2 * nw * 32 * 4 + 127) & ~127u;
   f.warp_stride = f.stage0 + FAST_STAGES * fast_stage_layout(L).total;
   f.total = f.warp0 + FAST_WARPS * f.warp_stride;
   return f;
@@ -273,12 +267,10 @@ __global__ void __launch_bounds__(FAST_THREADS, RG ? 3 : FAST_BLOCKS_PER_SM) pro
   const uint32_t a_wbase = a_smem + fl.warp0 + warp * fl.warp_stride;
   const uint32_t a_bars = a_wbase + fl.bars;
   const uint32_t a_park = a_wbase + fl.park + lane * 4;                 // + ((h*2 + arr)*NW + k) * 128
-  const uint32_t a_evq = a_wbase + fl.evq, a_tcm = a_wbase + fl.tcm;
   const uint32_t a_stage0 = a_wbase + fl.stage0;
 
   for (uint32_t k = threadIdx.x; k < fl.warp0 / 4; k += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[k] = 0;
   for (uint32_t k = lane; k < WT_READS * NW; k += 32) s_inv[k] = 0;
-  for (uint32_t k = lane; k < WT_READS * 2; k += 32) reinterpret_cast<uint32_t*>(wbase + fl.tcm)[k] = 0;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < FAST_STAGES; ++s) mbar_init(reinterpret_cast<uint64_t*>(wbase + fl.bars) + s, 1);
@@ -632,98 +624,30 @@ __global__ void __launch_bounds__(FAST_THREADS, RG ? 3 : FAST_BLOCKS_PER_SM) pro
         }
       }
     }
-    // ---- mismatching positions.  Words 0,1 share the even/odd bits of w0, words 2,3 of w1.  A lane's reads hold a
-    //      handful of events at most but the warp would pay the maximum over its lanes of a per-lane loop, so the events
-    //      of the whole tile are first written to a queue (a warp scan places every lane's run) and then taken one per
-    //      lane and round: pair from the parked words of the event's read, count by (position, pair), quality by pair,
-    //      and a bit of the read's T>C mask (collected in shared memory, read back by the read's own lane) ------------
+    // ---- mismatching positions, one at a time.  Words 0,1 share the even/odd bits of w0, words 2,3 of w1 -----------
     uint32_t tc_lo[2] = {0, 0}, tc_hi[2] = {0, 0};
-    __syncwarp();      // parked words, quality rows and N-call clears are read across lanes from here on
-    uint32_t mw0[2], mw1[2];
+    __syncwarp();      // parked words are read back by their own lane only; the fence orders the shared accesses
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      mw0[h] = mmv[h][0] | (NW > 1 ? (mmv[h][NW > 1 ? 1 : 0] << 1) : 0u);
-      mw1[h] = NW > 2 ? (mmv[h][NW > 2 ? 2 : 0] | (NW > 3 ? (mmv[h][NW > 3 ? 3 : 0] << 1) : 0u)) : 0u;
-    }
-    bool queued = false;
-    uint32_t n_ev = 0;
-    if (FAST_COOP_DRAIN) {
-      const uint32_t cnt = __popc(mw0[0]) + __popc(mw1[0]) + __popc(mw0[1]) + __popc(mw1[1]);
-      uint32_t inc = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(FULL, inc, d);
-        if (lane >= (uint32_t)d) inc += y;
-      }
-      n_ev = __shfl_sync(FULL, inc, 31);
-      queued = n_ev <= FAST_QCAP;
-      if (queued && n_ev) {
-        uint32_t slot = a_evq + 2u * (inc - cnt);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t w0 = mw0[h], w1 = mw1[h];
-          const uint32_t tag = (lane + 32u * (uint32_t)h) << 6;
-          while (w0 | w1) {
-            const bool first = NW <= 2 || w0 != 0;
-            const uint32_t word = first ? w0 : w1;
-            const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
-            const uint32_t rest = word & (word - 1u);
-            if (first) w0 = rest; else w1 = rest;
-            const uint32_t i = 16u * ((first ? 0u : 2u) + (b & 1u)) + (b >> 1);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(slot), "h"((unsigned short)(tag | i)) : "memory");
-            slot += 2u;
-          }
-        }
-        __syncwarp();
-        const bool emit = P.t2c_mask != nullptr;
-        for (uint32_t e = lane; e < n_ev; e += 32) {
-          unsigned short ev16;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ev16) : "r"(a_evq + 2u * e));
-          const uint32_t ev = ev16, rit = ev >> 6, i = ev & 63u;
-          const uint32_t k = i >> 4, sh = (i & 15u) * 2u;
-          const uint32_t a_src = a_wbase + fl.park + (rit & 31u) * 4u + (((rit >> 5) * 2u) * NW + k) * 128u;
-          const uint32_t rfw = lds32(a_src), rdw = lds32(a_src + NW * 128u);
-          const uint32_t pair = ((rfw >> sh) & 3u) * 4u + ((rdw >> sh) & 3u);
-          const int q = lds_s8(a_sb + lay.qual + rit * L + i);          // events come from reads of the shape only
-          red_s32(a_mm_cnt + (i * 16u + pair) * 4u, 1u);
-          red_s32(a_mm_q + pair * (FAST_QCOPIES * 4u), (uint32_t)q);
-          if (emit && pair == 13u)                                     // ref T, read C on the oriented strand
-            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a_tcm + rit * 8u + (i >> 5) * 4u), "r"(1u << (i & 31u)) : "memory");
-        }
-        if (emit) {
-          __syncwarp();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t a_m = a_tcm + (lane + 32u * (uint32_t)h) * 8u;
-            tc_lo[h] = lds32(a_m);
-            tc_hi[h] = lds32(a_m + 4u);
-            if (tc_lo[h] | tc_hi[h]) { sts32(a_m, 0u); sts32(a_m + 4u, 0u); }
-          }
-        }
-      }
-    }
-    if (!queued) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t w0 = mw0[h], w1 = mw1[h];
-        const uint32_t a_pk = a_park + (h * 2 * NW) * 128;
-        while (w0 | w1) {
-          const bool first = NW <= 2 || w0 != 0;
-          const uint32_t word = first ? w0 : w1;
-          const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
-          const uint32_t rest = word & (word - 1u);
-          if (first) w0 = rest; else w1 = rest;
-          const uint32_t k = (first ? 0u : 2u) + (b & 1u), sh = b & ~1u;
-          const uint32_t rfw = lds32(a_pk + k * 128), rdw = lds32(a_pk + (NW + k) * 128);
-          const uint32_t i = 16u * k + (b >> 1);
-          const uint32_t pair = ((rfw >> sh) & 3u) * 4u + ((rdw >> sh) & 3u);
-          const int q = lds_s8(a_qrow[h] + i);
-          red_s32(a_mm_cnt + (i * 16u + pair) * 4u, 1u);
-          red_s32(a_mm_q + pair * (FAST_QCOPIES * 4u), (uint32_t)q);
-          const uint32_t one = pair == 13u ? 1u : 0u;         // ref T, read C on the oriented strand
-          tc_lo[h] |= shl_clamp(one, i);
-          tc_hi[h] |= shl_clamp(one, i - 32u);               // i < 32 wraps to a huge amount: 0
-        }
+      uint32_t w0 = mmv[h][0] | (NW > 1 ? (mmv[h][NW > 1 ? 1 : 0] << 1) : 0u);
+      uint32_t w1 = NW > 2 ? (mmv[h][NW > 2 ? 2 : 0] | (NW > 3 ? (mmv[h][NW > 3 ? 3 : 0] << 1) : 0u)) : 0u;
+      const uint32_t a_pk = a_park + (h * 2 * NW) * 128;
+      while (w0 | w1) {
+        const bool first = NW <= 2 || w0 != 0;
+        const uint32_t word = first ? w0 : w1;
+        const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
+        const uint32_t rest = word & (word - 1u);
+        if (first) w0 = rest; else w1 = rest;
+        const uint32_t k = (first ? 0u : 2u) + (b & 1u), sh = b & ~1u;
+        const uint32_t rfw = lds32(a_pk + k * 128), rdw = lds32(a_pk + (NW + k) * 128);
+        const uint32_t i = 16u * k + (b >> 1);
+        const uint32_t pair = ((rfw >> sh) & 3u) * 4u + ((rdw >> sh) & 3u);
+        const int q = lds_s8(a_qrow[h] + i);
+        red_s32(a_mm_cnt + (i * 16u + pair) * 4u, 1u);
+        red_s32(a_mm_q + pair * (FAST_QCOPIES * 4u), (uint32_t)q);
+        const uint32_t one = pair == 13u ? 1u : 0u;         // ref T, read C on the oriented strand
+        tc_lo[h] |= shl_clamp(one, i);
+        tc_hi[h] |= shl_clamp(one, i - 32u);               // i < 32 wraps to a huge amount: 0
       }
     }
     // ---- rare: invalid reference positions in the window -- the quality of every invalid position went into the
