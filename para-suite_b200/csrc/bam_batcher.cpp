@@ -553,11 +553,59 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
     B->head = 0;
   }
   // ---- locate records -------------------------------------------------------------------------------------
+  // A record's place is known only from the block_size of the one before it: a chain.  The bytes at hand are cut into
+  // one span per thread; a thread whose span does not start the batch looks for the first offset from which a chain
+  // of plausible records runs (the test a BAM split guesser makes: block_size against the lengths inside the record,
+  // reference ids inside the header's range, a NUL-terminated printable name), all spans are walked at once, and the
+  // result is accepted only where every span's walk lands exactly on the start the next span assumed -- from the first
+  // span that does not, the chain is walked again the plain way.
   const double t_loc0 = now_s(), fill0 = B->t_fill;
   std::vector<uint64_t>& ro = B->rec_off;
   ro.clear();
   size_t o = 0;
-  while (ro.size() < B->max_batch) {
+  const int64_t n_ref = (int64_t)B->ref_names.size();
+  auto plausible = [&](const uint8_t* d, size_t p, size_t end) -> int {     // 1 yes, 0 no, -1 cannot tell (runs past `end`)
+    if (end - p < 36) return -1;
+    const uint32_t bs = rd32(d + p);
+    if (bs < 32 || bs > (1u << 26)) return 0;
+    const int32_t ref_id = (int32_t)rd32(d + p + 4), pos = (int32_t)rd32(d + p + 8), nref = (int32_t)rd32(d + p + 24);
+    const uint32_t l_name = d[p + 12], n_cig = rd16(d + p + 16), l_seq = rd32(d + p + 20);
+    if (ref_id < -1 || ref_id >= n_ref || nref < -1 || nref >= n_ref || pos < -1 || l_name == 0) return 0;
+    if (32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + (uint64_t)l_seq > bs) return 0;
+    if (end - p < 36 + (size_t)l_name) return -1;
+    if (d[p + 36 + l_name - 1] != 0) return 0;
+    for (uint32_t k = 0; k + 1 < l_name; ++k)
+      if (d[p + 36 + k] < 0x21 || d[p + 36 + k] > 0x7e) return 0;
+    return 1;
+  };
+  auto chain_start = [&](const uint8_t* d, size_t from, size_t end) -> size_t {   // first offset >= from that starts a chain
+    const size_t stop = std::min(end, from + ((size_t)4 << 20));
+    for (size_t p = from; p < stop; ++p) {
+      size_t q = p;
+      int k = 0, v = 1;
+      for (; k < 12; ++k) {
+        v = plausible(d, q, end);
+        if (v != 1) break;
+        q += 4 + (size_t)rd32(d + q);
+        if (q > end) { v = -1; break; }
+        if (q == end) break;
+      }
+      if (v == 1 || (v == -1 && k >= 3)) return p;
+    }
+    return (size_t)-1;
+  };
+  auto walk = [&](const uint8_t* d, size_t p, size_t until, size_t end, std::vector<uint64_t>& out, int* bad) -> size_t {
+    // complete records starting before `until`; stops in front of the first one that is malformed or runs past `end`
+    while (p < until && end - p >= 4) {
+      const uint32_t bs = rd32(d + p);
+      if (bs < 32) { *bad = 1; break; }
+      if (end - p < 4 + (size_t)bs) break;
+      out.push_back(p);
+      p += 4 + (size_t)bs;
+    }
+    return p;
+  };
+  for (;;) {
     if (B->buf.size() - o < 4) {
       int st = bam_fill(B, o + 4);
       if (st) return st;
@@ -566,15 +614,55 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
         break;
       }
     }
-    const uint32_t bs = rd32(B->buf.data() + o);
-    if (bs < 32) return bam_fail(B, PS_ERR_FORMAT, "malformed BAM record (block_size < 32)");
-    if (B->buf.size() - o < 4 + (size_t)bs) {
-      int st = bam_fill(B, o + 4 + (size_t)bs);
-      if (st) return st;
-      if (B->buf.size() - o < 4 + (size_t)bs) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM record");
+    const uint8_t* d = B->buf.data();
+    const size_t end = B->buf.size();
+    const int T = (end - o > ((size_t)8 << 20) && B->threads > 1) ? B->threads : 1;
+    int bad = 0;
+    if (T == 1) {
+      o = walk(d, o, end, end, ro, &bad);
+    } else {
+      std::vector<size_t> start(T + 1, (size_t)-1);
+      std::vector<std::vector<uint64_t>> part(T);
+      std::vector<size_t> stop_at(T, 0);
+      std::vector<int> tbad(T, 0);
+      start[0] = o;
+      start[T] = end;
+      parallel_for(T, (uint64_t)T - 1, [&](int, uint64_t lo, uint64_t hi) {
+        for (uint64_t t = lo + 1; t < hi + 1; ++t) start[t] = chain_start(d, o + (end - o) / T * t, end);
+      });
+      for (int t = T - 1; t >= 1; --t)
+        if (start[t] == (size_t)-1) start[t] = start[t + 1];          // no start found: the span before runs through
+      parallel_for(T, (uint64_t)T, [&](int, uint64_t lo, uint64_t hi) {
+        for (uint64_t t = lo; t < hi; ++t)
+          if (start[t] < start[t + 1]) stop_at[t] = walk(d, start[t], start[t + 1], end, part[t], &tbad[t]);
+          else stop_at[t] = start[t];
+      });
+      size_t p = o;
+      int t = 0;
+      for (; t < T; ++t) {
+        if (t > 0 && stop_at[t - 1] != start[t]) break;      // the chain does not arrive where span t assumed its start
+        ro.insert(ro.end(), part[t].begin(), part[t].end());
+        p = stop_at[t];
+        if (tbad[t]) { bad = 1; break; }
+      }
+      if (!bad && t < T && p < end) p = walk(d, p, end, end, ro, &bad);    // the plain way from where the spans disagree
+      o = p;
     }
-    ro.push_back(o);
-    o += 4 + (size_t)bs;
+    if (bad) return bam_fail(B, PS_ERR_FORMAT, "malformed BAM record (block_size < 32)");
+    if (ro.size() >= B->max_batch) {
+      if (ro.size() > B->max_batch) { o = ro[B->max_batch]; ro.resize(B->max_batch); }
+      break;
+    }
+    // the record at o is incomplete (or the bytes are used up): bring in more, or find the file's end
+    size_t want = o + 4;
+    if (B->buf.size() - o >= 4) want = o + 4 + (size_t)rd32(B->buf.data() + o);
+    const size_t before = B->buf.size();
+    int st = bam_fill(B, want);
+    if (st) return st;
+    if (B->buf.size() == before) {
+      if (B->buf.size() != o) return bam_fail(B, PS_ERR_FORMAT, "truncated BAM record");
+      break;
+    }
   }
   B->head = o;
   B->t_locate += (now_s() - t_loc0) - (B->t_fill - fill0);

@@ -255,3 +255,29 @@ def test_hand_encoded_bam_bytes(tmp_path):
                                   Record(16, "chrQ", 7, "2S3M", b"GGTCA", b"")], pf.reference())
     assert_batch_equal(got[0], exp, "hand-encoded BAM")
     pf.close()
+
+
+def test_parallel_record_location_equals_serial(tmp_path):
+    """More than 8 MB of records at hand: the batcher cuts them into one span per thread, finds a plausible chain start
+    in every span and walks all spans at once (bam_batcher.cpp: locate).  Same batches as the one-thread walk, also when
+    a batch boundary falls inside the bytes at hand."""
+    from parasuite_b200 import synth
+    from parasuite_b200.bamio import batch_to_records
+    ref = synth.synth_reference(77, [1_000_000, 500_000], n_run=500)
+    recs = batch_to_records(synth.synth_reads(ref, 110_000, 36, seed=3, special_ppm=5000), ref)
+    fa, bam = str(tmp_path / "r.fa"), str(tmp_path / "r.bam")
+    import numpy as np
+    k = np.arange(ref.n_bases, dtype=np.int64)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[(ref.seq2[k >> 4] >> ((k & 15) * 2).astype(np.uint32)) & 3].tobytes()
+    write_fasta(fa, [(ref.names[0], seq[:ref.lengths[0]]), (ref.names[1], seq[ref.lengths[0]:])])
+    write_bam(bam, list(zip(ref.names, ref.lengths)), recs)
+    pf = PackedFasta(fa)
+    for max_batch in (0, 40_000):
+        got = {}
+        for threads in (1, 6):
+            got[threads] = list(BamBatcher(bam, pf, max_batch_reads=max_batch, threads=threads))
+        assert len(got[1]) == len(got[6]) == (1 if max_batch == 0 else 3)
+        for a, b in zip(got[1], got[6]):
+            assert a.n_reads == b.n_reads
+            for f in ("meta", "ref_start", "bases2", "qual", "cigar", "exc"):
+                assert np.array_equal(getattr(a, f), getattr(b, f)), f
