@@ -3,7 +3,14 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-N=2
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 1800 $TR --master-port 29502 tools/run_config.py --configs 4 --reads4 250000000 > gpurun_out/r2_n${N}_config4.json 2> gpurun_out/r2_n${N}_config4.err
-timeout 900 $TR --master-port 29501 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2_n${N}_bench.json 2> gpurun_out/r2_n${N}_bench.err
+rm -f gpurun_out/r2_swz_variants.json
+for v in swz0 swz1 swz0 swz1; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 >> gpurun_out/r2_swz_variants.json 2>> gpurun_out/r2_swz_variants.err
+done
+for v in swz0 swz1; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --len 50 >> gpurun_out/r2_swz_variants.json 2>> gpurun_out/r2_swz_variants.err
+done
+timeout 1200 python -m pytest tests/test_gpu_pileup.py tests/test_gpu_fused.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py -x -q > gpurun_out/r2_swz_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_swz_tests.log
