@@ -445,7 +445,10 @@ def main():
     # ---- end-to-end leg: pinned HOST buffers through the C ABI, copies inside the timed region -------
     # one upload of the records serves both tools; every cluster and site record comes back to (pinned) host memory
     e2e_steps = args.e2e_steps or min(args.steps, 10)
-    pinned = PinnedBatch(batch)
+    # the compact host form of the batch (ps_read_batch: one flag byte per read instead of the meta word, no cigar stream
+    # -- every read of this workload is `36M` -- and qualities packed 6 bits each): 16 of 57 bytes per read less over the
+    # host link, expanded on the device by the upload, inside the timed region
+    pinned = PinnedBatch(batch, compact=True)
     gathered = torch.empty(world * BOUNDARY_WORDS, dtype=torch.int64, device=dev) if world > 1 else None
     mine_dev = torch.empty(BOUNDARY_WORDS, dtype=torch.int64, device=dev) if world > 1 else None
     mine_pin = torch.empty(BOUNDARY_WORDS, dtype=torch.int64).pin_memory() if world > 1 else None
@@ -634,6 +637,7 @@ def main():
                                       "all-gathered keys on the device, halo merge of the spanning cluster on the host",
                        "numa_cpus": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_form": ("compact (flags8 + uniform_cigar" + (" + qual6" if pinned.packed_qual else "") + ")") if pinned.compact else "full",
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
                     "h2d_gbs_per_rank": h2d / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
                     "h2d_ceiling_gbs_per_rank": h2d_ceiling_min,

@@ -111,7 +111,17 @@ typedef struct ps_read_batch {
   uint64_t exc_count;
   uint32_t max_len;               /* longest read of the batch when the producer knows it, else 0 (a hint: ragged batches of
                                      short reads are re-laid in rows of 16*ceil(min(max_len, max_read_length)/16) positions) */
-  uint32_t reserved;
+  /* Compact form of a HOST batch of the PAR-CLIP shape, for the calls that upload it (ps_profile_batch, ps_pileup_batch,
+   * ps_batch_upload): fewer bytes over the host link, expanded on the device by the upload.
+   *   uniform_cigar != 0 (with uniform_ncigar == 1): every read's one cigar op is this word; `cigar` may be NULL
+   *   flags8 != NULL (with uniform_len and uniform_ncigar): the PS_RF_* flags, one byte per read; `meta` may be NULL
+   *   qual6 != NULL (with uniform_len): the qualities packed 6 bits each -- four per three bytes, little endian,
+   *     ceil(L/4)*3 bytes per read, every quality <= 63 (no read with PS_RF_QUAL_MISSING); `qual` may be NULL,
+   *     qual_bytes still counts the unpacked bytes
+   * The view ps_batch_upload returns always holds the expanded `meta`, `cigar` and `qual`. */
+  uint32_t uniform_cigar;
+  const uint8_t* flags8;
+  const uint8_t* qual6;
 } ps_read_batch;
 
 /* ---- error profile ------------------------------------------------------------------------ */

@@ -824,7 +824,9 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   out->cigar_count = cigar_count;
   out->exc_count = exc_count;
   out->max_len = lens_max.load();
-  out->reserved = 0;
+  out->uniform_cigar = 0;
+  out->flags8 = nullptr;
+  out->qual6 = nullptr;
   B->ordinal += n;
   return 1;
 }

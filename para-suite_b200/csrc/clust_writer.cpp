@@ -223,6 +223,8 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
                          uint64_t n_closed, const ps_site* sites, int has_open, uint64_t open_first_read) {
   if (!w || !hb || (n_closed && !closed)) return PS_ERR_INVALID_ARG;
   if (!w->f_pileup) return cw_fail(w, PS_ERR_STATE, "writer is closed");
+  if (hb->n_reads && (!hb->meta || !hb->cigar || !hb->ref_start || !hb->bases2 || !hb->qual))
+    return cw_fail(w, PS_ERR_INVALID_ARG, "the writer reads the records on the host: the compact upload form (flags8 / uniform_cigar) is not accepted here");
   // ---- arithmetic of the flush for the new records, in order (running state lives in the flush object) ----------
   std::vector<ps_flush_row> rows(n_closed);
   if (n_closed) {

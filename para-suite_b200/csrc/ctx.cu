@@ -36,16 +36,45 @@ static DeviceBatch view_of(const ps_read_batch* b) {
   return v;
 }
 
-static int check_batch(ps_ctx* ctx, const ps_read_batch* b) {
+static int check_batch(ps_ctx* ctx, const ps_read_batch* b, bool allow_compact = false) {
   if (!b) return set_error(ctx, PS_ERR_INVALID_ARG, "batch is NULL");
   if (b->n_reads == 0) return PS_OK;
-  if (!b->meta || !b->ref_start || !b->bases2 || !b->qual || !b->cigar || !b->tile_exc_off || !b->exc)
+  const bool meta_ok = b->meta || (allow_compact && b->flags8 && b->uniform_len && b->uniform_ncigar);
+  const bool cigar_ok = b->cigar || (allow_compact && b->uniform_cigar && b->uniform_ncigar == 1);
+  const bool qual_ok = b->qual || (allow_compact && b->qual6 && b->uniform_len);
+  if (!meta_ok || !b->ref_start || !b->bases2 || !qual_ok || !cigar_ok || !b->tile_exc_off || !b->exc)
     return set_error(ctx, PS_ERR_INVALID_ARG, "batch has NULL streams");
   if ((!b->uniform_len && (!b->tile_base_off || !b->tile_qual_off)) || (!b->uniform_ncigar && !b->tile_cigar_off))
     return set_error(ctx, PS_ERR_INVALID_ARG, "variable-length batch without tile offsets");
   if (b->n_reads / PS_TILE_READS >= 0xFFFFFFFFull)
     return set_error(ctx, PS_ERR_INVALID_ARG, "batch too large (tile index is 32-bit)");
   return PS_OK;
+}
+
+// expansion of the compact host form (ps_read_batch: flags8, uniform_cigar) behind its upload
+__global__ void expand_meta_kernel(const uint8_t* __restrict__ flags8, uint32_t len_ncig, uint32_t* __restrict__ meta, uint64_t n) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+    meta[r] = len_ncig | ((uint32_t)flags8[r] << 24);
+}
+// qualities packed 6 bits each (four per three bytes) -> one byte each, rows of L bytes
+__global__ void unpack_qual6_kernel(const uint8_t* __restrict__ q6, uint8_t* __restrict__ qual, uint64_t n, uint32_t L) {
+  const uint32_t gpr = (L + 3) / 4;
+  const uint64_t total = n * gpr;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = g / gpr;
+    const uint32_t j = (uint32_t)(g - r * gpr);
+    const uint8_t* p = q6 + g * 3;
+    const uint32_t w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    uint8_t* o = qual + r * L + 4u * j;
+    const uint32_t v = (w & 63u) | (((w >> 6) & 63u) << 8) | (((w >> 12) & 63u) << 16) | (((w >> 18) & 63u) << 24);
+    const uint32_t left = L - 4u * j;
+    if (left >= 4u && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) *reinterpret_cast<uint32_t*>(o) = v;
+    else
+      for (uint32_t k = 0; k < left && k < 4u; ++k) o[k] = (uint8_t)(v >> (8u * k));
+  }
+}
+__global__ void fill_u32_kernel(uint32_t* __restrict__ out, uint32_t v, uint64_t n) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) out[r] = v;
 }
 
 // H2D copy of a host batch into one of the two staging slots (async on ctx->stream)
@@ -59,10 +88,17 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
   const uint64_t nt = (n + PS_TILE_READS - 1) / PS_TILE_READS;
   struct Item { DevBuf* d; const void* h; size_t bytes; };
   // qualities last: they are more than half of the bytes and only the profile kernel reads them
+  const bool compact_meta = hb->meta == nullptr, compact_cigar = hb->cigar == nullptr;
+  const bool packed_qual = with_qual && hb->qual == nullptr;
+  if ((compact_meta && !(hb->flags8 && hb->uniform_len && hb->uniform_ncigar)) ||
+      (compact_cigar && !(hb->uniform_cigar && hb->uniform_ncigar == 1)) || (packed_qual && !(hb->qual6 && hb->uniform_len)))
+    return set_error(ctx, PS_ERR_INVALID_ARG, "batch has NULL meta / cigar / qual streams without the compact form that replaces them");
+  const size_t q6_bytes = packed_qual ? (size_t)n * ((hb->uniform_len + 3) / 4) * 3 : 0;
   Item items[] = {
       {&s.meta, hb->meta, n * 4},
+      {&s.flags8, compact_meta ? hb->flags8 : nullptr, compact_meta ? (size_t)n : 0},
       {&s.ref_start, hb->ref_start, n * 4},
-      {&s.cigar, hb->cigar, (size_t)hb->cigar_count * 4},
+      {&s.cigar, hb->cigar, (size_t)(compact_cigar ? n : hb->cigar_count) * 4},
       {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
       {&s.tbo, hb->tile_base_off, hb->tile_base_off ? (nt + 1) * 8 : 0},
       {&s.tqo, hb->tile_qual_off, hb->tile_qual_off ? (nt + 1) * 8 : 0},
@@ -70,12 +106,35 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
       {&s.teo, hb->tile_exc_off, (nt + 1) * 4},
       {&s.exc, hb->exc, (size_t)hb->exc_count * 4},
       {&s.qual, hb->qual, with_qual ? (size_t)hb->qual_bytes : 0},   // the pileup never reads qualities
+      {&s.qual6, packed_qual ? hb->qual6 : nullptr, q6_bytes},
   };
   if (!ctx->staged_core[slot]) cudaEventCreateWithFlags(&ctx->staged_core[slot], cudaEventDisableTiming);
   for (auto& it : items) {
     PS_CUDA(ctx, it.d->reserve(it.bytes + 64));   // +64: kernels may read a few bytes past the last read
-    if (it.d == &s.qual) cudaEventRecord(ctx->staged_core[slot], ctx->stream);
-    if (it.bytes) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (it.d == &s.qual) {
+      // everything the pileup reads is on its way: expand the compact streams, then mark the point
+      const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+      if (compact_meta) {
+        expand_meta_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(s.flags8.p),
+                                                           PS_MAKE_META(hb->uniform_len, hb->uniform_ncigar, 0),
+                                                           static_cast<uint32_t*>(s.meta.p), n);
+        ctx->launches++;
+      }
+      if (compact_cigar) {
+        fill_u32_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(s.cigar.p), hb->uniform_cigar, n);
+        ctx->launches++;
+      }
+      if (compact_meta || compact_cigar) PS_CUDA(ctx, cudaGetLastError());
+      cudaEventRecord(ctx->staged_core[slot], ctx->stream);
+    }
+    if (it.bytes && it.h) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (packed_qual) {
+    const unsigned grid = (unsigned)std::min<uint64_t>((n * ((hb->uniform_len + 3) / 4) + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    unpack_qual6_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(s.qual6.p), static_cast<uint8_t*>(s.qual.p), n,
+                                                        hb->uniform_len);
+    ctx->launches++;
+    PS_CUDA(ctx, cudaGetLastError());
   }
   if (!ctx->staged_done[slot]) cudaEventCreateWithFlags(&ctx->staged_done[slot], cudaEventDisableTiming);
   cudaEventRecord(ctx->staged_done[slot], ctx->stream);   // host buffers of this batch may be reused once it has fired
@@ -93,7 +152,7 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
   v.exc = (const uint32_t*)s.exc.p;
   v.uniform_len = hb->uniform_len;
   v.uniform_ncigar = hb->uniform_ncigar;
-  v.cigar_count = hb->cigar_count;
+  v.cigar_count = compact_cigar ? n : hb->cigar_count;
   v.max_len = hb->max_len;
   *out = &s;
   return PS_OK;
@@ -191,7 +250,7 @@ void ps_destroy(ps_ctx* ctx) {
   ctx->rg_okmap.release(); ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
-    s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release();
+    s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release(); s.flags8.release(); s.qual6.release();
   }
   for (auto& b : ctx->pl_scratch) b.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -337,7 +396,7 @@ int ps_profile_batch_device(ps_ctx* ctx, const ps_read_batch* b, void* stream) {
 int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
   if (!ctx) return PS_ERR_INVALID_ARG;
   if (!ctx->profile_open) return set_error(ctx, PS_ERR_STATE, "ps_profile_begin not called");
-  int st = check_batch(ctx, hb);
+  int st = check_batch(ctx, hb, true);
   if (st) return st;
   if (hb->n_reads == 0) return PS_OK;
   cudaSetDevice(ctx->device);
@@ -356,7 +415,7 @@ int ps_profile_batch(ps_ctx* ctx, const ps_read_batch* hb) {
 
 int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* hb, ps_read_batch* dev_view) {
   if (!ctx || !dev_view) return PS_ERR_INVALID_ARG;
-  int st = check_batch(ctx, hb);
+  int st = check_batch(ctx, hb, true);
   if (st) return st;
   cudaSetDevice(ctx->device);
   StagedBatch* sb = nullptr;
@@ -367,6 +426,9 @@ int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* hb, ps_read_batch* dev_vie
   dev_view->meta = v.meta; dev_view->ref_start = v.ref_start; dev_view->bases2 = v.bases2; dev_view->qual = v.qual;
   dev_view->cigar = v.cigar; dev_view->tile_base_off = v.tile_base_off; dev_view->tile_qual_off = v.tile_qual_off;
   dev_view->tile_cigar_off = v.tile_cigar_off; dev_view->tile_exc_off = v.tile_exc_off; dev_view->exc = v.exc;
+  dev_view->cigar_count = v.cigar_count;
+  dev_view->flags8 = nullptr;          // the view is always in the expanded form
+  dev_view->qual6 = nullptr;
   return PS_OK;
 }
 

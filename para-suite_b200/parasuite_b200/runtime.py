@@ -58,21 +58,60 @@ class UploadedBatch:
 class PinnedBatch:
     """A ReadBatch copied into page-locked host memory (what the native batcher fills)."""
 
-    def __init__(self, host: ReadBatch):
+    def __init__(self, host: ReadBatch, compact: bool = False):
+        """compact=True: the compact host form of ps_read_batch where the batch allows it (uniform length, one cigar op
+        per read, the same op everywhere): one flag byte per read instead of the meta word, no cigar stream (7 bytes per
+        read less over the host link), and qualities packed 6 bits each when none exceeds 63 (a quarter of their bytes
+        less); the upload expands all three on the device."""
         import torch
         self.n_reads = host.n_reads
         self._t = {}
         s = host.as_struct()
+        n = host.n_reads
+        skip = set()
+        self.compact = False
+        if compact and n and host.uniform_len and host.uniform_ncigar == 1:
+            op = int(host.cigar[0])
+            if bool(np.all(np.asarray(host.cigar[:n]) == op)) and op != 0:
+                flags = (np.asarray(host.meta[:n]) >> np.uint32(24)).astype(np.uint8)
+                t = torch.from_numpy(flags).clone().pin_memory()
+                self._t["flags8"] = t
+                s.flags8 = t.data_ptr()
+                s.uniform_cigar = op
+                s.meta = None
+                s.cigar = None
+                skip = {"meta", "cigar"}
+                self.compact = True
+        qual_sent = host.qual_bytes
+        self.packed_qual = False
+        if compact and n and host.uniform_len:
+            L = host.uniform_len
+            q = np.asarray(host.qual[:n * L]).reshape(n, L)
+            missing = ((np.asarray(host.meta[:n]) >> np.uint32(24)) & abi.PS_RF_QUAL_MISSING) != 0
+            if int(q.max()) <= 63 and not bool(missing.any()):
+                g = (L + 3) // 4
+                qp = np.zeros((n, g * 4), dtype=np.uint32)
+                qp[:, :L] = q
+                qp = qp.reshape(n, g, 4)
+                w = qp[:, :, 0] | (qp[:, :, 1] << 6) | (qp[:, :, 2] << 12) | (qp[:, :, 3] << 18)
+                packed = np.stack((w & 255, (w >> 8) & 255, w >> 16), axis=2).astype(np.uint8).reshape(-1)
+                t = torch.from_numpy(np.ascontiguousarray(packed)).clone().pin_memory()
+                self._t["qual6"] = t
+                s.qual6 = t.data_ptr()
+                s.qual = None
+                skip = skip | {"qual"}
+                qual_sent = int(packed.size)
+                self.packed_qual = True
         for f in ReadBatch.FIELDS:
             a = getattr(host, f)
-            if a is None:
+            if a is None or f in skip:
                 continue
             t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8)).clone().pin_memory()
             self._t[f] = t
             setattr(s, f, t.data_ptr())
         self.struct = s
-        self.h2d_bytes = (host.n_reads * 8 + host.bases_bytes + host.qual_bytes + host.cigar_count * 4 +
-                          host.exc_count * 4 + (host.n_tiles + 1) * 28)
+        per_read = 5 if self.compact else 8 + 4 * host.cigar_count / max(n, 1)
+        self.h2d_bytes = int(n * per_read + host.bases_bytes + qual_sent + host.exc_count * 4 + (host.n_tiles + 1) * 28)
 
 
 class Context:

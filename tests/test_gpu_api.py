@@ -119,3 +119,59 @@ def test_handle_outlives_next_call(oracle):
             assert np.array_equal(g["sites"]["order_key"], e["sites"]["order_key"])
     finally:
         c.close()
+
+
+def test_compact_host_form_equals_the_full_one(oracle):
+    """ps_read_batch's compact host form (one flag byte per read instead of the meta word, no cigar stream when every
+    read has the same single op): the upload expands it on the device; profile, pileup and the returned device view are
+    the same as with the full arrays."""
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context, PinnedBatch
+    ref = synth.synth_reference(91, [1_500_000, 700_000], n_run=800)
+    batch = synth.synth_reads(ref, 200_003, 36, seed=14, n_ppm=3000)      # (special flags would kill the JVM in the pileup)
+    full, comp = PinnedBatch(batch), PinnedBatch(batch, compact=True)
+    assert comp.compact and comp.packed_qual and comp.h2d_bytes == full.h2d_bytes - (7 + 9) * batch.n_reads
+    ctx = Context(0)
+    try:
+        ctx.upload_reference(ref)
+        out = {}
+        for name, pb in (("full", full), ("compact", comp)):
+            view = ctx.upload(pb)
+            with ctx.pileup_run(view) as h:
+                pile = h.fetch(boundary=True)
+            ctx.profile_begin(51)
+            ctx.profile_batch_device(view)
+            out[name] = (ctx.profile_end(), pile)
+            ctx.profile_begin(51)                      # and through the calls that upload by themselves
+            ctx.profile_batch(pb)
+            assert np.array_equal(ctx.profile_end()["wide"], out[name][0]["wide"])
+            with ctx.pileup_run(pb) as h:
+                p2 = h.fetch(boundary=True)
+            assert np.array_equal(p2["clusters"], pile["clusters"]) and np.array_equal(p2["sites"], pile["sites"])
+        assert np.array_equal(out["full"][0]["wide"], out["compact"][0]["wide"])
+        assert np.array_equal(out["full"][1]["clusters"], out["compact"][1]["clusters"])
+        assert np.array_equal(out["full"][1]["sites"], out["compact"][1]["sites"])
+        assert np.array_equal(out["compact"][0]["wide"], oracle.profile_acc(ref, batch, 51, threads=4))
+        # a ragged batch has no compact form
+        rb = synth.trim_uniform(synth.synth_reads(ref, 10_000, 36, seed=15), 20)
+        assert not PinnedBatch(rb, compact=True).compact
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("L", [50, 17])
+def test_packed_qualities_for_lengths_that_are_no_multiple_of_four(oracle, L):
+    from parasuite_b200 import synth
+    from parasuite_b200.runtime import Context, PinnedBatch
+    ref = synth.synth_reference(92, [900_000], n_run=800)
+    batch = synth.synth_reads(ref, 50_001, L, seed=16, n_ppm=2000)
+    comp = PinnedBatch(batch, compact=True)
+    assert comp.packed_qual
+    ctx = Context(0)
+    try:
+        ctx.upload_reference(ref)
+        ctx.profile_begin(51)
+        ctx.profile_batch(comp)
+        assert np.array_equal(ctx.profile_end()["wide"], oracle.profile_acc(ref, batch, 51, threads=4))
+    finally:
+        ctx.close()
