@@ -454,17 +454,22 @@ def main():
     mine_pin = torch.empty(BOUNDARY_WORDS, dtype=torch.int64).pin_memory() if world > 1 else None
     got_pin = torch.empty(world * BOUNDARY_WORDS, dtype=torch.int64).pin_memory() if world > 1 else None
 
-    def step_e2e():
+    def step_e2e(view, more):
         # records in (one upload serves both tools; the quality bytes, more than half of it, go last).  The pileup starts
         # as soon as the other streams have arrived and its records travel back while the qualities are still on their
-        # way up; the profile kernel follows the upload.
-        view = ctx.upload(pinned)
+        # way up; the profile kernel follows the upload on a stream of its own, and the NEXT step's upload (into the other
+        # staging slot of the context) is queued before the host waits for this step's results, so the host link does
+        # not idle while the profile kernel of a step runs.  `view`: this step's upload, already queued.
+        # Returns (profile result, the next step's view).
+        nxt_view = None
         if world == 1:
             with ctx.pileup_run(view) as h:
                 pile["res_e2e"] = h.fetch(pinned=True, boundary=True)
             ctx.profile_begin(max_len)
-            ctx.profile_batch_device(view)
-            return ctx.profile_end()
+            ctx.profile_batch_device(view, stream.cuda_stream)
+            if more:
+                nxt_view = ctx.upload(pinned)
+            return ctx.profile_end(), nxt_view
         # N > 1: the carry-in stays on the device (key kernel + all-gather on a side stream, ordered behind the part of
         # the upload they read by the library), the all-reduce of the counts runs on its own stream, nothing waits on the
         # host until the records are fetched
@@ -477,6 +482,8 @@ def main():
         with torch.cuda.stream(red):
             dist.all_reduce(ctx.profile_acc_tensor())
         ctx.profile_set_stream(red.cuda_stream)
+        if more:
+            nxt_view = ctx.upload(pinned)
         with h:
             r = h.fetch(pinned=True, boundary=True)
             # halo merge: every shard's head partial goes to the rank in front of it (one small all-gather), which folds
@@ -494,14 +501,16 @@ def main():
                 nxt = unpack_head(w)
             r["merged_open"] = merge_boundary(r, nxt, batch.n_reads)
             pile["res_e2e"] = r
-        return ctx.profile_end()
+        return ctx.profile_end(), nxt_view
 
-    for _ in range(2):
-        step_e2e()
+    v = ctx.upload(pinned)
+    for k in range(2):
+        _, v = step_e2e(v, k == 0)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res_e2e = step_e2e()
+    v = ctx.upload(pinned)                           # the first step's upload is inside the timed region like all others
+    for k in range(e2e_steps):
+        res_e2e, v = step_e2e(v, k + 1 < e2e_steps)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)

@@ -3,6 +3,6 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_api.py tests/test_gpu_bam.py tests/test_gpu_stream.py tests/test_config1.py tests/test_gpu_profile.py -m gpu -x -q > gpurun_out/r2_compact_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/r2_compact_tests.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r2_compact_bench.json 2> gpurun_out/r2_compact_bench.err
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r2_pipe2_bench.json 2> gpurun_out/r2_pipe2_bench.err
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 900 $TR --master-port 29501 bench.py --gpus 2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r2_pipe2_bench_n2.json 2> gpurun_out/r2_pipe2_bench_n2.err
