@@ -527,6 +527,7 @@ def main():
     probe_dev = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     for _ in range(2):
         probe_dev.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()                          # the warm-up copies must be over before the clock starts
     barrier()
     t0 = time.perf_counter()
     for _ in range(6):
