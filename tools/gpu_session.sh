@@ -1,7 +1,7 @@
 #!/bin/bash
-# scratch: one gpurun call -- single-GPU bench record of the final code
+# scratch: one gpurun call
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_final_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2_final_ncu_list.log 2>&1
+rm -f gpurun_out/r2_cs_full.ncu-rep
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_generic_kernel' -s 2 -c 1 -o gpurun_out/r2_cs_full python tools/bench_kernels.py --reads 4000000 --len 150 --mode 1 --max-len 176 --iters 4 > gpurun_out/r2_cs_ncu.log 2>&1
