@@ -84,3 +84,70 @@ def test_gpu_tools_from_files(cfg, monkeypatch, window):
     assert ctr["double_stranded"] == cfg["exp"]["double_stranded"] and ctr["skipped_due_indel"] == cfg["exp"]["skipped_due_indel"]
     for k, path in FILES.items():
         assert open(path.format(out=out, bam=cfg["bam"])).read() == cfg["exp"]["clust_files"][k], k
+
+
+# ---- the example pipeline between the aligner and the two tools: comb (examples.sh:58), then error (:51) and clust (:65) ----
+@pytest.fixture(scope="module")
+def comb(tmp_path_factory, cfg):
+    from parasuite_b200.comb import comb_bam
+    d = tmp_path_factory.mktemp("config1_comb")
+    doc = json.loads(gzip.open(os.path.join(DIR, "comb.json.gz"), "rb").read())
+
+    def recs(rows):
+        return ([Record(f, rn, p, "" if c == "*" else c, s.encode(), bytes(q)) for _, f, rn, p, c, s, q, _ in rows],
+                [n.encode() for n, *_ in rows])
+    g, gn = recs(doc["genomic"])
+    t, tn = recs(doc["transcript"])
+    name, seq = cfg["contigs"][0]
+    gb, tb, ob = str(d / "genomic.bam"), str(d / "transcript.bam"), str(d / "combined.bam")
+    write_bam(gb, [(name, len(seq))], g, names=gn)
+    write_bam(tb, [(h, ln) for h, ln in doc["transcripts"]], t, sort_order="queryname", names=tn)
+    stats = comb_bam(gb, tb, ob)
+    return {"doc": doc, "stats": stats, "bam": ob, "dir": d}
+
+
+def test_comb_lifts_the_transcript_hits_like_the_restatement(comb):
+    from parasuite_b200.bamio import read_bam_records
+    doc, stats = comb["doc"], comb["stats"]
+    assert stats["mapped_reads"] == doc["stats"]["mapped_reads"] and stats["spliced_reads"] == doc["stats"]["spliced_reads"]
+    assert stats["missed_transcript_alignments"] == doc["stats"]["missed_transcript_alignments"]
+    assert stats["lifted_records"] == doc["stats"]["lifted"] > 1000 and stats["spliced_reads"] > 100
+    _, _, got = read_bam_records(comb["bam"])
+    assert len(got) == len(doc["combined"])
+    for a, (n, f, rn, p, c, s, q, mq) in zip(got, doc["combined"]):
+        assert (a["name"], a["flag"], a["rname"], a["pos"], a["cigar"], a["seq"].decode(), list(a["qual"]), a["mapq"]) == \
+               (n, f, rn, p, c or "*", s, q, mq if n.startswith("read") else 255)
+
+
+def test_cpu_tools_on_the_combined_records(comb, cfg, oracle):
+    from parasuite_b200.bamio import read_bam_records
+    from parasuite_b200.flush import ClustWriter, Flush
+    _, _, got = read_bam_records(comb["bam"])
+    recs = [Record(a["flag"], a["rname"], a["pos"], "" if a["cigar"] == "*" else a["cigar"], a["seq"], a["qual"]) for a in got]
+    ref = PackedReference.from_contigs(cfg["contigs"])
+    batch = ReadBatch.from_records(recs, ref)
+    check_profile(oracle.profile(ref, batch, 51), {"profile": comb["doc"]["profile"]})
+    res = oracle.pileup(ref, batch)
+    out = str(comb["dir"] / "cpu_clusters.tsv")
+    fl = Flush(ref.names, 1, vcf=cfg["vcf"])
+    w = ClustWriter(fl, cfg["fa"], out, comb["bam"])
+    w.feed(batch, 0, res["clusters"], res["sites"], None if res["open_cluster"] is None else int(res["open_cluster"]["first_read"]))
+    w.finish(res["counters"])
+    w.close()
+    for k, path in FILES.items():
+        assert open(path.format(out=out, bam=comb["bam"])).read() == comb["doc"]["clust_files"][k], k
+
+
+@pytest.mark.gpu
+def test_gpu_tools_on_the_combined_bam(comb, cfg):
+    from parasuite_b200.runtime import Context
+    ctx = Context(0)
+    try:
+        ctx.load_fasta(cfg["fa"])
+        check_profile(ctx.profile_bam(comb["bam"], 51), {"profile": comb["doc"]["profile"]})           # examples.sh:51
+        out = str(comb["dir"] / "gpu_clusters.tsv")
+        ctx.clust_bam(comb["bam"], out, cfg["vcf"], 1)                                                 # examples.sh:65
+    finally:
+        ctx.close()
+    for k, path in FILES.items():
+        assert open(path.format(out=out, bam=comb["bam"])).read() == comb["doc"]["clust_files"][k], k
