@@ -260,7 +260,25 @@ struct WarpAcc {
   long long q_acc[4];
   unsigned long long q_cnt[4];
   unsigned long long checked;
+  uint32_t mm_events;      // mismatch-quality events this lane has put into the warp's 32-bit cells since their last flush
 };
+
+// Mismatch qualities (sum and count by pair, ErrorProfiling.java:392-397) first go to 32 warp-private 32-bit cells with
+// native shared reductions -- a 64-bit shared atomicAdd is a compare-and-swap loop, and reads that compare shifted
+// sequence (soft clips, Q-quirk) bring a hundred such events each -- and from there to the block's 64-bit cells before a
+// cell could overflow (|q| <= 128, 2^18 events per lane).
+__device__ __forceinline__ void warp_q_flush(const GenericSmem& S, uint32_t wq32, WarpAcc& A) {
+  __syncwarp();
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(wq32 + lane * 4u));
+  if (v) {
+    atomicAdd(&S.s_q[lane], lane < 16 ? (unsigned long long)(long long)(int)v : (unsigned long long)v);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wq32 + lane * 4u), "r"(0u) : "memory");
+  }
+  A.mm_events = 0;
+  __syncwarp();
+}
 
 // what the count loop needs to know about a read that reached it
 struct ReadPlan {
@@ -271,8 +289,11 @@ struct ReadPlan {
 
 // Prologue of one read by ONE lane (32 reads of a warp-tile at a time): filters, FASTA range, cigar bounds, indel side
 // effects, uncaught exceptions of the walk (ErrorProfiling.java:155-306).
+// (the three run counters nearly every read touches -- processed, indel read, longer indel -- go to per-lane registers
+// `ctr`, summed once at the end of the kernel: a 64-bit shared atomicAdd is a compare-and-swap loop, and the 32 lanes
+// of a warp would all spin on the same cell)
 __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P, const GenericSmem& S, uint64_t r, uint32_t meta,
-                                                          const ReadOffsets& off) {
+                                                          const ReadOffsets& off, uint32_t (&ctr)[3]) {
   ReadPlan plan;
   plan.g0 = 0; plan.ml = 0; plan.bits = 0;
   const uint32_t max_len = P.lay.max_len;
@@ -300,7 +321,7 @@ __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P
     }
     if (bad) { raise_fault(P.fault, ordinal, PS_THROW_REF_RANGE); return plan; }
   }
-  atomicAdd(&S.s_ctr[PS_PC_NUM_READS_PROCESSED], 1ull);                        // :174
+  ++ctr[0];                        // :174
   if (R == 0) { raise_fault(P.fault, ordinal, PS_THROW_EMPTY_REF); return plan; }
   const uint32_t ml = L > R ? L : R;
   if (L != R) {   // :194-299, pass 1: bounds (skip), indel side effects, uncaught exceptions
@@ -323,10 +344,10 @@ __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P
           if (pm + q >= (int64_t)max_len) { raise_fault(P.fault, ordinal, PS_THROW_INDEL_POS); return plan; }
           atomicAdd(arr + (pm + q), 1u);
         }
-        if (n > 1) atomicAdd(&S.s_ctr[PS_PC_LONGER_INDELS], 1ull);
+        if (n > 1) ++ctr[2];
       }
     }
-    atomicAdd(&S.s_ctr[PS_PC_INDEL_READ], 1ull);                               // :296
+    ++ctr[1];                               // :296
     if (skip) { atomicAdd(&S.s_ctr[PS_PC_SKIPPED_READS], 1ull); return plan; } // :303-306
   }
   plan.g0 = g0; plan.ml = ml; plan.bits = (has_indel ? 1u : 0u) | (L != R ? 2u : 0u);
@@ -335,7 +356,8 @@ __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P
 
 // Count loop of one read by the WHOLE warp (ErrorProfiling.java:349-408).
 __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const GenericSmem& S, uint32_t convT, uint32_t pad,
-                                                  uint64_t r, uint32_t meta, ReadOffsets off, ReadPlan plan, WarpAcc& A) {
+                                                  uint32_t wq32, uint64_t r, uint32_t meta, ReadOffsets off, ReadPlan plan,
+                                                  WarpAcc& A) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t max_len = P.lay.max_len;
   const uint32_t flags = PS_META_FLAGS(meta), L = PS_META_LEN(meta), ncig = PS_META_NCIGAR(meta);
@@ -391,14 +413,16 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
             if (a == 0) { qa0 += qv; qc0++; } else if (a == 1) { qa1 += qv; qc1++; }
             else if (a == 2) { qa2 += qv; qc2++; } else { qa3 += qv; qc3++; }
           } else {
-            atomicAdd(&S.s_q[pair], (unsigned long long)(long long)qv);
-            atomicAdd(&S.s_q[16 + pair], 1ull);
+            red_shared_add(wq32 + pair * 4u, (uint32_t)qv);
+            red_shared_add(wq32 + (16u + pair) * 4u, 1u);
+            ++A.mm_events;
           }
         }
       }
       pm += n; pr += n; pq += n;
     }
   }
+  if (__any_sync(0xFFFFFFFFu, A.mm_events >= (1u << 18))) warp_q_flush(S, wq32, A);
   f_key = __reduce_min_sync(0xFFFFFFFFu, f_key);
   uint32_t f_i = f_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : f_key >> 1;
   uint32_t f_code = (f_key & 1u) ? PS_THROW_QUAL_RANGE : PS_THROW_POS_MAXLEN;
@@ -425,15 +449,19 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
   S.s_ctr = S.s_q + 32;
   S.s_conv = reinterpret_cast<uint32_t*>(S.s_ctr + 16);      // transposed here: [pair][pad]
   S.s_indel = S.s_conv + 16 * pad;
-  for (uint32_t k = threadIdx.x; k < 16 * pad + 2 * max_len; k += blockDim.x) S.s_conv[k] = 0;
+  uint32_t* s_wq = S.s_indel + 2 * max_len;                  // [warps][32] warp-private mismatch-quality cells
+  for (uint32_t k = threadIdx.x; k < 16 * pad + 2 * max_len + (PS_BLOCK_THREADS / 32) * 32; k += blockDim.x) S.s_conv[k] = 0;
   if (threadIdx.x < 48) S.s_q[threadIdx.x] = 0;   // s_q and s_ctr are contiguous
   __syncthreads();
   const uint32_t convT = (uint32_t)__cvta_generic_to_shared(S.s_conv);
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wq32 = (uint32_t)__cvta_generic_to_shared(s_wq) + (threadIdx.x >> 5) * 128u;
   WarpAcc A;
 #pragma unroll
   for (int b = 0; b < 4; ++b) { A.q_acc[b] = 0; A.q_cnt[b] = 0; }
   A.checked = 0;
+  A.mm_events = 0;
+  uint32_t ctr[3] = {0, 0, 0};      // processed, indel reads, longer indels
   unsigned int* counter = reinterpret_cast<unsigned int*>(P.fault + 3);   // zeroed by the launcher
   for (;;) {
     unsigned int wt = 0;
@@ -446,7 +474,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
     const ReadOffsets off = warp_read_offsets(P.b, q, r, in_range, meta);
     ReadPlan plan;
     plan.g0 = 0; plan.ml = 0; plan.bits = 0;
-    if (in_range) plan = profile_read_prologue(P, S, r, meta, off);
+    if (in_range) plan = profile_read_prologue(P, S, r, meta, off, ctr);
     uint32_t todo = __ballot_sync(0xFFFFFFFFu, plan.ml != 0);
     while (todo) {
       const int j = __ffs((int)todo) - 1;
@@ -459,10 +487,11 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
       pj.g0 = __shfl_sync(0xFFFFFFFFu, plan.g0, j);
       pj.ml = __shfl_sync(0xFFFFFFFFu, plan.ml, j);
       pj.bits = __shfl_sync(0xFFFFFFFFu, plan.bits, j);
-      profile_read_warp(P, S, convT, pad, q + j, __shfl_sync(0xFFFFFFFFu, meta, j), oj, pj, A);
+      profile_read_warp(P, S, convT, pad, wq32, q + j, __shfl_sync(0xFFFFFFFFu, meta, j), oj, pj, A);
       __syncwarp();
     }
   }
+  warp_q_flush(S, wq32, A);
   // per-lane registers -> shared
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
@@ -477,6 +506,14 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
     if (lane == 0 && c) atomicAdd(&S.s_ctr[PS_PC_TOTAL_BASES_CHECKED], c);
+  }
+  {
+    const int which[3] = {PS_PC_NUM_READS_PROCESSED, PS_PC_INDEL_READ, PS_PC_LONGER_INDELS};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, ctr[k]);    // a lane sees far fewer than 2^32 / 32 reads
+      if (lane == 0 && t) atomicAdd(&S.s_ctr[which[k]], (unsigned long long)t);
+    }
   }
   __syncthreads();
   // flush (the histogram is [pair][position] here)
@@ -622,7 +659,8 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   const uint64_t n_wt = (P.b.n_reads - first_read + 31) / 32;
   if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
   P.n_tiles = (uint32_t)n_wt;
-  size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4;
+  size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4 +
+                (PS_BLOCK_THREADS / 32) * 32 * 4;      // + the warps' 32-bit mismatch-quality cells
   // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
   cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

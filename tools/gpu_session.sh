@@ -3,5 +3,6 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-rm -f gpurun_out/r2_gen_full.ncu-rep
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_generic_kernel' -s 2 -c 1 -o gpurun_out/r2_gen_full python tools/bench_kernels.py --reads 4000000 --len 150 --mode 1 --max-len 176 --iters 4 > gpurun_out/r2_gen_ncu.log 2>&1
+timeout 1200 python -m pytest tests/test_gpu_profile.py tests/test_gpu_golden.py tests/test_gpu_bam.py tests/test_config1.py -m gpu -x -q > gpurun_out/r2_wq_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_wq_tests.log
+timeout 600 python tools/bench_kernels.py --reads 4000000 --len 150 --mode 1 --max-len 176 --iters 8 --check > gpurun_out/r2_wq_bench.json 2> gpurun_out/r2_wq_bench.err
