@@ -172,6 +172,12 @@ typedef struct ps_profile_result {
  *   | (+256*maxLen quality histogram with infer_qualities) */
 size_t ps_profile_acc_len(uint32_t max_read_length, uint32_t infer_qualities);
 
+/* The six output files of the `error` tool after the loop (ErrorProfiling.java:410-591): <bam>.errorprofile,
+ * .errorprofile.vcf, .qualityPerMismatch, .indels, .indelprofile, .qualities (empty without infer_qualities), from a
+ * filled result.  Host only.  *averaged_t2c_epr (may be NULL) receives the value of the "Averaged T2C" log line. */
+int ps_profile_write_files(const ps_profile_result* res, uint32_t max_read_length, uint32_t infer_qualities,
+                           const char* bam_path, double* averaged_t2c_epr, char* err, size_t err_cap);
+
 /* ---- T>C pileup ---------------------------------------------------------------------------- */
 typedef struct ps_cluster {      /* one closed cluster, state at PileupClusters.java:178 (before the SNP filter) */
   uint64_t first_read;           /* ordinal of the read that opened it */
@@ -323,6 +329,9 @@ int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts,
  * reference must have been loaded with ps_reference_load_fasta (the raw-case FASTA is read for the sequence columns). */
 int ps_clust_bam(ps_ctx* ctx, const char* bam_path, const char* out_path, const char* snp_vcf, uint32_t min_read_coverage,
                  ps_pileup_counters* counters_out, ps_fault* fault_out);
+/* The whole `error` tool from files (ErrorProfiling.inferErrorProfile without the plot): ps_profile_bam + the six
+ * output files next to the BAM (ps_profile_write_files).  counters_out: [PS_PC_COUNT] or NULL. */
+int ps_error_bam(ps_ctx* ctx, const char* bam_path, const ps_profile_opts* opts, int32_t* counters_out, ps_fault* fault_out);
 
 /* ---- `comb` tool (host only): transcript hits lifted to genomic coordinates, merged with the genomic hits ---------------
  * Replaces CombineGenomeTranscript.combine / printReadsToBamFile (utils/postprocessing/CombineGenomeTranscript.java:36-666;
@@ -357,6 +366,7 @@ const char* ps_multi_last_error(const ps_multi* m);
 int ps_multi_load_fasta(ps_multi* m, const char* fasta_path);
 int ps_multi_profile_bam(ps_multi* m, const char* bam_path, const ps_profile_opts* opts, ps_profile_result* out);
 int ps_multi_pileup_bam(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts, ps_pileup** out);
+int ps_multi_error_bam(ps_multi* m, const char* bam_path, const ps_profile_opts* opts, int32_t* counters_out, ps_fault* fault_out);
 int ps_multi_clust_bam(ps_multi* m, const char* bam_path, const char* out_path, const char* snp_vcf,
                        uint32_t min_read_coverage, ps_pileup_counters* counters_out, ps_fault* fault_out);
 

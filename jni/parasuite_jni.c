@@ -308,3 +308,36 @@ JNIEXPORT jlongArray JNICALL Java_utils_postprocessing_NativeCombine_combine(JNI
   if (pg) (*env)->ReleaseStringUTFChars(env, genomic, pg);
   return a;
 }
+
+/* package utils.errorprofile;  static native int[] errorTool(long ctx, boolean multi, String bam, int maxReadLength,
+ * boolean inferQualities);  -- the whole body of ErrorProfiling.inferErrorProfile (:96-621, without the plot): record loop
+ * on the GPU(s) and the six output files next to the BAM.  Returns the eight run counters (numReadsProcessed, unmapped,
+ * duplicates, startZero, indelRead, skippedReads, longerIndels, totalBasesChecked). */
+JNIEXPORT jintArray JNICALL Java_utils_errorprofile_NativeErrorProfile_errorTool(JNIEnv* env, jclass c, jlong h, jboolean multi,
+                                                                                 jstring bam, jint maxReadLength,
+                                                                                 jboolean inferQualities) {
+  (void)c;
+  if (!bam || maxReadLength <= 0) { throw_illegal(env, "errorTool: bam must not be null, maxReadLength must be positive"); return NULL; }
+  const char* pb = (*env)->GetStringUTFChars(env, bam, NULL);
+  jintArray a = NULL;
+  if (pb) {
+    ps_profile_opts o;
+    ps_fault fault;
+    int32_t ctr[PS_PC_COUNT];
+    memset(&o, 0, sizeof o);
+    memset(&fault, 0, sizeof fault);
+    o.max_read_length = (uint32_t)maxReadLength;
+    o.infer_qualities = inferQualities ? 1u : 0u;
+    const int st = multi ? ps_multi_error_bam((ps_multi*)(intptr_t)h, pb, &o, ctr, &fault)
+                         : ps_error_bam((ps_ctx*)(intptr_t)h, pb, &o, ctr, &fault);
+    if (st != PS_OK) {
+      if (multi) throw_message(env, ps_multi_last_error((ps_multi*)(intptr_t)h), st);
+      else throw_status(env, (ps_ctx*)(intptr_t)h, st);
+    } else {
+      a = (*env)->NewIntArray(env, PS_PC_COUNT);
+      if (a) (*env)->SetIntArrayRegion(env, a, 0, PS_PC_COUNT, (const jint*)ctr);
+    }
+    (*env)->ReleaseStringUTFChars(env, bam, pb);
+  }
+  return a;
+}

@@ -523,6 +523,37 @@ int ps_pileup_bam(ps_ctx* ctx, const char* bam_path, const ps_pileup_opts* opts,
   return st;
 }
 
+// The whole `error` tool from files (ErrorProfiling.inferErrorProfile, :96-621 without the plot): record loop on the
+// GPU(s), the six output files natively.
+int ps_multi_error_bam(ps_multi* m, const char* bam_path, const ps_profile_opts* opts, int32_t* counters_out, ps_fault* fault_out) {
+  if (!m || !bam_path || !opts) return PS_ERR_INVALID_ARG;
+  const uint32_t ml = opts->max_read_length;
+  std::vector<int32_t> pc((size_t)ml * 16), qpm(16), qpmc(16), ctr(PS_PC_COUNT);
+  std::vector<double> ins(ml), del(ml);
+  std::vector<int64_t> qh(opts->infer_qualities ? (size_t)ml * 256 : 0);
+  ps_profile_result r{};
+  r.position_conversions = pc.data(); r.quality_per_mismatch = qpm.data(); r.quality_per_mismatch_counts = qpmc.data();
+  r.insertions_per_pos = ins.data(); r.deletions_per_pos = del.data(); r.counters = ctr.data();
+  r.quality_hist = opts->infer_qualities ? qh.data() : nullptr;
+  int st = ps_multi_profile_bam(m, bam_path, opts, &r);
+  if (fault_out) *fault_out = r.fault;
+  if (st != PS_OK) return st;
+  char err[512];
+  st = ps_profile_write_files(&r, ml, opts->infer_qualities, bam_path, nullptr, err, sizeof err);
+  if (st != PS_OK) return multi_fail(m, st, err);
+  if (counters_out) memcpy(counters_out, ctr.data(), sizeof(int32_t) * PS_PC_COUNT);
+  return PS_OK;
+}
+
+int ps_error_bam(ps_ctx* ctx, const char* bam_path, const ps_profile_opts* opts, int32_t* counters_out, ps_fault* fault_out) {
+  if (!ctx || !bam_path || !opts) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");
+  ps_multi m;
+  borrow(m, ctx);
+  const int st = ps_multi_error_bam(&m, bam_path, opts, counters_out, fault_out);
+  if (st != PS_OK && !m.err.empty()) set_error(ctx, st, m.err);
+  return st;
+}
+
 int ps_clust_bam(ps_ctx* ctx, const char* bam_path, const char* out_path, const char* snp_vcf, uint32_t min_read_coverage,
                  ps_pileup_counters* counters_out, ps_fault* fault_out) {
   if (!ctx || !bam_path || !out_path) return set_error(ctx, PS_ERR_INVALID_ARG, "NULL argument");

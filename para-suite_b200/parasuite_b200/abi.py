@@ -152,9 +152,13 @@ EXPORTS = {
     "ps_profile_acc_len": (C.c_size_t, [C.c_uint32, C.c_uint32]),
     "ps_clust_bam": (C.c_int, [VP, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.POINTER(ps_pileup_counters),
                                C.POINTER(ps_fault)]),
+    "ps_profile_write_files": (C.c_int, [C.POINTER(ps_profile_result), C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_double),
+                                         C.c_char_p, C.c_size_t]),
     "ps_liftover_hit": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int32), C.c_char_p,
                                   C.c_size_t, C.POINTER(C.c_uint32)]),
     "ps_comb_bam": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ps_comb_stats), C.c_char_p, C.c_size_t]),
+    "ps_error_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_profile_opts), C.POINTER(C.c_int32), C.POINTER(ps_fault)]),
+    "ps_multi_error_bam": (C.c_int, [VP, C.c_char_p, C.POINTER(ps_profile_opts), C.POINTER(C.c_int32), C.POINTER(ps_fault)]),
     "ps_create_multi": (C.c_int, [C.POINTER(VP), C.POINTER(C.c_int), C.c_int]),
     "ps_destroy_multi": (None, [VP]),
     "ps_multi_device_count": (C.c_int, [VP]),

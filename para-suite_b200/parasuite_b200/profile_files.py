@@ -92,3 +92,36 @@ def write_profile_files(bam_path: str, res: Dict[str, np.ndarray], infer_qualiti
         with open(f"{bam_path}.{suffix}", "w") as f:
             f.write(texts[suffix])
     return texts
+
+
+def write_profile_files_native(bam_path: str, res: Dict[str, np.ndarray], infer_qualities: bool = False) -> float:
+    """The same six files written by the library (csrc/profile_writer.cpp: ps_profile_write_files).  Returns the value of
+    the 'Averaged T2C' log line."""
+    import ctypes as C
+    from . import abi
+    lib = abi.load_library()
+    keep = {
+        "pc": np.ascontiguousarray(res["position_conversions"], dtype=np.int32).reshape(-1),
+        "qpm": np.ascontiguousarray(res["quality_per_mismatch"], dtype=np.int32).reshape(-1),
+        "qpmc": np.ascontiguousarray(res["quality_per_mismatch_counts"], dtype=np.int32).reshape(-1),
+        "ins": np.ascontiguousarray(res["insertions_per_pos"], dtype=np.float64),
+        "dele": np.ascontiguousarray(res["deletions_per_pos"], dtype=np.float64),
+        "ctr": np.ascontiguousarray(res["counters"], dtype=np.int32),
+    }
+    r = abi.ps_profile_result()
+    r.position_conversions = keep["pc"].ctypes.data
+    r.quality_per_mismatch = keep["qpm"].ctypes.data
+    r.quality_per_mismatch_counts = keep["qpmc"].ctypes.data
+    r.insertions_per_pos = keep["ins"].ctypes.data
+    r.deletions_per_pos = keep["dele"].ctypes.data
+    r.counters = keep["ctr"].ctypes.data
+    if infer_qualities:
+        keep["qh"] = np.ascontiguousarray(res["quality_hist"], dtype=np.int64).reshape(-1)
+        r.quality_hist = keep["qh"].ctypes.data
+    m = keep["pc"].size // 16
+    avg = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    st = lib.ps_profile_write_files(C.byref(r), m, int(infer_qualities), bam_path.encode(), C.byref(avg), err, len(err))
+    if st != abi.PS_OK:
+        raise abi.PsError(st, err.value.decode() or lib.ps_strerror(st).decode())
+    return avg.value

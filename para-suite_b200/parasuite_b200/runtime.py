@@ -188,6 +188,16 @@ class Context:
         _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
         return {k: getattr(ctr, k) for k, _ in abi.ps_pileup_counters._fields_}
 
+    def error_bam(self, bam_path: str, max_read_length: int, infer_qualities: bool = False) -> np.ndarray:
+        """The whole `error` tool from files (ErrorProfiling.inferErrorProfile): writes <bam>.errorprofile,
+        .errorprofile.vcf, .qualityPerMismatch, .indels, .indelprofile, .qualities; returns the run counters."""
+        o = abi.ps_profile_opts(max_read_length, int(infer_qualities), 0, 0)
+        ctr = (C.c_int32 * abi.PS_PC_COUNT)()
+        f = abi.ps_fault()
+        st = self.lib.ps_error_bam(self.h, bam_path.encode(), C.byref(o), ctr, C.byref(f))
+        _check(self.lib, self.h, st, fault=(f.code, f.read_ordinal))
+        return np.array(list(ctr), dtype=np.int32)
+
     # ---- batches ---------------------------------------------------------------------------------
     def upload(self, batch) -> UploadedBatch:
         """One H2D copy of a host batch (ReadBatch / PinnedBatch); both tools can then run on the device view

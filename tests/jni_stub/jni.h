@@ -33,5 +33,7 @@ struct JNINativeInterface_ {
   jsize (*GetArrayLength)(JNIEnv*, jarray);
   jlongArray (*NewLongArray)(JNIEnv*, jsize);
   void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jsize, jsize, const jlong*);
+  jintArray (*NewIntArray)(JNIEnv*, jsize);
+  void (*SetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, const jint*);
 };
 #endif

@@ -70,3 +70,21 @@ def test_jni_shim_type_checks_against_stub_header():
     for sym in ("ps_create", "ps_destroy", "ps_reference_load_fasta", "ps_profile_bam", "ps_pileup_bam", "ps_pileup_next",
                 "ps_pileup_counters_get", "ps_pileup_close"):
         assert sym in src and sym in abi.EXPORTS
+
+
+def test_java_classes_declare_what_the_shim_exports():
+    """jni/java/**/*.java (the classes a maintainer drops into the reference's tree) and jni/parasuite_jni.c agree on the
+    set of native methods, class by class."""
+    import glob
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "jni")
+    shim = open(os.path.join(root, "parasuite_jni.c")).read()
+    exported = set(re.findall(r"JNICALL\s+Java_([A-Za-z0-9_]+)\(", shim))
+    declared = set()
+    for path in glob.glob(os.path.join(root, "java", "**", "*.java"), recursive=True):
+        src = open(path).read()
+        pkg = re.search(r"package\s+([\w.]+);", src).group(1)
+        cls = re.search(r"public final class (\w+)", src).group(1)
+        for name in re.findall(r"public static native [\w\[\]]+ (\w+)\(", src):
+            declared.add(f"{pkg.replace('.', '_')}_{cls}_{name}")
+    assert exported == declared and len(exported) >= 15

@@ -98,3 +98,35 @@ def test_bam_without_fasta_is_a_state_error(tmp_path):
         assert e.value.status == abi.PS_ERR_STATE
     finally:
         c.close()
+
+
+def test_error_tool_from_files(tmp_path, oracle):
+    """ps_error_bam: the whole `error` tool -- record loop on the GPU, the six output files natively -- against the Python
+    writer fed with the oracle's arrays."""
+    from parasuite_b200.profile_files import profile_file_texts
+    from parasuite_b200.runtime import Context
+    rng = random.Random(31)
+    contigs = random_genome(rng, n_contigs=2, length=4000, n_frac=0.01)
+    g = po.Genome(dict(contigs))
+    recs = []
+    for r in random_records(rng, contigs, 3000, kinds=("M", "M", "M", "indel"), Lrange=(18, 45), flags_special=0.03):
+        try:
+            po.profile(to_py([r]), g, 51)
+            recs.append(r)
+        except po.ReferenceWouldThrow:
+            pass
+    fa, bam = str(tmp_path / "r.fa"), str(tmp_path / "r.bam")
+    write_fasta(fa, contigs)
+    write_bam(bam, [(n, len(s)) for n, s in contigs], recs)
+    ref = PackedReference.from_contigs(contigs)
+    exp = oracle.profile(ref, ReadBatch.from_records(recs, ref), 51)
+    want = profile_file_texts(exp, False)
+    ctx = Context(0)
+    try:
+        ctx.load_fasta(fa)
+        ctr = ctx.error_bam(bam, 51)
+    finally:
+        ctx.close()
+    assert list(ctr) == [int(x) for x in exp["counters"]]
+    for k in ("errorprofile", "errorprofile.vcf", "qualityPerMismatch", "indels", "indelprofile", "qualities"):
+        assert open(f"{bam}.{k}").read() == want[k], k

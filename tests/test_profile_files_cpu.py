@@ -11,7 +11,7 @@ import py_oracle as po
 from helpers import kat_records, py_profile_dict, random_genome, random_records, to_py
 from kat_vectors import KAT_MAXLEN, KAT_REF, PROFILE_KATS
 from parasuite_b200.flush import java_double
-from parasuite_b200.profile_files import profile_file_texts, write_profile_files
+from parasuite_b200.profile_files import profile_file_texts, write_profile_files, write_profile_files_native
 
 EXACT = ("errorprofile", "errorprofile.vcf", "qualityPerMismatch", "indels", "indelprofile", "averaged_t2c_epr")
 
@@ -96,3 +96,37 @@ def test_empty_run_prints_nan():
     assert t["errorprofile"] == ("NaN\t" * 4 + "\n") * 4 and t["indelprofile"] == "0.0\t0.0"
     st = po.ProfileState(5)
     assert po.profile_outputs(st, False, java_double)["errorprofile"] == t["errorprofile"]
+
+
+@pytest.mark.parametrize("seed,infer_q", [(5, False), (6, True)])
+def test_native_writer_writes_the_same_files(tmp_path, seed, infer_q):
+    """csrc/profile_writer.cpp (ps_profile_write_files) against the Python writer: the five exact files byte for byte,
+    .qualities with the exact mean and the SD to 1e-12 (the two sum the histogram in different orders)."""
+    rng = random.Random(seed)
+    contigs = random_genome(rng, n_contigs=2, length=3000, n_frac=0.01, lower_frac=0.1)
+    g = po.Genome(dict(contigs))
+    recs = survivors(random_records(rng, contigs, 1500, kinds=("M", "M", "indel") if not infer_q else ("M", "M"), Lrange=(15, 40),
+                                    flags_special=0.03), g, 64)
+    st = po.profile(to_py(recs), g, 64, infer_qual=infer_q)
+    res = state_to_result(st, infer_q)
+    want = profile_file_texts(res, infer_q)
+    bam = str(tmp_path / "x.bam")
+    avg = write_profile_files_native(bam, res, infer_q)
+    assert java_double(avg) == want["averaged_t2c_epr"]
+    for k in EXACT:
+        if k == "averaged_t2c_epr":
+            continue
+        assert open(f"{bam}.{k}").read() == want[k], k
+    got_q = open(f"{bam}.qualities").read()
+    if not infer_q:
+        assert got_q == ""
+    else:
+        gl, wl = got_q.splitlines(), want["qualities"].splitlines()
+        assert len(gl) == len(wl) == 64
+        for a, b in zip(gl, wl):
+            (am, asd), (bm, bsd) = a.split("\t"), b.split("\t")
+            assert am == bm
+            if bsd != "NaN":
+                assert abs(float(asd) - float(bsd)) <= 1e-12 * max(1.0, abs(float(bsd)))
+            else:
+                assert asd == "NaN"
