@@ -647,7 +647,8 @@ def main():
                                       "all-gathered keys on the device, halo merge of the spanning cluster on the host",
                        "numa_cpus": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "host_form": ("compact (flags8 + uniform_cigar" + (" + qual6" if pinned.packed_qual else "") + ")") if pinned.compact else "full",
+                    "host_form": ("compact (flags8 + uniform_cigar" + (" + qual6" if pinned.packed_qual else "") +
+                                  (" + start16" if pinned.compact_start else "") + ")") if pinned.compact else "full",
                     "steps": e2e_steps, "ms_per_step": e2e_ms_max / e2e_steps,
                     "h2d_gbs_per_rank": h2d / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
                     "h2d_ceiling_gbs_per_rank": h2d_ceiling_min,

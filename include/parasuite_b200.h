@@ -118,10 +118,14 @@ typedef struct ps_read_batch {
    *   qual6 != NULL (with uniform_len): the qualities packed 6 bits each -- four per three bytes, little endian,
    *     ceil(L/4)*3 bytes per read, every quality <= 63 (no read with PS_RF_QUAL_MISSING); `qual` may be NULL,
    *     qual_bytes still counts the unpacked bytes
-   * The view ps_batch_upload returns always holds the expanded `meta`, `cigar` and `qual`. */
+   *   start16 != NULL (with tile_start): ref_start[r] = tile_start[r / PS_TILE_READS] + start16[r] -- a sorted batch
+   *     whose tiles of 256 reads each span less than 65536 bases; `ref_start` may be NULL
+   * The view ps_batch_upload returns always holds the expanded `meta`, `cigar`, `qual` and `ref_start`. */
   uint32_t uniform_cigar;
   const uint8_t* flags8;
   const uint8_t* qual6;
+  const uint16_t* start16;
+  const uint32_t* tile_start;
 } ps_read_batch;
 
 /* ---- error profile ------------------------------------------------------------------------ */

@@ -827,6 +827,8 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   out->uniform_cigar = 0;
   out->flags8 = nullptr;
   out->qual6 = nullptr;
+  out->start16 = nullptr;
+  out->tile_start = nullptr;
   B->ordinal += n;
   return 1;
 }

@@ -42,7 +42,8 @@ static int check_batch(ps_ctx* ctx, const ps_read_batch* b, bool allow_compact =
   const bool meta_ok = b->meta || (allow_compact && b->flags8 && b->uniform_len && b->uniform_ncigar);
   const bool cigar_ok = b->cigar || (allow_compact && b->uniform_cigar && b->uniform_ncigar == 1);
   const bool qual_ok = b->qual || (allow_compact && b->qual6 && b->uniform_len);
-  if (!meta_ok || !b->ref_start || !b->bases2 || !qual_ok || !cigar_ok || !b->tile_exc_off || !b->exc)
+  const bool start_ok = b->ref_start || (allow_compact && b->start16 && b->tile_start);
+  if (!meta_ok || !start_ok || !b->bases2 || !qual_ok || !cigar_ok || !b->tile_exc_off || !b->exc)
     return set_error(ctx, PS_ERR_INVALID_ARG, "batch has NULL streams");
   if ((!b->uniform_len && (!b->tile_base_off || !b->tile_qual_off)) || (!b->uniform_ncigar && !b->tile_cigar_off))
     return set_error(ctx, PS_ERR_INVALID_ARG, "variable-length batch without tile offsets");
@@ -73,6 +74,11 @@ __global__ void unpack_qual6_kernel(const uint8_t* __restrict__ q6, uint8_t* __r
       for (uint32_t k = 0; k < left && k < 4u; ++k) o[k] = (uint8_t)(v >> (8u * k));
   }
 }
+__global__ void expand_start_kernel(const uint16_t* __restrict__ start16, const uint32_t* __restrict__ tile_start,
+                                    uint32_t* __restrict__ ref_start, uint64_t n) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+    ref_start[r] = tile_start[r / PS_TILE_READS] + start16[r];
+}
 __global__ void fill_u32_kernel(uint32_t* __restrict__ out, uint32_t v, uint64_t n) {
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) out[r] = v;
 }
@@ -90,6 +96,9 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
   // qualities last: they are more than half of the bytes and only the profile kernel reads them
   const bool compact_meta = hb->meta == nullptr, compact_cigar = hb->cigar == nullptr;
   const bool packed_qual = with_qual && hb->qual == nullptr;
+  const bool compact_start = hb->ref_start == nullptr;
+  if (compact_start && !(hb->start16 && hb->tile_start))
+    return set_error(ctx, PS_ERR_INVALID_ARG, "batch has a NULL ref_start stream without start16 / tile_start");
   if ((compact_meta && !(hb->flags8 && hb->uniform_len && hb->uniform_ncigar)) ||
       (compact_cigar && !(hb->uniform_cigar && hb->uniform_ncigar == 1)) || (packed_qual && !(hb->qual6 && hb->uniform_len)))
     return set_error(ctx, PS_ERR_INVALID_ARG, "batch has NULL meta / cigar / qual streams without the compact form that replaces them");
@@ -98,6 +107,8 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
       {&s.meta, hb->meta, n * 4},
       {&s.flags8, compact_meta ? hb->flags8 : nullptr, compact_meta ? (size_t)n : 0},
       {&s.ref_start, hb->ref_start, n * 4},
+      {&s.start16, compact_start ? hb->start16 : nullptr, compact_start ? (size_t)n * 2 : 0},
+      {&s.tile_start, compact_start ? hb->tile_start : nullptr, compact_start ? (size_t)nt * 4 : 0},
       {&s.cigar, hb->cigar, (size_t)(compact_cigar ? n : hb->cigar_count) * 4},
       {&s.bases2, hb->bases2, (size_t)hb->bases_bytes},
       {&s.tbo, hb->tile_base_off, hb->tile_base_off ? (nt + 1) * 8 : 0},
@@ -124,7 +135,13 @@ int stage_batch(ps_ctx* ctx, const ps_read_batch* hb, bool with_qual, StagedBatc
         fill_u32_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(s.cigar.p), hb->uniform_cigar, n);
         ctx->launches++;
       }
-      if (compact_meta || compact_cigar) PS_CUDA(ctx, cudaGetLastError());
+      if (compact_start) {
+        expand_start_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint16_t*>(s.start16.p),
+                                                            static_cast<const uint32_t*>(s.tile_start.p),
+                                                            static_cast<uint32_t*>(s.ref_start.p), n);
+        ctx->launches++;
+      }
+      if (compact_meta || compact_cigar || compact_start) PS_CUDA(ctx, cudaGetLastError());
       cudaEventRecord(ctx->staged_core[slot], ctx->stream);
     }
     if (it.bytes && it.h) PS_CUDA(ctx, cudaMemcpyAsync(it.d->p, it.h, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -250,7 +267,7 @@ void ps_destroy(ps_ctx* ctx) {
   ctx->rg_okmap.release(); ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
   for (auto& s : ctx->staged) {
     s.meta.release(); s.ref_start.release(); s.bases2.release(); s.qual.release(); s.cigar.release();
-    s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release(); s.flags8.release(); s.qual6.release();
+    s.tbo.release(); s.tqo.release(); s.tco.release(); s.teo.release(); s.exc.release(); s.flags8.release(); s.qual6.release(); s.start16.release(); s.tile_start.release();
   }
   for (auto& b : ctx->pl_scratch) b.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -429,6 +446,8 @@ int ps_batch_upload(ps_ctx* ctx, const ps_read_batch* hb, ps_read_batch* dev_vie
   dev_view->cigar_count = v.cigar_count;
   dev_view->flags8 = nullptr;          // the view is always in the expanded form
   dev_view->qual6 = nullptr;
+  dev_view->start16 = nullptr;
+  dev_view->tile_start = nullptr;
   return PS_OK;
 }
 

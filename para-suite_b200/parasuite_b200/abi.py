@@ -72,7 +72,8 @@ class ps_read_batch(C.Structure):
                 ("tile_qual_off", C.c_void_p), ("tile_cigar_off", C.c_void_p), ("tile_exc_off", C.c_void_p),
                 ("exc", C.c_void_p), ("uniform_len", C.c_uint32), ("uniform_ncigar", C.c_uint32),
                 ("bases_bytes", C.c_uint64), ("qual_bytes", C.c_uint64), ("cigar_count", C.c_uint64),
-                ("exc_count", C.c_uint64), ("max_len", C.c_uint32), ("uniform_cigar", C.c_uint32), ("flags8", C.c_void_p), ("qual6", C.c_void_p)]
+                ("exc_count", C.c_uint64), ("max_len", C.c_uint32), ("uniform_cigar", C.c_uint32), ("flags8", C.c_void_p), ("qual6", C.c_void_p), ("start16", C.c_void_p),
+                ("tile_start", C.c_void_p)]
 
 
 class ps_comb_stats(C.Structure):

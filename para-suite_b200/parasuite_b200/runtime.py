@@ -82,6 +82,30 @@ class PinnedBatch:
                 s.cigar = None
                 skip = {"meta", "cigar"}
                 self.compact = True
+        start_sent = 4 * n
+        self.compact_start = False
+        if compact and n:
+            T = abi.PS_TILE_READS
+            st = np.asarray(host.ref_start[:n]).astype(np.int64)
+            fl = (np.asarray(host.meta[:n]) >> np.uint32(24))
+            live = (fl & (abi.PS_RF_UNMAPPED | abi.PS_RF_POS_ZERO)) == 0       # the others carry no defined start
+            nt = (n + T - 1) // T
+            big = np.int64(1) << 40
+            padded = np.full(nt * T, big, dtype=np.int64)
+            padded[:n] = np.where(live, st, big)
+            base = padded.reshape(nt, T).min(axis=1)
+            base = np.where(base == big, 0, base)
+            delta = np.where(live, st - np.repeat(base, T)[:n], 0)
+            if int(delta.max(initial=0)) <= 0xFFFF and int(delta.min(initial=0)) >= 0 and bool(np.all(st[~live] == st[~live])):
+                # reads without a defined start get the tile's base: nothing looks at their start
+                t16 = torch.from_numpy(delta.astype(np.uint16).view(np.uint8)).clone().pin_memory()
+                tb = torch.from_numpy(base.astype(np.uint32).view(np.uint8)).clone().pin_memory()
+                self._t["start16"], self._t["tile_start"] = t16, tb
+                s.start16, s.tile_start = t16.data_ptr(), tb.data_ptr()
+                s.ref_start = None
+                skip = skip | {"ref_start"}
+                start_sent = 2 * n + 4 * nt
+                self.compact_start = True
         qual_sent = host.qual_bytes
         self.packed_qual = False
         if compact and n and host.uniform_len:
@@ -110,8 +134,8 @@ class PinnedBatch:
             self._t[f] = t
             setattr(s, f, t.data_ptr())
         self.struct = s
-        per_read = 5 if self.compact else 8 + 4 * host.cigar_count / max(n, 1)
-        self.h2d_bytes = int(n * per_read + host.bases_bytes + qual_sent + host.exc_count * 4 + (host.n_tiles + 1) * 28)
+        per_read = 1 if self.compact else 4 + 4 * host.cigar_count / max(n, 1)
+        self.h2d_bytes = int(n * per_read + start_sent + host.bases_bytes + qual_sent + host.exc_count * 4 + (host.n_tiles + 1) * 28)
 
 
 class Context:

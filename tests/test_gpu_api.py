@@ -130,7 +130,9 @@ def test_compact_host_form_equals_the_full_one(oracle):
     ref = synth.synth_reference(91, [1_500_000, 700_000], n_run=800)
     batch = synth.synth_reads(ref, 200_003, 36, seed=14, n_ppm=3000)      # (special flags would kill the JVM in the pileup)
     full, comp = PinnedBatch(batch), PinnedBatch(batch, compact=True)
-    assert comp.compact and comp.packed_qual and comp.h2d_bytes == full.h2d_bytes - (7 + 9) * batch.n_reads
+    nt = (batch.n_reads + 255) // 256
+    assert comp.compact and comp.packed_qual and comp.compact_start
+    assert comp.h2d_bytes == full.h2d_bytes - (7 + 9 + 2) * batch.n_reads + 4 * nt
     ctx = Context(0)
     try:
         ctx.upload_reference(ref)
@@ -152,6 +154,14 @@ def test_compact_host_form_equals_the_full_one(oracle):
         assert np.array_equal(out["full"][1]["clusters"], out["compact"][1]["clusters"])
         assert np.array_equal(out["full"][1]["sites"], out["compact"][1]["sites"])
         assert np.array_equal(out["compact"][0]["wide"], oracle.profile_acc(ref, batch, 51, threads=4))
+        # reads without a defined start (unmapped, POS 0) travel with the tile's base as their start: the profile's
+        # filters never look at it
+        b2 = synth.synth_reads(ref, 60_000, 36, seed=17, special_ppm=20_000, n_ppm=3000)
+        c2 = PinnedBatch(b2, compact=True)
+        assert c2.compact_start
+        ctx.profile_begin(51)
+        ctx.profile_batch(c2)
+        assert np.array_equal(ctx.profile_end()["wide"], oracle.profile_acc(ref, b2, 51, threads=4))
         # a ragged batch has no compact form
         rb = synth.trim_uniform(synth.synth_reads(ref, 10_000, 36, seed=15), 20)
         assert not PinnedBatch(rb, compact=True).compact

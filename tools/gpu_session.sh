@@ -3,6 +3,6 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_profile.py tests/test_gpu_golden.py tests/test_gpu_bam.py tests/test_config1.py -m gpu -x -q > gpurun_out/r2_wq_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/r2_wq_tests.log
-timeout 600 python tools/bench_kernels.py --reads 4000000 --len 150 --mode 1 --max-len 176 --iters 8 --check > gpurun_out/r2_wq_bench.json 2> gpurun_out/r2_wq_bench.err
+timeout 900 python -m pytest tests/test_gpu_api.py tests/test_gpu_bam.py tests/test_gpu_stream.py -m gpu -x -q > gpurun_out/r2_compact_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_compact_tests.log
+timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
