@@ -3,6 +3,12 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_api.py tests/test_gpu_bam.py tests/test_gpu_stream.py -m gpu -x -q > gpurun_out/r2_compact_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/r2_compact_tests.log
-timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
+rm -f gpurun_out/r2_pf_variants.json
+for v in pf0 pf1 pf0 pf1; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --check >> gpurun_out/r2_pf_variants.json 2>> gpurun_out/r2_pf_variants.err
+done
+for v in pf0 pf1; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --len 50 --check >> gpurun_out/r2_pf_variants.json 2>> gpurun_out/r2_pf_variants.err
+done
