@@ -225,6 +225,8 @@ int ps_create(ps_ctx** out, int device) {
   if (const char* e = getenv("PARASUITE_B200_FLAG_SCAN_KERNEL")) ctx->pl_flag_scan_kernel = e[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PS_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->stream2 = nullptr; }
+  if (cudaStreamCreateWithFlags(&ctx->stream_rb, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->stream_rb = nullptr; }
+  if (cudaEventCreateWithFlags(&ctx->prof_done_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->prof_done_ev = nullptr; }
   for (int i = 0; i < PS_TIMER_RING; ++i) {
     cudaEventCreate(&ctx->ev_start[i]);
     cudaEventCreate(&ctx->ev_stop[i]);
@@ -262,6 +264,8 @@ void ps_destroy(ps_ctx* ctx) {
   for (auto& e : ctx->staged_done) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->staged_core) if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream_rb) cudaStreamDestroy(ctx->stream_rb);
+  if (ctx->prof_done_ev) cudaEventDestroy(ctx->prof_done_ev);
   ctx->ref_seq2.release(); ctx->ref_inv.release(); ctx->ref_contig.release();
   ctx->acc.release(); ctx->fault.release(); ctx->deferred.release(); ctx->t2c_mask.release();
   ctx->rg_okmap.release(); ctx->rg_off.release(); ctx->rg_bases.release(); ctx->rg_qual.release(); ctx->rg_op0.release();
@@ -344,7 +348,13 @@ constexpr size_t kEarlyReadbackMax = 64 << 10;   // with -q the vector holds a 2
 static void early_readback(ps_ctx* ctx, cudaStream_t s) {
   ctx->early_valid = false;
   if ((size_t)ctx->layout.total * 8 > kEarlyReadbackMax) return;
-  if (queue_readback(ctx, s) != cudaSuccess || cudaEventRecord(ctx->early_ev, s) != cudaSuccess) { cudaGetLastError(); return; }
+  // the copy goes to a stream of its own behind an event: on the kernels' stream it would sit between this tool's last
+  // kernel and whatever the caller queues next (the pileup kernels), two stream-op boundaries on the critical path
+  cudaStream_t rb = s;
+  if (ctx->stream_rb && ctx->prof_done_ev && cudaEventRecord(ctx->prof_done_ev, s) == cudaSuccess &&
+      cudaStreamWaitEvent(ctx->stream_rb, ctx->prof_done_ev, 0) == cudaSuccess)
+    rb = ctx->stream_rb;
+  if (queue_readback(ctx, rb) != cudaSuccess || cudaEventRecord(ctx->early_ev, rb) != cudaSuccess) { cudaGetLastError(); return; }
   ctx->early_valid = true;
   ctx->early_reads = ctx->reads_seen;
   ctx->early_stream = s;

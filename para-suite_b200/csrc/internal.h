@@ -122,6 +122,8 @@ struct ps_ctx {
   cudaEvent_t staged_done[2] = {nullptr, nullptr};
   cudaEvent_t staged_core[2] = {nullptr, nullptr};   // everything but the qualities of the slot's batch has arrived
   cudaStream_t stream2 = nullptr;                      // auxiliary stream: pileup of a batch whose qualities are still in flight
+  cudaStream_t stream_rb = nullptr;                    // read-back of the profile accumulators behind the last batch's kernel
+  cudaEvent_t prof_done_ev = nullptr;                  // that kernel's end, for stream_rb
   int staged_next = 0;
   uint64_t stage_serial = 0;   // uploads so far (a staged batch stays valid until the second-next one)
   // instrumentation

@@ -3,12 +3,6 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-rm -f gpurun_out/r2_pf_variants.json
-for v in pf0 pf1 pf0 pf1; do
-  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
-  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --check >> gpurun_out/r2_pf_variants.json 2>> gpurun_out/r2_pf_variants.err
-done
-for v in pf0 pf1; do
-  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
-  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --len 50 --check >> gpurun_out/r2_pf_variants.json 2>> gpurun_out/r2_pf_variants.err
-done
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/r2_rb_bench.json 2> gpurun_out/r2_rb_bench.err
+timeout 900 python -m pytest tests/test_gpu_profile.py tests/test_gpu_api.py tests/test_gpu_fused.py tests/test_gpu_distributed.py -m gpu -x -q > gpurun_out/r2_rb_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_rb_tests.log
