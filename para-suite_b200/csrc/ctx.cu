@@ -519,8 +519,10 @@ int ps_profile_end(ps_ctx* ctx, ps_profile_result* out) {
     PS_CUDA(ctx, cudaStreamSynchronize(ps));
   }
   ctx->early_valid = false;
-  // clear for the next run now, behind everything queued on that stream, instead of in front of its first kernel
-  if (clear_accumulators(ctx, acc_bytes, ps) == cudaSuccess) { ctx->clean_ptr = ctx->acc.p; ctx->clean_bytes = acc_bytes; }
+  // clear for the next run now instead of in front of its first kernel.  Every producer of the vector has completed (the
+  // host has just waited for the read-back that followed them), so the memsets need no place in the kernels' stream,
+  // where they would sit between whatever the caller has queued there (the pileup kernels) and the next run
+  if (clear_accumulators(ctx, acc_bytes, ctx->stream_rb ? ctx->stream_rb : ps) == cudaSuccess) { ctx->clean_ptr = ctx->acc.p; ctx->clean_bytes = acc_bytes; }
   else cudaGetLastError();
   unsigned long long fw;
   memcpy(&fw, static_cast<const char*>(ctx->h_acc) + acc_bytes, 8);
