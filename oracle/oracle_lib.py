@@ -21,12 +21,27 @@ SO = os.path.join(HERE, "_build", "libparasuite_oracle.so")
 _lib = None
 
 
-def build(force: bool = False) -> str:
+def _stale() -> bool:
     src = os.path.join(HERE, "parasuite_oracle.cpp")
     hdr = os.path.join(REPO, "include", "parasuite_b200.h")
-    stale = (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr))
-    if force or stale:
-        subprocess.check_call(["make", "-B", "-C", HERE], stdout=subprocess.DEVNULL)
+    return (not os.path.exists(SO)) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+
+
+def build(force: bool = False) -> str:
+    """Build the oracle if it is missing or older than its sources.  Safe when several processes call it at once (the
+    ranks of one torchrun job on a fresh box): one builds under a file lock, the others wait and find it up to date; the
+    Makefile writes under a temporary name and renames."""
+    if not (force or _stale()):
+        return SO
+    import fcntl
+    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    with open(os.path.join(HERE, "_build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():
+                subprocess.check_call(["make", "-B", "-C", HERE], stdout=subprocess.DEVNULL)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 
