@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -163,18 +164,48 @@ static int fasta_pack(const char* path, ps_packed_fasta* F, int threads) {
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
+// Page-locked slabs are expensive to make (cudaHostAlloc pins every page: ~0.1 s for a window of a few million reads),
+// and a process that runs `error` and then `clust` on one file, or a file after the other, would pay that per call: a
+// closed batcher hands its slabs to a small process-wide pool (at most kSlabPoolBytes), the next one takes them from there.
+struct SlabMem { uint8_t* p; size_t cap; };
+constexpr size_t kSlabPoolBytes = (size_t)3 << 30;
+std::mutex g_slab_mu;
+std::vector<SlabMem> g_slab_pool;
+size_t g_slab_pool_bytes = 0;
+
 struct Slab {            // one SoA batch in a single (page-locked when possible) allocation
   uint8_t* p = nullptr;
   size_t cap = 0;
   bool pinned = false;
   void release() {
     if (!p) return;
+    if (pinned) {
+      std::lock_guard<std::mutex> g(g_slab_mu);
+      if (g_slab_pool_bytes + cap <= kSlabPoolBytes && g_slab_pool.size() < 8) {
+        g_slab_pool.push_back({p, cap});
+        g_slab_pool_bytes += cap;
+        p = nullptr; cap = 0;
+        return;
+      }
+    }
     if (pinned) cudaFreeHost(p); else free(p);
     p = nullptr; cap = 0;
   }
   bool reserve(size_t n) {
     if (n <= cap) return true;
     release();
+    {
+      std::lock_guard<std::mutex> g(g_slab_mu);
+      int best = -1;
+      for (int k = 0; k < (int)g_slab_pool.size(); ++k)
+        if (g_slab_pool[k].cap >= n && (best < 0 || g_slab_pool[k].cap < g_slab_pool[best].cap)) best = k;
+      if (best >= 0) {
+        p = g_slab_pool[best].p; cap = g_slab_pool[best].cap; pinned = true;
+        g_slab_pool_bytes -= cap;
+        g_slab_pool.erase(g_slab_pool.begin() + best);
+        return true;
+      }
+    }
     const size_t want = n + n / 8 + 4096;
     void* q = nullptr;
     if (cudaHostAlloc(&q, want, cudaHostAllocDefault) == cudaSuccess) { p = (uint8_t*)q; pinned = true; }

@@ -11,6 +11,7 @@ from parasuite_b200.runtime import Context, DeviceBatch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--bam-reads", type=int, default=300_000)
+ap.add_argument("--bam-repeat", type=int, default=10, help="a second file with the records repeated this many times (profile only)")
 args = ap.parse_args()
 peak = 6552.0
 try:
@@ -68,4 +69,28 @@ with tempfile.TemporaryDirectory() as td:
         tq = time.perf_counter() - t0
     out["bam"].update({"profile_bam_reads_per_s": args.bam_reads / tp, "pileup_bam_reads_per_s": args.bam_reads / tq,
                        "host_threads": os.cpu_count()})
+    if args.bam_repeat > 1:
+        # a file large enough for the batcher's steady state: the same records repeated (the profile does not mind the
+        # order; the header still says coordinate-sorted)
+        import gzip, struct
+        from parasuite_b200.bamio import _bgzf_block
+        data = gzip.open(bam, "rb").read()
+        l_text, = struct.unpack_from("<I", data, 4)
+        o = 8 + l_text
+        n_ref, = struct.unpack_from("<I", data, o)
+        o += 4
+        for _ in range(n_ref):
+            ln, = struct.unpack_from("<I", data, o)
+            o += 8 + ln
+        big = os.path.join(td, "big.bam")
+        with open(big, "wb") as f:
+            stream_bytes = data[:o] + data[o:] * args.bam_repeat
+            for k in range(0, len(stream_bytes), 0xFF00):
+                f.write(_bgzf_block(stream_bytes[k:k + 0xFF00], 6))
+            f.write(_bgzf_block(b""))
+        n_big = args.bam_reads * args.bam_repeat
+        for _ in range(2):
+            t0 = time.perf_counter(); ctx.profile_bam(big, 51); tb = time.perf_counter() - t0
+        out["bam"]["big_file"] = {"reads": n_big, "bam_bytes": os.path.getsize(big), "profile_bam_reads_per_s": n_big / tb,
+                                  "note": "batcher-bound: BGZF inflate + record location + packing on the host threads"}
 print(json.dumps(out, indent=1))
