@@ -15,12 +15,14 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "parasuite_b200.h"
@@ -73,10 +75,21 @@ struct RawFasta {      // IndexedFastaSequenceFile: raw bytes (case kept) by con
     const Entry& x = e[(size_t)contig];
     if (stop > (int64_t)x.len) return 1;
     if (start < 1) return 2;
-    out.resize((size_t)(stop - start + 1));
-    for (int64_t b = start - 1, k = 0; b < stop; ++b, ++k) {
-      const uint64_t at = x.offset + (uint64_t)b / x.linebases * x.linewidth + (uint64_t)b % x.linebases;
-      out[(size_t)k] = at < n ? (char)p[at] : 'N';
+    const size_t len = (size_t)(stop - start + 1);
+    out.resize(len);
+    // one division for the first base, then whole line segments (a division per base was most of the writer's time)
+    const uint64_t b0 = (uint64_t)(start - 1);
+    uint64_t col = x.linebases ? b0 % x.linebases : 0;
+    uint64_t at = x.offset + (x.linebases ? b0 / x.linebases * x.linewidth : 0) + col;
+    size_t k = 0;
+    while (k < len) {
+      const size_t run = x.linebases ? (size_t)std::min<uint64_t>(len - k, x.linebases - col) : len - k;
+      if (at + run <= n) memcpy(&out[k], p + at, run);
+      else
+        for (size_t j = 0; j < run; ++j) out[k + j] = at + j < n ? (char)p[at + j] : 'N';
+      k += run;
+      at += run + (x.linewidth - x.linebases);
+      col = 0;
     }
     return 0;
   }
@@ -99,6 +112,18 @@ const char* kStrand[3] = {"+", "-", "+/-"};
 
 }  // namespace
 
+// Row text is put together by hand (to_chars + appends into one buffer per file, written out a megabyte at a time): the
+// rows are the writer's whole cost -- three fprintf calls with a dozen conversions each were 4 us per cluster, four times
+// what the record loop in front of them takes per cluster.
+struct RowBuf {
+  std::string s;
+  void num(long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); s.append(b, r.ptr); }
+  void unum(unsigned long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); s.append(b, r.ptr); }
+  void flush_to(FILE* f, bool force) {
+    if (s.size() >= ((size_t)1 << 20) || (force && !s.empty())) { fwrite(s.data(), 1, s.size(), f); s.clear(); }
+  }
+};
+
 struct ps_clust_writer {
   ps_flush* flush = nullptr;
   RawFasta fa;
@@ -109,6 +134,9 @@ struct ps_clust_writer {
   // the cluster being assembled (Java: tempClusterBytes, tempClusterEnd)
   bool have = false;
   std::string bytes;
+  RowBuf b_pileup, b_ccr_fa, b_ccr_tsv;      // rows not yet written
+  struct Job { ps_cluster c; ps_flush_row row; std::string bytes; };
+  std::vector<Job> jobs;                     // closed clusters of the feed in progress, rows still to be formatted
   int64_t cluster_end = 0;
   uint64_t cluster_first = 0;
   // closed records waiting for their cluster to end in the read stream
@@ -121,13 +149,19 @@ struct ps_clust_writer {
 static int cw_fail(ps_clust_writer* w, int st, const std::string& m) { w->err = m; return st; }
 
 static void cw_close_files(ps_clust_writer* w) {
+  if (w->f_pileup) w->b_pileup.flush_to(w->f_pileup, true);
+  if (w->f_ccr_fa) w->b_ccr_fa.flush_to(w->f_ccr_fa, true);
+  if (w->f_ccr_tsv) w->b_ccr_tsv.flush_to(w->f_ccr_tsv, true);
   for (FILE** f : {&w->f_pileup, &w->f_ccr_fa, &w->f_ccr_tsv, &w->f_report, &w->f_sitefreq, &w->f_sitepos})
     if (*f) { fclose(*f); *f = nullptr; }
 }
 
 // rows of one closed cluster (PileupClusters.java:262-343)
-static int cw_write_cluster(ps_clust_writer* w, const ps_cluster& c, const ps_flush_row& row) {
-  if (!row.emitted) return PS_OK;                                            // numReadsPerCluster < minReadCoverage (:180)
+struct RowOut { RowBuf pileup, ccr_fa, ccr_tsv; uint64_t rows = 0, ccr = 0, ccr_before = 0; };
+
+static void cw_format_cluster(const ps_clust_writer* w, const ps_cluster& c, const ps_flush_row& row, const std::string& bytes,
+                              RowOut& O) {
+  if (!row.emitted) return;                                            // numReadsPerCluster < minReadCoverage (:180)
   const std::string chr = c.contig < w->fa.e.size() ? w->fa.e[c.contig].name : std::string("?");
   const std::string id = "cl_" + std::to_string(c.running_id) + "_" + chr;   // :356
   const char* comb = kStrand[c.combined_strand < 3 ? c.combined_strand : 2];
@@ -135,24 +169,65 @@ static int cw_write_cluster(ps_clust_writer* w, const ps_cluster& c, const ps_fl
   if (row.has_ccr) {                                                         // tempBestMutationPos > 0 (:262)
     std::string ccr;
     const int rc = w->fa.fetch(c.contig, (int64_t)row.best_pos - 20, (int64_t)row.best_pos + 20, ccr);
-    if (rc == 2) w->ccr_start_before_contig++;
+    if (rc == 2) O.ccr_before++;
     if (rc != 0) ccr.clear();                                                // catch (SAMException) -> new byte[0] (:278)
     else if (c.combined_strand == 1) reverse_complement(ccr);                // getStrandOrientation().equals("-") (:271)
     for (char& ch : ccr) ch = (char)toupper((unsigned char)ch);              // :283-288
-    fprintf(w->f_ccr_fa, ">%s 20-anchor-20 %s:%s:%d-%d\n%s\n", id.c_str(), chr.c_str(), comb, row.best_pos - 20,
-            row.best_pos + 20, ccr.c_str());
-    fprintf(w->f_ccr_tsv, "Gene\t%s\t%s\t%s\t%d\t%d\t%d\t%d\t%s\t%d\t%u\t%u\t%u\t%s\t%u\t%s\n", id.c_str(), comb, chr.c_str(),
-            c.start, c.end, row.best_pos - 20, row.best_pos + 20, ccr.c_str(), row.best_pos, c.num_reads, row.num_t2c_sites,
-            row.best_count, java_double(row.best_value).c_str(), c.num_t2c, fraction.c_str());
-    w->ccr_written++;
+    {
+      RowBuf& o = O.ccr_fa;
+      o.s += '>'; o.s += id; o.s += " 20-anchor-20 "; o.s += chr; o.s += ':'; o.s += comb; o.s += ':';
+      o.num(row.best_pos - 20); o.s += '-'; o.num(row.best_pos + 20); o.s += '\n'; o.s += ccr; o.s += '\n';
+    }
+    {
+      RowBuf& o = O.ccr_tsv;
+      o.s += "Gene\t"; o.s += id; o.s += '\t'; o.s += comb; o.s += '\t'; o.s += chr; o.s += '\t';
+      o.num(c.start); o.s += '\t'; o.num(c.end); o.s += '\t'; o.num(row.best_pos - 20); o.s += '\t'; o.num(row.best_pos + 20);
+      o.s += '\t'; o.s += ccr; o.s += '\t'; o.num(row.best_pos); o.s += '\t'; o.unum(c.num_reads); o.s += '\t';
+      o.unum(row.num_t2c_sites); o.s += '\t'; o.unum(row.best_count); o.s += '\t'; o.s += java_double(row.best_value);
+      o.s += '\t'; o.unum(c.num_t2c); o.s += '\t'; o.s += fraction; o.s += '\n';
+    }
+    O.ccr++;
   }
-  std::string seq = w->bytes;
-  if (c.first_reverse) reverse_complement(seq);                              // :318-321
-  fprintf(w->f_pileup, "%s\t%s\t%d\t%d\t%s\t%u\t%u\t%u\t%s\t%s\t%s\t%zu\n", id.c_str(), chr.c_str(), c.start, c.end,
-          c.first_reverse ? "-" : "+", c.num_reads, c.num_t2c, row.num_t2c_sites, fraction.c_str(), seq.c_str(), comb,
-          seq.size());
-  w->rows_written++;
-  return PS_OK;
+  {
+    RowBuf& o = O.pileup;
+    o.s += id; o.s += '\t'; o.s += chr; o.s += '\t'; o.num(c.start); o.s += '\t'; o.num(c.end); o.s += '\t';
+    o.s += c.first_reverse ? '-' : '+'; o.s += '\t'; o.unum(c.num_reads); o.s += '\t'; o.unum(c.num_t2c); o.s += '\t';
+    o.unum(row.num_t2c_sites); o.s += '\t'; o.s += fraction; o.s += '\t';
+    const size_t at = o.s.size();
+    o.s += bytes;
+    if (c.first_reverse) {                                                     // :318-321, in place in the row
+      std::string seq(o.s, at);
+      reverse_complement(seq);
+      o.s.replace(at, std::string::npos, seq);
+    }
+    o.s += '\t'; o.s += comb; o.s += '\t'; o.unum(bytes.size()); o.s += '\n';
+  }
+  O.rows++;
+}
+
+// Formats the rows of the queued clusters on all host threads (the clusters are independent once the flush arithmetic
+// has run; every thread takes a contiguous range) and appends them to the files in cluster order.
+static void cw_write_jobs(ps_clust_writer* w) {
+  const size_t n = w->jobs.size();
+  if (n == 0) return;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, n / 256 + 1}));
+  std::vector<RowOut> outs(T);
+  auto work = [&](size_t t) {
+    for (size_t k = n * t / T; k < n * (t + 1) / T; ++k) cw_format_cluster(w, w->jobs[k].c, w->jobs[k].row, w->jobs[k].bytes, outs[t]);
+  };
+  if (T == 1) work(0);
+  else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < T; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+  }
+  for (size_t t = 0; t < T; ++t) {
+    w->b_pileup.s += outs[t].pileup.s; w->b_ccr_fa.s += outs[t].ccr_fa.s; w->b_ccr_tsv.s += outs[t].ccr_tsv.s;
+    w->b_pileup.flush_to(w->f_pileup, false); w->b_ccr_fa.flush_to(w->f_ccr_fa, false); w->b_ccr_tsv.flush_to(w->f_ccr_tsv, false);
+    w->rows_written += outs[t].rows; w->ccr_written += outs[t].ccr; w->ccr_start_before_contig += outs[t].ccr_before;
+  }
+  w->jobs.clear();
 }
 
 extern "C" {
@@ -243,10 +318,9 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
       w->starts.pop_front();
       if (w->have) {                                                        // the previous cluster is flushed (:178)
         if (w->pending.empty() || w->pending.front().c.first_read != w->cluster_first)
-          return cw_fail(w, PS_ERR_STATE, "cluster records and read stream disagree (records must be fed in order)");
-        const int st = cw_write_cluster(w, w->pending.front().c, w->pending.front().row);
+          { cw_write_jobs(w); return cw_fail(w, PS_ERR_STATE, "cluster records and read stream disagree (records must be fed in order)"); }
+        w->jobs.push_back({w->pending.front().c, w->pending.front().row, w->bytes});
         w->pending.pop_front();
-        if (st) return st;
       }
       w->have = true;
       w->cluster_first = ordinal;
@@ -260,14 +334,14 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
           const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
           if (rc != 0) {      // SAMException outside any try block: the JVM dies here
             w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
-            return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)");
+            { cw_write_jobs(w); return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)"); }
           }
           w->bytes += piece;
         }
         if (op != 1u) cur += len;                                           // every non-I element advances (:402-404)
       }
     } else {
-      if (!w->have) return cw_fail(w, PS_ERR_STATE, "a kept read in front of the first cluster start");
+      if (!w->have) { cw_write_jobs(w); return cw_fail(w, PS_ERR_STATE, "a kept read in front of the first cluster start"); }
       if (end > w->cluster_end) {                                           // :421
         int64_t cur = start;
         for (uint32_t e = 0; e < ncig; ++e) {
@@ -281,7 +355,7 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
             const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
             if (rc != 0) {
               w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
-              return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)");
+              { cw_write_jobs(w); return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)"); }
             }
             const int64_t overhang = w->cluster_end - cur + 1;               // :449
             if (overhang > 0) w->bytes.append(piece, (size_t)overhang, std::string::npos);   // mergeByteSubArrays (:453-457)
@@ -294,6 +368,7 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
     }
   }
   w->reads_fed += n;
+  cw_write_jobs(w);
   return PS_OK;
 }
 

@@ -69,6 +69,12 @@ with tempfile.TemporaryDirectory() as td:
         tq = time.perf_counter() - t0
     out["bam"].update({"profile_bam_reads_per_s": args.bam_reads / tp, "pileup_bam_reads_per_s": args.bam_reads / tq,
                        "host_threads": os.cpu_count()})
+    # the whole tools: loop + output files
+    for _ in range(2):
+        t0 = time.perf_counter(); ctx.error_bam(bam, 51); te = time.perf_counter() - t0
+        t0 = time.perf_counter(); ctr = ctx.clust_bam(bam, os.path.join(td, "clusters.tsv"), None, 1); tc = time.perf_counter() - t0
+    out["bam"].update({"error_tool_reads_per_s": args.bam_reads / te, "clust_tool_reads_per_s": args.bam_reads / tc,
+                       "clust_tool_clusters": int(ctr["n_clusters"])})
     if args.bam_repeat > 1:
         # a file large enough for the batcher's steady state: the same records repeated (the profile does not mind the
         # order; the header still says coordinate-sorted)
