@@ -389,7 +389,7 @@ void ps_fasta_free(ps_packed_fasta* f);
 /* Opens a coordinate-sorted BAM (PS_ERR_UNSORTED otherwise: ErrorProfiling.java:124-132).  Contigs are matched to the
  * FASTA by name; max_batch_reads = 0 picks a default; threads <= 0 uses the host cores. */
 int ps_bam_open(ps_bam** out, const char* bam_path, const ps_packed_fasta* ref, uint64_t max_batch_reads, int threads);
-/* 1: *batch filled (host pointers, valid until the second-next call); 0: end of file; < 0: status */
+/* 1: *batch filled (host pointers, valid until the third-next call); 0: end of file; < 0: status */
 int ps_bam_next(ps_bam* b, ps_read_batch* batch);
 const char* ps_bam_error(const ps_bam* b);
 void ps_bam_close(ps_bam* b);

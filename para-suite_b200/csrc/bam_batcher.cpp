@@ -258,8 +258,8 @@ struct ps_bam {
   const ps_packed_fasta* fa = nullptr;
   uint64_t max_batch = 0;
   int threads = 1;
-  Slab slab[2];
-  int cur = 0;
+  Slab slab[3];                    // a batch's arrays stay valid until the third-next ps_bam_next: the file tools keep one
+  int cur = 0;                     // window on the device, one with the host writer and fill the third
   uint64_t ordinal = 0;
   std::string err;
   std::vector<uint64_t> rec_off;   // scratch: offsets of the records of the batch being built
@@ -568,13 +568,12 @@ void ps_bam_close(ps_bam* b) {
   if (getenv("PARASUITE_B200_BATCHER_TIMING"))
     fprintf(stderr, "[ps_bam] inflate %.3f s, locate %.3f s, sizes %.3f s, pack %.3f s, %llu records, %d threads\n", b->t_fill, b->t_locate,
             b->t_pass1, b->t_pass2, (unsigned long long)b->ordinal, b->threads);
-  b->slab[0].release();
-  b->slab[1].release();
+  for (Slab& s : b->slab) s.release();
   delete b;
 }
 
 // Next batch of at most max_batch_reads records, in file order.  Returns 1 (batch filled; its arrays stay valid until
-// the second-next call), 0 at end of file, or a negative status.
+// the third-next call), 0 at end of file, or a negative status.
 int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   if (!B || !out) return PS_ERR_INVALID_ARG;
   if (!B->header_done) return bam_fail(B, PS_ERR_STATE, "BAM not open");
@@ -758,7 +757,7 @@ int ps_bam_next(ps_bam* B, ps_read_batch* out) {
   size_t off_tq = up(off_tb + (n_tiles + 1) * 8), off_tc = up(off_tq + (n_tiles + 1) * 8), off_te = up(off_tc + (n_tiles + 1) * 8);
   const size_t total = up(off_te + (n_tiles + 1) * 4);
   Slab& S = B->slab[B->cur];
-  B->cur ^= 1;
+  B->cur = (B->cur + 1) % 3;
   if (!S.reserve(total)) return bam_fail(B, PS_ERR_OOM, "out of host memory for the batch");
   uint32_t* meta = (uint32_t*)(S.p + off_meta);
   uint32_t* ref_start = (uint32_t*)(S.p + off_start);

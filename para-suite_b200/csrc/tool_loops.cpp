@@ -20,7 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -33,10 +36,14 @@ struct ps_multi {
   bool owns = true;
   ps_packed_fasta* fasta = nullptr;
   std::string err;
+  std::mutex err_mu;          // the window loop's sink thread reports errors too
 };
 
 static int multi_fail(ps_multi* m, int st, const std::string& msg) {
-  if (m) m->err = msg;
+  if (m) {
+    std::lock_guard<std::mutex> g(m->err_mu);
+    m->err = msg;
+  }
   return st;
 }
 
@@ -122,6 +129,7 @@ void merge_head(OpenCluster& o, const ps_cluster& hp, const std::vector<ps_site>
 // what one window hands to its consumer: the clusters that closed with it (site_begin / site_end index `sites`), and the
 // first read of the cluster still open behind it
 struct WindowOut {
+  ps_read_batch host{};        // copy of the window's batch descriptor (the arrays live in the batcher's slab)
   const ps_read_batch* batch;
   uint64_t first_ordinal;
   std::vector<ps_cluster> closed;
@@ -134,7 +142,7 @@ using WindowSink = std::function<int(const WindowOut&)>;
 struct InFlight {
   ps_ctx* ctx = nullptr;
   ps_pileup* h = nullptr;
-  ps_read_batch host{};       // the window's records (slab of the batcher: valid until the second-next ps_bam_next)
+  ps_read_batch host{};       // the window's records (slab of the batcher: valid until the third-next ps_bam_next)
   uint64_t offset = 0;
   bool live = false;
 };
@@ -157,6 +165,17 @@ int pileup_windows(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts
   OpenCluster open;
   uint64_t created = 0, offset = 0, window = 0;
   InFlight fl[2];
+  // The sink (the host writer of `clust`: cluster sequences, rows, files) runs on a thread of its own, one window at a
+  // time and in file order, while this thread decodes the next window: the batcher keeps three slabs, so the records
+  // of the window in the sink's hands stay valid until its successor has been handed over (which joins it first).
+  std::thread sink_thread;
+  int sink_rc = PS_OK;
+  auto join_sink = [&]() -> int {
+    if (sink_thread.joinable()) sink_thread.join();
+    const int rc = sink_rc;
+    sink_rc = PS_OK;
+    return rc;
+  };
 
   // completes window `f`: fetches its records, merges the boundary, hands the closed clusters to the sink
   auto complete = [&](InFlight& f) -> int {
@@ -177,8 +196,10 @@ int pileup_windows(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts
     counters->num_reads_processed += ctr.num_reads_processed;
     counters->skipped_due_indel += ctr.skipped_due_indel;
     counters->double_stranded += ctr.double_stranded;
-    WindowOut out;
-    out.batch = &f.host;
+    auto out_p = std::make_shared<WindowOut>();
+    WindowOut& out = *out_p;
+    out.host = f.host;
+    out.batch = &out.host;
     out.first_ordinal = f.offset;
     // head partial -> the open cluster
     {
@@ -244,7 +265,10 @@ int pileup_windows(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts
     out.open_first_read = open.have ? open.c.first_read : 0;
     counters->n_clusters += out.closed.size();
     counters->n_sites += out.sites.size();
-    return sink(out);
+    const int prev_rc = join_sink();                       // the window before this one has been written
+    if (prev_rc != PS_OK) return prev_rc;
+    sink_thread = std::thread([&sink, &sink_rc, out_p] { sink_rc = sink(*out_p); });
+    return PS_OK;
   };
 
   for (;; ++window) {
@@ -287,6 +311,10 @@ int pileup_windows(ps_multi* m, const char* bam_path, const ps_pileup_opts* opts
   for (int i = 0; i < 2 && st == PS_OK; ++i) {
     InFlight& f = fl[(window + i) & 1];
     if (f.live) st = complete(f);
+  }
+  {
+    const int rc = join_sink();
+    if (st == PS_OK) st = rc;
   }
   for (InFlight& f : fl)
     if (f.live) { ps_pileup_close(f.h); f.live = false; }
