@@ -3,7 +3,12 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_all_tests.log 2>&1
-echo "tests rc=$?" >> gpurun_out/r2_all_tests.log
-timeout 1500 python tools/bench_extra.py --bam-reads 1000000 --bam-repeat 1 > gpurun_out/r2_bench_extra_tools.json 2> gpurun_out/r2_bench_extra_tools.err
-PARASUITE_B200_WINDOW_READS=250000 PARASUITE_B200_BATCH_READS=250000 timeout 1500 python tools/bench_extra.py --bam-reads 1000000 --bam-repeat 1 > gpurun_out/r2_bench_extra_tools_w.json 2> gpurun_out/r2_bench_extra_tools_w.err
+rm -f gpurun_out/r2_rg_variants.json
+for v in rg3 rg4 rg3 rg4; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --check >> gpurun_out/r2_rg_variants.json 2>> gpurun_out/r2_rg_variants.err
+done
+for v in rg3 rg4; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --reads 4000000 --len 60 --max-len 64 --trim 30 --check >> gpurun_out/r2_rg_variants.json 2>> gpurun_out/r2_rg_variants.err
+done
