@@ -3,12 +3,8 @@
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-rm -f gpurun_out/r2_rg_variants.json
-for v in rg3 rg4 rg3 rg4; do
-  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
-  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --check >> gpurun_out/r2_rg_variants.json 2>> gpurun_out/r2_rg_variants.err
-done
-for v in rg3 rg4; do
-  lib=$PWD/para-suite_b200/lib/libparasuite_b200_$v.so
-  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --reads 4000000 --len 60 --max-len 64 --trim 30 --check >> gpurun_out/r2_rg_variants.json 2>> gpurun_out/r2_rg_variants.err
-done
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_all_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2_all_tests.log
+timeout 600 python tools/bench_kernels.py --reads 4000000 --len 44 --trim 18 --check > gpurun_out/r2_ragged_bench.json 2> gpurun_out/r2_ragged_bench.err
+timeout 600 python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --check > gpurun_out/r2_ragged_bench36.json 2>> gpurun_out/r2_ragged_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_ragged_launches.csv python tools/bench_kernels.py --reads 10000000 --len 36 --trim 20 --iters 4 > gpurun_out/r2_ragged_ncu.log 2>&1
