@@ -790,8 +790,13 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
     const uint32_t n_wt = (uint32_t)((b.n_reads + WT_READS - 1) / WT_READS);   // the fast kernel takes every read
     const uint32_t nw = (L + 15) / 16;
     cudaError_t e;
+    // read lengths sequencers commonly leave get an instantiation with the length as a compile-time constant (static loop
+    // bounds, the last word's counters packed): 20-25 % faster than the run-time-length ones
     if (L == 36) e = launch_fast<3, 6, 36>(ctx, P, n_wt, stream);
     else if (L == 50) e = launch_fast<4, 5, 50>(ctx, P, n_wt, stream);
+    else if (L == 51) e = launch_fast<4, 5, 51>(ctx, P, n_wt, stream);
+    else if (L == 40) e = launch_fast<3, 6, 40>(ctx, P, n_wt, stream);
+    else if (L == 32) e = launch_fast<2, 6, 32>(ctx, P, n_wt, stream);
     else if (nw == 1) e = launch_fast<1, 6, 0>(ctx, P, n_wt, stream);
     else if (nw == 2) e = launch_fast<2, 6, 0>(ctx, P, n_wt, stream);
     else if (nw == 3) e = launch_fast<3, 5, 0>(ctx, P, n_wt, stream);
@@ -858,10 +863,11 @@ cudaError_t launch_profile(ps_ctx* ctx, const DeviceBatch& b, uint64_t ordinal0,
       Q.first_read = c0;
       Q.off3 = nullptr;
       const uint32_t n_wt = (uint32_t)((cn + WT_READS - 1) / WT_READS);
-      if (nw == 1) e = launch_fast<1, 6, 0, true>(ctx, Q, n_wt, stream);
-      else if (nw == 2) e = launch_fast<2, 6, 0, true>(ctx, Q, n_wt, stream);
-      else if (nw == 3) e = launch_fast<3, 5, 0, true>(ctx, Q, n_wt, stream);
-      else e = launch_fast<4, 5, 0, true>(ctx, Q, n_wt, stream);
+      // (the row length S = 16 * nw is a compile-time constant of these instantiations)
+      if (nw == 1) e = launch_fast<1, 6, 16, true>(ctx, Q, n_wt, stream);
+      else if (nw == 2) e = launch_fast<2, 6, 32, true>(ctx, Q, n_wt, stream);
+      else if (nw == 3) e = launch_fast<3, 5, 48, true>(ctx, Q, n_wt, stream);
+      else e = launch_fast<4, 5, 64, true>(ctx, Q, n_wt, stream);
       if (e != cudaSuccess) return e;
       if (P.okmap && (e = launch_qhist(ctx, Q.b.qual, Q.b.meta, P.okmap, cn, S, 0, P.acc, stream)) != cudaSuccess) return e;
     }

@@ -94,7 +94,8 @@ def test_random_records(ctx, oracle, seed, kinds):
 
 
 @pytest.mark.parametrize("mode,L,max_len,n", [(0, 36, 51, 300_000), (0, 50, 51, 200_000), (1, 150, 176, 100_000),
-                                              (0, 17, 20, 50_001)])
+                                              (0, 17, 20, 50_001), (0, 40, 51, 100_003), (0, 51, 51, 100_003),
+                                              (0, 32, 40, 100_003), (0, 64, 64, 60_001), (0, 47, 51, 60_001)])
 def test_synthetic(ctx, oracle, mode, L, max_len, n):
     from parasuite_b200 import synth
     ref = synth.synth_reference(11 + L, [3_000_000, 2_000_000], n_run=2000)
