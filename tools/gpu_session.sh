@@ -1,7 +1,14 @@
 #!/bin/bash
-# scratch: one gpurun call -- last check of the final library
+# scratch: one gpurun call
 set -x
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_final_smoke.log 2>&1
+rm -f gpurun_out/r2_b5_variants.json
+for v in b5 "" b5 ""; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200${v:+_$v}.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --check >> gpurun_out/r2_b5_variants.json 2>> gpurun_out/r2_b5_variants.err
+done
+for v in b5 ""; do
+  lib=$PWD/para-suite_b200/lib/libparasuite_b200${v:+_$v}.so
+  PARASUITE_B200_LIB=$lib timeout 600 python tools/bench_kernels.py --iters 16 --len 50 --check >> gpurun_out/r2_b5_variants.json 2>> gpurun_out/r2_b5_variants.err
+done
