@@ -95,34 +95,57 @@ struct RawFasta {      // IndexedFastaSequenceFile: raw bytes (case kept) by con
   }
 };
 
-void reverse_complement(std::string& s) {   // htsjdk SequenceUtil.reverseComplement: only ACGTacgt are mapped
-  auto comp = [](char c) {
-    switch (c) {
-      case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
-      case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
-      default: return c;
-    }
-  };
-  const size_t n = s.size();
-  for (size_t i = 0; i < n / 2; ++i) { const char a = comp(s[i]), b = comp(s[n - 1 - i]); s[i] = b; s[n - 1 - i] = a; }
-  if (n & 1) s[n / 2] = comp(s[n / 2]);
+struct CompTable {     // htsjdk SequenceUtil.reverseComplement: only ACGTacgt are mapped
+  unsigned char t[256];
+  CompTable() {
+    for (int c = 0; c < 256; ++c) t[c] = (unsigned char)c;
+    const char* from = "ACGTacgt"; const char* to = "TGCAtgca";
+    for (int k = 0; k < 8; ++k) t[(unsigned char)from[k]] = (unsigned char)to[k];
+  }
+};
+const CompTable kComp;
+
+void reverse_complement(char* s, size_t n) {
+  for (size_t i = 0; i < n / 2; ++i) {
+    const char a = (char)kComp.t[(unsigned char)s[i]], b = (char)kComp.t[(unsigned char)s[n - 1 - i]];
+    s[i] = b; s[n - 1 - i] = a;
+  }
+  if (n & 1) s[n / 2] = (char)kComp.t[(unsigned char)s[n / 2]];
 }
 
 const char* kStrand[3] = {"+", "-", "+/-"};
 
 }  // namespace
 
-// Row text is put together by hand (to_chars + appends into one buffer per file, written out a megabyte at a time): the
-// rows are the writer's whole cost -- three fprintf calls with a dozen conversions each were 4 us per cluster, four times
-// what the record loop in front of them takes per cluster.
+// Row text is put together by hand (raw appends into one growing buffer per file, written out a megabyte at a time):
+// the rows are the writer's whole cost -- three fprintf calls with a dozen conversions each were 4 us per cluster, and
+// std::string appends with their capacity checks and temporaries were still 2.5.
 struct RowBuf {
-  std::string s;
-  void num(long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); s.append(b, r.ptr); }
-  void unum(unsigned long long v) { char b[24]; auto r = std::to_chars(b, b + sizeof b, v); s.append(b, r.ptr); }
+  char* d = nullptr;
+  size_t n = 0, cap = 0;
+  RowBuf() = default;
+  RowBuf(const RowBuf&) = delete;
+  RowBuf& operator=(const RowBuf&) = delete;
+  RowBuf(RowBuf&& o) noexcept : d(o.d), n(o.n), cap(o.cap) { o.d = nullptr; o.n = o.cap = 0; }
+  ~RowBuf() { free(d); }
+  char* room(size_t need) {               // a cursor with `need` bytes behind it; took() says how far it got
+    if (n + need > cap) {
+      cap = std::max<size_t>((n + need) * 2, (size_t)1 << 16);
+      d = (char*)realloc(d, cap);
+      if (!d) abort();
+    }
+    return d + n;
+  }
+  void took(char* end) { n = (size_t)(end - d); }
+  void append(const RowBuf& o) { if (o.n) { char* p = room(o.n); memcpy(p, o.d, o.n); n += o.n; } }
   void flush_to(FILE* f, bool force) {
-    if (s.size() >= ((size_t)1 << 20) || (force && !s.empty())) { fwrite(s.data(), 1, s.size(), f); s.clear(); }
+    if (n >= ((size_t)1 << 20) || (force && n)) { fwrite(d, 1, n, f); n = 0; }
   }
 };
+static inline char* put_s(char* p, const char* s, size_t n) { memcpy(p, s, n); return p + n; }
+static inline char* put_s(char* p, const std::string& s) { return put_s(p, s.data(), s.size()); }
+static inline char* put_i(char* p, long long v) { return std::to_chars(p, p + 24, v).ptr; }
+static inline char* put_u(char* p, unsigned long long v) { return std::to_chars(p, p + 24, v).ptr; }
 
 struct ps_clust_writer {
   ps_flush* flush = nullptr;
@@ -162,45 +185,58 @@ struct RowOut { RowBuf pileup, ccr_fa, ccr_tsv; uint64_t rows = 0, ccr = 0, ccr_
 static void cw_format_cluster(const ps_clust_writer* w, const ps_cluster& c, const ps_flush_row& row, const std::string& bytes,
                               RowOut& O) {
   if (!row.emitted) return;                                            // numReadsPerCluster < minReadCoverage (:180)
-  const std::string chr = c.contig < w->fa.e.size() ? w->fa.e[c.contig].name : std::string("?");
-  const std::string id = "cl_" + std::to_string(c.running_id) + "_" + chr;   // :356
+  static const std::string unknown("?");
+  const std::string& chr = c.contig < w->fa.e.size() ? w->fa.e[c.contig].name : unknown;
+  char id[64 + 2048];                                                  // "cl_" + running id + "_" + chromosome (:356)
+  size_t id_n;
+  {
+    char* p = put_s(id, "cl_", 3);
+    p = put_u(p, c.running_id);
+    *p++ = '_';
+    p = put_s(p, chr.data(), std::min<size_t>(chr.size(), 2047));      // (.fai names are read with %2047[^\t])
+    id_n = (size_t)(p - id);
+  }
   const char* comb = kStrand[c.combined_strand < 3 ? c.combined_strand : 2];
-  const std::string fraction = java_double(row.fraction);
+  const size_t comb_n = strlen(comb);
+  char fraction[40];
+  const size_t fraction_n = (size_t)(java_double_to(fraction, row.fraction) - fraction);
+  const size_t fixed = id_n + chr.size() + 512;                        // everything in a row but the sequences
   if (row.has_ccr) {                                                         // tempBestMutationPos > 0 (:262)
-    std::string ccr;
+    thread_local std::string ccr;
     const int rc = w->fa.fetch(c.contig, (int64_t)row.best_pos - 20, (int64_t)row.best_pos + 20, ccr);
     if (rc == 2) O.ccr_before++;
     if (rc != 0) ccr.clear();                                                // catch (SAMException) -> new byte[0] (:278)
-    else if (c.combined_strand == 1) reverse_complement(ccr);                // getStrandOrientation().equals("-") (:271)
-    for (char& ch : ccr) ch = (char)toupper((unsigned char)ch);              // :283-288
+    else if (c.combined_strand == 1) reverse_complement(&ccr[0], ccr.size());   // getStrandOrientation().equals("-") (:271)
+    for (char& ch : ccr) ch = (char)(ch - ((ch >= 'a' && ch <= 'z') ? 32 : 0));   // :283-288
     {
-      RowBuf& o = O.ccr_fa;
-      o.s += '>'; o.s += id; o.s += " 20-anchor-20 "; o.s += chr; o.s += ':'; o.s += comb; o.s += ':';
-      o.num(row.best_pos - 20); o.s += '-'; o.num(row.best_pos + 20); o.s += '\n'; o.s += ccr; o.s += '\n';
+      char* p = O.ccr_fa.room(fixed + ccr.size());
+      *p++ = '>'; p = put_s(p, id, id_n); p = put_s(p, " 20-anchor-20 ", 14); p = put_s(p, chr); *p++ = ':';
+      p = put_s(p, comb, comb_n); *p++ = ':'; p = put_i(p, row.best_pos - 20); *p++ = '-'; p = put_i(p, row.best_pos + 20);
+      *p++ = '\n'; p = put_s(p, ccr); *p++ = '\n';
+      O.ccr_fa.took(p);
     }
     {
-      RowBuf& o = O.ccr_tsv;
-      o.s += "Gene\t"; o.s += id; o.s += '\t'; o.s += comb; o.s += '\t'; o.s += chr; o.s += '\t';
-      o.num(c.start); o.s += '\t'; o.num(c.end); o.s += '\t'; o.num(row.best_pos - 20); o.s += '\t'; o.num(row.best_pos + 20);
-      o.s += '\t'; o.s += ccr; o.s += '\t'; o.num(row.best_pos); o.s += '\t'; o.unum(c.num_reads); o.s += '\t';
-      o.unum(row.num_t2c_sites); o.s += '\t'; o.unum(row.best_count); o.s += '\t'; o.s += java_double(row.best_value);
-      o.s += '\t'; o.unum(c.num_t2c); o.s += '\t'; o.s += fraction; o.s += '\n';
+      char* p = O.ccr_tsv.room(fixed + ccr.size());
+      p = put_s(p, "Gene\t", 5); p = put_s(p, id, id_n); *p++ = '\t'; p = put_s(p, comb, comb_n); *p++ = '\t';
+      p = put_s(p, chr); *p++ = '\t'; p = put_i(p, c.start); *p++ = '\t'; p = put_i(p, c.end); *p++ = '\t';
+      p = put_i(p, row.best_pos - 20); *p++ = '\t'; p = put_i(p, row.best_pos + 20); *p++ = '\t'; p = put_s(p, ccr); *p++ = '\t';
+      p = put_i(p, row.best_pos); *p++ = '\t'; p = put_u(p, c.num_reads); *p++ = '\t'; p = put_u(p, row.num_t2c_sites);
+      *p++ = '\t'; p = put_u(p, row.best_count); *p++ = '\t'; p = java_double_to(p, row.best_value); *p++ = '\t';
+      p = put_u(p, c.num_t2c); *p++ = '\t'; p = put_s(p, fraction, fraction_n); *p++ = '\n';
+      O.ccr_tsv.took(p);
     }
     O.ccr++;
   }
   {
-    RowBuf& o = O.pileup;
-    o.s += id; o.s += '\t'; o.s += chr; o.s += '\t'; o.num(c.start); o.s += '\t'; o.num(c.end); o.s += '\t';
-    o.s += c.first_reverse ? '-' : '+'; o.s += '\t'; o.unum(c.num_reads); o.s += '\t'; o.unum(c.num_t2c); o.s += '\t';
-    o.unum(row.num_t2c_sites); o.s += '\t'; o.s += fraction; o.s += '\t';
-    const size_t at = o.s.size();
-    o.s += bytes;
-    if (c.first_reverse) {                                                     // :318-321, in place in the row
-      std::string seq(o.s, at);
-      reverse_complement(seq);
-      o.s.replace(at, std::string::npos, seq);
-    }
-    o.s += '\t'; o.s += comb; o.s += '\t'; o.unum(bytes.size()); o.s += '\n';
+    char* p = O.pileup.room(fixed + bytes.size());
+    p = put_s(p, id, id_n); *p++ = '\t'; p = put_s(p, chr); *p++ = '\t'; p = put_i(p, c.start); *p++ = '\t'; p = put_i(p, c.end);
+    *p++ = '\t'; *p++ = c.first_reverse ? '-' : '+'; *p++ = '\t'; p = put_u(p, c.num_reads); *p++ = '\t'; p = put_u(p, c.num_t2c);
+    *p++ = '\t'; p = put_u(p, row.num_t2c_sites); *p++ = '\t'; p = put_s(p, fraction, fraction_n); *p++ = '\t';
+    char* seq = p;
+    p = put_s(p, bytes);
+    if (c.first_reverse) reverse_complement(seq, bytes.size());               // :318-321, in place in the row
+    *p++ = '\t'; p = put_s(p, comb, comb_n); *p++ = '\t'; p = put_u(p, bytes.size()); *p++ = '\n';
+    O.pileup.took(p);
   }
   O.rows++;
 }
@@ -222,12 +258,106 @@ static void cw_write_jobs(ps_clust_writer* w) {
     for (size_t t = 0; t < T; ++t) pool.emplace_back(work, t);
     for (auto& th : pool) th.join();
   }
+  auto put = [](RowBuf& held, RowBuf& fresh, FILE* f) {      // a large piece goes to the file as it is
+    if (fresh.n >= ((size_t)1 << 16)) { held.flush_to(f, true); fwrite(fresh.d, 1, fresh.n, f); }
+    else { held.append(fresh); held.flush_to(f, false); }
+  };
   for (size_t t = 0; t < T; ++t) {
-    w->b_pileup.s += outs[t].pileup.s; w->b_ccr_fa.s += outs[t].ccr_fa.s; w->b_ccr_tsv.s += outs[t].ccr_tsv.s;
-    w->b_pileup.flush_to(w->f_pileup, false); w->b_ccr_fa.flush_to(w->f_ccr_fa, false); w->b_ccr_tsv.flush_to(w->f_ccr_tsv, false);
+    put(w->b_pileup, outs[t].pileup, w->f_pileup); put(w->b_ccr_fa, outs[t].ccr_fa, w->f_ccr_fa); put(w->b_ccr_tsv, outs[t].ccr_tsv, w->f_ccr_tsv);
     w->rows_written += outs[t].rows; w->ccr_written += outs[t].ccr; w->ccr_start_before_contig += outs[t].ccr_before;
   }
   w->jobs.clear();
+}
+
+// ---- cluster sequence, read by read (PileupClusters.java:146-157, :347-480) ------------------------------------------------
+// The sequence of a cluster depends on the reads from its first one on and on nothing in front of it, and the first reads
+// are known before the loop starts (the kernels found them), so the records of a feed are walked in ranges that begin
+// at a cluster start, one range per host thread; the first range continues the cluster the previous feed left open.
+struct SeqState { bool have = false; uint64_t cluster_first = 0; int64_t cluster_end = 0; std::string bytes; };
+struct RangeOut {
+  std::vector<std::pair<uint64_t, std::string>> done;      // clusters that ended inside the range: first read, sequence
+  SeqState st;                                             // the cluster open at the end of the range
+  size_t starts_used = 0;
+  int status = PS_OK;
+  uint64_t fault_ordinal = 0;
+  const char* msg = nullptr;
+};
+static const char* const kDisagree = "cluster records and read stream disagree (records must be fed in order)";
+static const char* const kFetchPast = "cluster sequence: FASTA fetch past the contig (the JVM would die here)";
+
+static void cw_walk_range(const ps_clust_writer* w, const ps_read_batch* hb, uint64_t first_ordinal, uint64_t r_lo, uint64_t r_hi,
+                          uint64_t coff, const uint64_t* starts, size_t n_starts, RangeOut& O) {
+  SeqState& st = O.st;
+  std::string piece;
+  size_t sc = 0;
+  auto stop = [&](int status, const char* msg, uint64_t ordinal) { O.status = status; O.msg = msg; O.fault_ordinal = ordinal; O.starts_used = sc; };
+  for (uint64_t r = r_lo; r < r_hi; ++r) {
+    const uint32_t meta = hb->meta[r], flags = PS_META_FLAGS(meta), ncig = PS_META_NCIGAR(meta);
+    const uint32_t* cig = hb->cigar + coff;
+    coff += ncig;
+    const uint64_t ordinal = first_ordinal + r;
+    bool hasI = false, hasD = false, hasN = false;
+    int64_t R = 0;
+    for (uint32_t e = 0; e < ncig; ++e) {
+      const uint32_t op = cig[e] & 15u;
+      hasI |= op == 1u; hasD |= op == 2u; hasN |= op == 3u;
+      if ((0x18Du >> op) & 1u) R += cig[e] >> 4;
+    }
+    if ((flags & PS_RF_UNMAPPED) || ((hasI || hasD) && hasN)) {                // :146, :152-157
+      if (sc < n_starts && starts[sc] == ordinal) return stop(PS_ERR_STATE, kDisagree, ordinal);   // a cluster cannot begin here
+      continue;
+    }
+    // contig and 1-based start from the global offset (same coordinate space as the packed reference)
+    const uint64_t g = hb->ref_start[r];
+    size_t ci = 0;
+    {
+      size_t lo = 0, hi = w->fa.e.size();
+      while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (w->fa.off[mid] <= g) lo = mid; else hi = mid; }
+      ci = lo;
+    }
+    const int64_t start = (int64_t)(g - w->fa.off[ci]) + 1, end = start + R - 1;
+    if (sc < n_starts && starts[sc] == ordinal) {
+      ++sc;
+      if (st.have) O.done.emplace_back(st.cluster_first, std::move(st.bytes));   // the previous cluster is flushed (:178)
+      st.have = true;
+      st.cluster_first = ordinal;
+      st.cluster_end = end;                                                 // :347
+      st.bytes.clear();                                                     // :367
+      int64_t cur = start;
+      for (uint32_t e = 0; e < ncig; ++e) {
+        const uint32_t op = cig[e] & 15u;
+        const int64_t len = cig[e] >> 4;
+        if (op == 2u || op == 0u) {                                         // D or M only (:383-386)
+          if (w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece) != 0)     // SAMException outside any try block: the JVM dies here
+            return stop(PS_ERR_REFERENCE_WOULD_THROW, kFetchPast, ordinal);
+          st.bytes += piece;
+        }
+        if (op != 1u) cur += len;                                           // every non-I element advances (:402-404)
+      }
+    } else {
+      if (!st.have) return stop(PS_ERR_STATE, "a kept read in front of the first cluster start", ordinal);
+      if (end > st.cluster_end) {                                           // :421
+        int64_t cur = start;
+        for (uint32_t e = 0; e < ncig; ++e) {
+          const uint32_t op = cig[e] & 15u;
+          const int64_t len = cig[e] >> 4;
+          if (cur + len - 1 < st.cluster_end) {                             // :429-436
+            if (op != 1u) cur += len;
+            continue;
+          }
+          if (op == 2u || op == 0u) {
+            if (w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece) != 0) return stop(PS_ERR_REFERENCE_WOULD_THROW, kFetchPast, ordinal);
+            const int64_t overhang = st.cluster_end - cur + 1;              // :449
+            if (overhang > 0) st.bytes.append(piece, (size_t)overhang, std::string::npos);   // mergeByteSubArrays (:453-457)
+            else st.bytes.insert(0, piece);                                 // mergeByteArrays(additionalNucs, tempClusterBytes) (:462)
+          }
+          st.cluster_end = end;                                             // :480, inside the element loop
+          if (op != 1u) cur += len;
+        }
+      }
+    }
+  }
+  O.starts_used = sc;
 }
 
 extern "C" {
@@ -272,101 +402,93 @@ int ps_clust_writer_feed(ps_clust_writer* w, const ps_read_batch* hb, uint64_t f
   if (!w->f_pileup) return cw_fail(w, PS_ERR_STATE, "writer is closed");
   if (hb->n_reads && (!hb->meta || !hb->cigar || !hb->ref_start || !hb->bases2 || !hb->qual))
     return cw_fail(w, PS_ERR_INVALID_ARG, "the writer reads the records on the host: the compact upload form (flags8 / uniform_cigar) is not accepted here");
-  // ---- arithmetic of the flush for the new records, in order (running state lives in the flush object) ----------
-  std::vector<ps_flush_row> rows(n_closed);
-  if (n_closed) {
-    const int st = ps_flush_clusters(w->flush, closed, n_closed, sites, rows.data());
-    if (st != PS_OK) return cw_fail(w, st, ps_flush_error(w->flush));
-  }
   // a record whose cluster begins in this batch announces a start; so does the cluster still open behind the batch.  (A
   // record of a cluster that began in an earlier batch was announced then, as that batch's open cluster.)
-  for (uint64_t k = 0; k < n_closed; ++k) {
-    w->pending.push_back({closed[k], rows[k]});
-    if (closed[k].first_read >= first_ordinal) w->starts.push_back(closed[k].first_read);
-  }
-  if (has_open && open_first_read >= first_ordinal) w->starts.push_back(open_first_read);
-
-  // ---- the records: cluster sequence read by read -------------------------------------------------------------------
+  std::vector<uint64_t> starts(w->starts.begin(), w->starts.end());
+  w->starts.clear();
+  for (uint64_t k = 0; k < n_closed; ++k)
+    if (closed[k].first_read >= first_ordinal) starts.push_back(closed[k].first_read);
+  if (has_open && open_first_read >= first_ordinal) starts.push_back(open_first_read);
   const uint64_t n = hb->n_reads;
-  uint64_t coff = (!hb->uniform_ncigar && hb->tile_cigar_off) ? hb->tile_cigar_off[0] : 0;
-  std::string piece;
-  for (uint64_t r = 0; r < n; ++r) {
-    const uint32_t meta = hb->meta[r], flags = PS_META_FLAGS(meta), ncig = PS_META_NCIGAR(meta);
-    const uint32_t* cig = hb->cigar + coff;
-    coff += ncig;
-    if (flags & PS_RF_UNMAPPED) continue;                                   // :146
-    bool hasI = false, hasD = false, hasN = false;
-    int64_t R = 0;
-    for (uint32_t e = 0; e < ncig; ++e) {
-      const uint32_t op = cig[e] & 15u;
-      hasI |= op == 1u; hasD |= op == 2u; hasN |= op == 3u;
-      if ((0x18Du >> op) & 1u) R += cig[e] >> 4;
-    }
-    if ((hasI || hasD) && hasN) continue;                                   // :152-157
-    const uint64_t ordinal = first_ordinal + r;
-    // contig and 1-based start from the global offset (same coordinate space as the packed reference)
-    const uint64_t g = hb->ref_start[r];
-    size_t ci = 0;
-    {
-      size_t lo = 0, hi = w->fa.e.size();
-      while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (w->fa.off[mid] <= g) lo = mid; else hi = mid; }
-      ci = lo;
-    }
-    const int64_t start = (int64_t)(g - w->fa.off[ci]) + 1, end = start + R - 1;
-    const bool opens = !w->starts.empty() && w->starts.front() == ordinal;
-    if (opens) {
-      w->starts.pop_front();
-      if (w->have) {                                                        // the previous cluster is flushed (:178)
-        if (w->pending.empty() || w->pending.front().c.first_read != w->cluster_first)
-          { cw_write_jobs(w); return cw_fail(w, PS_ERR_STATE, "cluster records and read stream disagree (records must be fed in order)"); }
-        w->jobs.push_back({w->pending.front().c, w->pending.front().row, w->bytes});
-        w->pending.pop_front();
-      }
-      w->have = true;
-      w->cluster_first = ordinal;
-      w->cluster_end = end;                                                 // :347
-      w->bytes.clear();                                                     // :367
-      int64_t cur = start;
-      for (uint32_t e = 0; e < ncig; ++e) {
-        const uint32_t op = cig[e] & 15u;
-        const int64_t len = cig[e] >> 4;
-        if (op == 2u || op == 0u) {                                         // D or M only (:383-386)
-          const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
-          if (rc != 0) {      // SAMException outside any try block: the JVM dies here
-            w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
-            { cw_write_jobs(w); return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)"); }
-          }
-          w->bytes += piece;
-        }
-        if (op != 1u) cur += len;                                           // every non-I element advances (:402-404)
-      }
-    } else {
-      if (!w->have) { cw_write_jobs(w); return cw_fail(w, PS_ERR_STATE, "a kept read in front of the first cluster start"); }
-      if (end > w->cluster_end) {                                           // :421
-        int64_t cur = start;
-        for (uint32_t e = 0; e < ncig; ++e) {
-          const uint32_t op = cig[e] & 15u;
-          const int64_t len = cig[e] >> 4;
-          if (cur + len - 1 < w->cluster_end) {                             // :429-436
-            if (op != 1u) cur += len;
-            continue;
-          }
-          if (op == 2u || op == 0u) {
-            const int rc = w->fa.fetch((int64_t)ci, cur, cur + len - 1, piece);
-            if (rc != 0) {
-              w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = ordinal;
-              { cw_write_jobs(w); return cw_fail(w, PS_ERR_REFERENCE_WOULD_THROW, "cluster sequence: FASTA fetch past the contig (the JVM would die here)"); }
-            }
-            const int64_t overhang = w->cluster_end - cur + 1;               // :449
-            if (overhang > 0) w->bytes.append(piece, (size_t)overhang, std::string::npos);   // mergeByteSubArrays (:453-457)
-            else w->bytes.insert(0, piece);                                 // mergeByteArrays(additionalNucs, tempClusterBytes) (:462)
-          }
-          w->cluster_end = end;                                             // :480, inside the element loop
-          if (op != 1u) cur += len;
-        }
-      }
+  // ---- ranges of records, each beginning at a cluster start --------------------------------------------------------------
+  const unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, (size_t)(n / 32768 + 1)}));
+  if (const char* e = getenv("PARASUITE_B200_WRITER_THREADS")) T = std::max(1, atoi(e));
+  bool ordered = true;                   // the starts the kernels return are ascending ordinals inside the batch
+  for (size_t k = 0; k < starts.size() && ordered; ++k)
+    ordered = starts[k] >= first_ordinal && starts[k] - first_ordinal < n && (k == 0 || starts[k - 1] < starts[k]);
+  if (!ordered) T = 1;                   // (anything else is walked as one range, which reports it)
+  std::vector<size_t> cut{0};            // range t takes starts [cut[t], cut[t + 1])
+  for (size_t t = 1; t < T; ++t) {
+    const size_t k = (size_t)(std::lower_bound(starts.begin(), starts.end(), first_ordinal + n * t / T) - starts.begin());
+    if (k > cut.back() && k < starts.size()) cut.push_back(k);
+  }
+  T = cut.size();
+  cut.push_back(starts.size());
+  std::vector<uint64_t> r_lo(T + 1, 0), coff0(T, 0);
+  for (size_t t = 1; t < T; ++t) r_lo[t] = starts[cut[t]] - first_ordinal;
+  r_lo[T] = n;
+  coff0[0] = (!hb->uniform_ncigar && hb->tile_cigar_off) ? hb->tile_cigar_off[0] : 0;
+  if (T > 1) {                           // cigar offset of every range's first record
+    uint64_t c = coff0[0];
+    size_t t = 1;
+    for (uint64_t r = 0; r < n && t < T; ++r) {
+      if (r == r_lo[t]) coff0[t++] = c;
+      c += PS_META_NCIGAR(hb->meta[r]);
     }
   }
+  std::vector<RangeOut> outs(T);
+  outs[0].st.have = w->have;
+  outs[0].st.cluster_first = w->cluster_first;
+  outs[0].st.cluster_end = w->cluster_end;
+  outs[0].st.bytes = std::move(w->bytes);
+  w->bytes.clear();
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < T; ++t)
+    pool.emplace_back([&, t] { cw_walk_range(w, hb, first_ordinal, r_lo[t], r_lo[t + 1], coff0[t], starts.data() + cut[t], cut[t + 1] - cut[t], outs[t]); });
+  std::thread first;
+  if (T > 1) first = std::thread([&] { cw_walk_range(w, hb, first_ordinal, r_lo[0], r_lo[1], coff0[0], starts.data(), cut[1], outs[0]); });
+  // ---- meanwhile: arithmetic of the flush for the new records, in order (running state lives in the flush object) --------
+  std::vector<ps_flush_row> rows(n_closed);
+  const int flush_st = n_closed ? ps_flush_clusters(w->flush, closed, n_closed, sites, rows.data()) : PS_OK;
+  if (T == 1) cw_walk_range(w, hb, first_ordinal, 0, n, coff0[0], starts.data(), starts.size(), outs[0]);
+  else first.join();
+  for (auto& th : pool) th.join();
+  if (flush_st != PS_OK) return cw_fail(w, flush_st, ps_flush_error(w->flush));
+  for (uint64_t k = 0; k < n_closed; ++k) w->pending.push_back({closed[k], rows[k]});
+  // ---- the ranges in order: a cluster that ended pairs up with the oldest closed record still waiting -------------------
+  auto close_cluster = [&](uint64_t first_read, std::string&& bytes) {
+    if (w->pending.empty() || w->pending.front().c.first_read != first_read) return false;
+    w->jobs.push_back({w->pending.front().c, w->pending.front().row, std::move(bytes)});
+    w->pending.pop_front();
+    return true;
+  };
+  SeqState carry;
+  carry.have = false;
+  for (size_t t = 0; t < T; ++t) {
+    RangeOut& O = outs[t];
+    bool ok = true;
+    if (t > 0) {
+      // range t begins with the first read of a cluster: the one open at the end of range t - 1 ended there -- unless
+      // range t stopped before it took that read
+      if (O.starts_used == 0 && O.status != PS_OK) ok = true;
+      else if (carry.have) ok = close_cluster(carry.cluster_first, std::move(carry.bytes));
+    }
+    for (size_t k = 0; ok && k < O.done.size(); ++k) ok = close_cluster(O.done[k].first, std::move(O.done[k].second));
+    if (ok && O.status == PS_OK && O.starts_used != cut[t + 1] - cut[t] && T > 1) { ok = false; }
+    if (!ok || O.status != PS_OK) {
+      cw_write_jobs(w);
+      if (!ok) return cw_fail(w, PS_ERR_STATE, kDisagree);
+      if (O.status == PS_ERR_REFERENCE_WOULD_THROW) { w->fault.code = PS_THROW_REF_RANGE; w->fault.read_ordinal = O.fault_ordinal; }
+      return cw_fail(w, O.status, O.msg);
+    }
+    carry = std::move(O.st);
+  }
+  for (size_t k = outs[T - 1].starts_used + cut[T - 1]; k < starts.size(); ++k) w->starts.push_back(starts[k]);
+  w->have = carry.have;
+  w->cluster_first = carry.cluster_first;
+  w->cluster_end = carry.cluster_end;
+  w->bytes = std::move(carry.bytes);
   w->reads_fed += n;
   cw_write_jobs(w);
   return PS_OK;

@@ -22,58 +22,103 @@
 
 namespace {
 
+// std::stable_sort asks for a temporary buffer at every call; a cluster has a handful of sites
+template <typename It, typename Cmp>
+void stable_sort_small(It a, It b, Cmp less) {
+  if (b - a > 32) { std::stable_sort(a, b, less); return; }
+  for (It i = a == b ? b : a + 1; i < b; ++i) {
+    auto v = *i;
+    It j = i;
+    while (j > a && less(v, *(j - 1))) { *j = *(j - 1); --j; }
+    *j = v;
+  }
+}
+
 struct JMap {   // java.util.HashMap<Integer,Integer>, iteration order included
+  // Buckets are fixed arrays (a ninth key in one bucket is "unsupported" anyway) in one flat table, and the buckets in use
+  // are listed, so that clearing and walking the map costs what the cluster's few sites cost, not the table's size, and
+  // nothing is allocated per cluster.
   struct Node { int32_t k; int32_t v; };
-  std::vector<std::vector<Node>> table;
+  struct Bucket { uint32_t n; Node e[8]; };
+  std::vector<Bucket> table;
+  mutable std::vector<uint32_t> used;       // buckets that have held a node since the last clear (any order)
   size_t size = 0, threshold = 0;
   bool allocated = false, unsupported = false;
 
   static uint32_t hash(int32_t k) { const uint32_t h = (uint32_t)k; return h ^ (h >> 16); }
   static size_t table_size_for(size_t c) { size_t n = 1; while (n < c) n <<= 1; return std::min<size_t>(std::max<size_t>(n, 1), (size_t)1 << 30); }
+  void wipe() {
+    for (uint32_t j : used) table[j].n = 0;
+    used.clear();
+    size = 0;
+  }
+  void reset() {   // `new HashMap<>()`: no table yet (the storage is kept, all buckets empty)
+    wipe();
+    threshold = 0;
+    allocated = false;
+    unsupported = false;
+  }
+  void push(Bucket& b, uint32_t j, Node n) {
+    if (b.n >= 8) { unsupported = true; return; }   // treeifyBin: link order no longer follows insertion
+    if (b.n == 0) used.push_back(j);
+    b.e[b.n++] = n;
+  }
   void resize() {
     if (!allocated) {
       const size_t cap = threshold ? threshold : 16;
-      table.assign(cap, {});
+      if (table.size() != cap) table.assign(cap, Bucket{});
       threshold = cap * 3 / 4;
       allocated = true;
       return;
     }
     const size_t ocap = table.size(), ncap = ocap * 2;
-    std::vector<std::vector<Node>> nt(ncap);
-    for (size_t j = 0; j < ocap; ++j)
-      for (const Node& n : table[j]) nt[(hash(n.k) & ocap) ? j + ocap : j].push_back(n);   // lo / hi split keeps order
-    table.swap(nt);
+    std::vector<Bucket> old(ncap);
+    old.swap(table);
+    std::vector<uint32_t> was;
+    was.swap(used);
+    for (uint32_t j : was) {
+      const Bucket& b = old[j];
+      for (uint32_t q = 0; q < b.n; ++q) {          // lo / hi split keeps order
+        const uint32_t t = (hash(b.e[q].k) & ocap) ? j + (uint32_t)ocap : j;
+        push(table[t], t, b.e[q]);
+      }
+    }
     threshold = ncap * 3 / 4;
   }
   void put(int32_t k, int32_t v) {
     if (!allocated) resize();
-    std::vector<Node>& b = table[hash(k) & (table.size() - 1)];
-    for (Node& n : b)
-      if (n.k == k) { n.v = v; return; }
-    b.push_back({k, v});
-    if (b.size() >= 9) unsupported = true;   // treeifyBin: link order no longer follows insertion
+    const uint32_t j = hash(k) & (uint32_t)(table.size() - 1);
+    Bucket& b = table[j];
+    for (uint32_t q = 0; q < b.n; ++q)
+      if (b.e[q].k == k) { b.e[q].v = v; return; }
+    push(b, j, {k, v});
     if (++size > threshold) resize();
   }
   const int32_t* get(int32_t k) const {
     if (!allocated) return nullptr;
-    for (const Node& n : table[hash(k) & (table.size() - 1)])
-      if (n.k == k) return &n.v;
+    const Bucket& b = table[hash(k) & (table.size() - 1)];
+    for (uint32_t q = 0; q < b.n; ++q)
+      if (b.e[q].k == k) return &b.e[q].v;
     return nullptr;
   }
   void remove(int32_t k) {
     if (!allocated) return;
-    std::vector<Node>& b = table[hash(k) & (table.size() - 1)];
-    for (size_t j = 0; j < b.size(); ++j)
-      if (b[j].k == k) { b.erase(b.begin() + (ptrdiff_t)j); --size; return; }
+    Bucket& b = table[hash(k) & (table.size() - 1)];
+    for (uint32_t q = 0; q < b.n; ++q)
+      if (b.e[q].k == k) {
+        for (uint32_t z = q + 1; z < b.n; ++z) b.e[z - 1] = b.e[z];
+        --b.n; --size;
+        return;
+      }
   }
-  void clear() {
-    for (auto& b : table) b.clear();
-    size = 0;
-  }
+  void clear() { wipe(); }   // HashMap.clear(): the table stays
   template <typename F>
-  void for_each(F f) const {
-    for (const auto& b : table)
-      for (const Node& n : b) f(n.k, n.v);
+  void for_each(F f) const {   // table order: bucket index, then link order
+    std::sort(used.begin(), used.end());
+    for (uint32_t j : used) {
+      const Bucket& b = table[j];
+      for (uint32_t q = 0; q < b.n; ++q) f(b.e[q].k, b.e[q].v);
+    }
   }
   void put_all(const JMap& o) {   // HashMap.putMapEntries
     const size_t s = o.size;
@@ -94,6 +139,8 @@ struct ps_flush {
   std::vector<std::string> contig_query;   // contig name as SNPCalling.querySNP asks for it (leading "chr" stripped)
   std::unordered_map<std::string, std::unordered_set<int32_t>> snps;   // VCF rows with T in REF and C in ALT[0]
   JMap mutation_map;                        // the one map of the run (PileupClusters.java:126)
+  JMap tmp;                                 // storage of the per-cluster copy (:187), reset for every cluster
+  std::vector<std::pair<int32_t, uint32_t>> cov;
   ps_flush_totals totals{};
   std::vector<double> afi;                  // alleleFrequencyInformation
   std::string err;
@@ -172,11 +219,17 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
     // the iteration order -- and with it the anchor tie-break -- of every later cluster.
     order.clear();
     for (uint64_t s = cl.site_begin; s < cl.site_end; ++s) order.push_back(sites + s);
-    std::sort(order.begin(), order.end(), [](const ps_site* a, const ps_site* b) { return a->order_key < b->order_key; });
+    if (order.size() > 1) std::sort(order.begin(), order.end(), [](const ps_site* a, const ps_site* b) { return a->order_key < b->order_key; });
     JMap& mm = f->mutation_map;
     mm.clear();
-    std::unordered_map<int32_t, uint32_t> cov;                         // baseCoveredMap is only ever read at these keys
-    for (const ps_site* s : order) { mm.put(s->pos, (int32_t)s->t2c); cov[s->pos] = s->cov; }
+    std::vector<std::pair<int32_t, uint32_t>>& cov = f->cov;           // baseCoveredMap is only ever read at these keys
+    cov.clear();
+    for (const ps_site* s : order) { mm.put(s->pos, (int32_t)s->t2c); cov.push_back({s->pos, s->cov}); }
+    stable_sort_small(cov.begin(), cov.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    auto cov_at = [&](int32_t k) {                                     // the last value put under k
+      auto it = std::upper_bound(cov.begin(), cov.end(), k, [](int32_t key, const auto& e) { return key < e.first; });
+      return it == cov.begin() ? 0u : (it - 1)->second;
+    };
     if (mm.unsupported) {
       f->err = "a HashMap bucket would be treeified (9 T>C positions of one cluster in one bucket): iteration order not modelled";
       return PS_ERR_UNSUPPORTED;
@@ -185,7 +238,8 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
     row.emitted = 1;
     row.num_t2c_sites = (uint32_t)mm.size;                             // :181 (before the SNP filter)
     // SNP filter :187-201
-    JMap tmp;
+    JMap& tmp = f->tmp;
+    tmp.reset();
     tmp.put_all(mm);
     const std::unordered_set<int32_t>* known = nullptr;
     if (cl.contig < f->contig_query.size()) {
@@ -208,11 +262,11 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
       double best = 0.0;
       int32_t best_pos = -1;
       mm.for_each([&](int32_t k, int32_t v) {
-        const double val = (double)v / (double)cov[k];
+        const double val = (double)v / (double)cov_at(k);
         if (val >= best) { best = val; best_pos = k; }                 // the LAST maximum in iteration order wins
         sorted.push_back(val);
       });
-      std::stable_sort(sorted.begin(), sorted.end(), [](double a, double b) { return a > b; });   // Collections.reverseOrder()
+      stable_sort_small(sorted.begin(), sorted.end(), [](double a, double b) { return a > b; });   // Collections.reverseOrder()
       if (!sorted.empty()) {
         double sum = 0.0;
         for (double v : sorted) sum += v;                              // sumUpList :750-756
@@ -224,8 +278,10 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
             else afi.push_back(sorted[k]);
           }
           f->totals.num_crosslinked_clusters++;
-          for (int j = 0; j < 51; ++j)
-            if ((cl.mask51 >> j) & 1ull) { f->totals.allele_positions[j]++; f->totals.num_allele_positions++; }
+          for (uint64_t m = cl.mask51 & ((1ull << 51) - 1); m; m &= m - 1) {
+            f->totals.allele_positions[__builtin_ctzll(m)]++;
+            f->totals.num_allele_positions++;
+          }
         }
       }
       for (double v : sorted) fraction += v;                           // :258-260

@@ -76,9 +76,14 @@ def test_kat(tmp_path, oracle):
     assert stats["rows"] == 3
 
 
+@pytest.mark.parametrize("threads", [None, 5])
 @pytest.mark.parametrize("seed,kinds,min_cov,windows", [(1, ("M",), 1, 1), (2, ("M", "clip", "indel"), 2, 1),
                                                         (3, ("M", "clip", "indel", "splice"), 1, 4), (4, ("M",), 3, 7)])
-def test_random(tmp_path, oracle, seed, kinds, min_cov, windows):
+def test_random(tmp_path, oracle, monkeypatch, seed, kinds, min_cov, windows, threads):
+    """threads: the record loop of a feed is walked in that many ranges, each beginning at a cluster start (the default
+    takes one range for inputs this small)."""
+    if threads:
+        monkeypatch.setenv("PARASUITE_B200_WRITER_THREADS", str(threads))
     rng = random.Random(seed)
     contigs = random_genome(rng, n_contigs=3, length=30000, n_frac=0.003, lower_frac=0.3)
     recs = [r for r in random_records(rng, contigs, 5000, kinds=kinds, Lrange=(18, 30)) if r.pos > 0]
@@ -127,6 +132,44 @@ def test_fetch_past_contig_end_is_reported(tmp_path, oracle):
     with pytest.raises(abi.ReferenceWouldThrow) as e:
         run_native(tmp_path, oracle, contigs, recs, [], 1)
     assert e.value.fault == (abi.PS_THROW_REF_RANGE, 0)
+
+
+def test_fault_in_the_middle_of_a_feed(tmp_path, oracle, monkeypatch):
+    """The record the JVM dies on sits in the middle of the stream: the same fault is reported however many ranges the
+    feed is walked in, and the rows of the clusters that ended in front of it -- and only those -- are in the file."""
+    rng = random.Random(17)
+    contigs = random_genome(rng, n_contigs=2, length=20000, n_frac=0.0, lower_frac=0.1)
+    recs = [r for r in random_records(rng, contigs, 3000, kinds=("M",), Lrange=(18, 30)) if 0 < r.pos < 19900]
+    L0 = len(contigs[0][1])
+    bad = Record(0, contigs[0][0], L0 - 24, "10S20M", b"A" * 30, bytes([30] * 30))     # fetches up to L0 + 5
+    order = {n: i for i, (n, _) in enumerate(contigs)}
+    recs = sorted(recs + [bad], key=lambda r: (order[r.rname], r.pos))
+    at = recs.index(bad)
+    assert 500 < at < len(recs) - 500
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, contigs)
+    ref = PackedReference.from_contigs(contigs)
+    batch = ReadBatch.from_records(recs, ref)
+    res = oracle.pileup(ref, batch)
+
+    def run(threads):
+        monkeypatch.setenv("PARASUITE_B200_WRITER_THREADS", str(threads))
+        out = str(tmp_path / f"clusters{threads}.tsv")
+        w = ClustWriter(Flush(ref.names, 1, snps=[]), fa, out, str(tmp_path / "reads.bam"))
+        try:
+            with pytest.raises(abi.ReferenceWouldThrow) as e:
+                w.feed(batch, 0, res["clusters"], res["sites"], int(res["open_cluster"]["first_read"]))
+            assert e.value.fault == (abi.PS_THROW_REF_RANGE, at)
+        finally:
+            w.close()                                       # writes out what it holds
+        return open(out).read()
+    got = run(1)
+    # the stream cut in front of the bad record: the same rows, plus the cluster that the bad record ended if it began one
+    # (the end of a run never writes the last cluster, :502)
+    exp = po.clust_files(to_py(recs[:at]), po.Genome(dict(contigs)), po.SnpDb([]), 1)["pileup"]
+    assert got.startswith(exp) and got.count("\n") - exp.count("\n") <= 1 and got.count("\n") > 100
+    for threads in (2, 6):
+        assert run(threads) == got
 
 
 def test_java_double(oracle):
