@@ -258,14 +258,22 @@ static void cw_write_jobs(ps_clust_writer* w) {
     for (size_t t = 0; t < T; ++t) pool.emplace_back(work, t);
     for (auto& th : pool) th.join();
   }
-  auto put = [](RowBuf& held, RowBuf& fresh, FILE* f) {      // a large piece goes to the file as it is
-    if (fresh.n >= ((size_t)1 << 16)) { held.flush_to(f, true); fwrite(fresh.d, 1, fresh.n, f); }
-    else { held.append(fresh); held.flush_to(f, false); }
+  // every file takes its pieces in cluster order; the three files are written side by side
+  auto put_all = [&](RowBuf& held, RowBuf RowOut::*which, FILE* f) {
+    for (size_t t = 0; t < T; ++t) {
+      RowBuf& fresh = outs[t].*which;
+      if (fresh.n >= ((size_t)1 << 16)) { held.flush_to(f, true); fwrite(fresh.d, 1, fresh.n, f); }   // a large piece goes out as it is
+      else { held.append(fresh); held.flush_to(f, false); }
+    }
   };
-  for (size_t t = 0; t < T; ++t) {
-    put(w->b_pileup, outs[t].pileup, w->f_pileup); put(w->b_ccr_fa, outs[t].ccr_fa, w->f_ccr_fa); put(w->b_ccr_tsv, outs[t].ccr_tsv, w->f_ccr_tsv);
-    w->rows_written += outs[t].rows; w->ccr_written += outs[t].ccr; w->ccr_start_before_contig += outs[t].ccr_before;
+  if (n >= 4096) {
+    std::thread a([&] { put_all(w->b_ccr_fa, &RowOut::ccr_fa, w->f_ccr_fa); }), b([&] { put_all(w->b_ccr_tsv, &RowOut::ccr_tsv, w->f_ccr_tsv); });
+    put_all(w->b_pileup, &RowOut::pileup, w->f_pileup);
+    a.join(); b.join();
+  } else {
+    put_all(w->b_pileup, &RowOut::pileup, w->f_pileup); put_all(w->b_ccr_fa, &RowOut::ccr_fa, w->f_ccr_fa); put_all(w->b_ccr_tsv, &RowOut::ccr_tsv, w->f_ccr_tsv);
   }
+  for (size_t t = 0; t < T; ++t) { w->rows_written += outs[t].rows; w->ccr_written += outs[t].ccr; w->ccr_start_before_contig += outs[t].ccr_before; }
   w->jobs.clear();
 }
 

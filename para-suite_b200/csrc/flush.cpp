@@ -217,6 +217,11 @@ int ps_flush_clusters(ps_flush* f, const ps_cluster* clusters, uint64_t n, const
     // their first T>C was seen (ps_site.order_key).  The loop fills the ONE map of the run for every cluster, also for
     // those below minReadCoverage: their puts can grow the table, and clear() keeps the grown capacity, which decides
     // the iteration order -- and with it the anchor tie-break -- of every later cluster.
+    if (cl.site_end == cl.site_begin) {      // no T>C seen: the map is cleared and stays empty, every step below is a no-op
+      f->mutation_map.clear();
+      if (cl.num_reads >= f->min_cov) row.emitted = 1;
+      continue;
+    }
     order.clear();
     for (uint64_t s = cl.site_begin; s < cl.site_end; ++s) order.push_back(sites + s);
     if (order.size() > 1) std::sort(order.begin(), order.end(), [](const ps_site* a, const ps_site* b) { return a->order_key < b->order_key; });

@@ -172,6 +172,47 @@ def test_fault_in_the_middle_of_a_feed(tmp_path, oracle, monkeypatch):
         assert run(threads) == got
 
 
+def test_large_feed_default_threads_equal_one_range(tmp_path, oracle, monkeypatch):
+    """300 000 synthetic reads in one feed: the default (several ranges, rows formatted and the three row files written
+    side by side) writes the same bytes as one range on one thread, which the small cases above pin on the oracle."""
+    from parasuite_b200 import synth
+    ref = synth.synth_reference(7, [2_000_000], n_run=1000)
+    batch = synth.synth_reads(ref, 300_000, 36, seed=8)
+    codes = np.zeros(ref.n_bases, dtype=np.uint8)
+    for k in range(16):
+        codes[k::16] = ((ref.seq2[: (ref.n_bases + 15) // 16] >> (2 * k)) & 3)[: len(codes[k::16])]
+    asc = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+    asc[np.unpackbits(ref.inv.view(np.uint8), bitorder="little")[: ref.n_bases].astype(bool)] = ord("N")
+    fa = str(tmp_path / "ref.fa")
+    write_fasta(fa, [(ref.names[0], asc.tobytes())])
+    res = oracle.pileup(ref, batch)
+    assert len(res["clusters"]) > 8192
+
+    def run(tag, threads):
+        if threads:
+            monkeypatch.setenv("PARASUITE_B200_WRITER_THREADS", str(threads))
+        else:
+            monkeypatch.delenv("PARASUITE_B200_WRITER_THREADS", raising=False)
+        out, bam = str(tmp_path / f"{tag}.tsv"), str(tmp_path / f"{tag}.bam")
+        w = ClustWriter(Flush(ref.names, 1, snps=[]), fa, out, bam)
+        w.feed(batch, 0, res["clusters"], res["sites"], int(res["open_cluster"]["first_read"]))
+        stats = w.finish(res["counters"])
+        w.close()
+        return {k: open(v.format(out=out, bam=bam)).read() for k, v in FILES.items()}, stats
+    one, s1 = run("one", 1)
+    many, s2 = run("many", None)
+    assert s1 == s2 and s1["rows"] == len(res["clusters"])
+    for k in FILES:
+        assert one[k] == many[k], k
+    # spot check of a few rows against the reference text: the cluster sequence is the reference over [start, end]
+    for line in one["pileup"].splitlines()[1:2000:97]:
+        c = line.split("\t")
+        seq = asc[int(c[2]) - 1:int(c[3])].tobytes().decode()
+        if c[4] == "-":
+            seq = seq[::-1].translate(str.maketrans("ACGTacgt", "TGCAtgca"))
+        assert c[9] == seq and int(c[11]) == len(seq)
+
+
 def test_java_double(oracle):
     from parasuite_b200.flush import java_double
     for x in (0.5, 1.0, 1e-4, 1e7, 1 / 3, 0.0, 123456.789, 2.5e-5, 9999999.999, 0.001, 1e-3 - 1e-12, 2 / 3, 100.0, 1e22):
