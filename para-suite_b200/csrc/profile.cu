@@ -350,7 +350,21 @@ __device__ __forceinline__ ReadPlan profile_read_prologue(const ProfileParams& P
     ++ctr[1];                               // :296
     if (skip) { atomicAdd(&S.s_ctr[PS_PC_SKIPPED_READS], 1ull); return plan; } // :303-306
   }
-  plan.g0 = g0; plan.ml = ml; plan.bits = (has_indel ? 1u : 0u) | (L != R ? 2u : 0u);
+  // does [g0, g0 + R) hold an invalid reference base at all?  (a few mask words per read here, instead of a load and a
+  // test per column in the count loop; reads with long N gaps keep the per-column test)
+  bool ref_clean = false;
+  if (R <= 512u) {
+    const uint64_t last = g0 + R - 1u, w0 = g0 >> 5, w1 = last >> 5;
+    uint32_t any = 0;
+    for (uint64_t w = w0; w <= w1; ++w) {
+      uint32_t m = 0xFFFFFFFFu;
+      if (w == w0) m &= 0xFFFFFFFFu << (uint32_t)(g0 & 31u);
+      if (w == w1) m &= 0xFFFFFFFFu >> (31u - (uint32_t)(last & 31u));
+      any |= __ldg(P.ref.inv + w) & m;
+    }
+    ref_clean = any == 0;
+  }
+  plan.g0 = g0; plan.ml = ml; plan.bits = (has_indel ? 1u : 0u) | (L != R ? 2u : 0u) | (ref_clean ? 4u : 0u);
   return plan;
 }
 
@@ -365,7 +379,11 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
   const uint32_t* cig = P.b.cigar + off.cigar;
   const uint64_t g0 = plan.g0;
   const uint32_t ml = plan.ml;
-  const bool has_indel = (plan.bits & 1u) != 0, walked = (plan.bits & 2u) != 0;
+  const bool has_indel = (plan.bits & 1u) != 0, walked = (plan.bits & 2u) != 0, ref_clean = (plan.bits & 4u) != 0;
+  // the read's window of the reference: word pointers once, 32-bit offsets per column
+  const uint32_t* inv_w = P.ref.inv + (g0 >> 5);
+  const uint32_t* seq_w = P.ref.seq2 + (g0 >> 4);
+  const uint32_t g_in32 = (uint32_t)(g0 & 31u), g_in16 = (uint32_t)(g0 & 15u);
   // count loop :349-408
   const bool rev = flags & PS_RF_REVERSE;
   const bool has_inv = flags & PS_RF_HAS_INVALID;
@@ -393,12 +411,11 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
         if (!op_is_match(op)) continue;
       }
       for (uint32_t z = lane; z < n; z += 32) {
-        const uint64_t g = g0 + pr + z;
-        const uint32_t p = pq + z, col = pm + z;
-        bool ok = !((__ldg(P.ref.inv + (g >> 5)) >> (g & 31u)) & 1u);
+        const uint32_t p = pq + z, col = pm + z, gi = g_in32 + pr + z, gs = g_in16 + pr + z;
+        bool ok = ref_clean || !((__ldg(inv_w + (gi >> 5)) >> (gi & 31u)) & 1u);
         if (ok && has_inv) ok = !read_pos_invalid(P.b, xr, p);
         if (!ok) continue;
-        const uint32_t ra = (__ldg(P.ref.seq2 + (g >> 4)) >> (2u * (uint32_t)(g & 15u))) & 3u;
+        const uint32_t ra = (__ldg(seq_w + (gs >> 4)) >> (2u * (gs & 15u))) & 3u;
         const uint32_t rd = ((uint32_t)__ldg(rb + (p >> 2)) >> (2u * (p & 3u))) & 3u;
         const uint32_t pair = (ra * 4u + rd) ^ flip;
         const uint32_t i = rev ? ml - 1u - col : col;
