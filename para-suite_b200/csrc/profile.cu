@@ -256,18 +256,22 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
 // reductions into a [pair][position] histogram.  Matching-base quality sums and the base counter live in per-lane
 // registers for the whole kernel.  Same statements as profile_read_generic (ErrorProfiling.java:155-408).
 // ---------------------------------------------------------------------------------------------------------
-struct WarpAcc {
-  long long q_acc[4];
-  unsigned long long q_cnt[4];
-  unsigned long long checked;
+struct WarpAcc {          // 32-bit per lane, emptied into the block's 64-bit cells every 2^20 reads of the warp at the latest
+  int q_acc[4];
+  uint32_t q_cnt[4];
+  uint32_t checked;
   uint32_t mm_events;      // mismatch-quality events this lane has put into the warp's 32-bit cells since their last flush
+  uint32_t reads;          // reads the warp has counted since the last flush (a lane adds < 2^10 per read to any of the above)
 };
 
 // Mismatch qualities (sum and count by pair, ErrorProfiling.java:392-397) first go to 32 warp-private 32-bit cells with
 // native shared reductions -- a 64-bit shared atomicAdd is a compare-and-swap loop, and reads that compare shifted
 // sequence (soft clips, Q-quirk) bring a hundred such events each -- and from there to the block's 64-bit cells before a
 // cell could overflow (|q| <= 128, 2^18 events per lane).
-__device__ __forceinline__ void warp_q_flush(const GenericSmem& S, uint32_t wq32, WarpAcc& A) {
+#ifndef PS_FLUSH_INLINE
+#define PS_FLUSH_INLINE __forceinline__
+#endif
+__device__ PS_FLUSH_INLINE void warp_q_flush(const GenericSmem& S, uint32_t wq32, WarpAcc& A) {
   __syncwarp();
   const uint32_t lane = threadIdx.x & 31;
   uint32_t v;
@@ -277,6 +281,24 @@ __device__ __forceinline__ void warp_q_flush(const GenericSmem& S, uint32_t wq32
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(wq32 + lane * 4u), "r"(0u) : "memory");
   }
   A.mm_events = 0;
+  // the per-lane registers: matching-base quality sums and counts (by base), bases checked
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    long long t = A.q_acc[b];
+    unsigned long long c = A.q_cnt[b];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { t += __shfl_xor_sync(0xFFFFFFFFu, t, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d); }
+    if (lane == 0 && c) { atomicAdd(&S.s_q[b * 5], (unsigned long long)t); atomicAdd(&S.s_q[16 + b * 5], c); }
+    A.q_acc[b] = 0; A.q_cnt[b] = 0;
+  }
+  {
+    unsigned long long c = A.checked;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if (lane == 0 && c) atomicAdd(&S.s_ctr[PS_PC_TOTAL_BASES_CHECKED], c);
+    A.checked = 0;
+  }
+  A.reads = 0;
   __syncwarp();
 }
 
@@ -394,7 +416,7 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
   const uint8_t* rq = P.b.qual + off.qual;
   const uint32_t flip = rev ? 15u : 0u;           // complementing both bases: pair -> 15 - pair
   uint32_t f_key = 0xFFFFFFFFu;                   // first uncaught exception: min over (i << 1 | QUAL_RANGE)
-  long long qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;
+  int qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;
   uint32_t qc0 = 0, qc1 = 0, qc2 = 0, qc3 = 0, checked = 0;
   {
     uint32_t pr = 0, pq = 0, pm = 0;              // the read was not skipped: every block lies inside ml, R and L
@@ -439,7 +461,7 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
       pm += n; pr += n; pq += n;
     }
   }
-  if (__any_sync(0xFFFFFFFFu, A.mm_events >= (1u << 18))) warp_q_flush(S, wq32, A);
+  if (__any_sync(0xFFFFFFFFu, A.mm_events >= (1u << 18)) || A.reads >= (1u << 20)) warp_q_flush(S, wq32, A);
   f_key = __reduce_min_sync(0xFFFFFFFFu, f_key);
   uint32_t f_i = f_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : f_key >> 1;
   uint32_t f_code = (f_key & 1u) ? PS_THROW_QUAL_RANGE : PS_THROW_POS_MAXLEN;
@@ -451,6 +473,7 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
   A.q_acc[0] += qa0; A.q_acc[1] += qa1; A.q_acc[2] += qa2; A.q_acc[3] += qa3;
   A.q_cnt[0] += qc0; A.q_cnt[1] += qc1; A.q_cnt[2] += qc2; A.q_cnt[3] += qc3;
   A.checked += checked;
+  ++A.reads;
   if (P.lay.infer_q)
     for (uint32_t i = lane; i < ml; i += 32) atomicAdd(P.acc + P.lay.qhist + (size_t)i * 256 + __ldg(rq + i), 1ull);
 }
@@ -458,7 +481,10 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
 // Shared memory: s_q[32] u64 | s_ctr[16] u64 | histogram [16][pad] u32 (pad = max_len | 1) | s_indel[2*max_len] u32
 // Work unit = a warp-tile of 32 consecutive reads, handed out by an atomic counter: no block barrier in the loop.  The
 // tile's per-read stream offsets come from one warp scan; the warp then takes the 32 reads one after the other.
-__global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
+#ifndef PS_GENERIC_BLOCKS
+#define PS_GENERIC_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(PS_BLOCK_THREADS, PS_GENERIC_BLOCKS) profile_generic_kernel(const __grid_constant__ ProfileParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GenericSmem S;
   const uint32_t max_len = P.lay.max_len, pad = max_len | 1u;
@@ -478,6 +504,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
   for (int b = 0; b < 4; ++b) { A.q_acc[b] = 0; A.q_cnt[b] = 0; }
   A.checked = 0;
   A.mm_events = 0;
+  A.reads = 0;
   uint32_t ctr[3] = {0, 0, 0};      // processed, indel reads, longer indels
   unsigned int* counter = reinterpret_cast<unsigned int*>(P.fault + 3);   // zeroed by the launcher
   for (;;) {
@@ -508,22 +535,7 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, 3) profile_generic_kernel(co
       __syncwarp();
     }
   }
-  warp_q_flush(S, wq32, A);
-  // per-lane registers -> shared
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    long long t = A.q_acc[b];
-    unsigned long long c = A.q_cnt[b];
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) { t += __shfl_xor_sync(0xFFFFFFFFu, t, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d); }
-    if (lane == 0 && c) { atomicAdd(&S.s_q[b * 5], (unsigned long long)t); atomicAdd(&S.s_q[16 + b * 5], c); }
-  }
-  {
-    unsigned long long c = A.checked;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
-    if (lane == 0 && c) atomicAdd(&S.s_ctr[PS_PC_TOTAL_BASES_CHECKED], c);
-  }
+  warp_q_flush(S, wq32, A);                    // per-lane registers -> shared
   {
     const int which[3] = {PS_PC_NUM_READS_PROCESSED, PS_PC_INDEL_READ, PS_PC_LONGER_INDELS};
 #pragma unroll
