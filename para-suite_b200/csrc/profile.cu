@@ -499,6 +499,8 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, PS_GENERIC_BLOCKS) profile_g
   const uint32_t convT = (uint32_t)__cvta_generic_to_shared(S.s_conv);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t wq32 = (uint32_t)__cvta_generic_to_shared(s_wq) + (threadIdx.x >> 5) * 128u;
+  uint4* wstate = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(s_wq + (PS_BLOCK_THREADS / 32) * 32) + 15u) & ~(uintptr_t)15u) +
+                  (threadIdx.x >> 5) * 96u;
   WarpAcc A;
 #pragma unroll
   for (int b = 0; b < 4; ++b) { A.q_acc[b] = 0; A.q_cnt[b] = 0; }
@@ -520,18 +522,26 @@ __global__ void __launch_bounds__(PS_BLOCK_THREADS, PS_GENERIC_BLOCKS) profile_g
     plan.g0 = 0; plan.ml = 0; plan.bits = 0;
     if (in_range) plan = profile_read_prologue(P, S, r, meta, off, ctr);
     uint32_t todo = __ballot_sync(0xFFFFFFFFu, plan.ml != 0);
+    // what the lanes found goes to the warp's rows in shared memory: the count loop fetches a read's row with three
+    // broadcast loads, and none of it stays in registers across the loop (the kernel runs at 64 registers per thread)
+    __syncwarp();
+    wstate[lane * 3 + 0] = make_uint4((uint32_t)off.base, (uint32_t)(off.base >> 32), (uint32_t)off.qual, (uint32_t)(off.qual >> 32));
+    wstate[lane * 3 + 1] = make_uint4((uint32_t)off.cigar, (uint32_t)(off.cigar >> 32), (uint32_t)plan.g0, (uint32_t)(plan.g0 >> 32));
+    wstate[lane * 3 + 2] = make_uint4(plan.ml, plan.bits, meta, 0u);
+    __syncwarp();
     while (todo) {
       const int j = __ffs((int)todo) - 1;
       todo &= todo - 1;
+      const uint4 s0 = wstate[j * 3 + 0], s1 = wstate[j * 3 + 1], s2 = wstate[j * 3 + 2];
       ReadOffsets oj;
-      oj.base = __shfl_sync(0xFFFFFFFFu, off.base, j);
-      oj.qual = __shfl_sync(0xFFFFFFFFu, off.qual, j);
-      oj.cigar = __shfl_sync(0xFFFFFFFFu, off.cigar, j);
+      oj.base = (uint64_t)s0.x | ((uint64_t)s0.y << 32);
+      oj.qual = (uint64_t)s0.z | ((uint64_t)s0.w << 32);
+      oj.cigar = (uint64_t)s1.x | ((uint64_t)s1.y << 32);
       ReadPlan pj;
-      pj.g0 = __shfl_sync(0xFFFFFFFFu, plan.g0, j);
-      pj.ml = __shfl_sync(0xFFFFFFFFu, plan.ml, j);
-      pj.bits = __shfl_sync(0xFFFFFFFFu, plan.bits, j);
-      profile_read_warp(P, S, convT, pad, wq32, q + j, __shfl_sync(0xFFFFFFFFu, meta, j), oj, pj, A);
+      pj.g0 = (uint64_t)s1.z | ((uint64_t)s1.w << 32);
+      pj.ml = s2.x;
+      pj.bits = s2.y;
+      profile_read_warp(P, S, convT, pad, wq32, q + j, s2.z, oj, pj, A);
       __syncwarp();
     }
   }
@@ -689,7 +699,8 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
   P.n_tiles = (uint32_t)n_wt;
   size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4 +
-                (PS_BLOCK_THREADS / 32) * 32 * 4;      // + the warps' 32-bit mismatch-quality cells
+                (PS_BLOCK_THREADS / 32) * 32 * 4 +     // + the warps' 32-bit mismatch-quality cells
+                (PS_BLOCK_THREADS / 32) * 32 * 48 + 16; // + the warps' lane-per-read state (48 bytes per read, 16-byte aligned)
   // per launch: the attribute belongs to the (device, kernel) pair and a process may hold contexts on several GPUs
   cudaError_t e = cudaFuncSetAttribute(profile_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
