@@ -33,6 +33,7 @@ struct ProfileParams {
   uint64_t ordinal0;
   uint64_t first_read;        // generic kernel: first read it covers
   uint32_t n_tiles;           // generic kernel: tiles from first_read on;  fast kernel: number of super-tiles
+  uint32_t flush_reads;       // generic kernel: a warp empties its 32-bit per-lane sums after this many columns per lane (2^23)
   uint32_t* deferred;         // fast kernel: reads that need the generic routine (processed by profile_deferred_kernel)
   unsigned int* deferred_count;
   unsigned int* deferred_count_next;   // the counter of the run's next batch: cleared by this batch's deferred kernel
@@ -256,12 +257,12 @@ __device__ __forceinline__ void flush_generic(const ProfileParams& P, const Gene
 // reductions into a [pair][position] histogram.  Matching-base quality sums and the base counter live in per-lane
 // registers for the whole kernel.  Same statements as profile_read_generic (ErrorProfiling.java:155-408).
 // ---------------------------------------------------------------------------------------------------------
-struct WarpAcc {          // 32-bit per lane, emptied into the block's 64-bit cells every 2^20 reads of the warp at the latest
+struct WarpAcc {          // 32-bit per lane, emptied into the block's 64-bit cells before 2^23 columns per lane have gone in
   int q_acc[4];
   uint32_t q_cnt[4];
   uint32_t checked;
   uint32_t mm_events;      // mismatch-quality events this lane has put into the warp's 32-bit cells since their last flush
-  uint32_t reads;          // reads the warp has counted since the last flush (a lane adds < 2^10 per read to any of the above)
+  uint32_t reads;          // columns per lane (upper bound) the warp has counted since the last flush: a column adds at most 128
 };
 
 // Mismatch qualities (sum and count by pair, ErrorProfiling.java:392-397) first go to 32 warp-private 32-bit cells with
@@ -461,7 +462,7 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
       pm += n; pr += n; pq += n;
     }
   }
-  if (__any_sync(0xFFFFFFFFu, A.mm_events >= (1u << 18)) || A.reads >= (1u << 20)) warp_q_flush(S, wq32, A);
+  if (__any_sync(0xFFFFFFFFu, A.mm_events >= (1u << 18)) || A.reads >= P.flush_reads) warp_q_flush(S, wq32, A);
   f_key = __reduce_min_sync(0xFFFFFFFFu, f_key);
   uint32_t f_i = f_key == 0xFFFFFFFFu ? 0xFFFFFFFFu : f_key >> 1;
   uint32_t f_code = (f_key & 1u) ? PS_THROW_QUAL_RANGE : PS_THROW_POS_MAXLEN;
@@ -473,7 +474,7 @@ __device__ __forceinline__ void profile_read_warp(const ProfileParams& P, const 
   A.q_acc[0] += qa0; A.q_acc[1] += qa1; A.q_acc[2] += qa2; A.q_acc[3] += qa3;
   A.q_cnt[0] += qc0; A.q_cnt[1] += qc1; A.q_cnt[2] += qc2; A.q_cnt[3] += qc3;
   A.checked += checked;
-  ++A.reads;
+  A.reads += (ml + 31u) >> 5;                    // columns a lane may have counted for this read
   if (P.lay.infer_q)
     for (uint32_t i = lane; i < ml; i += 32) atomicAdd(P.acc + P.lay.qhist + (size_t)i * 256 + __ldg(rq + i), 1ull);
 }
@@ -698,6 +699,11 @@ static cudaError_t launch_generic(ps_ctx* ctx, ProfileParams P, uint64_t first_r
   const uint64_t n_wt = (P.b.n_reads - first_read + 31) / 32;
   if (n_wt > 0xFFFFFFF0ull) return cudaErrorInvalidValue;
   P.n_tiles = (uint32_t)n_wt;
+  P.flush_reads = 1u << 23;          // columns per lane: |quality| <= 128, so a sum stays below 2^30 + one read
+  if (const char* e = getenv("PARASUITE_B200_GENERIC_FLUSH_READS")) {   // tests: exercise the flush in the middle of a launch
+    const long v = atol(e);
+    if (v >= 1 && v <= (1l << 23)) P.flush_reads = (uint32_t)v;
+  }
   size_t smem = 48 * 8 + ((size_t)(ctx->layout.max_len | 1u) * 16 + 2 * (size_t)ctx->layout.max_len) * 4 +
                 (PS_BLOCK_THREADS / 32) * 32 * 4 +     // + the warps' 32-bit mismatch-quality cells
                 (PS_BLOCK_THREADS / 32) * 32 * 48 + 16; // + the warps' lane-per-read state (48 bytes per read, 16-byte aligned)

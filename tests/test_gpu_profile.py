@@ -105,6 +105,19 @@ def test_synthetic(ctx, oracle, mode, L, max_len, n):
     assert got["position_conversions"].sum() == got["counters"][7]
 
 
+@pytest.mark.parametrize("period", [1, 40, 5000])
+def test_warp_sums_flushed_in_the_middle_of_a_launch(ctx, oracle, monkeypatch, period):
+    """The warp-per-read kernel keeps its per-lane sums in 32 bits and empties them into the block's 64-bit cells before
+    2^23 columns per lane have gone in -- never reached at test sizes, so the period is shortened here (every read, every
+    few reads, a few times per warp): same counts."""
+    from parasuite_b200 import synth
+    monkeypatch.setenv("PARASUITE_B200_GENERIC_FLUSH_READS", str(period))
+    ref = synth.synth_reference(161, [3_000_000, 2_000_000], n_run=2000)
+    batch = synth.synth_reads(ref, 100_000, 150, seed=250, mode=1, special_ppm=500)
+    got = run_gpu(ctx, ref, batch, 176)
+    assert_profile_equal(got, oracle.profile(ref, batch, 176, threads=8), f"flush period {period}")
+
+
 def test_device_resident_and_multibatch(ctx, oracle):
     """Device-resident entry point, several batches per run (ordinals continue), host path equality."""
     import torch
